@@ -1,0 +1,49 @@
+"""Builds the in-tree native libraries (nvcc, sm_100a only). Run: python -m inquistr_b200.build"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+]
+
+
+def _stale(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_libinqcall(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    target = os.path.join(LIBDIR, "libinqcall.so")
+    sources = [os.path.join(CSRC, "inq_capi.cu"), os.path.join(CSRC, "inq_device.cuh"),
+               os.path.join(os.path.dirname(HERE), "include", "inqcall.h")]
+    if force or _stale(target, sources):
+        cmd = ["nvcc", *NVCC_FLAGS, "-o", target, sources[0]]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return target
+
+
+def build_all(force: bool = False, verbose: bool = False) -> list[str]:
+    out = [build_libinqcall(force, verbose)]
+    for name in ("build_libinqsynth", "build_cli"):
+        fn = globals().get(name)
+        if fn:
+            out.append(fn(force))
+    return out
+
+
+if __name__ == "__main__":
+    for p in build_all(force="--force" in sys.argv, verbose="-v" in sys.argv):
+        print(p)

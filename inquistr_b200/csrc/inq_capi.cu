@@ -1,0 +1,500 @@
+// inq_capi.cu -- extern "C" boundary of libinqcall.so (see include/inqcall.h).
+// Host-side orchestration only: device memory, H2D/D2H copies, kernel launches and timing.
+// No CPU implementation of the hot path lives here: without a CUDA device every entry fails.
+#include "../../include/inqcall.h"
+#include "inq_device.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace inq;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    uint64_t cap = 0;   // elements
+};
+
+enum { EV_START = 0, EV_INDEX, EV_JOIN, EV_CIGAR, EV_SCAN, EV_PAIRS, EV_MEDIAN, EV_D2H, EV_H2D0, EV_H2D1, EV_COUNT };
+
+}  // namespace
+
+struct inq_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int scan_ctas_per_sm = 1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // locus catalog
+    int32_t n_contigs = 0;
+    int64_t L = 0;
+    DevBuf<int64_t> contig_off;
+    DevBuf<int32_t> lstart, lend, lpmax;
+
+    // reads
+    uint64_t R = 0, C = 0;
+    DevBuf<int32_t> contig, rs, re;
+    DevBuf<uint8_t> mapq, hp, flags;
+    DevBuf<uint64_t> cig_off;
+    DevBuf<uint32_t> cigar;
+
+    // work buffers
+    DevBuf<uint32_t> cand_lo, cand_n, tile_first, ev_off, bcnt, boff, big_list;
+    DevBuf<uint64_t> desc_ev, desc_pos, desc_scan, vals;
+    DevBuf<uint2> events;
+    DevBuf<int64_t> t1, t2;
+    DevBuf<uint8_t> valid;
+    DevCounters *d_ctr = nullptr;
+    DevCounters *h_ctr = nullptr;     // pinned
+    uint32_t *h_total = nullptr;      // pinned
+
+    cudaEvent_t ev[EV_COUNT] = {};
+    float ms_h2d = 0.f;
+    uint64_t last_n_events = 0;
+};
+
+namespace {
+
+int fail(inq_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? INQ_ERR_NOMEM : INQ_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// grow-only device buffer; keeps the first `keep` elements
+template <typename T>
+int ensure(inq_ctx *ctx, DevBuf<T> &b, uint64_t need, uint64_t keep = 0, double growth = 1.0)
+{
+    if (need <= b.cap) return INQ_OK;
+    uint64_t cap = std::max<uint64_t>(need, (uint64_t)(b.cap * growth));
+    T *np = nullptr;
+    CU_TRY(ctx, cudaMalloc(&np, std::max<uint64_t>(cap, 1) * sizeof(T)));
+    if (keep && b.p) {
+        cudaError_t e = cudaMemcpyAsync(np, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(np); return fail(ctx, INQ_ERR_CUDA, "device copy failed: %s", cudaGetErrorString(e)); }
+    }
+    if (b.p) cudaFree(b.p);
+    b.p = np;
+    b.cap = cap;
+    return INQ_OK;
+}
+
+template <typename T>
+void release(DevBuf<T> &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+#define TRY(x) do { int rc_ = (x); if (rc_ != INQ_OK) return rc_; } while (0)
+
+uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+int reserve_reads(inq_ctx *ctx, uint64_t nR, uint64_t nC, double growth)
+{
+    const uint64_t R = ctx->R, C = ctx->C;
+    TRY(ensure(ctx, ctx->contig, nR, R, growth));
+    TRY(ensure(ctx, ctx->rs, nR, R, growth));
+    TRY(ensure(ctx, ctx->re, nR, R, growth));
+    TRY(ensure(ctx, ctx->mapq, nR, R, growth));
+    TRY(ensure(ctx, ctx->hp, nR, R, growth));
+    TRY(ensure(ctx, ctx->flags, nR, R, growth));
+    TRY(ensure(ctx, ctx->cig_off, nR + 1, R + 1, growth));
+    // CIGAR stream is padded with zero words up to a tile boundary (+1 tile of slack)
+    TRY(ensure(ctx, ctx->cigar, round_up(nC, kTileWords) + kTileWords, C, growth));
+    return INQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *inq_version(void) { return "inquistr-b200 0.1.0 (sm_100a)"; }
+
+const char *inq_last_error(const inq_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int inq_ctx_create(int device, inq_ctx **out)
+{
+    if (!out) return fail(nullptr, INQ_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, INQ_ERR_CUDA, "no CUDA device available (%s); libinqcall has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, INQ_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    inq_ctx *ctx = new inq_ctx();
+    ctx->device = device;
+    auto bail = [&](const char *what, cudaError_t err) {
+        int rc = fail(nullptr, INQ_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        inq_ctx_destroy(ctx);
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        fail(nullptr, INQ_ERR_CUDA, "device %d is sm_%d%d; libinqcall is built for sm_100a only", device, prop.major, prop.minor);
+        inq_ctx_destroy(ctx);
+        return INQ_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost(&ctx->h_total, 64)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaFuncSetAttribute(k_cigar_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(k_cigar_scan)", e);
+    int occ = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan, kScanThreads, sizeof(ScanSmem))) != cudaSuccess)
+        return bail("occupancy(k_cigar_scan)", e);
+    ctx->scan_ctas_per_sm = std::max(1, occ);
+    *out = ctx;
+    return INQ_OK;
+}
+
+void inq_ctx_destroy(inq_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    release(ctx->contig_off); release(ctx->lstart); release(ctx->lend); release(ctx->lpmax);
+    release(ctx->contig); release(ctx->rs); release(ctx->re);
+    release(ctx->mapq); release(ctx->hp); release(ctx->flags);
+    release(ctx->cig_off); release(ctx->cigar);
+    release(ctx->cand_lo); release(ctx->cand_n); release(ctx->tile_first); release(ctx->ev_off);
+    release(ctx->bcnt); release(ctx->boff); release(ctx->big_list);
+    release(ctx->desc_ev); release(ctx->desc_pos); release(ctx->desc_scan); release(ctx->vals);
+    release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_total) cudaFreeHost(ctx->h_total);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int inq_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return INQ_ERR_ARG;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? INQ_ERR_NOMEM : INQ_ERR_CUDA; }
+    return INQ_OK;
+}
+
+int inq_host_free(void *p)
+{
+    if (!p) return INQ_OK;
+    return cudaFreeHost(p) == cudaSuccess ? INQ_OK : INQ_ERR_CUDA;
+}
+
+int inq_set_loci(inq_ctx *ctx, int32_t n_contigs, const int64_t *contig_locus_offsets, const int32_t *start,
+                 const int32_t *end)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    if (n_contigs < 0 || !contig_locus_offsets) return fail(ctx, INQ_ERR_ARG, "inq_set_loci: bad contig table");
+    const int64_t L = contig_locus_offsets[n_contigs];
+    if (contig_locus_offsets[0] != 0 || L < 0) return fail(ctx, INQ_ERR_ARG, "inq_set_loci: offsets must start at 0");
+    for (int32_t c = 0; c < n_contigs; ++c)
+        if (contig_locus_offsets[c + 1] < contig_locus_offsets[c]) return fail(ctx, INQ_ERR_ARG, "inq_set_loci: offsets not monotonic");
+    if (L > 0 && (!start || !end)) return fail(ctx, INQ_ERR_ARG, "inq_set_loci: start/end are NULL");
+    if ((uint64_t)L * 2 + 2 > 0x7FFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "inq_set_loci: too many loci (%lld)", (long long)L);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->n_contigs = 0;
+    ctx->L = 0;
+    TRY(ensure(ctx, ctx->contig_off, (uint64_t)n_contigs + 1));
+    TRY(ensure(ctx, ctx->lstart, (uint64_t)L));
+    TRY(ensure(ctx, ctx->lend, (uint64_t)L));
+    TRY(ensure(ctx, ctx->lpmax, (uint64_t)L));
+    TRY(ensure(ctx, ctx->bcnt, 2 * (uint64_t)L + 1));
+    TRY(ensure(ctx, ctx->boff, 2 * (uint64_t)L + 1));
+    TRY(ensure(ctx, ctx->big_list, (uint64_t)L + 1));
+    TRY(ensure(ctx, ctx->desc_scan, (2 * (uint64_t)L + 1 + kXsTile - 1) / kXsTile + 1));
+    TRY(ensure(ctx, ctx->t1, (uint64_t)L));
+    TRY(ensure(ctx, ctx->t2, (uint64_t)L));
+    TRY(ensure(ctx, ctx->valid, (uint64_t)L));
+    cudaStream_t s = ctx->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->contig_off.p, contig_locus_offsets, ((size_t)n_contigs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (L) {
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->lstart.p, start, (size_t)L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->lend.p, end, (size_t)L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
+        k_locus_check<<<std::min<int64_t>((L + 255) / 256, 4096), 256, 0, s>>>(n_contigs, ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, &ctx->d_ctr->flags);
+        if (n_contigs > 0) k_locus_pmax<<<n_contigs, 1024, 0, s>>>(ctx->contig_off.p, ctx->lend.p, ctx->lpmax.p);
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    if (L) {
+        const unsigned f = ctx->h_ctr->flags;
+        if (f & 4u) return fail(ctx, INQ_ERR_LOCUS_ORDER, "a locus has end < start (the reference panics, repeats.rs:102-104)");
+        if (f & 2u) return fail(ctx, INQ_ERR_LOCUS_ORDER, "loci must be sorted by start within each contig");
+        if (f & 1u) return fail(ctx, INQ_ERR_LOCUS_START, "a locus has start < 10: start-10 underflows u32 in the reference (call.rs:285)");
+    }
+    ctx->n_contigs = n_contigs;
+    ctx->L = L;
+    return INQ_OK;
+}
+
+int inq_reserve_reads(inq_ctx *ctx, uint64_t n_reads, uint64_t n_cigar_words)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return reserve_reads(ctx, std::max(n_reads, ctx->R), std::max(n_cigar_words, ctx->C), 1.0);
+}
+
+int inq_clear_reads(inq_ctx *ctx)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    ctx->R = 0;
+    ctx->C = 0;
+    return INQ_OK;
+}
+
+int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_t *ref_start, const int32_t *ref_end,
+                   const uint8_t *mapq, const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off,
+                   const uint32_t *cigar_words)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    if (n == 0) return INQ_OK;
+    if (!contig || !ref_start || !ref_end || !mapq || !hp || !flags || !cigar_off)
+        return fail(ctx, INQ_ERR_ARG, "inq_push_reads: NULL array");
+    if (cigar_off[0] != 0) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: cigar_off[0] must be 0");
+    const uint64_t nw = cigar_off[n];
+    if (nw && !cigar_words) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: cigar_words is NULL");
+    if (ctx->R + n >= 0xFFFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "inq_push_reads: more than 2^32-2 reads");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(reserve_reads(ctx, ctx->R + n, ctx->C + nw, 1.5));
+    cudaStream_t s = ctx->stream;
+    const uint64_t R0 = ctx->R, C0 = ctx->C;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D0], s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->contig.p + R0, contig, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->rs.p + R0, ref_start, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->re.p + R0, ref_end, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->mapq.p + R0, mapq, n, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->hp.p + R0, hp, n, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p + R0, flags, n, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cig_off.p + R0, cigar_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (nw) CU_TRY(ctx, cudaMemcpyAsync(ctx->cigar.p + C0, cigar_words, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (C0) {
+        k_rebase_offsets<<<(unsigned)std::min<uint64_t>((n + 1 + 255) / 256, 8192), 256, 0, s>>>(ctx->cig_off.p + R0, n + 1, C0);
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    const uint64_t C1 = C0 + nw, Cpad = round_up(C1, kTileWords);
+    if (Cpad > C1) CU_TRY(ctx, cudaMemsetAsync(ctx->cigar.p + C1, 0, (Cpad - C1) * sizeof(uint32_t), s));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D1], s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));       // host arrays may be reused by the caller after return
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[EV_H2D0], ctx->ev[EV_H2D1]);
+    ctx->ms_h2d = (R0 == 0 ? 0.f : ctx->ms_h2d) + ms;
+    ctx->R = R0 + n;
+    ctx->C = C1;
+    return INQ_OK;
+}
+
+int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, int64_t *twice_h1, int64_t *twice_h2,
+                 uint8_t *valid_mask, inq_stats *stats)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    const int64_t L = ctx->L;
+    const uint64_t R = ctx->R, C = ctx->C;
+    if (L > 0 && (!twice_h1 || !twice_h2 || !valid_mask)) return fail(ctx, INQ_ERR_ARG, "inq_genotype: NULL output array");
+    if (minlen >= (1u << 28)) minlen = (1u << 28) - 1;       // BAM op lengths have 28 bits: nothing is longer
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t ntiles = (uint32_t)((C + kTileWords - 1) / kTileWords);
+    if ((C + kTileWords - 1) / kTileWords > 0x7FFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "too many CIGAR words");
+    const uint64_t nb = 2 * (uint64_t)L;                     // buckets
+    const uint32_t scan_tiles = (uint32_t)((nb + kXsTile - 1) / kXsTile);
+
+    TRY(ensure(ctx, ctx->cand_lo, R));
+    TRY(ensure(ctx, ctx->cand_n, R));
+    TRY(ensure(ctx, ctx->ev_off, R + 1));
+    TRY(ensure(ctx, ctx->tile_first, (uint64_t)ntiles + 1));
+    TRY(ensure(ctx, ctx->desc_ev, (uint64_t)ntiles + 1));
+    TRY(ensure(ctx, ctx->desc_pos, (uint64_t)ntiles + 1));
+    if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 8 + 4096));
+
+    ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
+    LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
+    uint32_t launches = 0;
+
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        launches = 0;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_START], s));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
+        if (nb) CU_TRY(ctx, cudaMemsetAsync(ctx->bcnt.p, 0, (nb + 1) * sizeof(uint32_t), s));
+        if (nb) CU_TRY(ctx, cudaMemsetAsync(ctx->boff.p, 0, (nb + 1) * sizeof(uint32_t), s));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->ev_off.p, 0, (R + 1) * sizeof(uint32_t), s));
+        if (ntiles) {
+            CU_TRY(ctx, cudaMemsetAsync(ctx->desc_ev.p, 0, (uint64_t)ntiles * sizeof(uint64_t), s));
+            CU_TRY(ctx, cudaMemsetAsync(ctx->desc_pos.p, 0, (uint64_t)ntiles * sizeof(uint64_t), s));
+            k_tile_index<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R, ntiles, ctx->tile_first.p);
+            ++launches;
+        }
+        if (scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, (uint64_t)scan_tiles * sizeof(uint64_t), s));
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_INDEX], s));
+
+        // K1: overlap join (count)
+        if (R && L) {
+            k_join_count<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->bcnt.p, ctx->d_ctr);
+            ++launches;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_JOIN], s));
+
+        // K2: CIGAR scan -> events
+        if (ntiles && L) {
+            ScanParams sp;
+            sp.cigar = ctx->cigar.p; sp.cig_off = ctx->cig_off.p; sp.rs = ctx->rs.p; sp.tile_first = ctx->tile_first.p;
+            sp.desc_ev = ctx->desc_ev.p; sp.desc_pos = ctx->desc_pos.p; sp.events = ctx->events.p; sp.ev_off = ctx->ev_off.p;
+            sp.ctr = ctx->d_ctr; sp.R = R; sp.ev_cap = ctx->events.cap; sp.ntiles = ntiles; sp.minlen = minlen;
+            const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
+            k_cigar_scan<<<grid, kScanThreads, sizeof(ScanSmem), s>>>(sp);
+            ++launches;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR], s));
+
+        // bucket offsets
+        if (scan_tiles) {
+            const unsigned grid = std::min<unsigned>(scan_tiles, (unsigned)ctx->sm_count * 4);
+            k_exclusive_scan<<<grid, kXsThreads, 0, s>>>(ctx->bcnt.p, ctx->boff.p, nb, scan_tiles, ctx->desc_scan.p, ctx->d_ctr);
+            ++launches;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_SCAN], s));
+        CU_TRY(ctx, cudaGetLastError());
+
+        // P is needed on the host to size the bucket storage
+        uint64_t P = 0;
+        if (nb) {
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->boff.p + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaStreamSynchronize(s));
+            P = *ctx->h_total;
+        }
+        TRY(ensure(ctx, ctx->vals, P + 1, 0, 1.25));
+
+        // K2b: window sums + scatter
+        if (R && L) {
+            k_pair_eval<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->events.p,
+                                                                   ctx->ev_off.p, ctx->boff.p, ctx->bcnt.p, ctx->vals.p,
+                                                                   ctx->vals.cap, ctx->d_ctr);
+            ++launches;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_PAIRS], s));
+
+        // K3: medians
+        if (L) {
+            k_locus_median<<<(unsigned)(((uint64_t)L * 32 + 255) / 256), 256, 0, s>>>((uint32_t)L, unphased, support, ctx->boff.p, ctx->vals.p,
+                                                                                     ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s>>>(unphased, support, ctx->boff.p, ctx->vals.p, ctx->t1.p, ctx->t2.p,
+                                                                                  ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+            launches += 2;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_MEDIAN], s));
+        CU_TRY(ctx, cudaGetLastError());
+
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+        if (L) {
+            CU_TRY(ctx, cudaMemcpyAsync(twice_h1, ctx->t1.p, (size_t)L * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaMemcpyAsync(twice_h2, ctx->t2.p, (size_t)L * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaMemcpyAsync(valid_mask, ctx->valid.p, (size_t)L, cudaMemcpyDeviceToHost, s));
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_D2H], s));
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+
+        const unsigned f = ctx->h_ctr->flags;
+        if (f & kFlagEventOverflow) {
+            // the event list was sized speculatively; the scan still counted every event
+            const uint64_t need = ctx->h_ctr->n_events + 4096;
+            release(ctx->events);
+            TRY(ensure(ctx, ctx->events, need));
+            continue;
+        }
+        if (f & kFlagCountOverflow) return fail(ctx, INQ_ERR_TOO_LARGE, "pair or event count exceeds 2^32");
+        if (f & kFlagValsOverflow) return fail(ctx, INQ_ERR_STATE, "internal: bucket storage overflow");
+        if (f & kFlagBadHp)
+            return fail(ctx, INQ_ERR_BAD_HP, "a read passing the phased filter carries HP outside {0,1,2} (the reference panics, call.rs:358)");
+        if (f & kFlagMedianEmpty)
+            return fail(ctx, INQ_ERR_MEDIAN_EMPTY, "support == 0 with a bucket without usable calls (the reference panics, call.rs:516)");
+        break;
+    }
+    if (ctx->h_ctr->flags & kFlagEventOverflow) return fail(ctx, INQ_ERR_STATE, "internal: event list overflow persists");
+    ctx->last_n_events = ctx->h_ctr->n_events;
+
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_loci = (uint64_t)L;
+        stats->n_reads = R;
+        stats->n_cigar_words = C;
+        stats->n_cigar_words_joined = ctx->h_ctr->n_words_joined;
+        stats->n_reads_joined = ctx->h_ctr->n_reads_joined;
+        stats->n_pairs = ctx->h_ctr->n_pairs;
+        stats->n_candidates = ctx->h_ctr->n_candidates;
+        stats->n_events = ctx->h_ctr->n_events;
+        stats->op_visits = ctx->h_ctr->op_visits;
+        stats->n_kernel_launches = launches;
+        stats->n_tiles = ntiles;
+        auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
+        stats->ms_total = el(EV_START, EV_MEDIAN);
+        stats->ms_index = el(EV_START, EV_INDEX);
+        stats->ms_join = el(EV_INDEX, EV_JOIN);
+        stats->ms_cigar = el(EV_JOIN, EV_CIGAR);
+        stats->ms_scan = el(EV_CIGAR, EV_SCAN);
+        stats->ms_pairs = el(EV_SCAN, EV_PAIRS);
+        stats->ms_median = el(EV_PAIRS, EV_MEDIAN);
+        stats->ms_d2h = el(EV_MEDIAN, EV_D2H);
+        stats->ms_h2d = ctx->ms_h2d;
+    }
+    return INQ_OK;
+}
+
+int inq_debug_events(inq_ctx *ctx, uint64_t *n_events, uint32_t *event_pos, int32_t *event_val, uint64_t cap,
+                     uint32_t *read_event_off)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t E = ctx->last_n_events;
+    if (n_events) *n_events = E;
+    if (read_event_off && ctx->ev_off.p)
+        CU_TRY(ctx, cudaMemcpy(read_event_off, ctx->ev_off.p, (ctx->R + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const uint64_t n = std::min(E, cap);
+    if (n && (event_pos || event_val)) {
+        uint2 *tmp = (uint2 *)malloc(n * sizeof(uint2));
+        if (!tmp) return fail(ctx, INQ_ERR_NOMEM, "host allocation failed");
+        cudaError_t e = cudaMemcpy(tmp, ctx->events.p, n * sizeof(uint2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { free(tmp); return fail(ctx, INQ_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
+        for (uint64_t i = 0; i < n; ++i) {
+            if (event_pos) event_pos[i] = tmp[i].x;
+            if (event_val) event_val[i] = (int32_t)tmp[i].y;
+        }
+        free(tmp);
+    }
+    return INQ_OK;
+}
+
+}  // extern "C"
