@@ -401,7 +401,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         // K2b: window sums + scatter
         if (R && L) {
             k_pair_eval<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->events.p,
-                                                                   ctx->ev_off.p, ctx->boff.p, ctx->bcnt.p, ctx->vals.p,
+                                                                   ctx->ev_off.p, ctx->events.cap, ctx->boff.p, ctx->bcnt.p, ctx->vals.p,
                                                                    ctx->vals.cap, ctx->d_ctr);
             ++launches;
         }

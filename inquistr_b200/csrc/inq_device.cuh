@@ -298,7 +298,7 @@ k_join_count(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ can
         cand_lo[r] = (uint32_t)lo;
         cand_n[r] = (uint32_t)n;
     }
-    uint32_t npass = 0;
+    uint32_t npass = 0, nvisit = 0;     // bucketed pairs; pairs the reference walks (incl. HP 0)
     bool bad_hp = false;
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     for (int j = 0; j < nmax; ++j) {
@@ -306,6 +306,7 @@ k_join_count(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ can
         if (j < n) {
             const int l = lo + j;
             if (pair_passes(unphased != 0, rs, re, __ldg(lv.start + l), __ldg(lv.end + l))) {
+                ++nvisit;                                       // call.rs:357 runs before the bucket lookup
                 if (unphased) bucket = 2u * (uint32_t)l;
                 else if (h > 2u) bad_hp = true;                 // call.rs:358 unwrap on None
                 else if (h != 0u) bucket = 2u * (uint32_t)l + (h - 1u);  // HP 0 lands in the ignored bucket
@@ -318,13 +319,14 @@ k_join_count(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ can
         }
     }
     // statistics (one atomic per warp per counter)
-    uint64_t words = 0;
-    if (live && npass) words = rv.cig_off[r + 1] - rv.cig_off[r];
+    uint64_t words = 0, nw = 0;
+    if (live && nvisit) nw = rv.cig_off[r + 1] - rv.cig_off[r];
+    if (npass) words = nw;
     const uint32_t cand_w = warp_sum((uint32_t)n);
     const uint32_t pass_w = warp_sum(npass);
     const uint32_t join_w = warp_sum((uint32_t)(npass != 0));
     const uint64_t words_w = warp_sum(words);
-    const uint64_t visits_w = warp_sum(words * npass);
+    const uint64_t visits_w = warp_sum(nw * nvisit);
     const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
     if (lane_id() == 0) {
         if (cand_w) atomicAdd(&ctr->n_candidates, (unsigned long long)cand_w);
@@ -657,7 +659,7 @@ k_exclusive_scan(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
 __global__ void __launch_bounds__(256)
 k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
             const uint32_t *__restrict__ cand_n, const uint2 *__restrict__ events,
-            const uint32_t *__restrict__ ev_off, const uint32_t *__restrict__ bucket_off,
+            const uint32_t *__restrict__ ev_off, uint64_t ev_cap, const uint32_t *__restrict__ bucket_off,
             uint32_t *__restrict__ bucket_cnt, uint64_t *__restrict__ vals, uint64_t vals_cap,
             DevCounters *__restrict__ ctr)
 {
@@ -674,8 +676,9 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             re = rv.re[r];
             h = rv.hp[r];
             is2d = (rv.flags[r] & 1u) != 0;
-            e0 = ev_off[r];
-            e1 = ev_off[r + 1];
+            // if the speculative event list overflowed the run is repeated; stay inside the allocation
+            e0 = (uint32_t)min((uint64_t)ev_off[r], ev_cap);
+            e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
         }
     }
     const int nmax = __reduce_max_sync(0xffffffffu, n);
