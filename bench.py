@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- `inquiSTR call` hot path on B200: STR loci genotyped / s and CIGAR ops / s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 3] [--scale S]
+
+A step = one pass of the hot path (join -> CIGAR scan -> pair sums -> medians) over the whole
+workload. `value` is measured with the reads already resident in HBM (CUDA events on the library's
+own stream); `e2e` is the same job through the C ABI from pinned HOST buffers (set_loci + push_reads
++ genotype, H2D and D2H inside the timed region). One process per GPU; for N > 1 the sorted locus
+catalog is range-sharded across ranks (no collective on the data path; torch.distributed is used
+for the barrier and the max-over-ranks only). Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs[] index + 1 (default 3 = headline)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome and catalog (tests)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class Clocks:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def algorithmic_bytes(st: dict) -> dict:
+    """bytes_alg = 4*C_j + 24*R + 12*L + 16*P + 17*L (each CIGAR word counted once)."""
+    Cj, R, L, P = st["n_cigar_words_joined"], st["n_reads"], st["n_loci"], st["n_pairs"]
+    Rj = st["n_reads_joined"]
+    return {
+        "pipeline": 4 * Cj + 24 * R + 12 * L + 16 * P + 17 * L,
+        # what the dominant kernel (k_cigar_scan) must touch: the joined reads' packed CIGAR words once,
+        # plus cigar_off (8 B) and ref_start (4 B) of those reads
+        "cigar_scan": 4 * Cj + 12 * Rj,
+    }
+
+
+def cpu_reference(w, threads: int, seconds: float):
+    """Times the oracle (CPU restatement of call.rs:103-158,279-522; the reference itself is a Rust
+    crate that cannot be built here) on a bounded sample of the workload's loci, all host threads."""
+    from oracle import oracle as O
+    n = w.n_loci
+    lc = w.locus_contig
+    ls = w.locus_start.astype(np.uint32)
+    le = w.locus_end.astype(np.uint32)
+    # probe on ~1% of the loci (evenly spaced), then size the sample to the time budget
+    probe = np.unique(np.linspace(0, n - 1, max(1, min(n, n // 100 + 1))).astype(np.int64))
+    t0 = time.perf_counter()
+    O.genotype_loci(w.reads, w.n_contigs, lc[probe], ls[probe], le[probe], w.minlen, w.support, w.unphased, threads)
+    t_probe = time.perf_counter() - t0          # includes building the read index (the oracle's "fetch")
+    t1 = time.perf_counter()
+    O.genotype_loci(w.reads, w.n_contigs, lc[probe], ls[probe], le[probe], w.minlen, w.support, w.unphased, threads)
+    t_probe2 = time.perf_counter() - t1
+    per_locus = max(t_probe2 / len(probe), 1e-9)
+    m = int(min(n, max(len(probe), seconds / per_locus)))
+    sel = np.unique(np.linspace(0, n - 1, m).astype(np.int64))
+    t2 = time.perf_counter()
+    rc, p1, p2, visits = O.genotype_loci(w.reads, w.n_contigs, lc[sel], ls[sel], le[sel], w.minlen, w.support,
+                                         w.unphased, threads)
+    dt = time.perf_counter() - t2
+    return {
+        "value": len(sel) / dt, "unit": "loci/s", "cores": threads, "kind": "port",
+        "sample": f"{len(sel)} of {n} loci (evenly spaced) against all {w.reads.n} resident reads, "
+                  f"{dt:.2f} s incl. in-memory read index build; per-locus fetch/BGZF inflate of the real "
+                  f"reference is NOT included (oracle restatement of call.rs, reference is Rust and cannot be built here)",
+        "op_visits_per_s": visits / dt, "seconds": dt, "rc": rc,
+    }, (sel, p1, p2)
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    threads = os.cpu_count() or 1
+
+    from synth.synth import make_workload
+
+    config_desc = {
+        "workload": None, "config_index": args.config, "scale": args.scale, "minlen": 5, "support": 3,
+        "sharding": f"locus catalog range-sharded over {world} rank(s), no collective",
+        "l2": "inputs (packed CIGAR stream) are far larger than the 126 MB L2; no flush needed",
+        "data_seed": args.config,
+    }
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        w = make_workload(args.config, scale=args.scale, threads=threads)
+        config_desc["workload"] = w.name
+        config_desc["unphased"] = bool(w.unphased)
+        vals = []
+        base = None
+        steps = max(1, args.steps)
+        per_step = max(2.0, min(args.cpu_seconds, 120.0 / (steps + max(args.warmup, 0))))
+        for i in range(max(args.warmup, 0) + steps):
+            base, _ = cpu_reference(w, threads, per_step)
+            if i >= args.warmup:
+                vals.append(base["value"])
+        v = float(np.mean(vals))
+        line = {
+            "impl": "reference", "metric": "str_loci_genotyped_per_s", "value": v, "unit": "loci/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * base["seconds"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config_desc,
+            "cpu_baseline": {**{k: base[k] for k in ("unit", "cores", "kind", "sample")}, "value": v},
+            "e2e": {"value": v, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cigar_op_visits_per_s": base["op_visits_per_s"], "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    import inquistr_b200 as q
+
+    t_gen = time.perf_counter()
+    w = make_workload(args.config, scale=args.scale, threads=max(1, threads // max(1, world)), pinned=True,
+                      shard=(rank, world))
+    t_gen = time.perf_counter() - t_gen
+    rd = w.reads
+    config_desc["workload"] = w.name
+    config_desc["unphased"] = bool(w.unphased)
+
+    ctx = q.Context(local_rank)
+    ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
+    ctx.reserve_reads(rd.n, len(rd.cigar))
+    ctx.push(rd)
+    out = (np.zeros(w.n_loci, np.int64), np.zeros(w.n_loci, np.int64), np.zeros(w.n_loci, np.uint8))
+
+    # warm-up (also sizes the speculative event / bucket buffers)
+    res = None
+    for _ in range(max(args.warmup, 3)):
+        res = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
+    st0 = res.stats
+
+    # ---- timed: device-resident inputs
+    clocks = Clocks(local_rank) if rank == 0 else None
+    barrier()
+    dev_ms, cigar_ms, stage_ms = 0.0, 0.0, {}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
+        s = res.stats
+        dev_ms += s["ms_total"]
+        cigar_ms += s["ms_cigar"]
+        for k in ("ms_index", "ms_join", "ms_cigar", "ms_scan", "ms_pairs", "ms_median", "ms_d2h"):
+            stage_ms[k] = stage_ms.get(k, 0.0) + s[k] / args.steps
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    dev_ms_max = max_over_ranks(dev_ms)
+    st = res.stats
+
+    # ---- timed: end to end from pinned host buffers through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
+            ctx.clear_reads()
+            ctx.push(rd)
+            res2 = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t1)
+        h2d = rd.nbytes() + w.locus_start.nbytes + w.locus_end.nbytes + w.contig_locus_off.nbytes
+        d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes
+        e2e = {"seconds_per_step": e2e_s / args.steps, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+               "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_h2d_last": res2.stats["ms_h2d"]}
+    clk = clocks.stop() if clocks else None
+
+    tot_loci = sum_over_ranks(st["n_loci"])
+    tot_words = sum_over_ranks(st["n_cigar_words"])
+    tot_words_j = sum_over_ranks(st["n_cigar_words_joined"])
+    tot_visits = sum_over_ranks(st["op_visits"])
+    tot_pairs = sum_over_ranks(st["n_pairs"])
+    tot_reads = sum_over_ranks(st["n_reads"])
+    sec_per_step = dev_ms_max / 1e3 / args.steps
+    value = tot_loci / sec_per_step
+
+    # ---- roofline of the dominant kernel (rank 0's shard)
+    peaks = {}
+    peak_src = "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak = float(peaks["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        peak = 6650.0
+    ab = algorithmic_bytes(st)
+    ms_cigar = cigar_ms / args.steps
+    achieved = ab["cigar_scan"] / (ms_cigar * 1e-3) / 1e9 if ms_cigar > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(f"config{args.config}_scale{args.scale:g}_gpus{world}")
+        if ent:
+            traffic = ent["k_cigar_scan_dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {
+        "kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": ab["cigar_scan"], "ms_per_launch": ms_cigar,
+        "bytes_streamed_per_launch": 4 * st["n_cigar_words"],
+        "streamed_GBps": 4 * st["n_cigar_words"] / (ms_cigar * 1e-3) / 1e9 if ms_cigar > 0 else 0.0,
+        "pipeline_algorithmic_bytes": ab["pipeline"],
+        "pipeline_GBps": ab["pipeline"] / (st["ms_total"] * 1e-3) / 1e9 if st["ms_total"] > 0 else 0.0,
+        "pipeline_frac": (ab["pipeline"] / (st["ms_total"] * 1e-3) / 1e9 / peak) if st["ms_total"] > 0 else 0.0,
+        "frac_of_nominal_8TBps": achieved / 8000.0,
+    }
+
+    # ---- CPU baseline (rank 0, N=1 only) + sampled parity check of the GPU result
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, (sel, p1, p2) = cpu_reference(w, threads, args.cpu_seconds)
+        g1, g2 = res.phase1[sel], res.phase2[sel]
+        ok = bool(np.array_equal(g1, p1, equal_nan=True) and np.array_equal(g2, p2, equal_nan=True))
+        parity = {"loci_checked": int(len(sel)), "bit_exact_vs_oracle": ok}
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "op_visits_per_s")}
+
+    if rank == 0:
+        line = {
+            "metric": "str_loci_genotyped_per_s", "value": value, "unit": "loci/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec_per_step * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": config_desc,
+            "cigar_ops_per_s": tot_words_j / sec_per_step,
+            "cigar_op_visits_per_s_reference_equivalent": tot_visits / sec_per_step,
+            "counts": {"loci": int(tot_loci), "reads": int(tot_reads), "cigar_words": int(tot_words),
+                       "cigar_words_joined": int(tot_words_j), "pairs": int(tot_pairs),
+                       "events_rank0": int(st["n_events"]), "tiles_rank0": int(st["n_tiles"])},
+            "stage_ms_rank0": stage_ms,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": None if e2e is None else {
+                "value": tot_loci / e2e["seconds_per_step"], "unit": "loci/s",
+                "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
+                "seconds_per_step": e2e["seconds_per_step"], "ms_h2d_rank0": e2e["ms_h2d_last"],
+                "cigar_ops_per_s": tot_words_j / e2e["seconds_per_step"]},
+            "gpu_launches": int(st["n_kernel_launches"]) * args.steps,
+            "clocks": clk,
+            "parity": parity,
+            "host": {"cores": threads, "gen_seconds": t_gen, "wall_resident_s": wall_resident},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -85,7 +85,7 @@ def load_library(path: str | None = None):
 
 
 def pinned_empty(n: int, dtype) -> np.ndarray:
-    """numpy array backed by inq_host_alloc pinned memory (freed when the array is collected)."""
+    """numpy array backed by inq_host_alloc pinned memory. Released with free_pinned() or at exit."""
     L = load_library()
     dt = np.dtype(dtype)
     p = C.c_void_p()
@@ -94,19 +94,18 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
         raise InqError(rc, "inq_host_alloc failed")
     buf = (C.c_char * max(1, n * dt.itemsize)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dt, count=n)
-    _PINNED[id(buf)] = (buf, p.value)
-    import weakref
-    weakref.finalize(arr, _free_pinned, id(buf))
+    _PINNED[p.value] = buf
     return arr
 
 
 _PINNED: dict = {}
 
 
-def _free_pinned(key):
-    ent = _PINNED.pop(key, None)
-    if ent is not None and _LIB is not None:
-        _LIB.inq_host_free(C.c_void_p(ent[1]))
+def free_pinned(arr: np.ndarray) -> None:
+    """Release a pinned_empty() array; the caller must not touch it (or views of it) afterwards."""
+    addr = arr.ctypes.data
+    if _PINNED.pop(addr, None) is not None and _LIB is not None:
+        _LIB.inq_host_free(C.c_void_p(addr))
 
 
 @dataclass

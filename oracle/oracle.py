@@ -145,17 +145,22 @@ class Reads:
         return cls(contig, rs, re_, mq, hp, fl, off, cig)
 
     def _struct(self):
-        s = _Reads()
-        s.n_reads = self.n
-        s.contig = self.contig.ctypes.data
-        s.ref_start = self.ref_start.ctypes.data
-        s.ref_end = self.ref_end.ctypes.data
-        s.mapq = self.mapq.ctypes.data
-        s.hp = self.hp.ctypes.data
-        s.flags = self.flags.ctypes.data
-        s.cigar_off = self.cigar_off.ctypes.data
-        s.cigar = self.cigar.ctypes.data
-        return s
+        return _reads_struct(self)
+
+
+_DTYPES = dict(contig=np.int32, ref_start=np.int32, ref_end=np.int32, mapq=np.uint8, hp=np.uint8,
+               flags=np.uint8, cigar_off=np.uint64, cigar=np.uint32)
+
+
+def _reads_struct(reads):
+    """C view of any object carrying the SoA attributes (oracle.Reads, synth.ReadSet)."""
+    s = _Reads()
+    s.n_reads = len(reads.contig)
+    for name, dt in _DTYPES.items():
+        a = getattr(reads, name)
+        assert a.dtype == dt and a.flags["C_CONTIGUOUS"], name
+        setattr(s, name, a.ctypes.data)
+    return s
 
 
 # --------------------------------------------------------------------------- C oracle
@@ -195,7 +200,7 @@ def genotype_loci(reads: Reads, n_contigs, locus_contig, locus_start, locus_end,
     p1 = np.full(n, np.nan, dtype=np.float64)
     p2 = np.full(n, np.nan, dtype=np.float64)
     visits = C.c_uint64(0)
-    s = reads._struct()
+    s = _reads_struct(reads)
     rc = lib().orc_genotype_loci(C.byref(s), int(n_contigs), n, lc.ctypes.data, ls.ctypes.data,
                                  le.ctypes.data, int(minlen), int(support), int(bool(unphased)),
                                  int(threads), p1.ctypes.data, p2.ctypes.data, C.byref(visits))
