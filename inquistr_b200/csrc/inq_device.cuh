@@ -384,16 +384,21 @@ struct ScanParams {
     uint32_t minlen;
 };
 
+constexpr int kMaxStarts = 512;             // read starts per tile staged in shared memory
+
 struct ScanSmem {
     alignas(128) uint32_t stage[kScanStages][kTileWords];
     uint32_t qpref[kQuadsPerTile];          // warp-local exclusive ref-consumption prefix per quad
     uint16_t qev[kQuadsPerTile];            // warp-local exclusive event-count prefix per quad
+    uint32_t st_pos1[kMaxStarts];           // per read starting in the tile: ref_start + 1 - S(start word)
+    uint16_t st_off[kMaxStarts];            // tile-local word index where that read's CIGAR starts
+    uint16_t st_ev[kMaxStarts];             // events in the tile before that word
     uint32_t wsum[kWarpsPerScanCta];
     uint32_t wev[kWarpsPerScanCta];
     alignas(8) uint64_t full[kScanStages];
-    uint32_t tile_id[kScanStages];
-    uint32_t carry_pos;
     uint64_t ev_base;
+    uint32_t carry_pos1;                    // carried-in read: ref_start + 1 + bases consumed before the tile
+    uint32_t vid;
 };
 
 __device__ __forceinline__ uint32_t tile_S(const ScanSmem &sm, const uint32_t *stage, uint32_t b, uint32_t tot)
@@ -429,33 +434,37 @@ k_cigar_scan(ScanParams p)
     if (tid == 0) {
         for (int s = 0; s < kScanStages; ++s) mbar_init(&sm.full[s], 1);
         fence_mbar_init();
+        // CTA id in scheduling order: look-back only ever waits on CTAs that are already running
+        sm.vid = atomicAdd(&p.ctr->tile_counter, 1u);
     }
     __syncthreads();
+    const uint64_t vid = sm.vid, stride = gridDim.x;
+    // tiles vid, vid+G, vid+2G, ...: neighbouring tiles are processed by different CTAs at the same time
     if (tid == 0) {
         for (int s = 0; s < kScanStages; ++s) {
-            const uint32_t t = atomicAdd(&p.ctr->tile_counter, 1u);
-            sm.tile_id[s] = t;
+            const uint64_t t = vid + (uint64_t)s * stride;
             if (t < p.ntiles) {
                 mbar_expect_tx(&sm.full[s], kTileBytes);
-                bulk_copy_g2s(sm.stage[s], p.cigar + (uint64_t)t * kTileWords, kTileBytes, &sm.full[s]);
+                bulk_copy_g2s(sm.stage[s], p.cigar + t * kTileWords, kTileBytes, &sm.full[s]);
             }
         }
     }
-    __syncthreads();
 
     for (uint32_t it = 0;; ++it) {
+        const uint64_t t64 = vid + (uint64_t)it * stride;
+        if (t64 >= p.ntiles) break;
+        const uint32_t t = (uint32_t)t64;
         const uint32_t s = it % kScanStages;
-        const uint32_t t = sm.tile_id[s];
-        if (t >= p.ntiles) break;                       // ids are handed out in increasing order
         mbar_wait(&sm.full[s], (it / kScanStages) & 1u);
         const uint32_t *stage = sm.stage[s];
         const uint64_t g0 = (uint64_t)t * kTileWords;
         const uint32_t rA = p.tile_first[t], rB = p.tile_first[t + 1];   // reads starting in this tile
+        const uint32_t nrs = rB - rA, nst = min(nrs, (uint32_t)kMaxStarts);
 
         // ---- phase A: per-warp scan of its 512 words (4 slabs of 32 lanes x uint4)
-        uint32_t excl[kSlabs], evx[kSlabs];
         uint32_t evmask = 0;
         {
+            uint32_t excl[kSlabs], evx[kSlabs];
             uint32_t cs[kSlabs], packed_ec = 0, carry = 0;
 #pragma unroll
             for (int j = 0; j < kSlabs; ++j) {
@@ -492,7 +501,7 @@ k_cigar_scan(ScanParams p)
         }
         __syncthreads();
 
-        // ---- phase B: tile totals, publish, look back (warp 0)
+        // ---- phase B: tile totals; warp 0 publishes + looks back while warps 1..7 stage the read starts
         uint32_t wbase = 0, webase = 0, tot_cons = 0, tot_ev = 0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerScanCta; ++w) {
@@ -502,7 +511,7 @@ k_cigar_scan(ScanParams p)
             tot_ev += b;
         }
         if (warp == 0) {
-            const bool has_boundary = rB > rA;
+            const bool has_boundary = nrs > 0;
             uint32_t trailing = tot_cons;
             if (has_boundary) {
                 const uint64_t b_last = p.cig_off[rB - 1] - g0;
@@ -523,7 +532,7 @@ k_cigar_scan(ScanParams p)
                 }
             }
             if (lane == 0) {
-                sm.carry_pos = (uint32_t)carry_pos;
+                sm.carry_pos1 = (rA > 0 ? (uint32_t)p.rs[rA - 1] : 0u) + 1u + (uint32_t)carry_pos;
                 sm.ev_base = ev_base;
                 if (t == p.ntiles - 1) {
                     p.ev_off[p.R] = (uint32_t)(ev_base + tot_ev);
@@ -531,15 +540,24 @@ k_cigar_scan(ScanParams p)
                     if (ev_base + tot_ev > 0xFFFFFFFFull) atomicOr(&p.ctr->flags, kFlagCountOverflow);
                 }
             }
+        } else {
+            for (uint32_t i = tid - 32; i < nst; i += kScanThreads - 32) {
+                const uint32_t r = rA + i;
+                const uint32_t b = (uint32_t)min(p.cig_off[r] - g0, (uint64_t)kTileWords);
+                sm.st_off[i] = (uint16_t)b;
+                sm.st_ev[i] = (uint16_t)tile_E(sm, stage, b, tot_ev, p.minlen);
+                sm.st_pos1[i] = (uint32_t)p.rs[r] + 1u - tile_S(sm, stage, b, tot_cons);
+            }
         }
         __syncthreads();
         const uint64_t ev_base = sm.ev_base;
-        const uint32_t carry_pos = sm.carry_pos;
 
         // ---- phase D1: first-event index of every read whose CIGAR starts in this tile
-        for (uint32_t r = rA + tid; r < rB; r += kScanThreads) {
-            const uint64_t b = p.cig_off[r] - g0;
-            p.ev_off[r] = (uint32_t)(ev_base + tile_E(sm, stage, (uint32_t)min(b, (uint64_t)kTileWords), tot_ev, p.minlen));
+        for (uint32_t i = tid; i < nrs; i += kScanThreads) {
+            uint32_t e;
+            if (i < nst) e = sm.st_ev[i];
+            else e = tile_E(sm, stage, (uint32_t)min(p.cig_off[rA + i] - g0, (uint64_t)kTileWords), tot_ev, p.minlen);
+            p.ev_off[rA + i] = (uint32_t)(ev_base + e);
         }
 
         // ---- phase D2: emit events (rare: a few per hundred words)
@@ -550,43 +568,48 @@ k_cigar_scan(ScanParams p)
             const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
             const uint32_t idx = q * 4 + k;
             const uint32_t w = stage[idx];
-            uint32_t s_here = wbase + excl[j], e_here = webase + evx[j];
+            uint32_t s_here = wbase + sm.qpref[q], e_here = webase + sm.qev[q];
             for (int kk = 0; kk < k; ++kk) {
                 const uint32_t wp = stage[q * 4 + kk];
                 s_here += cig_consume(wp);
                 e_here += cig_is_event(wp, p.minlen) ? 1u : 0u;
             }
-            // owning read: last r in [rA-1, rB) with cig_off[r] <= g0 + idx
-            const uint64_t g = g0 + idx;
-            uint32_t lo = rA, hi = rB;
+            // owning read: the last read start at or before this word
+            uint32_t lo = 0, hi = nst;
             while (lo < hi) {
-                const uint32_t mid = lo + ((hi - lo) >> 1);
-                if (p.cig_off[mid] <= g) lo = mid + 1; else hi = mid;
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sm.st_off[mid] <= idx) lo = mid + 1; else hi = mid;
             }
-            uint32_t consumed, r;
-            if (lo == rA) {                       // read carried in from an earlier tile
-                r = rA - 1;
-                consumed = carry_pos + s_here;
+            uint32_t pos1;
+            if (lo == 0) {
+                pos1 = sm.carry_pos1 + s_here;                           // read carried in from an earlier tile
+            } else if (lo == nst && nrs > nst) {
+                // more read starts than the staging area holds: search the tail in global memory
+                const uint64_t g = g0 + idx;
+                uint32_t a = rA + nst - 1, b = rB;
+                while (a < b) {
+                    const uint32_t mid = a + ((b - a) >> 1);
+                    if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
+                }
+                const uint32_t r = a - 1;
+                pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(sm, stage, (uint32_t)(p.cig_off[r] - g0), tot_cons);
             } else {
-                r = lo - 1;
-                consumed = s_here - tile_S(sm, stage, (uint32_t)(p.cig_off[r] - g0), tot_cons);
+                pos1 = sm.st_pos1[lo - 1] + s_here;                      // call.rs:380 cursor at this op
             }
             const uint32_t len = w >> 4, op = w & 15u;
-            const uint32_t pos1 = (uint32_t)p.rs[r] + 1u + consumed;     // call.rs:380 cursor at this op
             const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
             const uint64_t slot = ev_base + e_here;
             if (slot < p.ev_cap) p.events[slot] = make_uint2(pos1, (uint32_t)val);
             else atomicOr(&p.ctr->flags, kFlagEventOverflow);
         }
 
-        __syncthreads();                                // everyone is done with stage s
+        __syncthreads();                                // everyone is done with stage s and the staging arrays
         if (tid == 0) {
-            const uint32_t t2 = atomicAdd(&p.ctr->tile_counter, 1u);
-            sm.tile_id[s] = t2;
+            const uint64_t t2 = vid + (uint64_t)(it + kScanStages) * stride;
             if (t2 < p.ntiles) {
                 fence_proxy_async();
                 mbar_expect_tx(&sm.full[s], kTileBytes);
-                bulk_copy_g2s(sm.stage[s], p.cigar + (uint64_t)t2 * kTileWords, kTileBytes, &sm.full[s]);
+                bulk_copy_g2s(sm.stage[s], p.cigar + t2 * kTileWords, kTileBytes, &sm.full[s]);
             }
         }
     }
