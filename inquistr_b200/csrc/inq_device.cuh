@@ -385,42 +385,85 @@ struct ScanParams {
 };
 
 constexpr int kMaxStarts = 512;             // read starts per tile staged in shared memory
+constexpr int kAhead = 1;                   // tiles whose aggregates are published ahead of their look-back
+constexpr int kTables = kAhead + 1;
+
+struct TileTables {
+    uint32_t qpref[kQuadsPerTile];          // warp-local exclusive ref-consumption prefix per quad
+    uint16_t qev[kQuadsPerTile];            // warp-local exclusive event-count prefix per quad
+    uint32_t wsum[kWarpsPerScanCta];        // per-warp totals
+    uint32_t wev[kWarpsPerScanCta];
+};
 
 struct ScanSmem {
     alignas(128) uint32_t stage[kScanStages][kTileWords];
-    uint32_t qpref[kQuadsPerTile];          // warp-local exclusive ref-consumption prefix per quad
-    uint16_t qev[kQuadsPerTile];            // warp-local exclusive event-count prefix per quad
+    TileTables tab[kTables];
     uint32_t st_pos1[kMaxStarts];           // per read starting in the tile: ref_start + 1 - S(start word)
     uint16_t st_off[kMaxStarts];            // tile-local word index where that read's CIGAR starts
     uint16_t st_ev[kMaxStarts];             // events in the tile before that word
-    uint32_t wsum[kWarpsPerScanCta];
-    uint32_t wev[kWarpsPerScanCta];
     alignas(8) uint64_t full[kScanStages];
     uint64_t ev_base;
     uint32_t carry_pos1;                    // carried-in read: ref_start + 1 + bases consumed before the tile
     uint32_t vid;
 };
 
-__device__ __forceinline__ uint32_t tile_S(const ScanSmem &sm, const uint32_t *stage, uint32_t b, uint32_t tot)
+__device__ __forceinline__ uint32_t tile_S(const TileTables &tb, const uint32_t *stage, uint32_t b, uint32_t tot)
 {
     // reference bases consumed by tile words [0,b)
     if (b >= (uint32_t)kTileWords) return tot;
     const uint32_t q = b >> 2, w = q / kQuadsPerWarp;
-    uint32_t s = sm.qpref[q];
-    for (uint32_t i = 0; i < w; ++i) s += sm.wsum[i];
+    uint32_t s = tb.qpref[q];
+    for (uint32_t i = 0; i < w; ++i) s += tb.wsum[i];
     for (uint32_t k = 0; k < (b & 3u); ++k) s += cig_consume(stage[q * 4 + k]);
     return s;
 }
-__device__ __forceinline__ uint32_t tile_E(const ScanSmem &sm, const uint32_t *stage, uint32_t b, uint32_t tot,
+__device__ __forceinline__ uint32_t tile_E(const TileTables &tb, const uint32_t *stage, uint32_t b, uint32_t tot,
                                            uint32_t minlen)
 {
     // events among tile words [0,b)
     if (b >= (uint32_t)kTileWords) return tot;
     const uint32_t q = b >> 2, w = q / kQuadsPerWarp;
-    uint32_t s = sm.qev[q];
-    for (uint32_t i = 0; i < w; ++i) s += sm.wev[i];
+    uint32_t s = tb.qev[q];
+    for (uint32_t i = 0; i < w; ++i) s += tb.wev[i];
     for (uint32_t k = 0; k < (b & 3u); ++k) s += cig_is_event(stage[q * 4 + k], minlen) ? 1u : 0u;
     return s;
+}
+
+// Fused look-back over the two descriptor arrays of the CIGAR scan (one L2 round trip per window
+// for both): *carry_pos = reference bases the carried-in read consumed before tile t (sum back to
+// the nearest tile holding a read start), *ev_base = events before tile t.
+__device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos, const uint64_t *__restrict__ desc_ev,
+                                          int64_t t, uint64_t *carry_pos, uint64_t *ev_base)
+{
+    uint64_t acc_p = 0, acc_e = 0;
+    bool done_p = false, done_e = false;
+    int64_t base = t - 1;
+    while (true) {
+        const int64_t idx = base - (int64_t)lane_id();
+        uint64_t dp = kDescPrefix, de = kDescPrefix;    // tiles before 0: prefix 0
+        if (idx >= 0) {
+            do {
+                if (!done_p) dp = ld_relaxed_u64(desc_pos + idx);
+                if (!done_e) de = ld_relaxed_u64(desc_ev + idx);
+            } while ((dp >> 62) == 0 || (de >> 62) == 0);
+        }
+        if (!done_p) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (dp >> 62) == 2);
+            const int first = m ? (__ffs(m) - 1) : 32;
+            acc_p += warp_sum(((int)lane_id() <= first) ? (dp & kDescValueMask) : 0ull);
+            done_p = first < 32;
+        }
+        if (!done_e) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (de >> 62) == 2);
+            const int first = m ? (__ffs(m) - 1) : 32;
+            acc_e += warp_sum(((int)lane_id() <= first) ? (de & kDescValueMask) : 0ull);
+            done_e = first < 32;
+        }
+        if (done_p && done_e) break;
+        base -= 32;
+    }
+    *carry_pos = acc_p;
+    *ev_base = acc_e;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -440,9 +483,10 @@ k_cigar_scan(ScanParams p)
     __syncthreads();
     const uint64_t vid = sm.vid, stride = gridDim.x;
     // tiles vid, vid+G, vid+2G, ...: neighbouring tiles are processed by different CTAs at the same time
+    auto tile_of = [&](uint32_t itx) -> uint64_t { return vid + (uint64_t)itx * stride; };
     if (tid == 0) {
         for (int s = 0; s < kScanStages; ++s) {
-            const uint64_t t = vid + (uint64_t)s * stride;
+            const uint64_t t = tile_of(s);
             if (t < p.ntiles) {
                 mbar_expect_tx(&sm.full[s], kTileBytes);
                 bulk_copy_g2s(sm.stage[s], p.cigar + t * kTileWords, kTileBytes, &sm.full[s]);
@@ -450,84 +494,112 @@ k_cigar_scan(ScanParams p)
         }
     }
 
+    // phase A of pipeline slot itx: per-warp scan of its 512 words (4 slabs of 32 lanes x uint4);
+    // returns this thread's event bit mask (bit j*4+k <-> word k of its quad in slab j)
+    auto phase_a = [&](uint32_t itx) -> uint32_t {
+        const uint32_t s = itx % kScanStages;
+        mbar_wait(&sm.full[s], (itx / kScanStages) & 1u);
+        const uint32_t *stage = sm.stage[s];
+        TileTables &tb = sm.tab[itx % kTables];
+        uint32_t evmask = 0;
+        uint32_t excl[kSlabs], evx[kSlabs];
+        uint32_t cs[kSlabs], packed_ec = 0, carry = 0;
+#pragma unroll
+        for (int j = 0; j < kSlabs; ++j) {
+            const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
+            const uint4 v = reinterpret_cast<const uint4 *>(stage)[q];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            uint32_t c = 0, e = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                c += cig_consume(w4[k]);
+                if (cig_is_event(w4[k], p.minlen)) { evmask |= 1u << (j * 4 + k); ++e; }
+            }
+            cs[j] = c;
+            packed_ec |= e << (8 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < kSlabs; ++j) {
+            const uint32_t incl = warp_incl_scan(cs[j]);
+            excl[j] = carry + incl - cs[j];
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const uint32_t incl_ec = warp_incl_scan(packed_ec);      // 4 byte-lanes, each <= 128
+        const uint32_t tot_ec = __shfl_sync(0xffffffffu, incl_ec, 31);
+        uint32_t ecarry = 0;
+#pragma unroll
+        for (int j = 0; j < kSlabs; ++j) {
+            evx[j] = ecarry + ((incl_ec >> (8 * j)) & 0xFFu) - ((packed_ec >> (8 * j)) & 0xFFu);
+            ecarry += (tot_ec >> (8 * j)) & 0xFFu;
+            const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
+            tb.qpref[q] = excl[j];
+            tb.qev[q] = (uint16_t)evx[j];
+        }
+        if (lane == 0) { tb.wsum[warp] = carry; tb.wev[warp] = ecarry; }
+        return evmask;
+    };
+
+    // warp 0, after the block barrier that follows phase_a(itx): publish the tile's aggregates.
+    // A tile that holds a read start resets the position carry, so its descriptor is final at once.
+    auto publish = [&](uint32_t itx) {
+        const uint32_t t = (uint32_t)tile_of(itx);
+        const TileTables &tb = sm.tab[itx % kTables];
+        const uint32_t *stage = sm.stage[itx % kScanStages];
+        uint32_t tot_cons = 0, tot_ev = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerScanCta; ++w) { tot_cons += tb.wsum[w]; tot_ev += tb.wev[w]; }
+        const uint32_t rA = p.tile_first[t], rB = p.tile_first[t + 1];
+        uint32_t trailing = tot_cons;
+        if (rB > rA) {
+            const uint64_t b_last = p.cig_off[rB - 1] - (uint64_t)t * kTileWords;
+            trailing = tot_cons - tile_S(tb, stage, (uint32_t)min(b_last, (uint64_t)kTileWords), tot_cons);
+        }
+        if (lane == 0) {
+            st_relaxed_u64(p.desc_pos + t, (rB > rA ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
+            st_relaxed_u64(p.desc_ev + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tot_ev);
+        }
+    };
+
+    // pipeline fill
+    uint32_t evmask_next = 0;
+    if (tile_of(0) < p.ntiles) evmask_next = phase_a(0);
+    __syncthreads();
+    if (warp == 0 && tile_of(0) < p.ntiles) publish(0);
+
     for (uint32_t it = 0;; ++it) {
-        const uint64_t t64 = vid + (uint64_t)it * stride;
+        const uint64_t t64 = tile_of(it);
         if (t64 >= p.ntiles) break;
         const uint32_t t = (uint32_t)t64;
+        uint32_t evmask = evmask_next;
+        const bool have_next = tile_of(it + kAhead) < p.ntiles;
+        if (have_next) evmask_next = phase_a(it + kAhead);
+        __syncthreads();
+
         const uint32_t s = it % kScanStages;
-        mbar_wait(&sm.full[s], (it / kScanStages) & 1u);
         const uint32_t *stage = sm.stage[s];
+        const TileTables &tb = sm.tab[it % kTables];
         const uint64_t g0 = (uint64_t)t * kTileWords;
         const uint32_t rA = p.tile_first[t], rB = p.tile_first[t + 1];   // reads starting in this tile
         const uint32_t nrs = rB - rA, nst = min(nrs, (uint32_t)kMaxStarts);
-
-        // ---- phase A: per-warp scan of its 512 words (4 slabs of 32 lanes x uint4)
-        uint32_t evmask = 0;
-        {
-            uint32_t excl[kSlabs], evx[kSlabs];
-            uint32_t cs[kSlabs], packed_ec = 0, carry = 0;
-#pragma unroll
-            for (int j = 0; j < kSlabs; ++j) {
-                const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
-                const uint4 v = reinterpret_cast<const uint4 *>(stage)[q];
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                uint32_t c = 0, e = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    c += cig_consume(w4[k]);
-                    if (cig_is_event(w4[k], p.minlen)) { evmask |= 1u << (j * 4 + k); ++e; }
-                }
-                cs[j] = c;
-                packed_ec |= e << (8 * j);
-            }
-#pragma unroll
-            for (int j = 0; j < kSlabs; ++j) {
-                const uint32_t incl = warp_incl_scan(cs[j]);
-                excl[j] = carry + incl - cs[j];
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            const uint32_t incl_ec = warp_incl_scan(packed_ec);      // 4 byte-lanes, each <= 128
-            const uint32_t tot_ec = __shfl_sync(0xffffffffu, incl_ec, 31);
-            uint32_t ecarry = 0;
-#pragma unroll
-            for (int j = 0; j < kSlabs; ++j) {
-                evx[j] = ecarry + ((incl_ec >> (8 * j)) & 0xFFu) - ((packed_ec >> (8 * j)) & 0xFFu);
-                ecarry += (tot_ec >> (8 * j)) & 0xFFu;
-                const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
-                sm.qpref[q] = excl[j];
-                sm.qev[q] = (uint16_t)evx[j];
-            }
-            if (lane == 0) { sm.wsum[warp] = carry; sm.wev[warp] = ecarry; }
-        }
-        __syncthreads();
-
-        // ---- phase B: tile totals; warp 0 publishes + looks back while warps 1..7 stage the read starts
         uint32_t wbase = 0, webase = 0, tot_cons = 0, tot_ev = 0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerScanCta; ++w) {
-            const uint32_t a = sm.wsum[w], b = sm.wev[w];
+            const uint32_t a = tb.wsum[w], b = tb.wev[w];
             if (w < (int)warp) { wbase += a; webase += b; }
             tot_cons += a;
             tot_ev += b;
         }
+
+        // ---- phase B: warp 0 publishes the next tile, then looks back for this one (its predecessors
+        //      published one iteration ago); warps 1..7 stage this tile's read starts meanwhile
         if (warp == 0) {
-            const bool has_boundary = nrs > 0;
-            uint32_t trailing = tot_cons;
-            if (has_boundary) {
-                const uint64_t b_last = p.cig_off[rB - 1] - g0;
-                trailing = tot_cons - tile_S(sm, stage, (uint32_t)min(b_last, (uint64_t)kTileWords), tot_cons);
-            }
-            if (lane == 0) {
-                st_relaxed_u64(p.desc_pos + t, (has_boundary ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
-                st_relaxed_u64(p.desc_ev + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tot_ev);
-            }
+            if (have_next) publish(it + kAhead);
             uint64_t ev_base = 0, carry_pos = 0;
             if (t > 0) {
-                carry_pos = lookback(p.desc_pos, (int64_t)t);
-                ev_base = lookback(p.desc_ev, (int64_t)t);
+                lookback2(p.desc_pos, p.desc_ev, (int64_t)t, &carry_pos, &ev_base);
                 if (lane == 0) {
                     st_relaxed_u64(p.desc_ev + t, kDescPrefix | ((ev_base + tot_ev) & kDescValueMask));
-                    if (!has_boundary)
+                    if (nrs == 0)
                         st_relaxed_u64(p.desc_pos + t, kDescPrefix | ((carry_pos + tot_cons) & 0xFFFFFFFFull));
                 }
             }
@@ -545,8 +617,8 @@ k_cigar_scan(ScanParams p)
                 const uint32_t r = rA + i;
                 const uint32_t b = (uint32_t)min(p.cig_off[r] - g0, (uint64_t)kTileWords);
                 sm.st_off[i] = (uint16_t)b;
-                sm.st_ev[i] = (uint16_t)tile_E(sm, stage, b, tot_ev, p.minlen);
-                sm.st_pos1[i] = (uint32_t)p.rs[r] + 1u - tile_S(sm, stage, b, tot_cons);
+                sm.st_ev[i] = (uint16_t)tile_E(tb, stage, b, tot_ev, p.minlen);
+                sm.st_pos1[i] = (uint32_t)p.rs[r] + 1u - tile_S(tb, stage, b, tot_cons);
             }
         }
         __syncthreads();
@@ -556,7 +628,7 @@ k_cigar_scan(ScanParams p)
         for (uint32_t i = tid; i < nrs; i += kScanThreads) {
             uint32_t e;
             if (i < nst) e = sm.st_ev[i];
-            else e = tile_E(sm, stage, (uint32_t)min(p.cig_off[rA + i] - g0, (uint64_t)kTileWords), tot_ev, p.minlen);
+            else e = tile_E(tb, stage, (uint32_t)min(p.cig_off[rA + i] - g0, (uint64_t)kTileWords), tot_ev, p.minlen);
             p.ev_off[rA + i] = (uint32_t)(ev_base + e);
         }
 
@@ -568,7 +640,7 @@ k_cigar_scan(ScanParams p)
             const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
             const uint32_t idx = q * 4 + k;
             const uint32_t w = stage[idx];
-            uint32_t s_here = wbase + sm.qpref[q], e_here = webase + sm.qev[q];
+            uint32_t s_here = wbase + tb.qpref[q], e_here = webase + tb.qev[q];
             for (int kk = 0; kk < k; ++kk) {
                 const uint32_t wp = stage[q * 4 + kk];
                 s_here += cig_consume(wp);
@@ -592,7 +664,7 @@ k_cigar_scan(ScanParams p)
                     if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
                 }
                 const uint32_t r = a - 1;
-                pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(sm, stage, (uint32_t)(p.cig_off[r] - g0), tot_cons);
+                pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(tb, stage, (uint32_t)(p.cig_off[r] - g0), tot_cons);
             } else {
                 pos1 = sm.st_pos1[lo - 1] + s_here;                      // call.rs:380 cursor at this op
             }
@@ -603,9 +675,9 @@ k_cigar_scan(ScanParams p)
             else atomicOr(&p.ctr->flags, kFlagEventOverflow);
         }
 
-        __syncthreads();                                // everyone is done with stage s and the staging arrays
+        __syncthreads();                                // everyone is done with stage s, tab[it] and the staging arrays
         if (tid == 0) {
-            const uint64_t t2 = vid + (uint64_t)(it + kScanStages) * stride;
+            const uint64_t t2 = tile_of(it + kScanStages);
             if (t2 < p.ntiles) {
                 fence_proxy_async();
                 mbar_expect_tx(&sm.full[s], kTileBytes);
