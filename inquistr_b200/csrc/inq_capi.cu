@@ -49,6 +49,10 @@ struct inq_ctx {
     // work buffers
     DevBuf<uint32_t> cand_lo, cand_n, tile_first, ev_off, bcnt, boff, big_list;
     DevBuf<uint64_t> desc_ev, desc_pos, desc_scan, vals;
+    DevBuf<uint4> tile_meta;
+    CUtensorMap tmap;                 // 2-D view of the packed CIGAR stream: rows of 32 words, 128B swizzle
+    const void *tmap_base = nullptr;
+    uint64_t tmap_rows = 0;
     DevBuf<uint2> events;
     DevBuf<int64_t> t1, t2;
     DevBuf<uint8_t> valid;
@@ -113,6 +117,37 @@ void release(DevBuf<T> &b)
 
 uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// (re)build the TMA descriptor of the CIGAR stream: uint32 [rows][32], box = one 16 KB tile, 128B swizzle
+int make_tensor_map(inq_ctx *ctx, uint64_t n_words_padded)
+{
+    const uint64_t rows = n_words_padded / 32;
+    if (ctx->tmap_base == ctx->cigar.p && ctx->tmap_rows == rows) return INQ_OK;
+    static tmap_encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(ctx, INQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        encode = (tmap_encode_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {32, rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)(kTileWords / 32)};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = encode(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->cigar.p, gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, INQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    ctx->tmap_base = ctx->cigar.p;
+    ctx->tmap_rows = rows;
+    return INQ_OK;
+}
+
 int reserve_reads(inq_ctx *ctx, uint64_t nR, uint64_t nC, double growth)
 {
     const uint64_t R = ctx->R, C = ctx->C;
@@ -168,10 +203,10 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaMalloc(&ctx->d_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost(&ctx->h_total, 64)) != cudaSuccess) return bail("cudaMallocHost", e);
-    if ((e = cudaFuncSetAttribute(k_cigar_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_cigar_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_cigar_scan)", e);
     int occ = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan, kScanThreads, sizeof(ScanSmem))) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan, kScanThreads, kScanSmemBytes)) != cudaSuccess)
         return bail("occupancy(k_cigar_scan)", e);
     ctx->scan_ctas_per_sm = std::max(1, occ);
     *out = ctx;
@@ -190,7 +225,7 @@ void inq_ctx_destroy(inq_ctx *ctx)
     release(ctx->cand_lo); release(ctx->cand_n); release(ctx->tile_first); release(ctx->ev_off);
     release(ctx->bcnt); release(ctx->boff); release(ctx->big_list);
     release(ctx->desc_ev); release(ctx->desc_pos); release(ctx->desc_scan); release(ctx->vals);
-    release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
+    release(ctx->tile_meta); release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
@@ -339,6 +374,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     TRY(ensure(ctx, ctx->tile_first, (uint64_t)ntiles + 1));
     TRY(ensure(ctx, ctx->desc_ev, (uint64_t)ntiles + 1));
     TRY(ensure(ctx, ctx->desc_pos, (uint64_t)ntiles + 1));
+    TRY(ensure(ctx, ctx->tile_meta, (uint64_t)ntiles + 1));
+    if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
     if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 8 + 4096));
 
     ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
@@ -356,7 +393,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             CU_TRY(ctx, cudaMemsetAsync(ctx->desc_ev.p, 0, (uint64_t)ntiles * sizeof(uint64_t), s));
             CU_TRY(ctx, cudaMemsetAsync(ctx->desc_pos.p, 0, (uint64_t)ntiles * sizeof(uint64_t), s));
             k_tile_index<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R, ntiles, ctx->tile_first.p);
-            ++launches;
+            k_tile_meta<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->tile_first.p, ctx->cig_off.p, ctx->rs.p, ntiles, ctx->tile_meta.p);
+            launches += 2;
         }
         if (scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, (uint64_t)scan_tiles * sizeof(uint64_t), s));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_INDEX], s));
@@ -371,11 +409,11 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         // K2: CIGAR scan -> events
         if (ntiles && L) {
             ScanParams sp;
-            sp.cigar = ctx->cigar.p; sp.cig_off = ctx->cig_off.p; sp.rs = ctx->rs.p; sp.tile_first = ctx->tile_first.p;
+            sp.cig_off = ctx->cig_off.p; sp.rs = ctx->rs.p; sp.tile_meta = ctx->tile_meta.p;
             sp.desc_ev = ctx->desc_ev.p; sp.desc_pos = ctx->desc_pos.p; sp.events = ctx->events.p; sp.ev_off = ctx->ev_off.p;
             sp.ctr = ctx->d_ctr; sp.R = R; sp.ev_cap = ctx->events.cap; sp.ntiles = ntiles; sp.minlen = minlen;
             const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
-            k_cigar_scan<<<grid, kScanThreads, sizeof(ScanSmem), s>>>(sp);
+            k_cigar_scan<<<grid, kScanThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR], s));

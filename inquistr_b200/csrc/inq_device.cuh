@@ -13,6 +13,7 @@
 //   buckets: 2 per locus (H1,H2 | unphased: all,unused); cnt/off u32[2L+1]; vals u64[P]
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -369,10 +370,9 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 // reset at read boundaries), and compact every I/D/S op longer than minlen into an ordered event
 // list {1-based anchor position, signed length, soft-clip bit}. Each CIGAR word is read once.
 struct ScanParams {
-    const uint32_t *cigar;        // padded to a multiple of kTileWords, pad = 0
     const uint64_t *cig_off;      // R+1
     const int32_t *rs;            // ref_start
-    const uint32_t *tile_first;   // ntiles+1
+    const uint4 *tile_meta;       // ntiles: {first read starting in tile, #reads starting, last start offset, carried pos1}
     uint64_t *desc_ev;            // ntiles, zeroed
     uint64_t *desc_pos;           // ntiles, zeroed
     uint2 *events;
@@ -384,20 +384,42 @@ struct ScanParams {
     uint32_t minlen;
 };
 
-constexpr int kMaxStarts = 512;             // read starts per tile staged in shared memory
-constexpr int kAhead = 1;                   // tiles whose aggregates are published ahead of their look-back
-constexpr int kTables = kAhead + 1;
+// per-tile metadata, one thread per tile (k_tile_index ran before): everything the scan kernel would
+// otherwise have to fetch through dependent global loads on its critical path.
+//   x = rA: first read whose CIGAR starts inside the tile      y = number of such reads
+//   z = tile-local word offset of the last such read's start   w = ref_start(rA-1) + 1 (carried-in read)
+__global__ void k_tile_meta(const uint32_t *__restrict__ tile_first, const uint64_t *__restrict__ cig_off,
+                            const int32_t *__restrict__ rs, uint32_t ntiles, uint4 *__restrict__ meta)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t rA = tile_first[t], rB = tile_first[t + 1];
+    uint4 m;
+    m.x = rA;
+    m.y = rB - rA;
+    m.z = (rB > rA) ? (uint32_t)min(cig_off[rB - 1] - (uint64_t)t * kTileWords, (uint64_t)kTileWords) : 0u;
+    m.w = (rA > 0 ? (uint32_t)rs[rA - 1] : 0u) + 1u;
+    meta[t] = m;
+}
+
+constexpr int kMaxStarts = 256;             // read starts per tile staged in shared memory
+constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words per lane
+constexpr uint32_t kOpLut = 0x18Du | (0x16u << 16);     // bit op: consumes reference; bit 16+op: I/D/S
 
 struct TileTables {
-    uint32_t qpref[kQuadsPerTile];          // warp-local exclusive ref-consumption prefix per quad
-    uint16_t qev[kQuadsPerTile];            // warp-local exclusive event-count prefix per quad
-    uint32_t wsum[kWarpsPerScanCta];        // per-warp totals
+    uint32_t lpref[kScanThreads];           // warp-local exclusive ref-consumption prefix of each lane block
+    uint16_t lev[kScanThreads];             // warp-local exclusive event count of each lane block
+    uint32_t wsum[kWarpsPerScanCta];        // per-warp totals (phase A)
     uint32_t wev[kWarpsPerScanCta];
+    uint32_t wbase[kWarpsPerScanCta];       // exclusive per-warp bases (publish)
+    uint32_t webase[kWarpsPerScanCta];
+    uint32_t tot_cons, tot_ev;
 };
 
 struct ScanSmem {
-    alignas(128) uint32_t stage[kScanStages][kTileWords];
-    TileTables tab[kTables];
+    alignas(1024) uint32_t stage[kScanStages][kTileWords];   // 128B-swizzled by the TMA tensor map
+    alignas(16) uint4 meta[kScanStages];
+    TileTables tab[2];
     uint32_t st_pos1[kMaxStarts];           // per read starting in the tile: ref_start + 1 - S(start word)
     uint16_t st_off[kMaxStarts];            // tile-local word index where that read's CIGAR starts
     uint16_t st_ev[kMaxStarts];             // events in the tile before that word
@@ -406,47 +428,60 @@ struct ScanSmem {
     uint32_t carry_pos1;                    // carried-in read: ref_start + 1 + bases consumed before the tile
     uint32_t vid;
 };
+constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align the swizzled stages to 1 KB
 
-__device__ __forceinline__ uint32_t tile_S(const TileTables &tb, const uint32_t *stage, uint32_t b, uint32_t tot)
+// word index inside a tile -> word index in the 128B-swizzled stage buffer
+// (16-byte chunk index bits [2:4] ^= 128-byte row index bits [5:7])
+__device__ __forceinline__ uint32_t swz(uint32_t idx) { return idx ^ (((idx >> 5) & 7u) << 2); }
+
+__device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap *tmap, uint32_t row, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t tile_S(const TileTables &tb, const uint32_t *stage, uint32_t b)
 {
     // reference bases consumed by tile words [0,b)
-    if (b >= (uint32_t)kTileWords) return tot;
-    const uint32_t q = b >> 2, w = q / kQuadsPerWarp;
-    uint32_t s = tb.qpref[q];
-    for (uint32_t i = 0; i < w; ++i) s += tb.wsum[i];
-    for (uint32_t k = 0; k < (b & 3u); ++k) s += cig_consume(stage[q * 4 + k]);
+    if (b >= (uint32_t)kTileWords) return tb.tot_cons;
+    const uint32_t blk = b / kLaneWords;
+    uint32_t s = tb.wbase[blk >> 5] + tb.lpref[blk];
+    for (uint32_t i = blk * kLaneWords; i < b; ++i) s += cig_consume(stage[swz(i)]);
     return s;
 }
-__device__ __forceinline__ uint32_t tile_E(const TileTables &tb, const uint32_t *stage, uint32_t b, uint32_t tot,
-                                           uint32_t minlen)
+__device__ __forceinline__ uint32_t tile_E(const TileTables &tb, const uint32_t *stage, uint32_t b, uint32_t minlen)
 {
     // events among tile words [0,b)
-    if (b >= (uint32_t)kTileWords) return tot;
-    const uint32_t q = b >> 2, w = q / kQuadsPerWarp;
-    uint32_t s = tb.qev[q];
-    for (uint32_t i = 0; i < w; ++i) s += tb.wev[i];
-    for (uint32_t k = 0; k < (b & 3u); ++k) s += cig_is_event(stage[q * 4 + k], minlen) ? 1u : 0u;
+    if (b >= (uint32_t)kTileWords) return tb.tot_ev;
+    const uint32_t blk = b / kLaneWords;
+    uint32_t s = tb.webase[blk >> 5] + tb.lev[blk];
+    for (uint32_t i = blk * kLaneWords; i < b; ++i) s += cig_is_event(stage[swz(i)], minlen) ? 1u : 0u;
     return s;
 }
 
-// Fused look-back over the two descriptor arrays of the CIGAR scan (one L2 round trip per window
-// for both): *carry_pos = reference bases the carried-in read consumed before tile t (sum back to
-// the nearest tile holding a read start), *ev_base = events before tile t.
+// Fused look-back over the two descriptor arrays of the CIGAR scan. (dp, de) are the descriptors of
+// tiles t-1-lane loaded early by the caller (possibly still invalid); further windows are fetched here.
+//   *carry_pos = reference bases the carried-in read consumed before tile t (sum back to the nearest
+//                tile that holds a read start),   *ev_base = events before tile t.
 __device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos, const uint64_t *__restrict__ desc_ev,
-                                          int64_t t, uint64_t *carry_pos, uint64_t *ev_base)
+                                          int64_t t, uint64_t dp, uint64_t de, uint64_t *carry_pos, uint64_t *ev_base)
 {
     uint64_t acc_p = 0, acc_e = 0;
     bool done_p = false, done_e = false;
     int64_t base = t - 1;
+    bool preloaded = true;
     while (true) {
         const int64_t idx = base - (int64_t)lane_id();
-        uint64_t dp = kDescPrefix, de = kDescPrefix;    // tiles before 0: prefix 0
+        if (!preloaded) { dp = kDescPrefix; de = kDescPrefix; }      // tiles before 0: prefix 0
         if (idx >= 0) {
-            do {
+            while ((!done_p && (dp >> 62) == 0) || (!done_e && (de >> 62) == 0) || !preloaded) {
                 if (!done_p) dp = ld_relaxed_u64(desc_pos + idx);
                 if (!done_e) de = ld_relaxed_u64(desc_ev + idx);
-            } while ((dp >> 62) == 0 || (de >> 62) == 0);
+                preloaded = true;
+            }
         }
+        preloaded = false;
         if (!done_p) {
             const uint32_t m = __ballot_sync(0xffffffffu, (dp >> 62) == 2);
             const int first = m ? (__ffs(m) - 1) : 32;
@@ -467,12 +502,14 @@ __device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos,
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-k_cigar_scan(ScanParams p)
+k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw);
+    extern __shared__ unsigned char smem_raw[];
+    ScanSmem &sm = *reinterpret_cast<ScanSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t kTileBytes = kTileWords * 4;
+    constexpr uint32_t kRowsPerTile = kTileWords / 32;          // 128-byte rows
+    const uint32_t thr = (p.minlen << 4) | 15u;                 // (w >> 4) > minlen  <=>  w > thr
 
     if (tid == 0) {
         for (int s = 0; s < kScanStages; ++s) mbar_init(&sm.full[s], 1);
@@ -484,85 +521,70 @@ k_cigar_scan(ScanParams p)
     const uint64_t vid = sm.vid, stride = gridDim.x;
     // tiles vid, vid+G, vid+2G, ...: neighbouring tiles are processed by different CTAs at the same time
     auto tile_of = [&](uint32_t itx) -> uint64_t { return vid + (uint64_t)itx * stride; };
+    auto issue = [&](uint32_t s, uint64_t t) {
+        mbar_expect_tx(&sm.full[s], kTileBytes + 16u);
+        tma_load_tile(sm.stage[s], &tmap, (uint32_t)t * kRowsPerTile, &sm.full[s]);
+        bulk_copy_g2s(&sm.meta[s], p.tile_meta + t, 16u, &sm.full[s]);
+    };
     if (tid == 0) {
-        for (int s = 0; s < kScanStages; ++s) {
-            const uint64_t t = tile_of(s);
-            if (t < p.ntiles) {
-                mbar_expect_tx(&sm.full[s], kTileBytes);
-                bulk_copy_g2s(sm.stage[s], p.cigar + t * kTileWords, kTileBytes, &sm.full[s]);
-            }
-        }
+        for (int s = 0; s < kScanStages; ++s)
+            if (tile_of(s) < p.ntiles) issue(s, tile_of(s));
     }
 
-    // phase A of pipeline slot itx: per-warp scan of its 512 words (4 slabs of 32 lanes x uint4);
-    // returns this thread's event bit mask (bit j*4+k <-> word k of its quad in slab j)
-    auto phase_a = [&](uint32_t itx) -> uint32_t {
+    // this thread's 16 consecutive words live in 128-byte row tid/2, chunks 4*(tid&1)+j, swizzled
+    const uint32_t rowq = (tid >> 1) * 8, x0 = ((tid & 1u) << 2) ^ ((tid >> 1) & 7u);
+
+    // phase A of pipeline slot itx: one pass over the lane's 16 words, then two warp scans.
+    // evmask: bit i <-> word i of the lane block is an event; clast: bases consumed in the block
+    // before the LAST event of the block.
+    auto phase_a = [&](uint32_t itx, uint32_t &evmask, uint32_t &clast) {
         const uint32_t s = itx % kScanStages;
         mbar_wait(&sm.full[s], (itx / kScanStages) & 1u);
-        const uint32_t *stage = sm.stage[s];
-        TileTables &tb = sm.tab[itx % kTables];
-        uint32_t evmask = 0;
-        uint32_t excl[kSlabs], evx[kSlabs];
-        uint32_t cs[kSlabs], packed_ec = 0, carry = 0;
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(sm.stage[s]);
+        TileTables &tb = sm.tab[itx & 1u];
+        uint32_t c = 0;
+        evmask = 0;
+        clast = 0;
 #pragma unroll
-        for (int j = 0; j < kSlabs; ++j) {
-            const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
-            const uint4 v = reinterpret_cast<const uint4 *>(stage)[q];
+        for (int j = 0; j < 4; ++j) {
+            const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            uint32_t c = 0, e = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                c += cig_consume(w4[k]);
-                if (cig_is_event(w4[k], p.minlen)) { evmask |= 1u << (j * 4 + k); ++e; }
+                const uint32_t w = w4[k], lut = kOpLut >> (w & 15u);
+                if ((lut & 0x10000u) && w > thr) { evmask |= 1u << (j * 4 + k); clast = c; }
+                if (lut & 1u) c += w >> 4;
             }
-            cs[j] = c;
-            packed_ec |= e << (8 * j);
         }
-#pragma unroll
-        for (int j = 0; j < kSlabs; ++j) {
-            const uint32_t incl = warp_incl_scan(cs[j]);
-            excl[j] = carry + incl - cs[j];
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        const uint32_t incl_ec = warp_incl_scan(packed_ec);      // 4 byte-lanes, each <= 128
-        const uint32_t tot_ec = __shfl_sync(0xffffffffu, incl_ec, 31);
-        uint32_t ecarry = 0;
-#pragma unroll
-        for (int j = 0; j < kSlabs; ++j) {
-            evx[j] = ecarry + ((incl_ec >> (8 * j)) & 0xFFu) - ((packed_ec >> (8 * j)) & 0xFFu);
-            ecarry += (tot_ec >> (8 * j)) & 0xFFu;
-            const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
-            tb.qpref[q] = excl[j];
-            tb.qev[q] = (uint16_t)evx[j];
-        }
-        if (lane == 0) { tb.wsum[warp] = carry; tb.wev[warp] = ecarry; }
-        return evmask;
+        const uint32_t ne = __popc(evmask);
+        const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
+        tb.lpref[tid] = incl_c - c;
+        tb.lev[tid] = (uint16_t)(incl_e - ne);
+        if (lane == 31) { tb.wsum[warp] = incl_c; tb.wev[warp] = incl_e; }
     };
 
-    // warp 0, after the block barrier that follows phase_a(itx): publish the tile's aggregates.
-    // A tile that holds a read start resets the position carry, so its descriptor is final at once.
+    // warp 0, after the block barrier that follows phase_a(itx): per-warp bases + publish the tile's
+    // aggregates. A tile that holds a read start resets the position carry: its descriptor is final.
     auto publish = [&](uint32_t itx) {
         const uint32_t t = (uint32_t)tile_of(itx);
-        const TileTables &tb = sm.tab[itx % kTables];
-        const uint32_t *stage = sm.stage[itx % kScanStages];
-        uint32_t tot_cons = 0, tot_ev = 0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerScanCta; ++w) { tot_cons += tb.wsum[w]; tot_ev += tb.wev[w]; }
-        const uint32_t rA = p.tile_first[t], rB = p.tile_first[t + 1];
-        uint32_t trailing = tot_cons;
-        if (rB > rA) {
-            const uint64_t b_last = p.cig_off[rB - 1] - (uint64_t)t * kTileWords;
-            trailing = tot_cons - tile_S(tb, stage, (uint32_t)min(b_last, (uint64_t)kTileWords), tot_cons);
-        }
+        TileTables &tb = sm.tab[itx & 1u];
+        const uint32_t a = lane < kWarpsPerScanCta ? tb.wsum[lane] : 0u, b = lane < kWarpsPerScanCta ? tb.wev[lane] : 0u;
+        const uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
+        if (lane < kWarpsPerScanCta) { tb.wbase[lane] = ia - a; tb.webase[lane] = ib - b; }
+        const uint32_t tot_cons = __shfl_sync(0xffffffffu, ia, 31), tot_ev = __shfl_sync(0xffffffffu, ib, 31);
+        if (lane == 0) { tb.tot_cons = tot_cons; tb.tot_ev = tot_ev; }
+        __syncwarp();
         if (lane == 0) {
-            st_relaxed_u64(p.desc_pos + t, (rB > rA ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
+            const uint4 m = sm.meta[itx % kScanStages];
+            const uint32_t trailing = m.y ? tot_cons - tile_S(tb, sm.stage[itx % kScanStages], m.z) : tot_cons;
+            st_relaxed_u64(p.desc_pos + t, (m.y ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
             st_relaxed_u64(p.desc_ev + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tot_ev);
         }
     };
 
     // pipeline fill
-    uint32_t evmask_next = 0;
-    if (tile_of(0) < p.ntiles) evmask_next = phase_a(0);
+    uint32_t evmask_n = 0, clast_n = 0;
+    if (tile_of(0) < p.ntiles) phase_a(0, evmask_n, clast_n);
     __syncthreads();
     if (warp == 0 && tile_of(0) < p.ntiles) publish(0);
 
@@ -570,33 +592,38 @@ k_cigar_scan(ScanParams p)
         const uint64_t t64 = tile_of(it);
         if (t64 >= p.ntiles) break;
         const uint32_t t = (uint32_t)t64;
-        uint32_t evmask = evmask_next;
-        const bool have_next = tile_of(it + kAhead) < p.ntiles;
-        if (have_next) evmask_next = phase_a(it + kAhead);
-        __syncthreads();
-
         const uint32_t s = it % kScanStages;
         const uint32_t *stage = sm.stage[s];
-        const TileTables &tb = sm.tab[it % kTables];
+        const uint4 meta = sm.meta[s];
+        const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
         const uint64_t g0 = (uint64_t)t * kTileWords;
-        const uint32_t rA = p.tile_first[t], rB = p.tile_first[t + 1];   // reads starting in this tile
-        const uint32_t nrs = rB - rA, nst = min(nrs, (uint32_t)kMaxStarts);
-        uint32_t wbase = 0, webase = 0, tot_cons = 0, tot_ev = 0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerScanCta; ++w) {
-            const uint32_t a = tb.wsum[w], b = tb.wev[w];
-            if (w < (int)warp) { wbase += a; webase += b; }
-            tot_cons += a;
-            tot_ev += b;
+        uint32_t evmask = evmask_n;
+        const uint32_t clast = clast_n;
+
+        // early loads whose latency hides under phase A of the next tile
+        uint64_t dp = kDescPrefix, de = kDescPrefix, pre_off = 0;
+        int32_t pre_rs = 0;
+        if (warp == 0) {
+            const int64_t idx = (int64_t)t - 1 - (int64_t)lane;
+            if (idx >= 0) { dp = ld_relaxed_u64(p.desc_pos + idx); de = ld_relaxed_u64(p.desc_ev + idx); }
+        } else if (tid - 32 < nst) {
+            pre_off = p.cig_off[rA + tid - 32];
+            pre_rs = p.rs[rA + tid - 32];
         }
 
-        // ---- phase B: warp 0 publishes the next tile, then looks back for this one (its predecessors
-        //      published one iteration ago); warps 1..7 stage this tile's read starts meanwhile
+        const bool have_next = tile_of(it + 1) < p.ntiles;
+        if (have_next) phase_a(it + 1, evmask_n, clast_n);
+        __syncthreads();
+
+        const TileTables &tb = sm.tab[it & 1u];
+        // ---- phase B: warp 0 publishes the next tile, then resolves the look-back for this one (its
+        //      predecessors published one iteration ago); warps 1..7 stage this tile's read starts
         if (warp == 0) {
-            if (have_next) publish(it + kAhead);
+            if (have_next) publish(it + 1);
             uint64_t ev_base = 0, carry_pos = 0;
+            const uint32_t tot_cons = tb.tot_cons, tot_ev = tb.tot_ev;
             if (t > 0) {
-                lookback2(p.desc_pos, p.desc_ev, (int64_t)t, &carry_pos, &ev_base);
+                lookback2(p.desc_pos, p.desc_ev, (int64_t)t, dp, de, &carry_pos, &ev_base);
                 if (lane == 0) {
                     st_relaxed_u64(p.desc_ev + t, kDescPrefix | ((ev_base + tot_ev) & kDescValueMask));
                     if (nrs == 0)
@@ -604,7 +631,7 @@ k_cigar_scan(ScanParams p)
                 }
             }
             if (lane == 0) {
-                sm.carry_pos1 = (rA > 0 ? (uint32_t)p.rs[rA - 1] : 0u) + 1u + (uint32_t)carry_pos;
+                sm.carry_pos1 = meta.w + (uint32_t)carry_pos;
                 sm.ev_base = ev_base;
                 if (t == p.ntiles - 1) {
                     p.ev_off[p.R] = (uint32_t)(ev_base + tot_ev);
@@ -614,11 +641,11 @@ k_cigar_scan(ScanParams p)
             }
         } else {
             for (uint32_t i = tid - 32; i < nst; i += kScanThreads - 32) {
-                const uint32_t r = rA + i;
-                const uint32_t b = (uint32_t)min(p.cig_off[r] - g0, (uint64_t)kTileWords);
+                if (i != tid - 32) { pre_off = p.cig_off[rA + i]; pre_rs = p.rs[rA + i]; }
+                const uint32_t b = (uint32_t)min(pre_off - g0, (uint64_t)kTileWords);
                 sm.st_off[i] = (uint16_t)b;
-                sm.st_ev[i] = (uint16_t)tile_E(tb, stage, b, tot_ev, p.minlen);
-                sm.st_pos1[i] = (uint32_t)p.rs[r] + 1u - tile_S(tb, stage, b, tot_cons);
+                sm.st_ev[i] = (uint16_t)tile_E(tb, stage, b, p.minlen);
+                sm.st_pos1[i] = (uint32_t)pre_rs + 1u - tile_S(tb, stage, b);
             }
         }
         __syncthreads();
@@ -628,60 +655,62 @@ k_cigar_scan(ScanParams p)
         for (uint32_t i = tid; i < nrs; i += kScanThreads) {
             uint32_t e;
             if (i < nst) e = sm.st_ev[i];
-            else e = tile_E(tb, stage, (uint32_t)min(p.cig_off[rA + i] - g0, (uint64_t)kTileWords), tot_ev, p.minlen);
+            else e = tile_E(tb, stage, (uint32_t)min(p.cig_off[rA + i] - g0, (uint64_t)kTileWords), p.minlen);
             p.ev_off[rA + i] = (uint32_t)(ev_base + e);
         }
 
-        // ---- phase D2: emit events (rare: a few per hundred words)
-        while (evmask) {
-            const int bit = __ffs(evmask) - 1;
-            evmask &= evmask - 1;
-            const int j = bit >> 2, k = bit & 3;
-            const uint32_t q = warp * kQuadsPerWarp + j * 32 + lane;
-            const uint32_t idx = q * 4 + k;
-            const uint32_t w = stage[idx];
-            uint32_t s_here = wbase + tb.qpref[q], e_here = webase + tb.qev[q];
-            for (int kk = 0; kk < k; ++kk) {
-                const uint32_t wp = stage[q * 4 + kk];
-                s_here += cig_consume(wp);
-                e_here += cig_is_event(wp, p.minlen) ? 1u : 0u;
-            }
-            // owning read: the last read start at or before this word
-            uint32_t lo = 0, hi = nst;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (sm.st_off[mid] <= idx) lo = mid + 1; else hi = mid;
-            }
-            uint32_t pos1;
-            if (lo == 0) {
-                pos1 = sm.carry_pos1 + s_here;                           // read carried in from an earlier tile
-            } else if (lo == nst && nrs > nst) {
-                // more read starts than the staging area holds: search the tail in global memory
-                const uint64_t g = g0 + idx;
-                uint32_t a = rA + nst - 1, b = rB;
-                while (a < b) {
-                    const uint32_t mid = a + ((b - a) >> 1);
-                    if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
+        // ---- phase D2: emit this lane's events (about 1% of the words), last event of the block first
+        if (evmask) {
+            const uint32_t s_blk = tb.wbase[warp] + tb.lpref[tid], e_blk = tb.webase[warp] + tb.lev[tid];
+            bool first = true;
+            do {
+                const uint32_t bit = 31u - (uint32_t)__clz(evmask);
+                evmask ^= 1u << bit;
+                const uint32_t idx = tid * kLaneWords + bit;
+                const uint32_t w = stage[swz(idx)];
+                uint32_t s_in = clast;                                   // captured in phase A for the last event
+                if (!first) {
+                    s_in = 0;
+                    for (uint32_t i = idx - bit; i < idx; ++i) s_in += cig_consume(stage[swz(i)]);
                 }
-                const uint32_t r = a - 1;
-                pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(tb, stage, (uint32_t)(p.cig_off[r] - g0), tot_cons);
-            } else {
-                pos1 = sm.st_pos1[lo - 1] + s_here;                      // call.rs:380 cursor at this op
-            }
-            const uint32_t len = w >> 4, op = w & 15u;
-            const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
-            const uint64_t slot = ev_base + e_here;
-            if (slot < p.ev_cap) p.events[slot] = make_uint2(pos1, (uint32_t)val);
-            else atomicOr(&p.ctr->flags, kFlagEventOverflow);
+                first = false;
+                const uint32_t s_here = s_blk + s_in, e_here = e_blk + __popc(evmask);   // lower bits remain
+                // owning read: the last read start at or before this word
+                uint32_t lo = 0, hi = nst;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sm.st_off[mid] <= idx) lo = mid + 1; else hi = mid;
+                }
+                uint32_t pos1;
+                if (lo == 0) {
+                    pos1 = sm.carry_pos1 + s_here;                       // read carried in from an earlier tile
+                } else if (lo == nst && nrs > nst) {
+                    // more read starts than the staging area holds: search the tail in global memory
+                    const uint64_t g = g0 + idx;
+                    uint32_t a = rA + nst - 1, b = rA + nrs;
+                    while (a < b) {
+                        const uint32_t mid = a + ((b - a) >> 1);
+                        if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
+                    }
+                    const uint32_t r = a - 1;
+                    pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(tb, stage, (uint32_t)(p.cig_off[r] - g0));
+                } else {
+                    pos1 = sm.st_pos1[lo - 1] + s_here;                  // call.rs:380 cursor at this op
+                }
+                const uint32_t len = w >> 4, op = w & 15u;
+                const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
+                const uint64_t slot = ev_base + e_here;
+                if (slot < p.ev_cap) p.events[slot] = make_uint2(pos1, (uint32_t)val);
+                else atomicOr(&p.ctr->flags, kFlagEventOverflow);
+            } while (evmask);
         }
 
-        __syncthreads();                                // everyone is done with stage s, tab[it] and the staging arrays
+        __syncthreads();                                // everyone is done with stage s, tab[it&1] and the staging arrays
         if (tid == 0) {
             const uint64_t t2 = tile_of(it + kScanStages);
             if (t2 < p.ntiles) {
                 fence_proxy_async();
-                mbar_expect_tx(&sm.full[s], kTileBytes);
-                bulk_copy_g2s(sm.stage[s], p.cigar + t2 * kTileWords, kTileBytes, &sm.full[s]);
+                issue(s, t2);
             }
         }
     }
