@@ -206,7 +206,7 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaFuncSetAttribute(k_cigar_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_cigar_scan)", e);
     int occ = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan, kScanThreads, kScanSmemBytes)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan, kCtaThreads, kScanSmemBytes)) != cudaSuccess)
         return bail("occupancy(k_cigar_scan)", e);
     ctx->scan_ctas_per_sm = std::max(1, occ);
     *out = ctx;
@@ -413,7 +413,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             sp.desc_ev = ctx->desc_ev.p; sp.desc_pos = ctx->desc_pos.p; sp.events = ctx->events.p; sp.ev_off = ctx->ev_off.p;
             sp.ctr = ctx->d_ctr; sp.R = R; sp.ev_cap = ctx->events.cap; sp.ntiles = ntiles; sp.minlen = minlen;
             const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
-            k_cigar_scan<<<grid, kScanThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
+            k_cigar_scan<<<grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR], s));

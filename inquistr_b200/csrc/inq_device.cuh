@@ -402,8 +402,9 @@ __global__ void k_tile_meta(const uint32_t *__restrict__ tile_first, const uint6
     meta[t] = m;
 }
 
-constexpr int kMaxStarts = 256;             // read starts per tile staged in shared memory
-constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words per lane
+constexpr int kMaxStarts = 128;             // read starts per tile staged in shared memory
+constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words per compute lane
+constexpr int kCtaThreads = kScanThreads + 32;          // 8 compute warps + 1 control warp
 constexpr uint32_t kOpLut = 0x18Du | (0x16u << 16);     // bit op: consumes reference; bit 16+op: I/D/S
 
 struct TileTables {
@@ -416,16 +417,26 @@ struct TileTables {
     uint32_t tot_cons, tot_ev;
 };
 
+// read starts of one tile, staged by the control warp
+struct Staging {
+    uint32_t pos1[kMaxStarts];              // ref_start + 1 - S(start word): add S(word) for the op's anchor
+    uint16_t off[kMaxStarts];               // tile-local word index where the read's CIGAR starts
+    uint16_t ev[kMaxStarts];                // events in the tile before that word
+    uint16_t owner[kScanThreads];           // per lane block: (#starts before the block << 1) | block holds a start
+    uint64_t ev_base;                       // events before the tile (look-back)
+    uint32_t carry_pos1;                    // carried-in read: ref_start + 1 + bases consumed before the tile
+    uint32_t pad;
+};
+
 struct ScanSmem {
     alignas(1024) uint32_t stage[kScanStages][kTileWords];   // 128B-swizzled by the TMA tensor map
     alignas(16) uint4 meta[kScanStages];
     TileTables tab[2];
-    uint32_t st_pos1[kMaxStarts];           // per read starting in the tile: ref_start + 1 - S(start word)
-    uint16_t st_off[kMaxStarts];            // tile-local word index where that read's CIGAR starts
-    uint16_t st_ev[kMaxStarts];             // events in the tile before that word
-    alignas(8) uint64_t full[kScanStages];
-    uint64_t ev_base;
-    uint32_t carry_pos1;                    // carried-in read: ref_start + 1 + bases consumed before the tile
+    Staging stg[2];
+    alignas(8) uint64_t full[kScanStages];  // TMA landed                     (tx bytes)
+    uint64_t freeb[kScanStages];            // compute warps done with stage  (8 arrivals)
+    uint64_t bar_a[2];                      // phase A of a tile done         (8 arrivals)
+    uint64_t ready[2];                      // control data of a tile ready   (1 arrival)
     uint32_t vid;
 };
 constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align the swizzled stages to 1 KB
@@ -439,6 +450,10 @@ __device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ uint32_t tile_S(const TileTables &tb, const uint32_t *stage, uint32_t b)
@@ -460,28 +475,25 @@ __device__ __forceinline__ uint32_t tile_E(const TileTables &tb, const uint32_t 
     return s;
 }
 
-// Fused look-back over the two descriptor arrays of the CIGAR scan. (dp, de) are the descriptors of
-// tiles t-1-lane loaded early by the caller (possibly still invalid); further windows are fetched here.
+// Fused look-back over the two descriptor arrays of the CIGAR scan (one L2 round trip per window
+// of 32 tiles for both):
 //   *carry_pos = reference bases the carried-in read consumed before tile t (sum back to the nearest
 //                tile that holds a read start),   *ev_base = events before tile t.
 __device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos, const uint64_t *__restrict__ desc_ev,
-                                          int64_t t, uint64_t dp, uint64_t de, uint64_t *carry_pos, uint64_t *ev_base)
+                                          int64_t t, uint64_t *carry_pos, uint64_t *ev_base)
 {
     uint64_t acc_p = 0, acc_e = 0;
     bool done_p = false, done_e = false;
     int64_t base = t - 1;
-    bool preloaded = true;
     while (true) {
         const int64_t idx = base - (int64_t)lane_id();
-        if (!preloaded) { dp = kDescPrefix; de = kDescPrefix; }      // tiles before 0: prefix 0
+        uint64_t dp = kDescPrefix, de = kDescPrefix;    // tiles before 0: prefix 0
         if (idx >= 0) {
-            while ((!done_p && (dp >> 62) == 0) || (!done_e && (de >> 62) == 0) || !preloaded) {
+            do {
                 if (!done_p) dp = ld_relaxed_u64(desc_pos + idx);
                 if (!done_e) de = ld_relaxed_u64(desc_ev + idx);
-                preloaded = true;
-            }
+            } while ((dp >> 62) == 0 || (de >> 62) == 0);
         }
-        preloaded = false;
         if (!done_p) {
             const uint32_t m = __ballot_sync(0xffffffffu, (dp >> 62) == 2);
             const int first = m ? (__ffs(m) - 1) : 32;
@@ -501,18 +513,26 @@ __device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos,
     *ev_base = acc_e;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+// Warp-specialised persistent kernel, 288 threads:
+//   warps 0..7 (compute): phase A = one pass over 16 consecutive words per lane + two warp scans;
+//                         phase D = emit the lane's events. They never block on global memory.
+//   warp 8 (control)    : TMA issue, publishing tile aggregates, decoupled look-back, staging of the
+//                         read starts (ref_start, first-event index) and the ev_off[] writes.
+// The roles meet only through shared-memory mbarriers (full / bar_a / ready / freeb).
+__global__ void __launch_bounds__(kCtaThreads, 4)
 k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 {
-    extern __shared__ unsigned char smem_raw[];
-    ScanSmem &sm = *reinterpret_cast<ScanSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // keep the pointer in the shared address space (LDS/STS, not generic loads)
+    ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t kTileBytes = kTileWords * 4;
     constexpr uint32_t kRowsPerTile = kTileWords / 32;          // 128-byte rows
-    const uint32_t thr = (p.minlen << 4) | 15u;                 // (w >> 4) > minlen  <=>  w > thr
+    const bool is_control = warp == kWarpsPerScanCta;
 
     if (tid == 0) {
-        for (int s = 0; s < kScanStages; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < kScanStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.freeb[s], kWarpsPerScanCta); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sm.bar_a[b], kWarpsPerScanCta); mbar_init(&sm.ready[b], 1); }
         fence_mbar_init();
         // CTA id in scheduling order: look-back only ever waits on CTAs that are already running
         sm.vid = atomicAdd(&p.ctr->tile_counter, 1u);
@@ -521,109 +541,210 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     const uint64_t vid = sm.vid, stride = gridDim.x;
     // tiles vid, vid+G, vid+2G, ...: neighbouring tiles are processed by different CTAs at the same time
     auto tile_of = [&](uint32_t itx) -> uint64_t { return vid + (uint64_t)itx * stride; };
-    auto issue = [&](uint32_t s, uint64_t t) {
-        mbar_expect_tx(&sm.full[s], kTileBytes + 16u);
-        tma_load_tile(sm.stage[s], &tmap, (uint32_t)t * kRowsPerTile, &sm.full[s]);
-        bulk_copy_g2s(&sm.meta[s], p.tile_meta + t, 16u, &sm.full[s]);
-    };
-    if (tid == 0) {
-        for (int s = 0; s < kScanStages; ++s)
-            if (tile_of(s) < p.ntiles) issue(s, tile_of(s));
-    }
 
-    // this thread's 16 consecutive words live in 128-byte row tid/2, chunks 4*(tid&1)+j, swizzled
-    const uint32_t rowq = (tid >> 1) * 8, x0 = ((tid & 1u) << 2) ^ ((tid >> 1) & 7u);
+    if (!is_control) {
+        // =============================== compute warps ===============================
+        const uint32_t thr = (p.minlen << 4) | 15u;             // (w >> 4) > minlen  <=>  w > thr
+        // this thread's 16 consecutive words: 128-byte row tid/2, chunks 4*(tid&1)+j, swizzled
+        const uint32_t rowq = (tid >> 1) * 8, x0 = ((tid & 1u) << 2) ^ ((tid >> 1) & 7u);
 
-    // phase A of pipeline slot itx: one pass over the lane's 16 words, then two warp scans.
-    // evmask: bit i <-> word i of the lane block is an event; clast: bases consumed in the block
-    // before the LAST event of the block.
-    auto phase_a = [&](uint32_t itx, uint32_t &evmask, uint32_t &clast) {
-        const uint32_t s = itx % kScanStages;
-        mbar_wait(&sm.full[s], (itx / kScanStages) & 1u);
-        const uint4 *st4 = reinterpret_cast<const uint4 *>(sm.stage[s]);
-        TileTables &tb = sm.tab[itx & 1u];
-        uint32_t c = 0;
-        evmask = 0;
-        clast = 0;
+        // evmask: bit i <-> word i of the lane block is an event; clast: bases consumed inside the
+        // block before its LAST event
+        auto phase_a = [&](uint32_t itx, uint32_t &evmask, uint32_t &clast) {
+            const uint32_t s = itx % kScanStages;
+            mbar_wait(&sm.full[s], (itx / kScanStages) & 1u);
+            const uint4 *st4 = reinterpret_cast<const uint4 *>(sm.stage[s]);
+            TileTables &tb = sm.tab[itx & 1u];
+            uint32_t c = 0;
+            evmask = 0;
+            clast = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4; ++j) {
+                const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t w = w4[k], lut = kOpLut >> (w & 15u);
-                if ((lut & 0x10000u) && w > thr) { evmask |= 1u << (j * 4 + k); clast = c; }
-                if (lut & 1u) c += w >> 4;
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t w = w4[k], lut = kOpLut >> (w & 15u);
+                    const bool ev = ((lut & 0x10000u) != 0u) & (w > thr);
+                    evmask = ev ? (evmask | (1u << (j * 4 + k))) : evmask;
+                    clast = ev ? c : clast;
+                    c += (lut & 1u) ? (w >> 4) : 0u;
+                }
             }
-        }
-        const uint32_t ne = __popc(evmask);
-        const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
-        tb.lpref[tid] = incl_c - c;
-        tb.lev[tid] = (uint16_t)(incl_e - ne);
-        if (lane == 31) { tb.wsum[warp] = incl_c; tb.wev[warp] = incl_e; }
-    };
+            const uint32_t ne = __popc(evmask);
+            const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
+            tb.lpref[tid] = incl_c - c;
+            tb.lev[tid] = (uint16_t)(incl_e - ne);
+            if (lane == 31) { tb.wsum[warp] = incl_c; tb.wev[warp] = incl_e; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bar_a[itx & 1u]);
+        };
 
-    // warp 0, after the block barrier that follows phase_a(itx): per-warp bases + publish the tile's
-    // aggregates. A tile that holds a read start resets the position carry: its descriptor is final.
-    auto publish = [&](uint32_t itx) {
-        const uint32_t t = (uint32_t)tile_of(itx);
-        TileTables &tb = sm.tab[itx & 1u];
-        const uint32_t a = lane < kWarpsPerScanCta ? tb.wsum[lane] : 0u, b = lane < kWarpsPerScanCta ? tb.wev[lane] : 0u;
-        const uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
-        if (lane < kWarpsPerScanCta) { tb.wbase[lane] = ia - a; tb.webase[lane] = ib - b; }
-        const uint32_t tot_cons = __shfl_sync(0xffffffffu, ia, 31), tot_ev = __shfl_sync(0xffffffffu, ib, 31);
-        if (lane == 0) { tb.tot_cons = tot_cons; tb.tot_ev = tot_ev; }
-        __syncwarp();
+        uint32_t evmask_n = 0, clast_n = 0;
+        if (tile_of(0) < p.ntiles) phase_a(0, evmask_n, clast_n);
+        for (uint32_t it = 0;; ++it) {
+            if (tile_of(it) >= p.ntiles) break;
+            const uint32_t s = it % kScanStages;
+            uint32_t evmask = evmask_n;
+            const uint32_t clast = clast_n;
+            if (tile_of(it + 1) < p.ntiles) phase_a(it + 1, evmask_n, clast_n);
+
+            // ---- phase D: emit this lane's events (about 1% of the words), last event of the block first
+            {
+                // always taken (normally already complete): it also keeps this warp from overwriting
+                // tab[it&1] in its next phase A while the control warp still reads it
+                mbar_wait(&sm.ready[it & 1u], (it >> 1) & 1u);
+                if (evmask) {
+                    const uint32_t *stage = sm.stage[s];
+                    const TileTables &tb = sm.tab[it & 1u];
+                    const Staging &sg = sm.stg[it & 1u];
+                    const uint4 meta = sm.meta[s];
+                    const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
+                    const uint64_t g0 = (tile_of(it)) * kTileWords;
+                    const uint32_t s_blk = tb.wbase[warp] + tb.lpref[tid], e_blk = tb.webase[warp] + tb.lev[tid];
+                    const uint32_t own = sg.owner[tid];
+                    const uint64_t ev_base = sg.ev_base;
+                    bool first = true;
+                    do {
+                        const uint32_t bit = 31u - (uint32_t)__clz(evmask);
+                        evmask ^= 1u << bit;
+                        const uint32_t idx = tid * kLaneWords + bit;
+                        const uint32_t w = stage[swz(idx)];
+                        uint32_t s_in = clast;                           // captured in phase A for the last event
+                        if (!first) {
+                            s_in = 0;
+                            for (uint32_t i = idx - bit; i < idx; ++i) s_in += cig_consume(stage[swz(i)]);
+                        }
+                        first = false;
+                        const uint32_t s_here = s_blk + s_in, e_here = e_blk + __popc(evmask);  // lower bits remain
+                        // owning read = last read start at or before this word
+                        uint32_t lo = own >> 1;
+                        if (own & 1u) {                                  // a read starts inside this block
+                            uint32_t hi = nst;
+                            lo = 0;
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (sg.off[mid] <= idx) lo = mid + 1; else hi = mid;
+                            }
+                        }
+                        uint32_t pos1;
+                        if (lo == 0) {
+                            pos1 = sg.carry_pos1 + s_here;               // read carried in from an earlier tile
+                        } else if (lo == nst && nrs > nst) {
+                            // more read starts than the staging area holds: search the tail in global memory
+                            const uint64_t g = g0 + idx;
+                            uint32_t a = rA + nst - 1, b = rA + nrs;
+                            while (a < b) {
+                                const uint32_t mid = a + ((b - a) >> 1);
+                                if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
+                            }
+                            const uint32_t r = a - 1;
+                            pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(tb, stage, (uint32_t)(p.cig_off[r] - g0));
+                        } else {
+                            pos1 = sg.pos1[lo - 1] + s_here;             // call.rs:380 cursor at this op
+                        }
+                        const uint32_t len = w >> 4, op = w & 15u;
+                        const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
+                        const uint64_t slot = ev_base + e_here;
+                        if (slot < p.ev_cap) p.events[slot] = make_uint2(pos1, (uint32_t)val);
+                        else atomicOr(&p.ctr->flags, kFlagEventOverflow);
+                    } while (evmask);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.freeb[s]);        // this warp is done with stage s and tab/stg[it&1]
+        }
+    } else {
+        // =============================== control warp ===============================
+        auto issue = [&](uint32_t s, uint64_t t) {
+            mbar_expect_tx(&sm.full[s], kTileBytes + 16u);
+            tma_load_tile(sm.stage[s], &tmap, (uint32_t)t * kRowsPerTile, &sm.full[s]);
+            bulk_copy_g2s(&sm.meta[s], p.tile_meta + t, 16u, &sm.full[s]);
+        };
         if (lane == 0) {
-            const uint4 m = sm.meta[itx % kScanStages];
-            const uint32_t trailing = m.y ? tot_cons - tile_S(tb, sm.stage[itx % kScanStages], m.z) : tot_cons;
-            st_relaxed_u64(p.desc_pos + t, (m.y ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
-            st_relaxed_u64(p.desc_ev + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tot_ev);
-        }
-    };
-
-    // pipeline fill
-    uint32_t evmask_n = 0, clast_n = 0;
-    if (tile_of(0) < p.ntiles) phase_a(0, evmask_n, clast_n);
-    __syncthreads();
-    if (warp == 0 && tile_of(0) < p.ntiles) publish(0);
-
-    for (uint32_t it = 0;; ++it) {
-        const uint64_t t64 = tile_of(it);
-        if (t64 >= p.ntiles) break;
-        const uint32_t t = (uint32_t)t64;
-        const uint32_t s = it % kScanStages;
-        const uint32_t *stage = sm.stage[s];
-        const uint4 meta = sm.meta[s];
-        const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
-        const uint64_t g0 = (uint64_t)t * kTileWords;
-        uint32_t evmask = evmask_n;
-        const uint32_t clast = clast_n;
-
-        // early loads whose latency hides under phase A of the next tile
-        uint64_t dp = kDescPrefix, de = kDescPrefix, pre_off = 0;
-        int32_t pre_rs = 0;
-        if (warp == 0) {
-            const int64_t idx = (int64_t)t - 1 - (int64_t)lane;
-            if (idx >= 0) { dp = ld_relaxed_u64(p.desc_pos + idx); de = ld_relaxed_u64(p.desc_ev + idx); }
-        } else if (tid - 32 < nst) {
-            pre_off = p.cig_off[rA + tid - 32];
-            pre_rs = p.rs[rA + tid - 32];
+            for (int s = 0; s < kScanStages; ++s)
+                if (tile_of(s) < p.ntiles) issue(s, tile_of(s));
         }
 
-        const bool have_next = tile_of(it + 1) < p.ntiles;
-        if (have_next) phase_a(it + 1, evmask_n, clast_n);
-        __syncthreads();
+        // after phase A of slot itx: per-warp bases + publish the tile's aggregates. A tile that holds a
+        // read start resets the position carry, so its position descriptor is final at once.
+        auto publish = [&](uint32_t itx) {
+            const uint32_t t = (uint32_t)tile_of(itx);
+            TileTables &tb = sm.tab[itx & 1u];
+            mbar_wait(&sm.full[itx % kScanStages], (itx / kScanStages) & 1u);   // already complete: acquire the TMA data
+            const uint32_t a = lane < kWarpsPerScanCta ? tb.wsum[lane] : 0u, b = lane < kWarpsPerScanCta ? tb.wev[lane] : 0u;
+            const uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
+            if (lane < kWarpsPerScanCta) { tb.wbase[lane] = ia - a; tb.webase[lane] = ib - b; }
+            const uint32_t tot_cons = __shfl_sync(0xffffffffu, ia, 31), tot_ev = __shfl_sync(0xffffffffu, ib, 31);
+            if (lane == 0) { tb.tot_cons = tot_cons; tb.tot_ev = tot_ev; }
+            __syncwarp();
+            if (lane == 0) {
+                const uint4 m = sm.meta[itx % kScanStages];
+                const uint32_t trailing = m.y ? tot_cons - tile_S(tb, sm.stage[itx % kScanStages], m.z) : tot_cons;
+                st_relaxed_u64(p.desc_pos + t, (m.y ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
+                st_relaxed_u64(p.desc_ev + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tot_ev);
+            }
+        };
 
-        const TileTables &tb = sm.tab[it & 1u];
-        // ---- phase B: warp 0 publishes the next tile, then resolves the look-back for this one (its
-        //      predecessors published one iteration ago); warps 1..7 stage this tile's read starts
-        if (warp == 0) {
-            if (have_next) publish(it + 1);
-            uint64_t ev_base = 0, carry_pos = 0;
+        // stage the read starts of slot itx (needs publish(itx)): offsets, event ranks, position bases, and
+        // the per-lane-block owner table that replaces a binary search for most events
+        auto staging = [&](uint32_t itx) {
+            const uint32_t s = itx % kScanStages;
+            const TileTables &tb = sm.tab[itx & 1u];
+            Staging &sg = sm.stg[itx & 1u];
+            const uint32_t *stage = sm.stage[s];
+            const uint4 meta = sm.meta[s];
+            const uint32_t rA = meta.x, nst = min(meta.y, (uint32_t)kMaxStarts);
+            const uint64_t g0 = tile_of(itx) * kTileWords;
+            uint32_t *own32 = reinterpret_cast<uint32_t *>(sg.owner);
+#pragma unroll
+            for (int k = 0; k < kScanThreads / 64; ++k) own32[lane + 32 * k] = 0u;
+            __syncwarp();
+            for (uint32_t i = lane; i < nst; i += 32) {
+                const uint32_t r = rA + i;
+                const uint32_t b = (uint32_t)min(p.cig_off[r] - g0, (uint64_t)kTileWords);
+                sg.off[i] = (uint16_t)b;
+                sg.ev[i] = (uint16_t)tile_E(tb, stage, b, p.minlen);
+                sg.pos1[i] = (uint32_t)p.rs[r] + 1u - tile_S(tb, stage, b);
+                if (b < (uint32_t)kTileWords) {
+                    const uint32_t blk = b / kLaneWords;
+                    atomicAdd(&own32[blk >> 1], (blk & 1u) ? 0x10000u : 1u);      // u16 histogram, counts <= 128
+                }
+            }
+            __syncwarp();
+            // exclusive scan of the histogram: lane owns blocks [8*lane, 8*lane+8)
+            uint32_t cnt[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { cnt[k] = sg.owner[lane * 8 + k]; sum += cnt[k]; }
+            uint32_t run = warp_incl_scan(sum) - sum;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sg.owner[lane * 8 + k] = (uint16_t)((run << 1) | (cnt[k] ? 1u : 0u));
+                run += cnt[k];
+            }
+        };
+
+        if (tile_of(0) < p.ntiles) {
+            mbar_wait(&sm.bar_a[0], 0);
+            publish(0);
+            staging(0);
+        }
+        for (uint32_t it = 0;; ++it) {
+            const uint64_t t64 = tile_of(it);
+            if (t64 >= p.ntiles) break;
+            const uint32_t t = (uint32_t)t64;
+            const uint32_t s = it % kScanStages;
+            const TileTables &tb = sm.tab[it & 1u];
+            Staging &sg = sm.stg[it & 1u];
+            const uint4 meta = sm.meta[s];
+            const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
             const uint32_t tot_cons = tb.tot_cons, tot_ev = tb.tot_ev;
+
+            // look back (predecessors published one iteration ago), finish this tile's control data
+            uint64_t ev_base = 0, carry_pos = 0;
             if (t > 0) {
-                lookback2(p.desc_pos, p.desc_ev, (int64_t)t, dp, de, &carry_pos, &ev_base);
+                lookback2(p.desc_pos, p.desc_ev, (int64_t)t, &carry_pos, &ev_base);
                 if (lane == 0) {
                     st_relaxed_u64(p.desc_ev + t, kDescPrefix | ((ev_base + tot_ev) & kDescValueMask));
                     if (nrs == 0)
@@ -631,87 +752,43 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
                 }
             }
             if (lane == 0) {
-                sm.carry_pos1 = meta.w + (uint32_t)carry_pos;
-                sm.ev_base = ev_base;
+                sg.carry_pos1 = meta.w + (uint32_t)carry_pos;
+                sg.ev_base = ev_base;
+            }
+            // first-event index of every read whose CIGAR starts in this tile
+            for (uint32_t i = lane; i < nrs; i += 32) {
+                uint32_t e;
+                if (i < nst) e = sg.ev[i];
+                else e = tile_E(tb, sm.stage[s], (uint32_t)min(p.cig_off[rA + i] - (uint64_t)t * kTileWords, (uint64_t)kTileWords), p.minlen);
+                p.ev_off[rA + i] = (uint32_t)(ev_base + e);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&sm.ready[it & 1u]);
                 if (t == p.ntiles - 1) {
                     p.ev_off[p.R] = (uint32_t)(ev_base + tot_ev);
                     p.ctr->n_events = ev_base + tot_ev;
                     if (ev_base + tot_ev > 0xFFFFFFFFull) atomicOr(&p.ctr->flags, kFlagCountOverflow);
                 }
             }
-        } else {
-            for (uint32_t i = tid - 32; i < nst; i += kScanThreads - 32) {
-                if (i != tid - 32) { pre_off = p.cig_off[rA + i]; pre_rs = p.rs[rA + i]; }
-                const uint32_t b = (uint32_t)min(pre_off - g0, (uint64_t)kTileWords);
-                sm.st_off[i] = (uint16_t)b;
-                sm.st_ev[i] = (uint16_t)tile_E(tb, stage, b, p.minlen);
-                sm.st_pos1[i] = (uint32_t)pre_rs + 1u - tile_S(tb, stage, b);
+
+            // next tile: aggregates out as early as possible, then its staging
+            if (tile_of(it + 1) < p.ntiles) {
+                mbar_wait(&sm.bar_a[(it + 1) & 1u], ((it + 1) >> 1) & 1u);
+                publish(it + 1);
+                staging(it + 1);
             }
-        }
-        __syncthreads();
-        const uint64_t ev_base = sm.ev_base;
 
-        // ---- phase D1: first-event index of every read whose CIGAR starts in this tile
-        for (uint32_t i = tid; i < nrs; i += kScanThreads) {
-            uint32_t e;
-            if (i < nst) e = sm.st_ev[i];
-            else e = tile_E(tb, stage, (uint32_t)min(p.cig_off[rA + i] - g0, (uint64_t)kTileWords), p.minlen);
-            p.ev_off[rA + i] = (uint32_t)(ev_base + e);
-        }
-
-        // ---- phase D2: emit this lane's events (about 1% of the words), last event of the block first
-        if (evmask) {
-            const uint32_t s_blk = tb.wbase[warp] + tb.lpref[tid], e_blk = tb.webase[warp] + tb.lev[tid];
-            bool first = true;
-            do {
-                const uint32_t bit = 31u - (uint32_t)__clz(evmask);
-                evmask ^= 1u << bit;
-                const uint32_t idx = tid * kLaneWords + bit;
-                const uint32_t w = stage[swz(idx)];
-                uint32_t s_in = clast;                                   // captured in phase A for the last event
-                if (!first) {
-                    s_in = 0;
-                    for (uint32_t i = idx - bit; i < idx; ++i) s_in += cig_consume(stage[swz(i)]);
+            // refill stage s once the compute warps are done with it
+            mbar_wait(&sm.freeb[s], (it / kScanStages) & 1u);
+            if (lane == 0) {
+                const uint64_t t2 = tile_of(it + kScanStages);
+                if (t2 < p.ntiles) {
+                    fence_proxy_async();
+                    issue(s, t2);
                 }
-                first = false;
-                const uint32_t s_here = s_blk + s_in, e_here = e_blk + __popc(evmask);   // lower bits remain
-                // owning read: the last read start at or before this word
-                uint32_t lo = 0, hi = nst;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (sm.st_off[mid] <= idx) lo = mid + 1; else hi = mid;
-                }
-                uint32_t pos1;
-                if (lo == 0) {
-                    pos1 = sm.carry_pos1 + s_here;                       // read carried in from an earlier tile
-                } else if (lo == nst && nrs > nst) {
-                    // more read starts than the staging area holds: search the tail in global memory
-                    const uint64_t g = g0 + idx;
-                    uint32_t a = rA + nst - 1, b = rA + nrs;
-                    while (a < b) {
-                        const uint32_t mid = a + ((b - a) >> 1);
-                        if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
-                    }
-                    const uint32_t r = a - 1;
-                    pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(tb, stage, (uint32_t)(p.cig_off[r] - g0));
-                } else {
-                    pos1 = sm.st_pos1[lo - 1] + s_here;                  // call.rs:380 cursor at this op
-                }
-                const uint32_t len = w >> 4, op = w & 15u;
-                const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
-                const uint64_t slot = ev_base + e_here;
-                if (slot < p.ev_cap) p.events[slot] = make_uint2(pos1, (uint32_t)val);
-                else atomicOr(&p.ctr->flags, kFlagEventOverflow);
-            } while (evmask);
-        }
-
-        __syncthreads();                                // everyone is done with stage s, tab[it&1] and the staging arrays
-        if (tid == 0) {
-            const uint64_t t2 = tile_of(it + kScanStages);
-            if (t2 < p.ntiles) {
-                fence_proxy_async();
-                issue(s, t2);
             }
+            __syncwarp();
         }
     }
 }
