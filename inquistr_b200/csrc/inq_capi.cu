@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -412,6 +413,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             sp.cig_off = ctx->cig_off.p; sp.rs = ctx->rs.p; sp.tile_meta = ctx->tile_meta.p;
             sp.desc_ev = ctx->desc_ev.p; sp.desc_pos = ctx->desc_pos.p; sp.events = ctx->events.p; sp.ev_off = ctx->ev_off.p;
             sp.ctr = ctx->d_ctr; sp.R = R; sp.ev_cap = ctx->events.cap; sp.ntiles = ntiles; sp.minlen = minlen;
+            { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
             const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
             k_cigar_scan<<<grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;

@@ -22,8 +22,8 @@ namespace inq {
 // ----------------------------------------------------------------------------------------------
 // constants
 constexpr int kWarp = 32;
-constexpr int kTileWords = 4096;            // CIGAR words per tile (16 KB)
-constexpr int kScanThreads = 256;           // 8 warps, 512 words per warp, 16 per lane
+constexpr int kTileWords = 8192;            // CIGAR words per tile (32 KB)
+constexpr int kScanThreads = 512;           // 16 compute warps, 512 words per warp, 16 per lane
 constexpr int kScanStages = 3;              // smem ring of bulk-copied tiles
 constexpr int kQuadsPerTile = kTileWords / 4;
 constexpr int kWarpsPerScanCta = kScanThreads / kWarp;
@@ -105,6 +105,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// same, but lets the hardware park the warp for up to ~`ns` per probe instead of spinning on issue slots
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(ns)
         : "memory");
 }
 __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
@@ -382,6 +395,7 @@ struct ScanParams {
     uint64_t ev_cap;
     uint32_t ntiles;
     uint32_t minlen;
+    uint32_t debug;               // timing experiments only (INQ_SCAN_DEBUG): results are wrong when != 0
 };
 
 // per-tile metadata, one thread per tile (k_tile_index ran before): everything the scan kernel would
@@ -402,7 +416,7 @@ __global__ void k_tile_meta(const uint32_t *__restrict__ tile_first, const uint6
     meta[t] = m;
 }
 
-constexpr int kMaxStarts = 128;             // read starts per tile staged in shared memory
+constexpr int kMaxStarts = 256;             // read starts per tile staged in shared memory
 constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words per compute lane
 constexpr int kCtaThreads = kScanThreads + 32;          // 8 compute warps + 1 control warp
 constexpr uint32_t kOpLut = 0x18Du | (0x16u << 16);     // bit op: consumes reference; bit 16+op: I/D/S
@@ -519,7 +533,7 @@ __device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos,
 //   warp 8 (control)    : TMA issue, publishing tile aggregates, decoupled look-back, staging of the
 //                         read starts (ref_start, first-event index) and the ev_off[] writes.
 // The roles meet only through shared-memory mbarriers (full / bar_a / ready / freeb).
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, 2)
 k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -558,6 +572,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             uint32_t c = 0;
             evmask = 0;
             clast = 0;
+            if (!(p.debug & 8u))
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
@@ -593,8 +608,8 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             {
                 // always taken (normally already complete): it also keeps this warp from overwriting
                 // tab[it&1] in its next phase A while the control warp still reads it
-                mbar_wait(&sm.ready[it & 1u], (it >> 1) & 1u);
-                if (evmask) {
+                mbar_wait_parked(&sm.ready[it & 1u], (it >> 1) & 1u, 2000u);
+                if (evmask && !(p.debug & 1u)) {
                     const uint32_t *stage = sm.stage[s];
                     const TileTables &tb = sm.tab[it & 1u];
                     const Staging &sg = sm.stg[it & 1u];
@@ -688,7 +703,8 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 
         // stage the read starts of slot itx (needs publish(itx)): offsets, event ranks, position bases, and
         // the per-lane-block owner table that replaces a binary search for most events
-        auto staging = [&](uint32_t itx) {
+        // (pre_off, pre_rs): cig_off / ref_start of read start `lane` of the slot, loaded early by the caller
+        auto staging = [&](uint32_t itx, uint64_t pre_off, int32_t pre_rs) {
             const uint32_t s = itx % kScanStages;
             const TileTables &tb = sm.tab[itx & 1u];
             Staging &sg = sm.stg[itx & 1u];
@@ -702,33 +718,46 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             __syncwarp();
             for (uint32_t i = lane; i < nst; i += 32) {
                 const uint32_t r = rA + i;
-                const uint32_t b = (uint32_t)min(p.cig_off[r] - g0, (uint64_t)kTileWords);
+                if (i >= 32) { pre_off = p.cig_off[r]; pre_rs = p.rs[r]; }
+                const uint32_t b = (uint32_t)min(pre_off - g0, (uint64_t)kTileWords);
                 sg.off[i] = (uint16_t)b;
                 sg.ev[i] = (uint16_t)tile_E(tb, stage, b, p.minlen);
-                sg.pos1[i] = (uint32_t)p.rs[r] + 1u - tile_S(tb, stage, b);
+                sg.pos1[i] = (uint32_t)pre_rs + 1u - tile_S(tb, stage, b);
                 if (b < (uint32_t)kTileWords) {
                     const uint32_t blk = b / kLaneWords;
-                    atomicAdd(&own32[blk >> 1], (blk & 1u) ? 0x10000u : 1u);      // u16 histogram, counts <= 128
+                    atomicAdd(&own32[blk >> 1], (blk & 1u) ? 0x10000u : 1u);      // u16 histogram, counts <= kMaxStarts
                 }
             }
             __syncwarp();
-            // exclusive scan of the histogram: lane owns blocks [8*lane, 8*lane+8)
-            uint32_t cnt[8], sum = 0;
+            // exclusive scan of the histogram: lane owns kScanThreads/32 consecutive blocks
+            constexpr int kPer = kScanThreads / 32;
+            uint32_t cnt[kPer], sum = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { cnt[k] = sg.owner[lane * 8 + k]; sum += cnt[k]; }
+            for (int k = 0; k < kPer; ++k) { cnt[k] = sg.owner[lane * kPer + k]; sum += cnt[k]; }
             uint32_t run = warp_incl_scan(sum) - sum;
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                sg.owner[lane * 8 + k] = (uint16_t)((run << 1) | (cnt[k] ? 1u : 0u));
+            for (int k = 0; k < kPer; ++k) {
+                sg.owner[lane * kPer + k] = (uint16_t)((run << 1) | (cnt[k] ? 1u : 0u));
                 run += cnt[k];
             }
         };
+        // early loads for the staging of slot itx (its tile and metadata must have landed)
+        auto prefetch_starts = [&](uint32_t itx, uint64_t &pre_off, int32_t &pre_rs) {
+            const uint32_t s = itx % kScanStages;
+            mbar_wait_parked(&sm.full[s], (itx / kScanStages) & 1u, 1000u);
+            const uint4 meta = sm.meta[s];
+            pre_off = 0;
+            pre_rs = 0;
+            if (lane < meta.y) { pre_off = p.cig_off[meta.x + lane]; pre_rs = p.rs[meta.x + lane]; }
+        };
 
         if (tile_of(0) < p.ntiles) {
-            mbar_wait(&sm.bar_a[0], 0);
+            uint64_t po; int32_t pr;
+            prefetch_starts(0, po, pr);
+            mbar_wait_parked(&sm.bar_a[0], 0, 1000u);
             publish(0);
-            staging(0);
+            staging(0, po, pr);
         }
         for (uint32_t it = 0;; ++it) {
             const uint64_t t64 = tile_of(it);
@@ -740,10 +769,14 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             const uint4 meta = sm.meta[s];
             const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
             const uint32_t tot_cons = tb.tot_cons, tot_ev = tb.tot_ev;
+            const bool have_next = tile_of(it + 1) < p.ntiles;
+            uint64_t pre_off = 0;
+            int32_t pre_rs = 0;
+            if (have_next && !(p.debug & 4u)) prefetch_starts(it + 1, pre_off, pre_rs);   // latency overlaps the look-back below
 
             // look back (predecessors published one iteration ago), finish this tile's control data
             uint64_t ev_base = 0, carry_pos = 0;
-            if (t > 0) {
+            if (t > 0 && !(p.debug & 2u)) {
                 lookback2(p.desc_pos, p.desc_ev, (int64_t)t, &carry_pos, &ev_base);
                 if (lane == 0) {
                     st_relaxed_u64(p.desc_ev + t, kDescPrefix | ((ev_base + tot_ev) & kDescValueMask));
@@ -756,6 +789,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
                 sg.ev_base = ev_base;
             }
             // first-event index of every read whose CIGAR starts in this tile
+            if (!(p.debug & 16u))
             for (uint32_t i = lane; i < nrs; i += 32) {
                 uint32_t e;
                 if (i < nst) e = sg.ev[i];
@@ -773,14 +807,14 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             }
 
             // next tile: aggregates out as early as possible, then its staging
-            if (tile_of(it + 1) < p.ntiles) {
-                mbar_wait(&sm.bar_a[(it + 1) & 1u], ((it + 1) >> 1) & 1u);
-                publish(it + 1);
-                staging(it + 1);
+            if (have_next) {
+                mbar_wait_parked(&sm.bar_a[(it + 1) & 1u], ((it + 1) >> 1) & 1u, 1000u);
+                if (!(p.debug & 16u)) publish(it + 1);
+                if (!(p.debug & 4u)) staging(it + 1, pre_off, pre_rs);
             }
 
             // refill stage s once the compute warps are done with it
-            mbar_wait(&sm.freeb[s], (it / kScanStages) & 1u);
+            mbar_wait_parked(&sm.freeb[s], (it / kScanStages) & 1u, 1000u);
             if (lane == 0) {
                 const uint64_t t2 = tile_of(it + kScanStages);
                 if (t2 < p.ntiles) {
