@@ -240,7 +240,7 @@ def main():
         s = res.stats
         dev_ms += s["ms_total"]
         cigar_ms += s["ms_cigar"]
-        for k in ("ms_index", "ms_join", "ms_cigar", "ms_scan", "ms_pairs", "ms_median", "ms_d2h"):
+        for k in ("ms_index", "ms_join", "ms_cigar", "ms_fixup", "ms_scan", "ms_pairs", "ms_median", "ms_d2h"):
             stage_ms[k] = stage_ms.get(k, 0.0) + s[k] / args.steps
     barrier()
     wall_resident = time.perf_counter() - t0

@@ -69,9 +69,10 @@ typedef struct inq_stats {
     uint32_t n_kernel_launches;  /* kernels launched by the call */
     uint32_t n_tiles;            /* CIGAR tiles scanned */
     float ms_total;              /* first kernel start -> last kernel end */
-    float ms_index;              /* tile index + memsets */
+    float ms_index;              /* memsets */
     float ms_join;               /* K1 read x locus overlap join (count) */
-    float ms_cigar;              /* K2 segmented CIGAR scan (dominant kernel) */
+    float ms_cigar;              /* K2 CIGAR scan (dominant kernel) */
+    float ms_fixup;              /* warp-tile prefix scans + per-read event fix-up */
     float ms_scan;               /* bucket offset scan */
     float ms_pairs;              /* K2b per-pair window sums + scatter into buckets */
     float ms_median;             /* K3 per-locus sort / support filter / median */

@@ -37,7 +37,7 @@ class Stats(C.Structure):
         ("n_pairs", C.c_uint64), ("n_candidates", C.c_uint64), ("n_events", C.c_uint64),
         ("op_visits", C.c_uint64), ("n_kernel_launches", C.c_uint32), ("n_tiles", C.c_uint32),
         ("ms_total", C.c_float), ("ms_index", C.c_float), ("ms_join", C.c_float),
-        ("ms_cigar", C.c_float), ("ms_scan", C.c_float), ("ms_pairs", C.c_float),
+        ("ms_cigar", C.c_float), ("ms_fixup", C.c_float), ("ms_scan", C.c_float), ("ms_pairs", C.c_float),
         ("ms_median", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
     ]
 

@@ -23,7 +23,7 @@ struct DevBuf {
     uint64_t cap = 0;   // elements
 };
 
-enum { EV_START = 0, EV_INDEX, EV_JOIN, EV_CIGAR, EV_SCAN, EV_PAIRS, EV_MEDIAN, EV_D2H, EV_H2D0, EV_H2D1, EV_COUNT };
+enum { EV_START = 0, EV_INDEX, EV_JOIN, EV_CIGAR, EV_FIXUP, EV_SCAN, EV_PAIRS, EV_MEDIAN, EV_D2H, EV_H2D0, EV_H2D1, EV_COUNT };
 
 }  // namespace
 
@@ -48,9 +48,11 @@ struct inq_ctx {
     DevBuf<uint32_t> cigar;
 
     // work buffers
-    DevBuf<uint32_t> cand_lo, cand_n, tile_first, ev_off, bcnt, boff, big_list;
-    DevBuf<uint64_t> desc_ev, desc_pos, desc_scan, vals;
-    DevBuf<uint4> tile_meta;
+    DevBuf<uint32_t> cand_lo, cand_n, ev_off, gstart, bcnt, boff, big_list;
+    DevBuf<uint32_t> blkpref, wt_cons, wt_ev, wt_sbase;
+    DevBuf<uint16_t> blkev;
+    DevBuf<uint64_t> desc_scan, desc_wt, vals;
+    DevBuf<uint2> evraw;
     CUtensorMap tmap;                 // 2-D view of the packed CIGAR stream: rows of 32 words, 128B swizzle
     const void *tmap_base = nullptr;
     uint64_t tmap_rows = 0;
@@ -223,10 +225,12 @@ void inq_ctx_destroy(inq_ctx *ctx)
     release(ctx->contig); release(ctx->rs); release(ctx->re);
     release(ctx->mapq); release(ctx->hp); release(ctx->flags);
     release(ctx->cig_off); release(ctx->cigar);
-    release(ctx->cand_lo); release(ctx->cand_n); release(ctx->tile_first); release(ctx->ev_off);
+    release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off); release(ctx->gstart);
+    release(ctx->blkpref); release(ctx->blkev); release(ctx->wt_cons); release(ctx->wt_ev); release(ctx->wt_sbase);
+    release(ctx->desc_wt); release(ctx->evraw);
     release(ctx->bcnt); release(ctx->boff); release(ctx->big_list);
-    release(ctx->desc_ev); release(ctx->desc_pos); release(ctx->desc_scan); release(ctx->vals);
-    release(ctx->tile_meta); release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
+    release(ctx->desc_scan); release(ctx->vals);
+    release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
@@ -369,15 +373,23 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     const uint64_t nb = 2 * (uint64_t)L;                     // buckets
     const uint32_t scan_tiles = (uint32_t)((nb + kXsTile - 1) / kXsTile);
 
+    const uint64_t n_wt = (uint64_t)ntiles * kWarpsPerScanCta;                 // 512-word warp tiles
+    const uint32_t wt_scan_tiles = (uint32_t)((n_wt + kXsTile - 1) / kXsTile);
     TRY(ensure(ctx, ctx->cand_lo, R));
     TRY(ensure(ctx, ctx->cand_n, R));
     TRY(ensure(ctx, ctx->ev_off, R + 1));
-    TRY(ensure(ctx, ctx->tile_first, (uint64_t)ntiles + 1));
-    TRY(ensure(ctx, ctx->desc_ev, (uint64_t)ntiles + 1));
-    TRY(ensure(ctx, ctx->desc_pos, (uint64_t)ntiles + 1));
-    TRY(ensure(ctx, ctx->tile_meta, (uint64_t)ntiles + 1));
+    TRY(ensure(ctx, ctx->gstart, R + 1));
+    TRY(ensure(ctx, ctx->blkpref, (uint64_t)ntiles * kScanThreads + 1));
+    TRY(ensure(ctx, ctx->blkev, (uint64_t)ntiles * kScanThreads + 1));
+    TRY(ensure(ctx, ctx->wt_cons, n_wt + 1));
+    TRY(ensure(ctx, ctx->wt_ev, n_wt + 1));
+    TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
+    TRY(ensure(ctx, ctx->desc_wt, 2 * ((uint64_t)wt_scan_tiles + 1)));
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
-    if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 8 + 4096));
+    const unsigned scan_grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
+    if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 16 + 4096));
+    // warp-tile storage hands out kEvChunk-slot chunks: every resident warp may strand one chunk
+    if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, ctx->events.cap + (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kWarpsPerScanCta * kEvChunk));
 
     ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
     LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
@@ -389,14 +401,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
         if (nb) CU_TRY(ctx, cudaMemsetAsync(ctx->bcnt.p, 0, (nb + 1) * sizeof(uint32_t), s));
         if (nb) CU_TRY(ctx, cudaMemsetAsync(ctx->boff.p, 0, (nb + 1) * sizeof(uint32_t), s));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->ev_off.p, 0, (R + 1) * sizeof(uint32_t), s));
-        if (ntiles) {
-            CU_TRY(ctx, cudaMemsetAsync(ctx->desc_ev.p, 0, (uint64_t)ntiles * sizeof(uint64_t), s));
-            CU_TRY(ctx, cudaMemsetAsync(ctx->desc_pos.p, 0, (uint64_t)ntiles * sizeof(uint64_t), s));
-            k_tile_index<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R, ntiles, ctx->tile_first.p);
-            k_tile_meta<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->tile_first.p, ctx->cig_off.p, ctx->rs.p, ntiles, ctx->tile_meta.p);
-            launches += 2;
-        }
+        if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->ev_off.p, 0, (R + 1) * sizeof(uint32_t), s));
+        if (wt_scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, 2 * ((uint64_t)wt_scan_tiles + 1) * sizeof(uint64_t), s));
         if (scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, (uint64_t)scan_tiles * sizeof(uint64_t), s));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_INDEX], s));
 
@@ -407,23 +413,38 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_JOIN], s));
 
-        // K2: CIGAR scan -> events
+        // K2: CIGAR scan -> warp-tile tables + raw events, then prefix sums and the per-read fix-up
         if (ntiles && L) {
             ScanParams sp;
-            sp.cig_off = ctx->cig_off.p; sp.rs = ctx->rs.p; sp.tile_meta = ctx->tile_meta.p;
-            sp.desc_ev = ctx->desc_ev.p; sp.desc_pos = ctx->desc_pos.p; sp.events = ctx->events.p; sp.ev_off = ctx->ev_off.p;
-            sp.ctr = ctx->d_ctr; sp.R = R; sp.ev_cap = ctx->events.cap; sp.ntiles = ntiles; sp.minlen = minlen;
+            sp.blkpref = ctx->blkpref.p; sp.blkev = ctx->blkev.p; sp.wt_cons = ctx->wt_cons.p; sp.wt_ev = ctx->wt_ev.p;
+            sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
+            sp.ntiles = ntiles; sp.minlen = minlen;
             { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
-            const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
-            k_cigar_scan<<<grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
+            k_cigar_scan<<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR], s));
+        if (ntiles && L) {
+            const unsigned g = std::min<unsigned>(wt_scan_tiles, (unsigned)ctx->sm_count * 4);
+            k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->wt_cons.p, ctx->wt_cons.p, n_wt, wt_scan_tiles, ctx->desc_wt.p,
+                                                      &ctx->d_ctr->scan_counter[0], nullptr);
+            k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->wt_ev.p, ctx->wt_ev.p, n_wt, wt_scan_tiles, ctx->desc_wt.p + wt_scan_tiles + 1,
+                                                      &ctx->d_ctr->scan_counter[1], &ctx->d_ctr->flags);
+            k_read_starts<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R, ctx->cigar.p, ctx->wt_cons.p, ctx->wt_ev.p,
+                                                                           ctx->blkpref.p, ctx->blkev.p, minlen, ctx->ev_off.p,
+                                                                           ctx->gstart.p, ctx->d_ctr);
+            k_event_fixup<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->ev_off.p, ctx->gstart.p,
+                                                                       ctx->wt_cons.p, ctx->wt_ev.p, ctx->wt_sbase.p, ctx->evraw.p,
+                                                                       ctx->evraw.cap, ctx->events.p, ctx->events.cap, ctx->d_ctr);
+            launches += 4;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_FIXUP], s));
 
         // bucket offsets
         if (scan_tiles) {
             const unsigned grid = std::min<unsigned>(scan_tiles, (unsigned)ctx->sm_count * 4);
-            k_exclusive_scan<<<grid, kXsThreads, 0, s>>>(ctx->bcnt.p, ctx->boff.p, nb, scan_tiles, ctx->desc_scan.p, ctx->d_ctr);
+            k_exclusive_scan<<<grid, kXsThreads, 0, s>>>(ctx->bcnt.p, ctx->boff.p, nb, scan_tiles, ctx->desc_scan.p,
+                                                         &ctx->d_ctr->scan_counter[2], &ctx->d_ctr->flags);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_SCAN], s));
@@ -469,10 +490,13 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
 
         const unsigned f = ctx->h_ctr->flags;
         if (f & kFlagEventOverflow) {
-            // the event list was sized speculatively; the scan still counted every event
+            // the event buffers were sized speculatively; the scan still counted every event and slot
             const uint64_t need = ctx->h_ctr->n_events + 4096;
+            const uint64_t need_raw = ctx->h_ctr->ev_alloc + (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kWarpsPerScanCta * kEvChunk;
             release(ctx->events);
+            release(ctx->evraw);
             TRY(ensure(ctx, ctx->events, need));
+            TRY(ensure(ctx, ctx->evraw, need_raw));
             continue;
         }
         if (f & kFlagCountOverflow) return fail(ctx, INQ_ERR_TOO_LARGE, "pair or event count exceeds 2^32");
@@ -504,7 +528,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         stats->ms_index = el(EV_START, EV_INDEX);
         stats->ms_join = el(EV_INDEX, EV_JOIN);
         stats->ms_cigar = el(EV_JOIN, EV_CIGAR);
-        stats->ms_scan = el(EV_CIGAR, EV_SCAN);
+        stats->ms_fixup = el(EV_CIGAR, EV_FIXUP);
+        stats->ms_scan = el(EV_FIXUP, EV_SCAN);
         stats->ms_pairs = el(EV_SCAN, EV_PAIRS);
         stats->ms_median = el(EV_PAIRS, EV_MEDIAN);
         stats->ms_d2h = el(EV_MEDIAN, EV_D2H);

@@ -53,9 +53,10 @@ struct DevCounters {
     unsigned long long n_words_joined;
     unsigned long long op_visits;
     unsigned long long n_events;
+    unsigned long long ev_alloc;      // event slots handed out to warps (chunks)
     unsigned int flags;
     unsigned int tile_counter;
-    unsigned int scan_counter;
+    unsigned int scan_counter[4];
     unsigned int big_count;
     unsigned int big_cursor;
     unsigned int pad;
@@ -232,21 +233,6 @@ __global__ void k_rebase_offsets(uint64_t *__restrict__ off, uint64_t n, uint64_
 }
 
 // ----------------------------------------------------------------------------------------------
-// tile index: tile_first[t] = first read r with cig_off[r] >= t * kTileWords  (t < ntiles),
-// tile_first[ntiles] = R. Reads whose CIGAR starts inside tile t are [tile_first[t], tile_first[t+1]).
-__global__ void k_tile_index(const uint64_t *__restrict__ cig_off, uint64_t R, uint32_t ntiles,
-                             uint32_t *__restrict__ tile_first)
-{
-    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (r > R) return;
-    if (r == R) tile_first[ntiles] = (uint32_t)R;
-    uint64_t t_lo = (r == 0) ? 0 : cig_off[r - 1] / kTileWords + 1;
-    uint64_t t_hi = cig_off[r] / kTileWords;
-    if (r == R) t_hi = ntiles;                       // tiles that start past the last offset
-    for (uint64_t t = t_lo; t <= t_hi && t < ntiles; ++t) tile_first[t] = (uint32_t)r;
-}
-
-// ----------------------------------------------------------------------------------------------
 // K1: read x locus overlap join, counting pass. One thread per read, warp-uniform candidate loop,
 // warp-aggregated atomics into the per-bucket counters.
 //
@@ -377,81 +363,42 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 }
 
 // ----------------------------------------------------------------------------------------------
-// K2: segmented CIGAR scan. Persistent CTAs pull 16 KB tiles of the flat packed-CIGAR stream
-// through a 3-stage shared-memory ring filled by TMA 1-D bulk copies, compute the running
-// reference consumption (warp-shuffle scans, carried across tiles by decoupled look-back and
-// reset at read boundaries), and compact every I/D/S op longer than minlen into an ordered event
-// list {1-based anchor position, signed length, soft-clip bit}. Each CIGAR word is read once.
+// K2: CIGAR scan. Persistent CTAs stream 32 KB tiles of the flat packed-CIGAR array through a
+// 3-stage shared-memory ring filled by TMA (2-D tensor map, 128B swizzle). Every compute warp owns
+// one 512-word "warp tile" per tile, each lane 16 consecutive words. One pass over the words gives
+// the lane's reference consumption (call.rs:384-392,404) and its event mask (I/D/S ops longer than
+// minlen, call.rs:388,394,400); two warp scans turn that into warp-local prefixes. Nothing in this
+// kernel depends on another CTA or on read boundaries: it writes
+//   blkpref/blkev : warp-local exclusive prefixes at every 16-word block
+//   wt_cons/wt_ev : totals per warp tile (prefix-summed afterwards by k_exclusive_scan)
+//   evraw         : {bases consumed inside the warp tile before the op, (signed len << 1) | is_S}
+//                   for every event, stored per warp tile in chunks handed out by one atomic
+// and k_read_starts / k_event_fixup turn these into per-read event lists with absolute anchors.
+// Each CIGAR word is read from HBM exactly once.
 struct ScanParams {
-    const uint64_t *cig_off;      // R+1
-    const int32_t *rs;            // ref_start
-    const uint4 *tile_meta;       // ntiles: {first read starting in tile, #reads starting, last start offset, carried pos1}
-    uint64_t *desc_ev;            // ntiles, zeroed
-    uint64_t *desc_pos;           // ntiles, zeroed
-    uint2 *events;
-    uint32_t *ev_off;             // R+1
+    uint32_t *blkpref;            // [ntiles * kScanThreads]
+    uint16_t *blkev;              // [ntiles * kScanThreads]
+    uint32_t *wt_cons;            // [n_wt + 1]
+    uint32_t *wt_ev;              // [n_wt + 1]
+    uint32_t *wt_sbase;           // [n_wt] storage slot of the warp tile's first event
+    uint2 *evraw;
     DevCounters *ctr;
-    uint64_t R;
-    uint64_t ev_cap;
+    uint64_t raw_cap;             // capacity of evraw (slots)
     uint32_t ntiles;
     uint32_t minlen;
     uint32_t debug;               // timing experiments only (INQ_SCAN_DEBUG): results are wrong when != 0
 };
 
-// per-tile metadata, one thread per tile (k_tile_index ran before): everything the scan kernel would
-// otherwise have to fetch through dependent global loads on its critical path.
-//   x = rA: first read whose CIGAR starts inside the tile      y = number of such reads
-//   z = tile-local word offset of the last such read's start   w = ref_start(rA-1) + 1 (carried-in read)
-__global__ void k_tile_meta(const uint32_t *__restrict__ tile_first, const uint64_t *__restrict__ cig_off,
-                            const int32_t *__restrict__ rs, uint32_t ntiles, uint4 *__restrict__ meta)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const uint32_t rA = tile_first[t], rB = tile_first[t + 1];
-    uint4 m;
-    m.x = rA;
-    m.y = rB - rA;
-    m.z = (rB > rA) ? (uint32_t)min(cig_off[rB - 1] - (uint64_t)t * kTileWords, (uint64_t)kTileWords) : 0u;
-    m.w = (rA > 0 ? (uint32_t)rs[rA - 1] : 0u) + 1u;
-    meta[t] = m;
-}
-
-constexpr int kMaxStarts = 256;             // read starts per tile staged in shared memory
 constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words per compute lane
-constexpr int kCtaThreads = kScanThreads + 32;          // 8 compute warps + 1 control warp
+constexpr int kWarpTileWords = 32 * kLaneWords;         // 512
+constexpr int kCtaThreads = kScanThreads + 32;          // 16 compute warps + 1 TMA producer warp
 constexpr uint32_t kOpLut = 0x18Du | (0x16u << 16);     // bit op: consumes reference; bit 16+op: I/D/S
-
-struct TileTables {
-    uint32_t lpref[kScanThreads];           // warp-local exclusive ref-consumption prefix of each lane block
-    uint16_t lev[kScanThreads];             // warp-local exclusive event count of each lane block
-    uint32_t wsum[kWarpsPerScanCta];        // per-warp totals (phase A)
-    uint32_t wev[kWarpsPerScanCta];
-    uint32_t wbase[kWarpsPerScanCta];       // exclusive per-warp bases (publish)
-    uint32_t webase[kWarpsPerScanCta];
-    uint32_t tot_cons, tot_ev;
-};
-
-// read starts of one tile, staged by the control warp
-struct Staging {
-    uint32_t pos1[kMaxStarts];              // ref_start + 1 - S(start word): add S(word) for the op's anchor
-    uint16_t off[kMaxStarts];               // tile-local word index where the read's CIGAR starts
-    uint16_t ev[kMaxStarts];                // events in the tile before that word
-    uint16_t owner[kScanThreads];           // per lane block: (#starts before the block << 1) | block holds a start
-    uint64_t ev_base;                       // events before the tile (look-back)
-    uint32_t carry_pos1;                    // carried-in read: ref_start + 1 + bases consumed before the tile
-    uint32_t pad;
-};
+constexpr uint32_t kEvChunk = 1024;                     // event slots a warp takes per atomic
 
 struct ScanSmem {
     alignas(1024) uint32_t stage[kScanStages][kTileWords];   // 128B-swizzled by the TMA tensor map
-    alignas(16) uint4 meta[kScanStages];
-    TileTables tab[2];
-    Staging stg[2];
     alignas(8) uint64_t full[kScanStages];  // TMA landed                     (tx bytes)
-    uint64_t freeb[kScanStages];            // compute warps done with stage  (8 arrivals)
-    uint64_t bar_a[2];                      // phase A of a tile done         (8 arrivals)
-    uint64_t ready[2];                      // control data of a tile ready   (1 arrival)
-    uint32_t vid;
+    uint64_t freeb[kScanStages];            // compute warps done with stage  (one arrival per warp)
 };
 constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align the swizzled stages to 1 KB
 
@@ -470,69 +417,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ uint32_t tile_S(const TileTables &tb, const uint32_t *stage, uint32_t b)
-{
-    // reference bases consumed by tile words [0,b)
-    if (b >= (uint32_t)kTileWords) return tb.tot_cons;
-    const uint32_t blk = b / kLaneWords;
-    uint32_t s = tb.wbase[blk >> 5] + tb.lpref[blk];
-    for (uint32_t i = blk * kLaneWords; i < b; ++i) s += cig_consume(stage[swz(i)]);
-    return s;
-}
-__device__ __forceinline__ uint32_t tile_E(const TileTables &tb, const uint32_t *stage, uint32_t b, uint32_t minlen)
-{
-    // events among tile words [0,b)
-    if (b >= (uint32_t)kTileWords) return tb.tot_ev;
-    const uint32_t blk = b / kLaneWords;
-    uint32_t s = tb.webase[blk >> 5] + tb.lev[blk];
-    for (uint32_t i = blk * kLaneWords; i < b; ++i) s += cig_is_event(stage[swz(i)], minlen) ? 1u : 0u;
-    return s;
-}
-
-// Fused look-back over the two descriptor arrays of the CIGAR scan (one L2 round trip per window
-// of 32 tiles for both):
-//   *carry_pos = reference bases the carried-in read consumed before tile t (sum back to the nearest
-//                tile that holds a read start),   *ev_base = events before tile t.
-__device__ __forceinline__ void lookback2(const uint64_t *__restrict__ desc_pos, const uint64_t *__restrict__ desc_ev,
-                                          int64_t t, uint64_t *carry_pos, uint64_t *ev_base)
-{
-    uint64_t acc_p = 0, acc_e = 0;
-    bool done_p = false, done_e = false;
-    int64_t base = t - 1;
-    while (true) {
-        const int64_t idx = base - (int64_t)lane_id();
-        uint64_t dp = kDescPrefix, de = kDescPrefix;    // tiles before 0: prefix 0
-        if (idx >= 0) {
-            do {
-                if (!done_p) dp = ld_relaxed_u64(desc_pos + idx);
-                if (!done_e) de = ld_relaxed_u64(desc_ev + idx);
-            } while ((dp >> 62) == 0 || (de >> 62) == 0);
-        }
-        if (!done_p) {
-            const uint32_t m = __ballot_sync(0xffffffffu, (dp >> 62) == 2);
-            const int first = m ? (__ffs(m) - 1) : 32;
-            acc_p += warp_sum(((int)lane_id() <= first) ? (dp & kDescValueMask) : 0ull);
-            done_p = first < 32;
-        }
-        if (!done_e) {
-            const uint32_t m = __ballot_sync(0xffffffffu, (de >> 62) == 2);
-            const int first = m ? (__ffs(m) - 1) : 32;
-            acc_e += warp_sum(((int)lane_id() <= first) ? (de & kDescValueMask) : 0ull);
-            done_e = first < 32;
-        }
-        if (done_p && done_e) break;
-        base -= 32;
-    }
-    *carry_pos = acc_p;
-    *ev_base = acc_e;
-}
-
-// Warp-specialised persistent kernel, 288 threads:
-//   warps 0..7 (compute): phase A = one pass over 16 consecutive words per lane + two warp scans;
-//                         phase D = emit the lane's events. They never block on global memory.
-//   warp 8 (control)    : TMA issue, publishing tile aggregates, decoupled look-back, staging of the
-//                         read starts (ref_start, first-event index) and the ev_off[] writes.
-// The roles meet only through shared-memory mbarriers (full / bar_a / ready / freeb).
 __global__ void __launch_bounds__(kCtaThreads, 2)
 k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 {
@@ -542,287 +426,172 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t kTileBytes = kTileWords * 4;
     constexpr uint32_t kRowsPerTile = kTileWords / 32;          // 128-byte rows
-    const bool is_control = warp == kWarpsPerScanCta;
 
     if (tid == 0) {
         for (int s = 0; s < kScanStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.freeb[s], kWarpsPerScanCta); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&sm.bar_a[b], kWarpsPerScanCta); mbar_init(&sm.ready[b], 1); }
         fence_mbar_init();
-        // CTA id in scheduling order: look-back only ever waits on CTAs that are already running
-        sm.vid = atomicAdd(&p.ctr->tile_counter, 1u);
     }
     __syncthreads();
-    const uint64_t vid = sm.vid, stride = gridDim.x;
-    // tiles vid, vid+G, vid+2G, ...: neighbouring tiles are processed by different CTAs at the same time
-    auto tile_of = [&](uint32_t itx) -> uint64_t { return vid + (uint64_t)itx * stride; };
+    const uint64_t stride = gridDim.x;
+    auto tile_of = [&](uint32_t itx) -> uint64_t { return blockIdx.x + (uint64_t)itx * stride; };
 
-    if (!is_control) {
-        // =============================== compute warps ===============================
-        const uint32_t thr = (p.minlen << 4) | 15u;             // (w >> 4) > minlen  <=>  w > thr
-        // this thread's 16 consecutive words: 128-byte row tid/2, chunks 4*(tid&1)+j, swizzled
-        const uint32_t rowq = (tid >> 1) * 8, x0 = ((tid & 1u) << 2) ^ ((tid >> 1) & 7u);
-
-        // evmask: bit i <-> word i of the lane block is an event; clast: bases consumed inside the
-        // block before its LAST event
-        auto phase_a = [&](uint32_t itx, uint32_t &evmask, uint32_t &clast) {
-            const uint32_t s = itx % kScanStages;
-            mbar_wait(&sm.full[s], (itx / kScanStages) & 1u);
-            const uint4 *st4 = reinterpret_cast<const uint4 *>(sm.stage[s]);
-            TileTables &tb = sm.tab[itx & 1u];
-            uint32_t c = 0;
-            evmask = 0;
-            clast = 0;
-            if (!(p.debug & 8u))
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t w = w4[k], lut = kOpLut >> (w & 15u);
-                    const bool ev = ((lut & 0x10000u) != 0u) & (w > thr);
-                    evmask = ev ? (evmask | (1u << (j * 4 + k))) : evmask;
-                    clast = ev ? c : clast;
-                    c += (lut & 1u) ? (w >> 4) : 0u;
-                }
-            }
-            const uint32_t ne = __popc(evmask);
-            const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
-            tb.lpref[tid] = incl_c - c;
-            tb.lev[tid] = (uint16_t)(incl_e - ne);
-            if (lane == 31) { tb.wsum[warp] = incl_c; tb.wev[warp] = incl_e; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.bar_a[itx & 1u]);
-        };
-
-        uint32_t evmask_n = 0, clast_n = 0;
-        if (tile_of(0) < p.ntiles) phase_a(0, evmask_n, clast_n);
-        for (uint32_t it = 0;; ++it) {
-            if (tile_of(it) >= p.ntiles) break;
-            const uint32_t s = it % kScanStages;
-            uint32_t evmask = evmask_n;
-            const uint32_t clast = clast_n;
-            if (tile_of(it + 1) < p.ntiles) phase_a(it + 1, evmask_n, clast_n);
-
-            // ---- phase D: emit this lane's events (about 1% of the words), last event of the block first
-            {
-                // always taken (normally already complete): it also keeps this warp from overwriting
-                // tab[it&1] in its next phase A while the control warp still reads it
-                mbar_wait_parked(&sm.ready[it & 1u], (it >> 1) & 1u, 2000u);
-                if (evmask && !(p.debug & 1u)) {
-                    const uint32_t *stage = sm.stage[s];
-                    const TileTables &tb = sm.tab[it & 1u];
-                    const Staging &sg = sm.stg[it & 1u];
-                    const uint4 meta = sm.meta[s];
-                    const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
-                    const uint64_t g0 = (tile_of(it)) * kTileWords;
-                    const uint32_t s_blk = tb.wbase[warp] + tb.lpref[tid], e_blk = tb.webase[warp] + tb.lev[tid];
-                    const uint32_t own = sg.owner[tid];
-                    const uint64_t ev_base = sg.ev_base;
-                    bool first = true;
-                    do {
-                        const uint32_t bit = 31u - (uint32_t)__clz(evmask);
-                        evmask ^= 1u << bit;
-                        const uint32_t idx = tid * kLaneWords + bit;
-                        const uint32_t w = stage[swz(idx)];
-                        uint32_t s_in = clast;                           // captured in phase A for the last event
-                        if (!first) {
-                            s_in = 0;
-                            for (uint32_t i = idx - bit; i < idx; ++i) s_in += cig_consume(stage[swz(i)]);
-                        }
-                        first = false;
-                        const uint32_t s_here = s_blk + s_in, e_here = e_blk + __popc(evmask);  // lower bits remain
-                        // owning read = last read start at or before this word
-                        uint32_t lo = own >> 1;
-                        if (own & 1u) {                                  // a read starts inside this block
-                            uint32_t hi = nst;
-                            lo = 0;
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if (sg.off[mid] <= idx) lo = mid + 1; else hi = mid;
-                            }
-                        }
-                        uint32_t pos1;
-                        if (lo == 0) {
-                            pos1 = sg.carry_pos1 + s_here;               // read carried in from an earlier tile
-                        } else if (lo == nst && nrs > nst) {
-                            // more read starts than the staging area holds: search the tail in global memory
-                            const uint64_t g = g0 + idx;
-                            uint32_t a = rA + nst - 1, b = rA + nrs;
-                            while (a < b) {
-                                const uint32_t mid = a + ((b - a) >> 1);
-                                if (p.cig_off[mid] <= g) a = mid + 1; else b = mid;
-                            }
-                            const uint32_t r = a - 1;
-                            pos1 = (uint32_t)p.rs[r] + 1u + s_here - tile_S(tb, stage, (uint32_t)(p.cig_off[r] - g0));
-                        } else {
-                            pos1 = sg.pos1[lo - 1] + s_here;             // call.rs:380 cursor at this op
-                        }
-                        const uint32_t len = w >> 4, op = w & 15u;
-                        const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
-                        const uint64_t slot = ev_base + e_here;
-                        if (slot < p.ev_cap) p.events[slot] = make_uint2(pos1, (uint32_t)val);
-                        else atomicOr(&p.ctr->flags, kFlagEventOverflow);
-                    } while (evmask);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.freeb[s]);        // this warp is done with stage s and tab/stg[it&1]
-        }
-    } else {
-        // =============================== control warp ===============================
-        auto issue = [&](uint32_t s, uint64_t t) {
-            mbar_expect_tx(&sm.full[s], kTileBytes + 16u);
-            tma_load_tile(sm.stage[s], &tmap, (uint32_t)t * kRowsPerTile, &sm.full[s]);
-            bulk_copy_g2s(&sm.meta[s], p.tile_meta + t, 16u, &sm.full[s]);
-        };
+    if (warp == kWarpsPerScanCta) {
+        // =============================== TMA producer warp ===============================
         if (lane == 0) {
-            for (int s = 0; s < kScanStages; ++s)
-                if (tile_of(s) < p.ntiles) issue(s, tile_of(s));
-        }
-
-        // after phase A of slot itx: per-warp bases + publish the tile's aggregates. A tile that holds a
-        // read start resets the position carry, so its position descriptor is final at once.
-        auto publish = [&](uint32_t itx) {
-            const uint32_t t = (uint32_t)tile_of(itx);
-            TileTables &tb = sm.tab[itx & 1u];
-            mbar_wait(&sm.full[itx % kScanStages], (itx / kScanStages) & 1u);   // already complete: acquire the TMA data
-            const uint32_t a = lane < kWarpsPerScanCta ? tb.wsum[lane] : 0u, b = lane < kWarpsPerScanCta ? tb.wev[lane] : 0u;
-            const uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
-            if (lane < kWarpsPerScanCta) { tb.wbase[lane] = ia - a; tb.webase[lane] = ib - b; }
-            const uint32_t tot_cons = __shfl_sync(0xffffffffu, ia, 31), tot_ev = __shfl_sync(0xffffffffu, ib, 31);
-            if (lane == 0) { tb.tot_cons = tot_cons; tb.tot_ev = tot_ev; }
-            __syncwarp();
-            if (lane == 0) {
-                const uint4 m = sm.meta[itx % kScanStages];
-                const uint32_t trailing = m.y ? tot_cons - tile_S(tb, sm.stage[itx % kScanStages], m.z) : tot_cons;
-                st_relaxed_u64(p.desc_pos + t, (m.y ? kDescPrefix : kDescAggregate) | (uint64_t)trailing);
-                st_relaxed_u64(p.desc_ev + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tot_ev);
-            }
-        };
-
-        // stage the read starts of slot itx (needs publish(itx)): offsets, event ranks, position bases, and
-        // the per-lane-block owner table that replaces a binary search for most events
-        // (pre_off, pre_rs): cig_off / ref_start of read start `lane` of the slot, loaded early by the caller
-        auto staging = [&](uint32_t itx, uint64_t pre_off, int32_t pre_rs) {
-            const uint32_t s = itx % kScanStages;
-            const TileTables &tb = sm.tab[itx & 1u];
-            Staging &sg = sm.stg[itx & 1u];
-            const uint32_t *stage = sm.stage[s];
-            const uint4 meta = sm.meta[s];
-            const uint32_t rA = meta.x, nst = min(meta.y, (uint32_t)kMaxStarts);
-            const uint64_t g0 = tile_of(itx) * kTileWords;
-            uint32_t *own32 = reinterpret_cast<uint32_t *>(sg.owner);
-#pragma unroll
-            for (int k = 0; k < kScanThreads / 64; ++k) own32[lane + 32 * k] = 0u;
-            __syncwarp();
-            for (uint32_t i = lane; i < nst; i += 32) {
-                const uint32_t r = rA + i;
-                if (i >= 32) { pre_off = p.cig_off[r]; pre_rs = p.rs[r]; }
-                const uint32_t b = (uint32_t)min(pre_off - g0, (uint64_t)kTileWords);
-                sg.off[i] = (uint16_t)b;
-                sg.ev[i] = (uint16_t)tile_E(tb, stage, b, p.minlen);
-                sg.pos1[i] = (uint32_t)pre_rs + 1u - tile_S(tb, stage, b);
-                if (b < (uint32_t)kTileWords) {
-                    const uint32_t blk = b / kLaneWords;
-                    atomicAdd(&own32[blk >> 1], (blk & 1u) ? 0x10000u : 1u);      // u16 histogram, counts <= kMaxStarts
-                }
-            }
-            __syncwarp();
-            // exclusive scan of the histogram: lane owns kScanThreads/32 consecutive blocks
-            constexpr int kPer = kScanThreads / 32;
-            uint32_t cnt[kPer], sum = 0;
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) { cnt[k] = sg.owner[lane * kPer + k]; sum += cnt[k]; }
-            uint32_t run = warp_incl_scan(sum) - sum;
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                sg.owner[lane * kPer + k] = (uint16_t)((run << 1) | (cnt[k] ? 1u : 0u));
-                run += cnt[k];
-            }
-        };
-        // early loads for the staging of slot itx (its tile and metadata must have landed)
-        auto prefetch_starts = [&](uint32_t itx, uint64_t &pre_off, int32_t &pre_rs) {
-            const uint32_t s = itx % kScanStages;
-            mbar_wait_parked(&sm.full[s], (itx / kScanStages) & 1u, 1000u);
-            const uint4 meta = sm.meta[s];
-            pre_off = 0;
-            pre_rs = 0;
-            if (lane < meta.y) { pre_off = p.cig_off[meta.x + lane]; pre_rs = p.rs[meta.x + lane]; }
-        };
-
-        if (tile_of(0) < p.ntiles) {
-            uint64_t po; int32_t pr;
-            prefetch_starts(0, po, pr);
-            mbar_wait_parked(&sm.bar_a[0], 0, 1000u);
-            publish(0);
-            staging(0, po, pr);
-        }
-        for (uint32_t it = 0;; ++it) {
-            const uint64_t t64 = tile_of(it);
-            if (t64 >= p.ntiles) break;
-            const uint32_t t = (uint32_t)t64;
-            const uint32_t s = it % kScanStages;
-            const TileTables &tb = sm.tab[it & 1u];
-            Staging &sg = sm.stg[it & 1u];
-            const uint4 meta = sm.meta[s];
-            const uint32_t rA = meta.x, nrs = meta.y, nst = min(nrs, (uint32_t)kMaxStarts);
-            const uint32_t tot_cons = tb.tot_cons, tot_ev = tb.tot_ev;
-            const bool have_next = tile_of(it + 1) < p.ntiles;
-            uint64_t pre_off = 0;
-            int32_t pre_rs = 0;
-            if (have_next && !(p.debug & 4u)) prefetch_starts(it + 1, pre_off, pre_rs);   // latency overlaps the look-back below
-
-            // look back (predecessors published one iteration ago), finish this tile's control data
-            uint64_t ev_base = 0, carry_pos = 0;
-            if (t > 0 && !(p.debug & 2u)) {
-                lookback2(p.desc_pos, p.desc_ev, (int64_t)t, &carry_pos, &ev_base);
-                if (lane == 0) {
-                    st_relaxed_u64(p.desc_ev + t, kDescPrefix | ((ev_base + tot_ev) & kDescValueMask));
-                    if (nrs == 0)
-                        st_relaxed_u64(p.desc_pos + t, kDescPrefix | ((carry_pos + tot_cons) & 0xFFFFFFFFull));
-                }
-            }
-            if (lane == 0) {
-                sg.carry_pos1 = meta.w + (uint32_t)carry_pos;
-                sg.ev_base = ev_base;
-            }
-            // first-event index of every read whose CIGAR starts in this tile
-            if (!(p.debug & 16u))
-            for (uint32_t i = lane; i < nrs; i += 32) {
-                uint32_t e;
-                if (i < nst) e = sg.ev[i];
-                else e = tile_E(tb, sm.stage[s], (uint32_t)min(p.cig_off[rA + i] - (uint64_t)t * kTileWords, (uint64_t)kTileWords), p.minlen);
-                p.ev_off[rA + i] = (uint32_t)(ev_base + e);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&sm.ready[it & 1u]);
-                if (t == p.ntiles - 1) {
-                    p.ev_off[p.R] = (uint32_t)(ev_base + tot_ev);
-                    p.ctr->n_events = ev_base + tot_ev;
-                    if (ev_base + tot_ev > 0xFFFFFFFFull) atomicOr(&p.ctr->flags, kFlagCountOverflow);
-                }
-            }
-
-            // next tile: aggregates out as early as possible, then its staging
-            if (have_next) {
-                mbar_wait_parked(&sm.bar_a[(it + 1) & 1u], ((it + 1) >> 1) & 1u, 1000u);
-                if (!(p.debug & 16u)) publish(it + 1);
-                if (!(p.debug & 4u)) staging(it + 1, pre_off, pre_rs);
-            }
-
-            // refill stage s once the compute warps are done with it
-            mbar_wait_parked(&sm.freeb[s], (it / kScanStages) & 1u, 1000u);
-            if (lane == 0) {
-                const uint64_t t2 = tile_of(it + kScanStages);
-                if (t2 < p.ntiles) {
+            for (uint32_t it = 0;; ++it) {
+                const uint64_t t = tile_of(it);
+                if (t >= p.ntiles) break;
+                const uint32_t s = it % kScanStages;
+                if (it >= (uint32_t)kScanStages) {
+                    mbar_wait_parked(&sm.freeb[s], ((it / kScanStages) - 1u) & 1u, 1000u);
                     fence_proxy_async();
-                    issue(s, t2);
                 }
+                mbar_expect_tx(&sm.full[s], kTileBytes);
+                tma_load_tile(sm.stage[s], &tmap, (uint32_t)t * kRowsPerTile, &sm.full[s]);
             }
-            __syncwarp();
+        }
+        return;
+    }
+
+    // =============================== compute warps ===============================
+    const uint32_t thr = (p.minlen << 4) | 15u;                 // (w >> 4) > minlen  <=>  w > thr
+    // this thread's 16 consecutive words: 128-byte row tid/2, chunks 4*(tid&1)+j, swizzled
+    const uint32_t rowq = (tid >> 1) * 8, x0 = ((tid & 1u) << 2) ^ ((tid >> 1) & 7u);
+    uint64_t chunk_cur = 0, chunk_end = 0;                      // this warp's private range of event slots
+
+    for (uint32_t it = 0;; ++it) {
+        const uint64_t t = tile_of(it);
+        if (t >= p.ntiles) break;
+        const uint32_t s = it % kScanStages;
+        mbar_wait(&sm.full[s], (it / kScanStages) & 1u);
+        const uint32_t *stage = sm.stage[s];
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
+
+        // ---- one pass over the lane's 16 words. evmask: bit i <-> word i is an event;
+        //      clast: bases consumed inside the block before its LAST event
+        uint32_t c = 0, evmask = 0, clast = 0;
+        if (!(p.debug & 8u))
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w = w4[k], lut = kOpLut >> (w & 15u);
+                const bool ev = ((lut & 0x10000u) != 0u) & (w > thr);
+                evmask = ev ? (evmask | (1u << (j * 4 + k))) : evmask;
+                clast = ev ? c : clast;
+                c += (lut & 1u) ? (w >> 4) : 0u;
+            }
+        }
+        const uint32_t ne = __popc(evmask);
+        const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
+        const uint32_t excl_c = incl_c - c, excl_e = incl_e - ne;
+        const uint32_t tot_e = __shfl_sync(0xffffffffu, incl_e, 31);
+        const uint64_t gblk = t * kScanThreads + tid;           // global 16-word block index
+        if (!(p.debug & 16u)) {
+            p.blkpref[gblk] = excl_c;
+            p.blkev[gblk] = (uint16_t)excl_e;
+        }
+
+        // ---- event slots: contiguous per warp tile, taken from a warp-private chunk
+        uint64_t sbase = chunk_cur;
+        if (tot_e) {
+            if (chunk_end - chunk_cur < tot_e) {
+                unsigned long long base = 0;
+                const uint32_t n = max(kEvChunk, tot_e);
+                if (lane == 0) base = atomicAdd(&p.ctr->ev_alloc, (unsigned long long)n);
+                chunk_cur = __shfl_sync(0xffffffffu, base, 0);
+                chunk_end = chunk_cur + n;
+                sbase = chunk_cur;
+            }
+            chunk_cur += tot_e;
+        }
+        if (lane == 31 && !(p.debug & 16u)) {
+            const uint64_t gw = t * kWarpsPerScanCta + warp;    // global warp-tile index
+            p.wt_cons[gw] = incl_c;
+            p.wt_ev[gw] = incl_e;
+            p.wt_sbase[gw] = (uint32_t)sbase;
+        }
+
+        // ---- emit this lane's events (about 1% of the words), last event of the block first
+        if (evmask && !(p.debug & 1u)) {
+            bool first = true;
+            do {
+                const uint32_t bit = 31u - (uint32_t)__clz(evmask);
+                evmask ^= 1u << bit;
+                const uint32_t idx = tid * kLaneWords + bit;
+                const uint32_t w = stage[swz(idx)];
+                uint32_t s_in = clast;                          // captured above for the last event
+                if (!first) {
+                    s_in = 0;
+                    for (uint32_t i = idx - bit; i < idx; ++i) s_in += cig_consume(stage[swz(i)]);
+                }
+                first = false;
+                const uint32_t len = w >> 4, op = w & 15u;
+                const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
+                const uint64_t slot = sbase + excl_e + __popc(evmask);   // lower bits remain in evmask
+                if (slot < p.raw_cap) p.evraw[slot] = make_uint2(excl_c + s_in, (uint32_t)val);
+                else atomicOr(&p.ctr->flags, kFlagEventOverflow);
+            } while (evmask);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.freeb[s]);                // this warp is done with stage s
+    }
+}
+
+// per read: index of its first event in CIGAR order and the stream-wide consumption prefix at its
+// first word. wt_cons / wt_ev hold EXCLUSIVE prefixes here (k_exclusive_scan ran in between).
+__global__ void __launch_bounds__(256)
+k_read_starts(const uint64_t *__restrict__ cig_off, uint64_t R, const uint32_t *__restrict__ cigar,
+              const uint32_t *__restrict__ wt_cons, const uint32_t *__restrict__ wt_ev,
+              const uint32_t *__restrict__ blkpref, const uint16_t *__restrict__ blkev, uint32_t minlen,
+              uint32_t *__restrict__ ev_off, uint32_t *__restrict__ gstart, DevCounters *__restrict__ ctr)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r > R) return;
+    const uint64_t g = cig_off[r];
+    const uint64_t gw = g / kWarpTileWords;
+    uint32_t e = wt_ev[gw], c = wt_cons[gw];
+    if (g % kWarpTileWords) {
+        const uint64_t blk = g / kLaneWords;
+        e += blkev[blk];
+        c += blkpref[blk];
+        for (uint64_t i = blk * kLaneWords; i < g; ++i) {
+            const uint32_t w = __ldg(cigar + i);
+            c += cig_consume(w);
+            e += cig_is_event(w, minlen) ? 1u : 0u;
+        }
+    }
+    ev_off[r] = e;
+    if (r < R) gstart[r] = c;
+    else ctr->n_events = e;
+}
+
+// per read: move its events from warp-tile storage into CIGAR order and make the anchors absolute:
+// pos1 = ref_start + 1 + bases consumed by the read before the op (the u32 cursor of call.rs:380).
+__global__ void __launch_bounds__(256)
+k_event_fixup(const uint64_t *__restrict__ cig_off, const int32_t *__restrict__ rs, uint64_t R,
+              const uint32_t *__restrict__ ev_off, const uint32_t *__restrict__ gstart,
+              const uint32_t *__restrict__ wt_cons, const uint32_t *__restrict__ wt_ev,
+              const uint32_t *__restrict__ wt_sbase, const uint2 *__restrict__ evraw, uint64_t raw_cap,
+              uint2 *__restrict__ events, uint64_t ev_cap, DevCounters *__restrict__ ctr)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const uint32_t e0 = ev_off[r], e1 = ev_off[r + 1];
+    if (e0 == e1) return;
+    const uint32_t base = (uint32_t)rs[r] + 1u - gstart[r];
+    uint64_t gw = cig_off[r] / kWarpTileWords;
+    uint32_t lo = wt_ev[gw], hi = wt_ev[gw + 1];
+    for (uint32_t e = e0; e < e1; ++e) {
+        while (e >= hi) { ++gw; lo = hi; hi = wt_ev[gw + 1]; }
+        const uint64_t slot = (uint64_t)wt_sbase[gw] + (e - lo);
+        if (e < ev_cap && slot < raw_cap) {
+            const uint2 raw = evraw[slot];
+            events[e] = make_uint2(base + wt_cons[gw] + raw.x, raw.y);
+        } else {
+            atomicOr(&ctr->flags, kFlagEventOverflow);
         }
     }
 }
@@ -834,15 +603,15 @@ constexpr int kXsItems = 8;
 constexpr int kXsTile = kXsThreads * kXsItems;
 
 __global__ void __launch_bounds__(kXsThreads)
-k_exclusive_scan(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t n, uint32_t ntiles,
-                 uint64_t *__restrict__ desc, DevCounters *__restrict__ ctr)
+k_exclusive_scan(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t ntiles,
+                 uint64_t *__restrict__ desc, unsigned int *__restrict__ tile_counter, unsigned int *__restrict__ overflow_flags)
 {
     __shared__ uint32_t wsum[kXsThreads / 32];
     __shared__ uint32_t tile_s;
     __shared__ uint64_t base_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     while (true) {
-        if (tid == 0) tile_s = atomicAdd(&ctr->scan_counter, 1u);
+        if (tid == 0) tile_s = atomicAdd(tile_counter, 1u);
         __syncthreads();
         const uint32_t t = tile_s;
         if (t >= ntiles) break;
@@ -873,7 +642,7 @@ k_exclusive_scan(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ui
                 base_s = base;
                 if (t == ntiles - 1) {
                     out[n] = (uint32_t)(base + total);
-                    if (base + total > 0xFFFFFFFFull) atomicOr(&ctr->flags, kFlagCountOverflow);
+                    if (overflow_flags && base + total > 0xFFFFFFFFull) atomicOr(overflow_flags, kFlagCountOverflow);
                 }
             }
         }
