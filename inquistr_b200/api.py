@@ -193,7 +193,7 @@ class Context:
         self.n_reads += n
 
     def push(self, reads):
-        """reads: any object with the SoA attributes (oracle.Reads, synth output)."""
+        """reads: any object carrying the SoA attributes of include/inqcall.h:inq_push_reads."""
         self.push_reads(reads.contig, reads.ref_start, reads.ref_end, reads.mapq, reads.hp,
                         reads.flags, reads.cigar_off, reads.cigar)
 

@@ -188,8 +188,9 @@ def make_workload(config: int, scale: float = 1.0, seed: int | None = None, thre
         assert rc == 0
 
     # ---- shard: contiguous slice of the sorted catalog
+    from inquistr_b200.shard import split_catalog
     rank, world = shard
-    lo, hi = (nl * rank) // world, (nl * (rank + 1)) // world
+    lo, hi = split_catalog(nl, world)[rank]
     lcontig = np.repeat(np.arange(nc, dtype=np.int32), np.diff(off))
 
     # ---- regions where reads are placed

@@ -135,3 +135,60 @@ def test_error_codes(ctx):
     with pytest.raises(q.InqError) as ei:
         ctx.set_loci([0, 1], [500], [450])
     assert ei.value.code == -13
+
+
+@pytest.mark.parametrize("name", ["random_edge_cases", "expansion_panel"])
+def test_golden_fixtures(ctx, name):
+    """committed golden vectors (tests/golden/make_golden.py) through the C ABI"""
+    from tests.test_cpu_suite import load_golden, parse_run
+    z, rd, runs = load_golden(name)
+    ctx.set_loci(z["contig_off"], z["locus_start"], z["locus_end"])
+    ctx.clear_reads()
+    ctx.push(rd)
+    for key in runs:
+        minlen, support, unphased = parse_run(key)
+        res = ctx.genotype(minlen, support, unphased)
+        assert same(res.phase1, z[key + "_p1"]) and same(res.phase2, z[key + "_p2"]), key
+        assert res.stats["op_visits"] == int(z[key + "_visits"])
+
+
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.02), (3, 0.004), (4, 1.0), (5, 0.002)])
+def test_baseline_configs_small(ctx, cfg, scale):
+    """every BASELINE.json configuration (shrunk) against the oracle, incl. the unphased run of each"""
+    from synth.synth import make_workload
+    w = make_workload(cfg, scale=scale, threads=4)
+    ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
+    ctx.clear_reads()
+    ctx.push(w.reads)
+    for unphased in (w.unphased, not w.unphased):
+        res = ctx.genotype(w.minlen, w.support, unphased)
+        rc, p1, p2, visits = O.genotype_loci(w.reads, w.n_contigs, w.locus_contig, w.locus_start.astype(np.uint32),
+                                             w.locus_end.astype(np.uint32), w.minlen, w.support, unphased, threads=8)
+        assert rc == 0 and same(res.phase1, p1) and same(res.phase2, p2)
+        assert res.stats["op_visits"] == visits
+
+
+def test_size_independent_properties(ctx):
+    """properties that hold at any size: idempotence, permutation invariance of the read order,
+    monotonicity in support (a valid median never appears when support grows)"""
+    from synth.synth import make_workload
+    from inquistr_b200 import shard as S
+    w = make_workload(3, scale=0.01, threads=4)
+    ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
+    ctx.clear_reads(); ctx.push(w.reads)
+    a = ctx.genotype(5, 3, False)
+    b = ctx.genotype(5, 3, False)
+    assert same(a.phase1, b.phase1) and same(a.phase2, b.phase2)
+    perm = np.random.default_rng(0).permutation(w.reads.n)
+    mask = np.zeros(w.reads.n, bool); mask[:] = True
+    sub = S.take_reads(w.reads, mask)
+    rd = O.Reads(**sub)
+    n_cig = (rd.cigar_off[1:] - rd.cigar_off[:-1]).astype(np.int64)
+    off = np.zeros(rd.n + 1, np.uint64); off[1:] = np.cumsum(n_cig[perm])
+    cig = np.concatenate([rd.cigar[int(rd.cigar_off[i]):int(rd.cigar_off[i + 1])] for i in perm])
+    ctx.clear_reads()
+    ctx.push_reads(rd.contig[perm], rd.ref_start[perm], rd.ref_end[perm], rd.mapq[perm], rd.hp[perm], rd.flags[perm], off, cig)
+    c = ctx.genotype(5, 3, False)
+    assert same(a.phase1, c.phase1) and same(a.phase2, c.phase2)
+    d = ctx.genotype(5, 6, False)
+    assert np.all((d.valid & ~a.valid) == 0)
