@@ -35,12 +35,24 @@ def build_libinqcall(force: bool = False, verbose: bool = False) -> str:
     return target
 
 
+def build_cli(force: bool = False) -> str:
+    """C++ host `inquistr-b200` (CLI, BGZF/BAM reader, BED, TSV) linked against libinqcall.so."""
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    target = os.path.join(bindir, "inquistr-b200")
+    host = os.path.join(CSRC, "host")
+    sources = [os.path.join(host, "main.cpp"), os.path.join(host, "bam_reader.cpp")]
+    deps = sources + [os.path.join(host, "bam_reader.hpp"), os.path.join(os.path.dirname(HERE), "include", "inqcall.h"),
+                      os.path.join(LIBDIR, "libinqcall.so")]
+    if force or _stale(target, deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", target, *sources,
+                               "-L" + LIBDIR, "-linqcall", "-lz", "-Wl,-rpath,$ORIGIN/../lib"])
+    return target
+
+
 def build_all(force: bool = False, verbose: bool = False) -> list[str]:
     out = [build_libinqcall(force, verbose)]
-    for name in ("build_libinqsynth", "build_cli"):
-        fn = globals().get(name)
-        if fn:
-            out.append(fn(force))
+    out.append(build_cli(force))
     return out
 
 

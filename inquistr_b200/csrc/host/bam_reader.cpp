@@ -1,0 +1,317 @@
+// bam_reader.cpp -- see bam_reader.hpp. SAM/BAM spec v1 section 4 (BGZF 4.1, BAM 4.2).
+#include "bam_reader.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+namespace inqhost {
+
+namespace {
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
+
+struct Block {
+    size_t in_off, in_len;     // raw deflate payload inside the batch's compressed buffer
+    size_t out_off, out_len;
+    uint32_t crc;
+};
+
+bool inflate_block(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len, uint32_t crc)
+{
+    if (out_len == 0) return true;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef *>(in);
+    zs.avail_in = (uInt)in_len;
+    zs.next_out = out;
+    zs.avail_out = (uInt)out_len;
+    int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END || zs.total_out != out_len) return false;
+    return crc32(crc32(0L, Z_NULL, 0), out, (uInt)out_len) == crc;
+}
+
+}  // namespace
+
+int BamHeader::tid(const std::string &name) const
+{
+    for (size_t i = 0; i < ref_names.size(); ++i)
+        if (ref_names[i] == name) return (int)i;
+    return -1;
+}
+
+BamReader::~BamReader()
+{
+    if (fp_) fclose(fp_);
+}
+
+bool BamReader::open(const std::string &path, int threads)
+{
+    threads_ = std::max(1, threads);
+    fp_ = fopen(path.c_str(), "rb");
+    if (!fp_) { err_ = "cannot open " + path; return false; }
+    return parse_header();
+}
+
+// read and inflate the next batch of BGZF blocks
+bool BamReader::fill()
+{
+    buf_.clear();
+    cur_ = 0;
+    if (eof_) return false;
+    constexpr size_t kBatchBlocks = 1024;          // up to 64 MB inflated per batch
+    std::vector<uint8_t> comp;
+    std::vector<Block> blocks;
+    size_t out_total = 0;
+    while (blocks.size() < kBatchBlocks) {
+        uint8_t h[12];
+        size_t n = fread(h, 1, 12, fp_);
+        if (n == 0) { eof_ = true; break; }
+        if (n != 12 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { err_ = "not a BGZF block (bad gzip header)"; return false; }
+        const uint16_t xlen = rd16(h + 10);
+        std::vector<uint8_t> extra(xlen);
+        if (fread(extra.data(), 1, xlen, fp_) != xlen) { err_ = "truncated BGZF extra field"; return false; }
+        int bsize = -1;
+        for (size_t i = 0; i + 4 <= extra.size();) {
+            const uint16_t slen = rd16(&extra[i + 2]);
+            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= extra.size()) bsize = rd16(&extra[i + 4]);
+            i += 4 + slen;
+        }
+        if (bsize < 0) { err_ = "BGZF block without BC subfield"; return false; }
+        const long remaining = (long)bsize + 1 - 12 - xlen;     // deflate payload + crc32 + isize
+        if (remaining < 8) { err_ = "corrupt BGZF block size"; return false; }
+        const size_t off = comp.size();
+        comp.resize(off + (size_t)remaining);
+        if (fread(&comp[off], 1, (size_t)remaining, fp_) != (size_t)remaining) { err_ = "truncated BGZF block"; return false; }
+        Block b;
+        b.in_off = off;
+        b.in_len = (size_t)remaining - 8;
+        b.crc = rd32(&comp[off + remaining - 8]);
+        b.out_len = rd32(&comp[off + remaining - 4]);
+        b.out_off = out_total;
+        out_total += b.out_len;
+        blocks.push_back(b);
+    }
+    if (blocks.empty()) return false;
+    buf_.resize(out_total);
+    std::atomic<size_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= blocks.size()) break;
+            const Block &b = blocks[i];
+            if (!inflate_block(&comp[b.in_off], b.in_len, buf_.data() + b.out_off, b.out_len, b.crc)) bad.store(1);
+        }
+    };
+    const int nt = (int)std::min<size_t>((size_t)threads_, blocks.size());
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (bad.load()) { err_ = "BGZF inflate / CRC failure"; return false; }
+    total_out_ += out_total;
+    return true;
+}
+
+bool BamReader::read_exact(void *dst, size_t n)
+{
+    uint8_t *d = static_cast<uint8_t *>(dst);
+    while (n) {
+        if (cur_ == buf_.size()) {
+            if (!fill()) return false;
+            if (buf_.empty()) continue;          // empty BGZF block (EOF marker) in the middle
+        }
+        const size_t k = std::min(n, buf_.size() - cur_);
+        memcpy(d, buf_.data() + cur_, k);
+        cur_ += k;
+        d += k;
+        n -= k;
+    }
+    return true;
+}
+
+bool BamReader::parse_header()
+{
+    uint8_t magic[4];
+    if (!read_exact(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM file (bad magic)"; return false; }
+    uint8_t b4[4];
+    if (!read_exact(b4, 4)) { err_ = "truncated BAM header"; return false; }
+    const uint32_t l_text = rd32(b4);
+    header_.text.resize(l_text);
+    if (l_text && !read_exact(&header_.text[0], l_text)) { err_ = "truncated BAM header text"; return false; }
+    if (!read_exact(b4, 4)) { err_ = "truncated BAM header"; return false; }
+    const uint32_t n_ref = rd32(b4);
+    for (uint32_t i = 0; i < n_ref; ++i) {
+        if (!read_exact(b4, 4)) { err_ = "truncated BAM reference list"; return false; }
+        const uint32_t l_name = rd32(b4);
+        std::string name(l_name, '\0');
+        if (l_name && !read_exact(&name[0], l_name)) { err_ = "truncated BAM reference list"; return false; }
+        if (!name.empty() && name.back() == '\0') name.pop_back();
+        if (!read_exact(b4, 4)) { err_ = "truncated BAM reference list"; return false; }
+        header_.ref_names.push_back(name);
+        header_.ref_lens.push_back((int64_t)rd32(b4));
+    }
+    return true;
+}
+
+bool BamReader::next(BamRecordView &rec)
+{
+    uint8_t b4[4];
+    // EOF is only legal at a record boundary
+    if (cur_ == buf_.size()) {
+        while (true) {
+            if (!fill()) return false;
+            if (!buf_.empty()) break;
+        }
+    }
+    if (!read_exact(b4, 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
+    const uint32_t block_size = rd32(b4);
+    if (block_size < 32) { err_ = "corrupt BAM record"; return false; }
+    rec_.resize(block_size);
+    if (!read_exact(rec_.data(), block_size)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
+    const uint8_t *p = rec_.data();
+    rec.tid = rdi32(p);
+    rec.pos = rdi32(p + 4);
+    const uint32_t l_read_name = p[8];
+    rec.mapq = p[9];
+    uint32_t n_cigar = rd16(p + 12);
+    rec.flag = rd16(p + 14);
+    const uint32_t l_seq = rd32(p + 16);
+    size_t off = 32 + l_read_name;
+    const size_t cigar_off = off;
+    off += (size_t)n_cigar * 4;
+    off += (l_seq + 1) / 2 + l_seq;
+    if (off > block_size) { err_ = "corrupt BAM record (fields exceed block)"; return false; }
+
+    // aux: HP, SA, CG
+    rec.hp_type = HpType::Absent;
+    rec.hp_value = 0;
+    rec.has_sa = false;
+    rec.sa_is_string = false;
+    rec.sa.clear();
+    const uint8_t *cg_data = nullptr;
+    uint32_t cg_count = 0;
+    while (off + 3 <= block_size) {
+        const uint8_t t0 = p[off], t1 = p[off + 1], ty = p[off + 2];
+        off += 3;
+        size_t vlen = 0;
+        const uint8_t *v = p + off;
+        switch (ty) {
+        case 'A': case 'c': case 'C': vlen = 1; break;
+        case 's': case 'S': vlen = 2; break;
+        case 'i': case 'I': case 'f': vlen = 4; break;
+        case 'Z': case 'H': {
+            const void *z = memchr(v, 0, block_size - off);
+            if (!z) { err_ = "corrupt BAM aux string"; return false; }
+            vlen = (size_t)((const uint8_t *)z - v) + 1;
+            break;
+        }
+        case 'B': {
+            if (off + 5 > block_size) { err_ = "corrupt BAM aux array"; return false; }
+            const uint8_t sub = v[0];
+            const uint32_t cnt = rd32(v + 1);
+            size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+            vlen = 5 + (size_t)cnt * es;
+            if (t0 == 'C' && t1 == 'G' && sub == 'I') { cg_data = v + 5; cg_count = cnt; }
+            break;
+        }
+        default: err_ = "unknown BAM aux type"; return false;
+        }
+        if (off + vlen > block_size) { err_ = "corrupt BAM aux field"; return false; }
+        if (t0 == 'H' && t1 == 'P') {
+            switch (ty) {
+            case 'C': rec.hp_type = HpType::U8; rec.hp_value = v[0]; break;
+            case 'i': rec.hp_type = HpType::I32; rec.hp_value = rdi32(v); break;
+            case 'c': rec.hp_type = HpType::OtherInt; rec.hp_value = (int8_t)v[0]; break;
+            case 's': rec.hp_type = HpType::OtherInt; rec.hp_value = (int16_t)rd16(v); break;
+            case 'S': rec.hp_type = HpType::OtherInt; rec.hp_value = rd16(v); break;
+            case 'I': rec.hp_type = HpType::OtherInt; rec.hp_value = rd32(v); break;
+            default: rec.hp_type = HpType::NotInt; break;
+            }
+        } else if (t0 == 'S' && t1 == 'A') {
+            rec.has_sa = true;
+            rec.sa_is_string = (ty == 'Z');
+            if (ty == 'Z') rec.sa.assign((const char *)v, vlen - 1);
+        }
+        off += vlen;
+    }
+
+    // CIGAR (aligned copy); long CIGARs live in CG:B,I when the in-record CIGAR is <l_seq>S<rlen>N
+    const uint8_t *cg_src = p + cigar_off;
+    if (cg_data && n_cigar >= 1) {
+        const uint32_t w0 = rd32(p + cigar_off);
+        if ((w0 & 0xF) == 4 && (w0 >> 4) == l_seq) { cg_src = cg_data; n_cigar = cg_count; }
+    }
+    cg_.resize(n_cigar);
+    if (n_cigar) memcpy(cg_.data(), cg_src, (size_t)n_cigar * 4);
+    rec.cigar = cg_.data();
+    rec.n_cigar = n_cigar;
+
+    int64_t rlen = 0;
+    if (!(rec.flag & 0x4)) {
+        for (uint32_t i = 0; i < n_cigar; ++i) {
+            const uint32_t op = cg_[i] & 0xF;
+            if ((0x18Du >> op) & 1u) rlen += cg_[i] >> 4;       // M,D,N,=,X
+        }
+    }
+    if (rlen == 0) rlen = 1;
+    rec.end = (int32_t)(rec.pos + rlen);
+    return true;
+}
+
+int64_t cigar_text_to_rlen(const std::string &cigar)
+{
+    int64_t rlen = 0, num = 0;
+    for (char c : cigar) {
+        if (c >= '0' && c <= '9') { num = num * 10 + (c - '0'); continue; }
+        if (c == 'M' || c == '=' || c == 'X' || c == 'D' || c == 'N') rlen += num;
+        num = 0;
+    }
+    return rlen;
+}
+
+bool is_accidental_2d(const BamRecordView &rec, bool *panic)
+{
+    *panic = false;
+    if (!rec.has_sa) return false;                                   // call.rs:425-427
+    if (!rec.sa_is_string) { *panic = true; return false; }          // call.rs:431
+    const char strand = rec.is_reverse() ? '-' : '+';                // call.rs:422
+    // call.rs:434: split on ';', ignore empty entries
+    std::vector<std::string> entries;
+    size_t a = 0;
+    while (a <= rec.sa.size()) {
+        size_t b = rec.sa.find(';', a);
+        if (b == std::string::npos) b = rec.sa.size();
+        if (b > a) entries.push_back(rec.sa.substr(a, b - a));
+        a = b + 1;
+    }
+    if (entries.size() > 1) return false;                            // call.rs:436-438
+    if (entries.empty()) { *panic = true; return false; }            // sa_entries[0] on an empty Vec
+    std::vector<std::string> f;
+    a = 0;
+    const std::string &e = entries[0];
+    while (a <= e.size()) {
+        size_t b = e.find(',', a);
+        if (b == std::string::npos) b = e.size();
+        f.push_back(e.substr(a, b - a));
+        a = b + 1;
+    }
+    if (f.size() < 4 || f[2].empty()) { *panic = true; return false; }
+    if (strand == f[2][0]) return false;                             // call.rs:441-443
+    char *endp = nullptr;
+    const long long sa_start = strtoll(f[1].c_str(), &endp, 10);     // call.rs:450 (1-based POS used as is)
+    if (endp == f[1].c_str() || *endp) { *panic = true; return false; }
+    const long long sa_end = sa_start + cigar_text_to_rlen(f[3]);    // call.rs:451
+    const long long lo = std::max<long long>(rec.pos, sa_start), hi = std::min<long long>(rec.end, sa_end);
+    return lo < hi;                                                  // call.rs:454
+}
+
+}  // namespace inqhost

@@ -1,0 +1,80 @@
+// bam_reader.hpp -- sequential BGZF/BAM decoder on zlib (htslib is not available in this image).
+// Replaces what rust-htslib does for the reference's `call` path: header @SQ names/lengths
+// (call.rs:161-180) and, per record, reference_start / reference_end (bam_endpos), mapq, strand,
+// CIGAR (incl. the CG:B,I long-CIGAR convention), HP and SA aux tags (call.rs:297-299,382,422-423,483).
+// SEQ/QUAL are skipped, never copied.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace inqhost {
+
+struct BamHeader {
+    std::string text;
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    int tid(const std::string &name) const;   // -1 if absent
+};
+
+// how an integer aux value was typed in the file (rust-htslib Aux variants the reference matches on)
+enum class HpType : uint8_t { Absent, U8, I32, OtherInt, NotInt };
+
+struct BamRecordView {
+    int32_t tid = -1;
+    int32_t pos = -1;
+    int32_t end = 0;             // bam_endpos: pos + max(1, reference length); pos + 1 if unmapped
+    uint8_t mapq = 0;
+    uint16_t flag = 0;
+    const uint32_t *cigar = nullptr;   // BAM packed words (points into the record or into the CG tag)
+    uint32_t n_cigar = 0;
+    HpType hp_type = HpType::Absent;
+    int64_t hp_value = 0;
+    bool has_sa = false;
+    bool sa_is_string = false;
+    std::string sa;              // SA:Z value when present
+    bool is_reverse() const { return (flag & 0x10) != 0; }
+};
+
+// Streaming reader: BGZF blocks are read in batches and inflated by a small thread pool, records are
+// parsed in file order.
+class BamReader {
+public:
+    BamReader() = default;
+    ~BamReader();
+    BamReader(const BamReader &) = delete;
+    BamReader &operator=(const BamReader &) = delete;
+
+    // returns false and sets error() on failure
+    bool open(const std::string &path, int threads);
+    const BamHeader &header() const { return header_; }
+    // next alignment record; false at EOF or on error (check error())
+    bool next(BamRecordView &rec);
+    const std::string &error() const { return err_; }
+    uint64_t bytes_inflated() const { return total_out_; }
+
+private:
+    bool fill();                                   // inflate the next batch of blocks into buf_
+    bool read_exact(void *dst, size_t n);          // from the inflated stream, across batches
+    bool parse_header();
+
+    FILE *fp_ = nullptr;
+    int threads_ = 1;
+    BamHeader header_;
+    std::string err_;
+    std::vector<uint8_t> buf_;                     // inflated bytes of the current batch
+    size_t cur_ = 0;
+    bool eof_ = false;
+    uint64_t total_out_ = 0;
+    std::vector<uint8_t> rec_;                     // current record body
+    std::vector<uint32_t> cg_;                     // aligned copy of a CG:B,I long CIGAR
+};
+
+// call.rs:461-477
+int64_t cigar_text_to_rlen(const std::string &cigar);
+// call.rs:415-459 ; *panic set when the reference would panic (SA not a string)
+bool is_accidental_2d(const BamRecordView &rec, bool *panic);
+
+}  // namespace inqhost

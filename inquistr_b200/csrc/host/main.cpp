@@ -1,0 +1,465 @@
+// inquistr-b200 -- C++ host of the `inquiSTR call` drop-in (the reference host is Rust; no Rust
+// toolchain exists in this image). Mirrors, above the C ABI of libinqcall.so:
+//   CLI flags + defaults            src/main.rs:28-64
+//   driver, sample name, header     src/call.rs:76-159
+//   targets / validation            src/call.rs:161-202, src/repeats.rs:13-45,96-115
+//   per-record fields               src/call.rs:297-299,349-352,415-459,482-491
+//   ordering + row format           src/call.rs:27-65
+// stdout carries only the TSV; diagnostics go to stderr. A Rust panic in the reference maps to exit
+// code 101 here, `std::process::exit(1)` to 1, clap usage errors to 2.
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cinttypes>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/inqcall.h"
+#include "bam_reader.hpp"
+
+using namespace inqhost;
+
+namespace {
+
+struct Args {
+    std::string bam;
+    bool has_region = false, has_region_file = false, has_sample = false, has_reference = false;
+    std::string region, region_file, sample_name, reference;
+    uint32_t minlen = 5;
+    uint64_t support = 3;
+    uint64_t threads = 1;
+    bool unphased = false;
+    int device = 0;               // extension: CUDA device (also INQ_DEVICE)
+    std::string stats_json;       // extension: timing side file
+};
+
+const char *kHelp =
+    "Call lengths\n\n"
+    "Usage: inquistr-b200 call [OPTIONS] <BAM>\n\n"
+    "Arguments:\n"
+    "  <BAM>  bam file to call STRs in\n\n"
+    "Options:\n"
+    "  -r, --region <REGION>            region string to genotype expansion in\n"
+    "  -R, --region-file <REGION_FILE>  Bed file with region(s) to genotype expansion(s) in\n"
+    "  -m, --minlen <MINLEN>            minimal length of insertion/deletion operation [default: 5]\n"
+    "  -s, --support <SUPPORT>          minimal number of supporting reads [default: 3]\n"
+    "  -t, --threads <THREADS>          Number of parallel threads to use [default: 1]\n"
+    "  -u, --unphased                   If reads have to be considered unphased\n"
+    "      --sample-name <SAMPLE_NAME>  sample name to use in output\n"
+    "      --reference <REFERENCE>      reference fasta for cram decoding\n"
+    "      --device <N>                 (extension) CUDA device to run on [default: 0]\n"
+    "      --stats-json <FILE>          (extension) write counters and device timings as JSON\n"
+    "  -h, --help                       Print help\n";
+
+[[noreturn]] void usage_error(const std::string &msg)
+{
+    fprintf(stderr, "error: %s\n\nUsage: inquistr-b200 call [OPTIONS] <BAM>\n\nFor more information, try '--help'.\n", msg.c_str());
+    exit(2);
+}
+[[noreturn]] void panic(const std::string &msg)
+{
+    // a panic in the reference: message on stderr, exit code 101
+    fprintf(stderr, "thread 'main' panicked: %s\n", msg.c_str());
+    exit(101);
+}
+
+bool parse_u64(const std::string &s, uint64_t *out)
+{
+    if (s.empty()) return false;
+    uint64_t v = 0;
+    for (char c : s) {
+        if (c < '0' || c > '9') return false;
+        if (v > (UINT64_MAX - (uint64_t)(c - '0')) / 10) return false;
+        v = v * 10 + (uint64_t)(c - '0');
+    }
+    *out = v;
+    return true;
+}
+
+Args parse_args(int argc, char **argv)
+{
+    Args a;
+    if (const char *d = getenv("INQ_DEVICE")) a.device = atoi(d);
+    std::vector<std::string> v(argv + 1, argv + argc);
+    if (v.empty() || v[0] == "-h" || v[0] == "--help" || v[0] == "help") {
+        printf("Tool to genotype STRs from long reads (B200 build of the `call` hot path)\n\n"
+               "Usage: inquistr-b200 <COMMAND>\n\nCommands:\n  call  Call lengths\n  help  Print this message\n");
+        exit(v.empty() ? 2 : 0);
+    }
+    if (v[0] == "-V" || v[0] == "--version") { printf("inquistr-b200 %s\n", inq_version()); exit(0); }
+    if (v[0] != "call") usage_error("unrecognized subcommand '" + v[0] + "' (only `call` is implemented in this build)");
+    if (v.size() == 1) { fputs(kHelp, stderr); exit(2); }                 // arg_required_else_help (main.rs:27)
+    bool have_bam = false;
+    auto need = [&](size_t &i, const std::string &name) -> std::string {
+        if (i + 1 >= v.size()) usage_error("a value is required for '" + name + "' but none was supplied");
+        return v[++i];
+    };
+    auto set_opt = [&](const std::string &name, const std::string &val) {
+        uint64_t n = 0;
+        if (name == "region") { a.region = val; a.has_region = true; }
+        else if (name == "region-file") { a.region_file = val; a.has_region_file = true; }
+        else if (name == "minlen") { if (!parse_u64(val, &n) || n > UINT32_MAX) usage_error("invalid value '" + val + "' for '--minlen <MINLEN>'"); a.minlen = (uint32_t)n; }
+        else if (name == "support") { if (!parse_u64(val, &n)) usage_error("invalid value '" + val + "' for '--support <SUPPORT>'"); a.support = n; }
+        else if (name == "threads") { if (!parse_u64(val, &n)) usage_error("invalid value '" + val + "' for '--threads <THREADS>'"); a.threads = n; }
+        else if (name == "sample-name") { a.sample_name = val; a.has_sample = true; }
+        else if (name == "reference") { a.reference = val; a.has_reference = true; }
+        else if (name == "device") { if (!parse_u64(val, &n)) usage_error("invalid value for '--device'"); a.device = (int)n; }
+        else if (name == "stats-json") a.stats_json = val;
+        else usage_error("unexpected argument '--" + name + "' found");
+    };
+    const std::map<char, std::string> shorts = {{'r', "region"}, {'R', "region-file"}, {'m', "minlen"}, {'s', "support"}, {'t', "threads"}};
+    bool only_positional = false;
+    for (size_t i = 1; i < v.size(); ++i) {
+        const std::string &s = v[i];
+        if (!only_positional && s == "--") { only_positional = true; continue; }
+        if (!only_positional && s.rfind("--", 0) == 0) {
+            std::string name = s.substr(2), val;
+            const size_t eq = name.find('=');
+            if (name == "help") { fputs(kHelp, stdout); exit(0); }
+            if (name == "unphased") { a.unphased = true; continue; }
+            if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); }
+            else val = need(i, "--" + name);
+            set_opt(name, val);
+        } else if (!only_positional && s.size() >= 2 && s[0] == '-') {
+            for (size_t k = 1; k < s.size(); ++k) {
+                const char c = s[k];
+                if (c == 'u') { a.unphased = true; continue; }
+                if (c == 'h') { fputs(kHelp, stdout); exit(0); }
+                auto it = shorts.find(c);
+                if (it == shorts.end()) usage_error(std::string("unexpected argument '-") + c + "' found");
+                std::string val = s.substr(k + 1);
+                if (!val.empty() && val[0] == '=') val = val.substr(1);
+                if (val.empty()) val = need(i, std::string("-") + c);
+                set_opt(it->second, val);
+                break;
+            }
+        } else {
+            if (have_bam) usage_error("unexpected argument '" + s + "' found");
+            a.bam = s;
+            have_bam = true;
+        }
+    }
+    if (!have_bam) usage_error("the following required arguments were not provided:\n  <BAM>");
+    return a;
+}
+
+bool is_file(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+bool starts_with(const std::string &s, const char *p) { return s.rfind(p, 0) == 0; }
+bool ends_with(const std::string &s, const char *p)
+{
+    const size_t n = strlen(p);
+    return s.size() >= n && s.compare(s.size() - n, n, p) == 0;
+}
+void replace_all(std::string &s, const std::string &from, const std::string &to)
+{
+    for (size_t p = 0; (p = s.find(from, p)) != std::string::npos; p += to.size()) s.replace(p, from.size(), to);
+}
+
+// call.rs:91-100: PathBuf::file_stem then .replace(".bam","").replace(".cram","")
+std::string sample_from_path(const std::string &path)
+{
+    size_t slash = path.find_last_of('/');
+    std::string name = slash == std::string::npos ? path : path.substr(slash + 1);
+    size_t dot = name.find_last_of('.');
+    if (dot != std::string::npos && dot != 0) name = name.substr(0, dot);
+    replace_all(name, ".bam", "");
+    replace_all(name, ".cram", "");
+    return name;
+}
+
+// human_sort 0.2.2 `compare` (Cargo.lock dependency; published algorithm restated): numeric runs
+// compare as u32 numbers, other chars compare individually, exhaustion falls back to string order.
+int human_compare(const std::string &a, const std::string &b)
+{
+    size_t i = 0, j = 0;
+    while (i < a.size() && j < b.size()) {
+        const bool da = a[i] >= '0' && a[i] <= '9', db = b[j] >= '0' && b[j] <= '9';
+        if (da && db) {
+            uint32_t x = 0, y = 0;
+            while (i < a.size() && a[i] >= '0' && a[i] <= '9') x = x * 10u + (uint32_t)(a[i++] - '0');
+            while (j < b.size() && b[j] >= '0' && b[j] <= '9') y = y * 10u + (uint32_t)(b[j++] - '0');
+            if (x != y) return x < y ? -1 : 1;
+        } else {
+            const unsigned char ca = (unsigned char)a[i], cb = (unsigned char)b[j];
+            if (ca != cb) return ca < cb ? -1 : 1;
+            ++i;
+            ++j;
+        }
+    }
+    const int c = a.compare(b);
+    return (c > 0) - (c < 0);
+}
+
+// Rust `{}` of an f64 that is NaN or a multiple of 0.5 (call.rs:57-65)
+std::string fmt_phase(int64_t twice, bool valid)
+{
+    if (!valid) return "NaN";
+    char buf[64];
+    if ((twice & 1) == 0) snprintf(buf, sizeof(buf), "%" PRId64, twice / 2);
+    else if (twice == -1) snprintf(buf, sizeof(buf), "-0.5");
+    else snprintf(buf, sizeof(buf), "%" PRId64 ".5", twice / 2);
+    return buf;
+}
+
+struct Locus {
+    std::string chrom;
+    uint32_t start, end;
+    int tid;
+};
+
+// repeats.rs:96-115
+Locus new_interval(const std::string &chrom, uint64_t start64, uint64_t end64, const BamHeader &h)
+{
+    if (start64 > UINT32_MAX || end64 > UINT32_MAX) panic("called `Result::unwrap()` on an `Err` value: TryFromIntError(())");   // repeats.rs:91-92
+    const uint32_t start = (uint32_t)start64, end = (uint32_t)end64;
+    if (end < start)
+        panic("End coordinate is smaller than start coordinate for " + chrom + ":" + std::to_string(start) + "-" + std::to_string(end));
+    const int tid = h.tid(chrom);
+    if (tid >= 0 && (int64_t)end < h.ref_lens[tid]) return Locus{chrom, start, end, tid};
+    panic("Chromosome " + chrom + " is not in the fasta file or the end coordinate is out of bounds");
+}
+
+// repeats.rs:13-29: split(':')[0], split(':')[1].split('-')[0..1], parse::<u32>
+Locus parse_region(const std::string &reg, const BamHeader &h)
+{
+    const size_t colon = reg.find(':');
+    if (colon == std::string::npos) panic("index out of bounds: the len is 1 but the index is 1");
+    const std::string chrom = reg.substr(0, colon);
+    std::string interval = reg.substr(colon + 1);
+    const size_t colon2 = interval.find(':');
+    if (colon2 != std::string::npos) interval = interval.substr(0, colon2);
+    const size_t dash = interval.find('-');
+    if (dash == std::string::npos) panic("index out of bounds: the len is 1 but the index is 1");
+    std::string s0 = interval.substr(0, dash), s1 = interval.substr(dash + 1);
+    const size_t dash2 = s1.find('-');
+    if (dash2 != std::string::npos) s1 = s1.substr(0, dash2);
+    uint64_t a = 0, b = 0;
+    auto parse_u32 = [](std::string s, uint64_t *out) {        // Rust's u32::from_str accepts a leading '+'
+        if (!s.empty() && s[0] == '+') s = s.substr(1);
+        return parse_u64(s, out) && *out <= UINT32_MAX;
+    };
+    if (!parse_u32(s0, &a) || !parse_u32(s1, &b)) panic("called `Result::unwrap()` on an `Err` value: ParseIntError { kind: InvalidDigit }");
+    return new_interval(chrom, a, b, h);
+}
+
+// repeats.rs:30-45 via bio::io::bed::Reader (csv: tab separated, no header, '#' comments)
+std::vector<Locus> parse_bed(const std::string &path, const BamHeader &h)
+{
+    std::ifstream in(path);
+    if (!in) panic("Problem reading bed file!: Os { code: 2, kind: NotFound, message: \"No such file or directory\" }");
+    std::vector<Locus> out;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] == '#') continue;
+        std::vector<std::string> f;
+        size_t a = 0;
+        while (f.size() < 3) {
+            size_t b = line.find('\t', a);
+            if (b == std::string::npos) { f.push_back(line.substr(a)); break; }
+            f.push_back(line.substr(a, b - a));
+            a = b + 1;
+        }
+        uint64_t s = 0, e = 0;
+        if (f.size() < 3 || !parse_u64(f[1], &s) || !parse_u64(f[2], &e)) panic("Error reading bed record.: " + line);
+        out.push_back(new_interval(f[0], s, e, h));
+    }
+    return out;
+}
+
+#define INQ_CHECK(ctx, call)                                                                        \
+    do {                                                                                            \
+        int rc_ = (call);                                                                           \
+        if (rc_ != INQ_OK) {                                                                        \
+            const char *m_ = inq_last_error(ctx);                                                   \
+            if (rc_ == INQ_ERR_BAD_HP || rc_ == INQ_ERR_MEDIAN_EMPTY || rc_ == INQ_ERR_LOCUS_START) \
+                panic(m_);                                                                          \
+            fprintf(stderr, "ERROR: %s (code %d)\n", m_, rc_);                                      \
+            exit(1);                                                                                \
+        }                                                                                           \
+    } while (0)
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    const Args args = parse_args(argc, argv);
+
+    // call.rs:87-90
+    if (!is_file(args.bam) && !starts_with(args.bam, "s3") && !starts_with(args.bam, "https://")) {
+        fprintf(stderr, "ERROR: path to bam file %s is not valid!\n\n", args.bam.c_str());
+        return 1;
+    }
+    if (!is_file(args.bam)) {
+        fprintf(stderr, "ERROR: remote input (%s) is not supported by this build (no libcurl/htslib); use a local BAM\n", args.bam.c_str());
+        return 1;
+    }
+    if (ends_with(args.bam, ".cram")) {
+        fprintf(stderr, "ERROR: CRAM input is not supported by this build (no htslib CRAM codec); convert to BAM\n");
+        return 1;
+    }
+    const std::string sample = args.has_sample ? args.sample_name : sample_from_path(args.bam);   // call.rs:91-100
+
+    const int host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    BamReader bam;
+    if (!bam.open(args.bam, host_threads)) panic("Error opening local BAM: " + bam.error());     // call.rs:242-243
+    const BamHeader &hdr = bam.header();
+
+    // call.rs:182-202
+    std::vector<Locus> loci;
+    if (args.has_region && !args.has_region_file) loci.push_back(parse_region(args.region, hdr));
+    else if (!args.has_region && args.has_region_file) loci = parse_bed(args.region_file, hdr);
+    else {
+        fprintf(stderr, "ERROR: Specify a region string (-r) or a region_file (-R)!\n\n");
+        return 1;
+    }
+    for (const Locus &l : loci)
+        if (l.start < 10) panic("attempt to subtract with overflow (locus " + l.chrom + ":" + std::to_string(l.start) + " has start < 10, call.rs:285)");
+    if (args.support > UINT32_MAX) panic("support does not fit the device counter");
+
+    // catalog sorted by (tid, start); ties keep BED order
+    const size_t L = loci.size();
+    std::vector<uint32_t> order(L);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (loci[a].tid != loci[b].tid) return loci[a].tid < loci[b].tid;
+        return loci[a].start < loci[b].start;
+    });
+    const int n_contigs = (int)hdr.ref_names.size();
+    std::vector<int64_t> contig_off(n_contigs + 1, 0);
+    std::vector<int32_t> lstart(L), lend(L), pmax(L);
+    for (size_t i = 0; i < L; ++i) {
+        const Locus &l = loci[order[i]];
+        contig_off[l.tid + 1]++;
+        lstart[i] = (int32_t)l.start;
+        lend[i] = (int32_t)l.end;
+    }
+    for (int c = 0; c < n_contigs; ++c) contig_off[c + 1] += contig_off[c];
+    for (int c = 0; c < n_contigs; ++c) {
+        int32_t m = INT32_MIN;
+        for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) { m = std::max(m, lend[i]); pmax[i] = m; }
+    }
+
+    inq_ctx *ctx = nullptr;
+    if (inq_ctx_create(args.device, &ctx) != INQ_OK) {
+        fprintf(stderr, "ERROR: %s\n", inq_last_error(nullptr));
+        return 1;
+    }
+    INQ_CHECK(ctx, inq_set_loci(ctx, n_contigs, contig_off.data(), lstart.data(), lend.data()));
+
+    // one sequential pass over the BAM; keep the records htslib's fetch would yield for some locus:
+    // pos < end+10 && endpos > start-10
+    std::vector<int32_t> r_contig, r_start, r_end;
+    std::vector<uint8_t> r_mapq, r_hp, r_flags;
+    std::vector<uint64_t> r_off{0};
+    std::vector<uint32_t> r_cigar;
+    uint64_t n_records = 0, n_kept = 0;
+    auto flush = [&]() {
+        if (r_contig.empty()) return;
+        INQ_CHECK(ctx, inq_push_reads(ctx, r_contig.size(), r_contig.data(), r_start.data(), r_end.data(), r_mapq.data(),
+                                      r_hp.data(), r_flags.data(), r_off.data(), r_cigar.data()));
+        r_contig.clear(); r_start.clear(); r_end.clear(); r_mapq.clear(); r_hp.clear(); r_flags.clear();
+        r_off.assign(1, 0); r_cigar.clear();
+    };
+    BamRecordView rec;
+    while (bam.next(rec)) {
+        ++n_records;
+        if (rec.tid < 0 || rec.tid >= n_contigs) continue;
+        const int64_t l0 = contig_off[rec.tid], l1 = contig_off[rec.tid + 1];
+        if (l0 == l1) continue;
+        // loci with start - 10 < endpos, and among them one with end + 10 > pos
+        const int64_t hi = std::lower_bound(lstart.begin() + l0, lstart.begin() + l1, (int32_t)std::min<int64_t>((int64_t)rec.end + 10, INT32_MAX)) - lstart.begin();
+        if (hi == l0 || (int64_t)pmax[hi - 1] + 10 <= (int64_t)rec.pos) continue;
+        // a record the reference would fetch: its aux tags are inspected there too
+        uint8_t hp = 0xFF;
+        if (!args.unphased) {                                              // get_phase, call.rs:482-491
+            switch (rec.hp_type) {
+            case HpType::Absent: break;
+            case HpType::U8: hp = (uint8_t)rec.hp_value; break;
+            case HpType::I32: hp = (uint8_t)rec.hp_value; break;           // `v as u8`
+            default: panic("Unexpected type of Aux for HP (call.rs:487)");
+            }
+            if (hp == 0xFF && rec.hp_type != HpType::Absent) panic("HP value 255 cannot be represented (reserved for 'no tag')");
+        }
+        bool sa_panic = false;
+        bool has_clip = false;
+        for (uint32_t i = 0; i < rec.n_cigar && !has_clip; ++i) has_clip = (rec.cigar[i] & 0xF) == 4;
+        const bool two_d = has_clip ? is_accidental_2d(rec, &sa_panic) : false;   // only consulted on S ops (call.rs:394)
+        if (sa_panic) panic("Unexpected type of Aux for SA (call.rs:431)");
+        r_contig.push_back(rec.tid);
+        r_start.push_back(rec.pos);
+        r_end.push_back(rec.end);
+        r_mapq.push_back(rec.mapq);
+        r_hp.push_back(hp);
+        r_flags.push_back(two_d ? INQ_FLAG_ACCIDENTAL_2D : 0);
+        r_cigar.insert(r_cigar.end(), rec.cigar, rec.cigar + rec.n_cigar);
+        r_off.push_back(r_cigar.size());
+        ++n_kept;
+        if (r_cigar.size() >= (64u << 20) || r_contig.size() >= (8u << 20)) flush();
+    }
+    if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
+    flush();
+
+    std::vector<int64_t> t1(L), t2(L);
+    std::vector<uint8_t> valid(L);
+    inq_stats st;
+    memset(&st, 0, sizeof(st));
+    INQ_CHECK(ctx, inq_genotype(ctx, args.minlen, (uint32_t)args.support, args.unphased ? 1 : 0, t1.data(), t2.data(), valid.data(), &st));
+
+    // output order: -t 1 BED order (call.rs:149-157); -t > 1 sorted by (human chrom, start) (call.rs:137-145)
+    std::vector<uint32_t> pos_of(L);                 // BED index -> catalog position
+    for (size_t i = 0; i < L; ++i) pos_of[order[i]] = (uint32_t)i;
+    std::vector<uint32_t> out_order(L);
+    std::iota(out_order.begin(), out_order.end(), 0u);
+    if (args.threads > 1)
+        std::stable_sort(out_order.begin(), out_order.end(), [&](uint32_t a, uint32_t b) {
+            const int c = human_compare(loci[a].chrom, loci[b].chrom);
+            if (c != 0) return c < 0;
+            return loci[a].start < loci[b].start;
+        });
+    std::string out;
+    out.reserve(64 + L * 48);
+    out += "chromosome\tbegin\tend\t" + sample + "_H1\t" + sample + "_H2\n";    // call.rs:101
+    for (uint32_t bi : out_order) {
+        const Locus &l = loci[bi];
+        const uint32_t p = pos_of[bi];
+        out += l.chrom;
+        out += '\t';
+        out += std::to_string(l.start);
+        out += '\t';
+        out += std::to_string(l.end);
+        out += '\t';
+        out += fmt_phase(t1[p], valid[p] & INQ_VALID_H1);
+        out += '\t';
+        out += fmt_phase(t2[p], valid[p] & INQ_VALID_H2);
+        out += '\n';
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    fflush(stdout);
+
+    if (!args.stats_json.empty()) {
+        FILE *f = fopen(args.stats_json.c_str(), "w");
+        if (f) {
+            fprintf(f, "{\"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
+                       ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
+                       ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u}\n",
+                    n_records, n_kept, bam.bytes_inflated(), st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
+                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches);
+            fclose(f);
+        }
+    }
+    inq_ctx_destroy(ctx);
+    return 0;
+}

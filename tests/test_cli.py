@@ -1,0 +1,190 @@
+"""`inquistr-b200 call` (C++ host above the C ABI): CLI behaviour without a GPU, and byte-for-byte
+TSV parity against the oracle with a GPU. Mirrors the reference's own call tests
+(call.rs:525-605): region, region file, unphased, wrong chromosome (should panic), header length."""
+import functools
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import bamio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "inquistr_b200", "bin", "inquistr-b200")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from inquistr_b200 import build
+    build.build_libinqcall()
+    return build.build_cli()
+
+
+def run(cli, *args, **kw):
+    return subprocess.run([cli, *args], capture_output=True, timeout=300, **kw)
+
+
+@pytest.fixture(scope="module")
+def chr7_bam(tmp_path_factory):
+    """stand-in for test-data/small-test.bam: chr7 (159,345,973 bp) with reads around test.bed's locus"""
+    from synth.synth import make_workload
+    w = make_workload(1, threads=2)
+    d = tmp_path_factory.mktemp("cli")
+    path = str(d / "small-test.sorted.bam")
+    bamio.reads_to_bam(path, ["chr6", "chr7"], [170805979, 159345973],
+                       O.Reads(w.reads.contig + 1, w.reads.ref_start, w.reads.ref_end, w.reads.mapq, w.reads.hp,
+                               w.reads.flags, w.reads.cigar_off, w.reads.cigar))
+    bed = str(d / "test.bed")
+    open(bed, "w").write("chr7\t154778571\t154779363\n")
+    return path, bed, w
+
+
+def test_help_and_usage(cli):
+    r = run(cli, "call")
+    assert r.returncode == 2 and b"Usage: inquistr-b200 call [OPTIONS] <BAM>" in r.stderr     # arg_required_else_help
+    r = run(cli, "call", "--help")
+    assert r.returncode == 0 and b"--region-file <REGION_FILE>" in r.stdout and b"[default: 5]" in r.stdout
+    r = run(cli, "call", "--bogus", "x.bam")
+    assert r.returncode == 2
+
+
+def test_invalid_bam_path_exits_1(cli):
+    r = run(cli, "call", "-r", "chr7:100-200", "/nonexistent/x.bam")
+    assert r.returncode == 1 and b"is not valid" in r.stderr and r.stdout == b""          # call.rs:87-90
+
+
+def test_needs_region_or_bed(cli, chr7_bam):
+    bam, bed, _ = chr7_bam
+    r = run(cli, "call", bam)
+    assert r.returncode == 1 and b"Specify a region string (-r) or a region_file (-R)!" in r.stderr   # call.rs:197-200
+    r = run(cli, "call", "-r", "chr7:154778571-154779363", "-R", bed, bam)
+    assert r.returncode == 1
+
+
+def test_wrong_chromosome_panics(cli, chr7_bam):
+    bam, _, _ = chr7_bam
+    r = run(cli, "call", "-r", "7:154778571-154779363", bam)                              # call.rs:584-598
+    assert r.returncode == 101 and b"is not in the fasta file or the end coordinate is out of bounds" in r.stderr
+    r = run(cli, "call", "-r", "chr7:154778571-159345973", bam)                           # end must be < LN (call.rs:600-605)
+    assert r.returncode == 101
+    r = run(cli, "call", "-r", "chr7:200-100", bam)
+    assert r.returncode == 101 and b"End coordinate is smaller than start coordinate" in r.stderr
+    r = run(cli, "call", "-r", "chr7:5-100", bam)
+    assert r.returncode == 101                                                            # start - 10 underflows u32
+
+
+def test_unsupported_inputs_say_so(cli, tmp_path):
+    p = tmp_path / "x.cram"
+    p.write_bytes(b"CRAM")
+    r = run(cli, "call", "-r", "chr7:100-200", str(p))
+    assert r.returncode == 1 and b"CRAM input is not supported" in r.stderr
+    r = run(cli, "call", "-r", "chr7:100-200", "https://example.org/x.bam")
+    assert r.returncode == 1 and b"not supported" in r.stderr
+    q = tmp_path / "bad.bam"
+    q.write_bytes(b"not a bam at all, definitely")
+    r = run(cli, "call", "-r", "chr7:100-200", str(q))
+    assert r.returncode == 101 and b"Error opening local BAM" in r.stderr
+
+
+def test_fails_loudly_without_gpu(cli, chr7_bam):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    bam, bed, _ = chr7_bam
+    r = run(cli, "call", "-R", bed, bam)
+    assert r.returncode == 1 and b"no CPU fallback" in r.stderr and r.stdout == b""
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def expected_tsv(sample, names, loci, p1, p2, threads):
+    """loci: list of (chrom, start, end) in BED order; -t 1 keeps it, -t >1 sorts (call.rs:137-157)"""
+    idx = list(range(len(loci)))
+    if threads > 1:
+        def cmp(a, b):
+            c = O.human_compare(loci[a][0], loci[b][0])
+            return c if c else (loci[a][1] > loci[b][1]) - (loci[a][1] < loci[b][1])
+        idx.sort(key=functools.cmp_to_key(cmp))
+    lines = [f"chromosome\tbegin\tend\t{sample}_H1\t{sample}_H2"]
+    lines += [O.format_row(loci[i][0], loci[i][1], loci[i][2], p1[i], p2[i]) for i in idx]
+    return ("\n".join(lines) + "\n").encode()
+
+
+@pytest.mark.gpu
+def test_reference_smoke_cases_tsv(cli, chr7_bam):
+    """the reference's test_region / test_region_bed / test_unphased, with the bytes checked"""
+    bam, bed, w = chr7_bam
+    rd = O.Reads(w.reads.contig + 1, w.reads.ref_start, w.reads.ref_end, w.reads.mapq, w.reads.hp, w.reads.flags,
+                 w.reads.cigar_off, w.reads.cigar)
+    for unphased in (False, True):
+        rc, p1, p2, _ = O.genotype_loci(rd, 2, [1], [154778571], [154779363], 5, 3, unphased)
+        exp = expected_tsv("small-test.sorted", None, [("chr7", 154778571, 154779363)], p1, p2, 4)
+        for args in (["-r", "chr7:154778571-154779363", "-t", "4"], ["-R", bed], ["-R", bed, "-t", "4", "-m", "5", "-s", "3"]):
+            r = run(cli, "call", *args, *(["-u"] if unphased else []), bam)
+            assert r.returncode == 0, r.stderr
+            assert r.stdout == exp
+    r = run(cli, "call", "-R", bed, "--sample-name", "NA12878", bam)
+    assert r.stdout.startswith(b"chromosome\tbegin\tend\tNA12878_H1\tNA12878_H2\n")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 4])
+def test_multi_contig_bed_ordering_and_2d(cli, tmp_path, threads):
+    """unsorted multi-contig BED: BED order for -t 1, human-sorted for -t 4; SA-derived 2D flags; HP:i"""
+    from tests.datagen import make_case
+    case = make_case(77, n_contigs=4, n_loci=150, n_reads=1500)
+    names = ["chr10", "chr2", "chrX", "chr1_KI270706v1_random"]
+    lens = [60_000] * 4
+    rd = case["reads"]
+    order = np.lexsort((rd.ref_start, rd.contig))                       # coordinate-sorted file
+    off = np.zeros(rd.n + 1, np.uint64)
+    n_cig = (rd.cigar_off[1:] - rd.cigar_off[:-1]).astype(np.int64)
+    off[1:] = np.cumsum(n_cig[order])
+    cig = np.concatenate([rd.cigar[int(rd.cigar_off[i]):int(rd.cigar_off[i + 1])] for i in order])
+    srd = O.Reads(rd.contig[order], rd.ref_start[order], rd.ref_end[order], rd.mapq[order], rd.hp[order], rd.flags[order], off, cig)
+    bam = str(tmp_path / "multi.bam")
+    bamio.reads_to_bam(bam, names, lens, srd, hp_type="i")
+    perm = np.random.default_rng(5).permutation(len(case["locus_start"]))
+    loci = [(names[int(case["locus_contig"][i])], int(case["locus_start"][i]), int(case["locus_end"][i])) for i in perm]
+    bed = str(tmp_path / "loci.bed")
+    with open(bed, "w") as f:
+        f.write("# comment line\n")
+        for c, s, e in loci:
+            f.write(f"{c}\t{s}\t{e}\tsome\textra\n")
+    for unphased in (False, True):
+        rc, p1, p2, _ = O.genotype_loci(srd, 4, case["locus_contig"][perm], case["locus_start"][perm].astype(np.uint32),
+                                        case["locus_end"][perm].astype(np.uint32), 5, 3, unphased)
+        assert rc == 0
+        r = run(cli, "call", "-R", bed, "-t", str(threads), *(["-u"] if unphased else []), bam)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == expected_tsv("multi", names, loci, p1, p2, threads)
+
+
+@pytest.mark.gpu
+def test_long_cigar_cg_tag_and_bad_hp(cli, tmp_path):
+    # one read with > 65535 CIGAR ops goes through the CG:B,I convention
+    n = 70_000
+    words = np.empty(2 * n + 1, np.uint32)
+    words[0::2] = (3 << 4) | 0
+    words[1::2] = (1 << 4) | 1
+    words[2001] = (9 << 4) | 1                                  # the only insertion longer than 5
+    rlen = 3 * (n + 1)
+    recs = [bamio.encode_record(0, 1000, 60, 0, words, name=b"long%d" % i, hp=1 + (i % 2), end=1000 + rlen) for i in range(8)]
+    bam = str(tmp_path / "long.bam")
+    bamio.write_bam(bam, ["chr1"], [1_000_000], recs)
+    r = run(cli, "call", "-r", "chr1:4000-4010", "-s", "2", bam)        # insertion anchored at 1000+3*1001+1 = 4004
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines()[1] == b"chr1\t4000\t4010\t9\t9"
+    # HP outside {0,1,2} on a read that passes the filter: the reference panics (call.rs:358)
+    recs = [bamio.encode_record(0, 1000, 60, 0, words[:200], name=b"x%d" % i, hp=3, end=1000 + 3 * 100) for i in range(4)]
+    bad = str(tmp_path / "badhp.bam")
+    bamio.write_bam(bad, ["chr1"], [1_000_000], recs)
+    r = run(cli, "call", "-r", "chr1:1100-1110", bad)
+    assert r.returncode == 101
+    r = run(cli, "call", "-r", "chr1:1100-1110", "-u", bad)             # unphased never looks at HP
+    assert r.returncode == 0
+    # HP stored as an int16: rust-htslib yields Aux::I16 and the reference panics (call.rs:487)
+    recs = [bamio.encode_record(0, 1000, 60, 0, words[:200], name=b"y", hp=1, hp_type="s", end=1300)]
+    bamio.write_bam(bad, ["chr1"], [1_000_000], recs)
+    assert run(cli, "call", "-r", "chr1:1100-1110", bad).returncode == 101
