@@ -48,7 +48,8 @@ struct inq_ctx {
     DevBuf<uint32_t> cigar;
 
     // work buffers
-    DevBuf<uint32_t> cand_lo, cand_n, ev_off, gstart, bcnt, boff, big_list;
+    DevBuf<uint32_t> cand_lo, cand_n, ev_off, gstart, delta, lcnt, seg_off, big_list;
+    DevBuf<unsigned long long> cursor;
     DevBuf<uint32_t> blkpref, wt_cons, wt_ev, wt_sbase;
     DevBuf<uint16_t> blkev;
     DevBuf<uint64_t> desc_scan, desc_wt, vals;
@@ -228,7 +229,7 @@ void inq_ctx_destroy(inq_ctx *ctx)
     release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off); release(ctx->gstart);
     release(ctx->blkpref); release(ctx->blkev); release(ctx->wt_cons); release(ctx->wt_ev); release(ctx->wt_sbase);
     release(ctx->desc_wt); release(ctx->evraw);
-    release(ctx->bcnt); release(ctx->boff); release(ctx->big_list);
+    release(ctx->delta); release(ctx->lcnt); release(ctx->seg_off); release(ctx->cursor); release(ctx->big_list);
     release(ctx->desc_scan); release(ctx->vals);
     release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
@@ -272,10 +273,12 @@ int inq_set_loci(inq_ctx *ctx, int32_t n_contigs, const int64_t *contig_locus_of
     TRY(ensure(ctx, ctx->lstart, (uint64_t)L));
     TRY(ensure(ctx, ctx->lend, (uint64_t)L));
     TRY(ensure(ctx, ctx->lpmax, (uint64_t)L));
-    TRY(ensure(ctx, ctx->bcnt, 2 * (uint64_t)L + 1));
-    TRY(ensure(ctx, ctx->boff, 2 * (uint64_t)L + 1));
+    TRY(ensure(ctx, ctx->delta, (uint64_t)L + 2));
+    TRY(ensure(ctx, ctx->lcnt, (uint64_t)L + 3));
+    TRY(ensure(ctx, ctx->seg_off, (uint64_t)L + 2));
+    TRY(ensure(ctx, ctx->cursor, (uint64_t)L + 1));
     TRY(ensure(ctx, ctx->big_list, (uint64_t)L + 1));
-    TRY(ensure(ctx, ctx->desc_scan, (2 * (uint64_t)L + 1 + kXsTile - 1) / kXsTile + 1));
+    TRY(ensure(ctx, ctx->desc_scan, 2 * (((uint64_t)L + 2 + kXsTile - 1) / kXsTile + 1)));
     TRY(ensure(ctx, ctx->t1, (uint64_t)L));
     TRY(ensure(ctx, ctx->t2, (uint64_t)L));
     TRY(ensure(ctx, ctx->valid, (uint64_t)L));
@@ -370,9 +373,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     cudaStream_t s = ctx->stream;
     const uint32_t ntiles = (uint32_t)((C + kTileWords - 1) / kTileWords);
     if ((C + kTileWords - 1) / kTileWords > 0x7FFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "too many CIGAR words");
-    const uint64_t nb = 2 * (uint64_t)L;                     // buckets
-    const uint32_t scan_tiles = (uint32_t)((nb + kXsTile - 1) / kXsTile);
-
+    const uint32_t loc_scan_tiles = (uint32_t)(((uint64_t)L + 1 + kXsTile - 1) / kXsTile);
     const uint64_t n_wt = (uint64_t)ntiles * kWarpsPerScanCta;                 // 512-word warp tiles
     const uint32_t wt_scan_tiles = (uint32_t)((n_wt + kXsTile - 1) / kXsTile);
     TRY(ensure(ctx, ctx->cand_lo, R));
@@ -387,29 +388,40 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     TRY(ensure(ctx, ctx->desc_wt, 2 * ((uint64_t)wt_scan_tiles + 1)));
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
     const unsigned scan_grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
+    const uint64_t raw_slack = (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kWarpsPerScanCta * kEvChunk;
     if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 16 + 4096));
     // warp-tile storage hands out kEvChunk-slot chunks: every resident warp may strand one chunk
-    if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, ctx->events.cap + (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kWarpsPerScanCta * kEvChunk));
+    if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, ctx->events.cap + raw_slack));
 
     ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
     LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
     uint32_t launches = 0;
+    const bool work = R && L;
 
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
         launches = 0;
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_START], s));
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
-        if (nb) CU_TRY(ctx, cudaMemsetAsync(ctx->bcnt.p, 0, (nb + 1) * sizeof(uint32_t), s));
-        if (nb) CU_TRY(ctx, cudaMemsetAsync(ctx->boff.p, 0, (nb + 1) * sizeof(uint32_t), s));
+        if (L) {
+            CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
+            CU_TRY(ctx, cudaMemsetAsync(ctx->seg_off.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
+            CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s));
+            CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s));
+        }
         if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->ev_off.p, 0, (R + 1) * sizeof(uint32_t), s));
         if (wt_scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, 2 * ((uint64_t)wt_scan_tiles + 1) * sizeof(uint64_t), s));
-        if (scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, (uint64_t)scan_tiles * sizeof(uint64_t), s));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_INDEX], s));
 
-        // K1: overlap join (count)
-        if (R && L) {
-            k_join_count<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->bcnt.p, ctx->d_ctr);
-            ++launches;
+        // K1: candidate ranges + difference array, then the per-locus segment offsets
+        if (work) {
+            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+            const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
+            // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
+            k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
+                                                      &ctx->d_ctr->scan_counter[2], nullptr);
+            k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->lcnt.p + 1, ctx->seg_off.p, (uint64_t)L, loc_scan_tiles,
+                                                      ctx->desc_scan.p + loc_scan_tiles + 1, &ctx->d_ctr->scan_counter[3], &ctx->d_ctr->flags);
+            launches += 3;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_JOIN], s));
 
@@ -439,41 +451,33 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             launches += 4;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_FIXUP], s));
-
-        // bucket offsets
-        if (scan_tiles) {
-            const unsigned grid = std::min<unsigned>(scan_tiles, (unsigned)ctx->sm_count * 4);
-            k_exclusive_scan<<<grid, kXsThreads, 0, s>>>(ctx->bcnt.p, ctx->boff.p, nb, scan_tiles, ctx->desc_scan.p,
-                                                         &ctx->d_ctr->scan_counter[2], &ctx->d_ctr->flags);
-            ++launches;
-        }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_SCAN], s));
         CU_TRY(ctx, cudaGetLastError());
 
-        // P is needed on the host to size the bucket storage
-        uint64_t P = 0;
-        if (nb) {
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->boff.p + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        // the call buffer holds one slot per candidate; its size is only known on the device. It is
+        // sized from the previous run when there was one (checked afterwards), otherwise read back now.
+        if (work) CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (work && ctx->vals.cap == 0) {
             CU_TRY(ctx, cudaStreamSynchronize(s));
-            P = *ctx->h_total;
+            TRY(ensure(ctx, ctx->vals, (uint64_t)*ctx->h_total + 1));
         }
-        TRY(ensure(ctx, ctx->vals, P + 1, 0, 1.25));
 
-        // K2b: window sums + scatter
-        if (R && L) {
+        // K2b: filter + window sums + scatter
+        if (work) {
             k_pair_eval<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->events.p,
-                                                                   ctx->ev_off.p, ctx->events.cap, ctx->boff.p, ctx->bcnt.p, ctx->vals.p,
-                                                                   ctx->vals.cap, ctx->d_ctr);
+                                                                   ctx->ev_off.p, ctx->events.cap, ctx->seg_off.p, ctx->cursor.p,
+                                                                   ctx->vals.p, ctx->vals.cap, ctx->d_ctr);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_PAIRS], s));
 
         // K3: medians
         if (L) {
-            k_locus_median<<<(unsigned)(((uint64_t)L * 32 + 255) / 256), 256, 0, s>>>((uint32_t)L, unphased, support, ctx->boff.p, ctx->vals.p,
-                                                                                     ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
-            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s>>>(unphased, support, ctx->boff.p, ctx->vals.p, ctx->t1.p, ctx->t2.p,
-                                                                                  ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+            k_locus_median<<<(unsigned)(((uint64_t)L * 32 + 255) / 256), 256, 0, s>>>((uint32_t)L, unphased, support, ctx->seg_off.p, ctx->cursor.p,
+                                                                                     ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
+                                                                                     ctx->big_list.p, ctx->d_ctr);
+            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s>>>(unphased, support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p, ctx->vals.cap,
+                                                                                  ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
             launches += 2;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_MEDIAN], s));
@@ -489,20 +493,28 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         CU_TRY(ctx, cudaStreamSynchronize(s));
 
         const unsigned f = ctx->h_ctr->flags;
+        bool retry = false;
         if (f & kFlagEventOverflow) {
             // the event buffers were sized speculatively; the scan still counted every event and slot
             const uint64_t need = ctx->h_ctr->n_events + 4096;
-            const uint64_t need_raw = ctx->h_ctr->ev_alloc + (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kWarpsPerScanCta * kEvChunk;
+            const uint64_t need_raw = ctx->h_ctr->ev_alloc + raw_slack;
             release(ctx->events);
             release(ctx->evraw);
             TRY(ensure(ctx, ctx->events, need));
             TRY(ensure(ctx, ctx->evraw, need_raw));
-            continue;
+            retry = true;
         }
+        if (work && (uint64_t)*ctx->h_total + 1 > ctx->vals.cap) {
+            release(ctx->vals);
+            TRY(ensure(ctx, ctx->vals, (uint64_t)*ctx->h_total + 1));
+            retry = true;
+        }
+        if (retry) continue;
         if (f & kFlagCountOverflow) return fail(ctx, INQ_ERR_TOO_LARGE, "pair or event count exceeds 2^32");
-        if (f & kFlagValsOverflow) return fail(ctx, INQ_ERR_STATE, "internal: bucket storage overflow");
+        if (f & kFlagValsOverflow) return fail(ctx, INQ_ERR_STATE, "internal: call buffer overflow");
         if (f & kFlagBadHp)
-            return fail(ctx, INQ_ERR_BAD_HP, "a read passing the phased filter carries HP outside {0,1,2} (the reference panics, call.rs:358)");
+            return fail(ctx, INQ_ERR_BAD_HP, "read %llu passes the phased filter but carries HP %u, outside {0,1,2} (the reference panics, call.rs:358)",
+                        (unsigned long long)ctx->h_ctr->bad_hp_read, ctx->h_ctr->bad_hp_value);
         if (f & kFlagMedianEmpty)
             return fail(ctx, INQ_ERR_MEDIAN_EMPTY, "support == 0 with a bucket without usable calls (the reference panics, call.rs:516)");
         break;

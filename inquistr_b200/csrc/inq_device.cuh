@@ -1,16 +1,17 @@
 // inq_device.cuh -- sm_100a kernels of the `inquiSTR call` hot path.
 //
 // Reference semantics being reproduced (files under /root/reference/src, v0.13.0):
-//   K1  k_join_count      read x locus overlap join + filter   call.rs:288,297-301,338,349-355
+//   K1  k_join_ranges     read x locus overlap join (ranges)   call.rs:288,338
 //   K2  k_cigar_scan      segmented CIGAR scan -> event list   call.rs:377-413 (position cursor + op tests)
-//   K2b k_pair_eval       per pair window sum + bucket scatter call.rs:388-403 (window test), 304,358
+//   K2b k_pair_eval       filter, window sum, bucket scatter   call.rs:297-301,349-355,388-403,304,358
 //   K3  k_locus_median*   sort / split / support / median      call.rs:308-321,365-369,497-522
 //
 // Layout in HBM (all structure-of-arrays):
 //   reads : contig/ref_start/ref_end int32[R], mapq/hp/flags u8[R], cig_off u64[R+1], cigar u32[C]
 //   loci  : start/end/pmax_end int32[L] sorted by (contig,start), contig_off int64[n_contigs+1]
 //   events: uint2{pos1 (1-based anchor, u32), val = (signed len << 1) | is_softclip}[E], ev_off u32[R+1]
-//   buckets: 2 per locus (H1,H2 | unphased: all,unused); cnt/off u32[2L+1]; vals u64[P]
+//   calls : one segment per locus sized by its candidate count (seg_off u32[L+1]); H1 from the front,
+//           H2 from the back (cursor u64[L] = front count | back count << 32); vals u64[#candidates]
 #pragma once
 
 #include <cuda.h>
@@ -59,7 +60,8 @@ struct DevCounters {
     unsigned int scan_counter[4];
     unsigned int big_count;
     unsigned int big_cursor;
-    unsigned int pad;
+    unsigned int bad_hp_value;        // diagnostics: HP value and read index of one offending read
+    unsigned long long bad_hp_read;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -275,67 +277,33 @@ __device__ __forceinline__ void candidate_range(bool unphased, const LocusView &
     if (hi < lo) hi = lo;
 }
 
+// K1: per read, the contiguous range [lo, lo+n) of catalog loci whose window it can pair with
+// (two binary searches over the sorted, L2-resident catalog). Instead of visiting the candidates,
+// the kernel adds +1/-1 to a difference array; its prefix sum is the number of candidate reads of
+// every locus, which sizes that locus' segment of the call buffer (an upper bound on its pairs).
 __global__ void __launch_bounds__(256)
-k_join_count(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ cand_lo, uint32_t *__restrict__ cand_n,
-             uint32_t *__restrict__ bucket_cnt, DevCounters *__restrict__ ctr)
+k_join_ranges(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ cand_lo, uint32_t *__restrict__ cand_n,
+              uint32_t *__restrict__ delta /* L+1, zeroed */, DevCounters *__restrict__ ctr)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const bool live = r < rv.R;
     int lo = 0, n = 0;
-    int32_t rs = 0, re = 0;
-    uint32_t h = 0;
-    if (live) {
+    if (r < rv.R) {
         const int c = rv.contig[r];
-        const uint32_t mq = rv.mapq[r];
-        h = rv.hp[r];
+        const uint32_t mq = rv.mapq[r], h = rv.hp[r];
         if (c >= 0 && c < lv.n_contigs && mq > 10u && (unphased || h != 0xFFu)) {
-            rs = rv.rs[r];
-            re = rv.re[r];
             int hi;
-            candidate_range(unphased != 0, lv, c, rs, re, lo, hi);
+            candidate_range(unphased != 0, lv, c, rv.rs[r], rv.re[r], lo, hi);
             n = hi - lo;
+            if (n > 0) {
+                atomicAdd(delta + lo, 1u);
+                atomicAdd(delta + hi, 0xFFFFFFFFu);              // -1 (mod 2^32)
+            }
         }
         cand_lo[r] = (uint32_t)lo;
         cand_n[r] = (uint32_t)n;
     }
-    uint32_t npass = 0, nvisit = 0;     // bucketed pairs; pairs the reference walks (incl. HP 0)
-    bool bad_hp = false;
-    const int nmax = __reduce_max_sync(0xffffffffu, n);
-    for (int j = 0; j < nmax; ++j) {
-        uint32_t bucket = 0xFFFFFFFFu;
-        if (j < n) {
-            const int l = lo + j;
-            if (pair_passes(unphased != 0, rs, re, __ldg(lv.start + l), __ldg(lv.end + l))) {
-                ++nvisit;                                       // call.rs:357 runs before the bucket lookup
-                if (unphased) bucket = 2u * (uint32_t)l;
-                else if (h > 2u) bad_hp = true;                 // call.rs:358 unwrap on None
-                else if (h != 0u) bucket = 2u * (uint32_t)l + (h - 1u);  // HP 0 lands in the ignored bucket
-            }
-        }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
-        if (bucket != 0xFFFFFFFFu) {
-            ++npass;
-            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(bucket_cnt + bucket, (uint32_t)__popc(peers));
-        }
-    }
-    // statistics (one atomic per warp per counter)
-    uint64_t words = 0, nw = 0;
-    if (live && nvisit) nw = rv.cig_off[r + 1] - rv.cig_off[r];
-    if (npass) words = nw;
-    const uint32_t cand_w = warp_sum((uint32_t)n);
-    const uint32_t pass_w = warp_sum(npass);
-    const uint32_t join_w = warp_sum((uint32_t)(npass != 0));
-    const uint64_t words_w = warp_sum(words);
-    const uint64_t visits_w = warp_sum(nw * nvisit);
-    const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
-    if (lane_id() == 0) {
-        if (cand_w) atomicAdd(&ctr->n_candidates, (unsigned long long)cand_w);
-        if (pass_w) atomicAdd(&ctr->n_pairs, (unsigned long long)pass_w);
-        if (join_w) atomicAdd(&ctr->n_reads_joined, (unsigned long long)join_w);
-        if (words_w) atomicAdd(&ctr->n_words_joined, (unsigned long long)words_w);
-        if (visits_w) atomicAdd(&ctr->op_visits, (unsigned long long)visits_w);
-        if (bad_w) atomicOr(&ctr->flags, kFlagBadHp);
-    }
+    const uint32_t cand_w = __reduce_add_sync(0xffffffffu, (uint32_t)n);
+    if (lane_id() == 0 && cand_w) atomicAdd(&ctr->n_candidates, (unsigned long long)cand_w);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -658,13 +626,15 @@ k_exclusive_scan(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t ntiles,
 }
 
 // ----------------------------------------------------------------------------------------------
-// K2b: per (read, locus) pair, sum the read's events anchored inside the locus window
-// (call.rs:388,394,400: start < P && P < end) and scatter the packed call into its bucket.
+// K2b: per (read, locus) candidate: the filter (call.rs:297-300 / 350-352), the sum of the read's
+// events anchored inside the locus window (call.rs:388,394,400: start < P && P < end) and the
+// scatter of the packed call into the locus' segment: H1 (or every unphased call) grows from the
+// front of the segment, H2 from its back; one 64-bit atomic per pair hands out the slot.
 __global__ void __launch_bounds__(256)
 k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
             const uint32_t *__restrict__ cand_n, const uint2 *__restrict__ events,
-            const uint32_t *__restrict__ ev_off, uint64_t ev_cap, const uint32_t *__restrict__ bucket_off,
-            uint32_t *__restrict__ bucket_cnt, uint64_t *__restrict__ vals, uint64_t vals_cap,
+            const uint32_t *__restrict__ ev_off, uint64_t ev_cap, const uint32_t *__restrict__ seg_off,
+            unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
             DevCounters *__restrict__ ctr)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -685,50 +655,67 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
         }
     }
+    uint32_t npass = 0, nvisit = 0;     // bucketed pairs; pairs the reference walks (incl. HP 0)
+    bool bad_hp = false;
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     for (int j = 0; j < nmax; ++j) {
-        uint32_t bucket = 0xFFFFFFFFu;
-        uint64_t key = 0;
-        if (j < n) {
-            const int l = lo + j;
-            const int32_t ls = __ldg(lv.start + l), le = __ldg(lv.end + l);
-            if (pair_passes(unphased != 0, rs, re, ls, le)) {
-                if (unphased) bucket = 2u * (uint32_t)l;
-                else if (h == 1u || h == 2u) bucket = 2u * (uint32_t)l + (h - 1u);
+        if (j >= n) continue;
+        const int l = lo + j;
+        const int32_t ls = __ldg(lv.start + l), le = __ldg(lv.end + l);
+        if (!pair_passes(unphased != 0, rs, re, ls, le)) continue;
+        ++nvisit;                                           // call.rs:357 runs before the bucket lookup
+        if (!unphased) {
+            if (h > 2u) {                                    // call.rs:358 unwrap on None
+                bad_hp = true;
+                ctr->bad_hp_value = h;
+                ctr->bad_hp_read = r;
+                continue;
             }
-            if (bucket != 0xFFFFFFFFu) {
-                const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
-                // first event with pos1 > start_ext
-                uint32_t a = e0, b = e1;
-                while (a < b) {
-                    const uint32_t m = a + ((b - a) >> 1);
-                    if (events[m].x > start_ext) b = m; else a = m + 1;
-                }
-                int64_t call = 0;
-                uint32_t clip = 0;
-                for (uint32_t e = a; e < e1; ++e) {
-                    const uint2 ev = events[e];
-                    if (!(ev.x < end_ext)) break;
-                    const int32_t v = (int32_t)ev.y;
-                    const uint32_t is_s = (uint32_t)v & 1u;
-                    if (is_s && is2d) continue;              // call.rs:394 !is_accidental_2d(&r)
-                    call += (int64_t)(v >> 1);
-                    clip |= is_s;
-                }
-                key = ((uint64_t)(call + kCallBias) << 1) | clip;
-            }
+            if (h == 0u) continue;                          // HP 0 lands in the ignored bucket
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
-        if (bucket != 0xFFFFFFFFu) {
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if ((int)lane_id() == leader) old = atomicSub(bucket_cnt + bucket, (uint32_t)__popc(peers));
-            old = __shfl_sync(peers, old, leader);
-            const uint32_t rank = __popc(peers & lanemask_lt());
-            const uint64_t slot = (uint64_t)bucket_off[bucket] + (old - 1u - rank);
-            if (slot < vals_cap) vals[slot] = key;
-            else atomicOr(&ctr->flags, kFlagValsOverflow);
+        ++npass;
+        const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
+        // first event with pos1 > start_ext
+        uint32_t a = e0, b = e1;
+        while (a < b) {
+            const uint32_t m = a + ((b - a) >> 1);
+            if (events[m].x > start_ext) b = m; else a = m + 1;
         }
+        int64_t call = 0;
+        uint32_t clip = 0;
+        for (uint32_t e = a; e < e1; ++e) {
+            const uint2 ev = events[e];
+            if (!(ev.x < end_ext)) break;
+            const int32_t v = (int32_t)ev.y;
+            const uint32_t is_s = (uint32_t)v & 1u;
+            if (is_s && is2d) continue;                     // call.rs:394 !is_accidental_2d(&r)
+            call += (int64_t)(v >> 1);
+            clip |= is_s;
+        }
+        const uint64_t key = ((uint64_t)(call + kCallBias) << 1) | clip;
+        const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
+        const bool back = !unphased && h == 2u;
+        const unsigned long long old = atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
+        const uint32_t k = back ? (uint32_t)(old >> 32) : (uint32_t)old;
+        const uint64_t slot = back ? (uint64_t)seg + (cap - 1u - k) : (uint64_t)seg + k;
+        if (k < cap && slot < vals_cap) vals[slot] = key;
+        else atomicOr(&ctr->flags, kFlagValsOverflow);
+    }
+    // statistics (one atomic per warp per counter)
+    uint64_t words = 0, nw = 0;
+    if (nvisit) nw = rv.cig_off[r + 1] - rv.cig_off[r];
+    if (npass) words = nw;
+    const uint32_t pass_w = __reduce_add_sync(0xffffffffu, npass);
+    const uint32_t join_w = __reduce_add_sync(0xffffffffu, (uint32_t)(npass != 0));
+    const uint64_t words_w = warp_sum(words);
+    const uint64_t visits_w = warp_sum(nw * nvisit);
+    const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
+    if (lane_id() == 0) {
+        if (pass_w) atomicAdd(&ctr->n_pairs, (unsigned long long)pass_w);
+        if (join_w) atomicAdd(&ctr->n_reads_joined, (unsigned long long)join_w);
+        if (words_w) atomicAdd(&ctr->n_words_joined, (unsigned long long)words_w);
+        if (visits_w) atomicAdd(&ctr->op_visits, (unsigned long long)visits_w);
+        if (bad_w) atomicOr(&ctr->flags, kFlagBadHp);
     }
 }
 
@@ -826,20 +813,22 @@ __device__ __forceinline__ bool warp_median_part(const uint64_t (&key)[K], uint3
     return true;
 }
 
+// A locus' segment [seg, seg+cap) holds its H1 calls at the front and its H2 calls at the back
+// (unphased: everything at the front). nf/nb = number of front/back entries; n1 = split point of
+// the sorted run (phased: nf, unphased: (nf)/2).
 template <int K>
-__device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, uint32_t b0, uint32_t n1, uint32_t ntot,
-                                           bool phased, uint32_t support, int64_t *t1, int64_t *t2, uint32_t *valid,
-                                           bool *panicked)
+__device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, uint32_t seg, uint32_t cap, uint32_t nf,
+                                           uint32_t nb, uint32_t n1, bool phased, uint32_t support, int64_t *t1,
+                                           int64_t *t2, uint32_t *valid, bool *panicked)
 {
+    const uint32_t ntot = nf + nb;
     uint64_t key[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t i = k * 32 + lane_id();
         uint64_t v = kKeyInf;
-        if (i < ntot) {
-            v = vals[b0 + i];
-            if (phased && i >= n1) v |= kKeyHapBit;
-        }
+        if (i < nf) v = vals[seg + i];
+        else if (i < ntot) v = vals[seg + cap - nb + (i - nf)] | (phased ? kKeyHapBit : 0ull);
         key[k] = v;
     }
     warp_sort<K>(key);
@@ -851,21 +840,28 @@ __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, ui
 constexpr int kMedianWarpMax = 128;         // loci with more calls go to the CTA kernel
 
 __global__ void __launch_bounds__(256)
-k_locus_median(uint32_t L, int unphased, uint32_t support, const uint32_t *__restrict__ bucket_off,
-               const uint64_t *__restrict__ vals, int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2,
-               uint8_t *__restrict__ valid, uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
+k_locus_median(uint32_t L, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
+               const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ vals, uint64_t vals_cap,
+               int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
+               uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
 {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (l >= L) return;
-    const uint32_t b0 = bucket_off[2 * l], b1 = bucket_off[2 * l + 1], b2 = bucket_off[2 * l + 2];
-    const uint32_t ntot = b2 - b0;
-    const uint32_t n1 = unphased ? (ntot >> 1) : (b1 - b0);        // call.rs:314 split_at(len/2)
+    const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
+    if ((uint64_t)seg + cap > vals_cap) {               // speculatively sized call buffer too small: the run is repeated
+        if (lane_id() == 0) atomicOr(&ctr->flags, kFlagValsOverflow);
+        return;
+    }
+    const unsigned long long cur = cursor[l];
+    const uint32_t nf = min((uint32_t)cur, cap), nb = min((uint32_t)(cur >> 32), cap - nf);
+    const uint32_t ntot = nf + nb;
+    const uint32_t n1 = unphased ? (ntot >> 1) : nf;               // call.rs:314 split_at(len/2)
     int64_t t1 = 0, t2 = 0;
     uint32_t vm = 0;
     bool panicked = false;
-    if (ntot <= 32) warp_locus<1>(vals, b0, n1, ntot, !unphased, support, &t1, &t2, &vm, &panicked);
-    else if (ntot <= 64) warp_locus<2>(vals, b0, n1, ntot, !unphased, support, &t1, &t2, &vm, &panicked);
-    else if (ntot <= kMedianWarpMax) warp_locus<4>(vals, b0, n1, ntot, !unphased, support, &t1, &t2, &vm, &panicked);
+    if (ntot <= 32) warp_locus<1>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+    else if (ntot <= 64) warp_locus<2>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+    else if (ntot <= kMedianWarpMax) warp_locus<4>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
     else {
         if (lane_id() == 0) big_list[atomicAdd(&ctr->big_count, 1u)] = l;
         return;
@@ -944,7 +940,8 @@ __device__ __forceinline__ void block_part_median(volatile uint64_t *a, uint32_t
 }
 
 __global__ void __launch_bounds__(kBigThreads)
-k_locus_median_big(int unphased, uint32_t support, const uint32_t *__restrict__ bucket_off, uint64_t *__restrict__ vals,
+k_locus_median_big(int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
+                   const unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
                    int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
                    const uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
 {
@@ -959,21 +956,30 @@ k_locus_median_big(int unphased, uint32_t support, const uint32_t *__restrict__ 
         const uint32_t item = item_s;
         if (item >= ctr->big_count) break;
         const uint32_t l = big_list[item];
-        const uint32_t b0 = bucket_off[2 * l], b1 = bucket_off[2 * l + 1], b2 = bucket_off[2 * l + 2];
-        const uint32_t ntot = b2 - b0;
-        const uint32_t n1 = unphased ? (ntot >> 1) : (b1 - b0);
+        const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
+        if ((uint64_t)seg + cap > vals_cap) { __syncthreads(); continue; }     // see k_locus_median
+        const unsigned long long cur = cursor[l];
+        const uint32_t nf = min((uint32_t)cur, cap), nb = min((uint32_t)(cur >> 32), cap - nf);
+        uint32_t ntot = nf + nb;
+        const uint32_t n1 = unphased ? (ntot >> 1) : nf;
+        const uint32_t n2 = ntot - n1;
         volatile uint64_t *a;
         if (ntot <= (uint32_t)kBigSmemKeys) {
             for (uint32_t i = tid; i < ntot; i += blockDim.x) {
-                uint64_t v = vals[b0 + i];
-                if (!unphased && i >= n1) v |= kKeyHapBit;
+                uint64_t v;
+                if (i < nf) v = vals[seg + i];
+                else v = vals[seg + cap - nb + (i - nf)] | (unphased ? 0ull : kKeyHapBit);
                 skeys[i] = v;
             }
             a = skeys;
         } else {
-            if (!unphased)
-                for (uint32_t i = n1 + tid; i < ntot; i += blockDim.x) vals[b0 + i] |= kKeyHapBit;
-            a = vals + b0;
+            // sort the whole segment in place; the unused gap between front and back becomes +inf keys
+            for (uint32_t i = nf + tid; i < cap; i += blockDim.x) {
+                if (i < cap - nb) vals[seg + i] = kKeyInf;
+                else if (!unphased) vals[seg + i] |= kKeyHapBit;
+            }
+            a = vals + seg;
+            ntot = cap;
         }
         __syncthreads();
         // all-ascending bitonic network with virtual +inf padding (comparators touching i >= ntot are no-ops)
@@ -1003,7 +1009,7 @@ k_locus_median_big(int unphased, uint32_t support, const uint32_t *__restrict__ 
         bool ok1, ok2, panicked = false;
         block_part_median(a, 0, n1, support, &t1, &ok1, &panicked, sh_cnt, &sh_acc);
         __syncthreads();
-        block_part_median(a, n1, ntot - n1, support, &t2, &ok2, &panicked, sh_cnt, &sh_acc);
+        block_part_median(a, n1, n2, support, &t2, &ok2, &panicked, sh_cnt, &sh_acc);
         if (tid == 0) {
             twice_h1[l] = t1;
             twice_h2[l] = t2;
