@@ -48,10 +48,10 @@ struct inq_ctx {
     DevBuf<uint32_t> cigar;
 
     // work buffers
-    DevBuf<uint32_t> cand_lo, cand_n, ev_off, gstart, delta, lcnt, seg_off, big_list;
+    DevBuf<uint32_t> cand_lo, cand_n, ev_off, delta, lcnt, seg_off, big_list;
     DevBuf<unsigned long long> cursor;
-    DevBuf<uint32_t> blkpref, wt_cons, wt_ev, wt_sbase;
-    DevBuf<uint16_t> blkev;
+    DevBuf<uint32_t> wt_sbase;
+    DevBuf<uint2> blk, wt;
     DevBuf<uint64_t> desc_scan, desc_wt, vals;
     DevBuf<uint2> evraw;
     CUtensorMap tmap;                 // 2-D view of the packed CIGAR stream: rows of 32 words, 128B swizzle
@@ -226,8 +226,8 @@ void inq_ctx_destroy(inq_ctx *ctx)
     release(ctx->contig); release(ctx->rs); release(ctx->re);
     release(ctx->mapq); release(ctx->hp); release(ctx->flags);
     release(ctx->cig_off); release(ctx->cigar);
-    release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off); release(ctx->gstart);
-    release(ctx->blkpref); release(ctx->blkev); release(ctx->wt_cons); release(ctx->wt_ev); release(ctx->wt_sbase);
+    release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off);
+    release(ctx->blk); release(ctx->wt); release(ctx->wt_sbase);
     release(ctx->desc_wt); release(ctx->evraw);
     release(ctx->delta); release(ctx->lcnt); release(ctx->seg_off); release(ctx->cursor); release(ctx->big_list);
     release(ctx->desc_scan); release(ctx->vals);
@@ -379,11 +379,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     TRY(ensure(ctx, ctx->cand_lo, R));
     TRY(ensure(ctx, ctx->cand_n, R));
     TRY(ensure(ctx, ctx->ev_off, R + 1));
-    TRY(ensure(ctx, ctx->gstart, R + 1));
-    TRY(ensure(ctx, ctx->blkpref, (uint64_t)ntiles * kScanThreads + 1));
-    TRY(ensure(ctx, ctx->blkev, (uint64_t)ntiles * kScanThreads + 1));
-    TRY(ensure(ctx, ctx->wt_cons, n_wt + 1));
-    TRY(ensure(ctx, ctx->wt_ev, n_wt + 1));
+    TRY(ensure(ctx, ctx->blk, (uint64_t)ntiles * kScanThreads + 1));
+    TRY(ensure(ctx, ctx->wt, n_wt + 2));
     TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
     TRY(ensure(ctx, ctx->desc_wt, 2 * ((uint64_t)wt_scan_tiles + 1)));
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
@@ -428,7 +425,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         // K2: CIGAR scan -> warp-tile tables + raw events, then prefix sums and the per-read fix-up
         if (ntiles && L) {
             ScanParams sp;
-            sp.blkpref = ctx->blkpref.p; sp.blkev = ctx->blkev.p; sp.wt_cons = ctx->wt_cons.p; sp.wt_ev = ctx->wt_ev.p;
+            sp.blk = ctx->blk.p; sp.wt = ctx->wt.p;
             sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
             sp.ntiles = ntiles; sp.minlen = minlen;
             { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
@@ -438,17 +435,13 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR], s));
         if (ntiles && L) {
             const unsigned g = std::min<unsigned>(wt_scan_tiles, (unsigned)ctx->sm_count * 4);
-            k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->wt_cons.p, ctx->wt_cons.p, n_wt, wt_scan_tiles, ctx->desc_wt.p,
-                                                      &ctx->d_ctr->scan_counter[0], nullptr);
-            k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->wt_ev.p, ctx->wt_ev.p, n_wt, wt_scan_tiles, ctx->desc_wt.p + wt_scan_tiles + 1,
-                                                      &ctx->d_ctr->scan_counter[1], &ctx->d_ctr->flags);
-            k_read_starts<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R, ctx->cigar.p, ctx->wt_cons.p, ctx->wt_ev.p,
-                                                                           ctx->blkpref.p, ctx->blkev.p, minlen, ctx->ev_off.p,
-                                                                           ctx->gstart.p, ctx->d_ctr);
-            k_event_fixup<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->ev_off.p, ctx->gstart.p,
-                                                                       ctx->wt_cons.p, ctx->wt_ev.p, ctx->wt_sbase.p, ctx->evraw.p,
-                                                                       ctx->evraw.cap, ctx->events.p, ctx->events.cap, ctx->d_ctr);
-            launches += 4;
+            k_exclusive_scan2<<<g, kXsThreads, 0, s>>>(ctx->wt.p, n_wt, wt_scan_tiles, ctx->desc_wt.p, ctx->desc_wt.p + wt_scan_tiles + 1,
+                                                       &ctx->d_ctr->scan_counter[0], &ctx->d_ctr->flags);
+            const uint64_t fix_warps = (R + 1 + 30) / 31;
+            k_read_fixup<<<(unsigned)((fix_warps * 32 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->cigar.p, ctx->wt.p, ctx->blk.p,
+                                                                                 ctx->wt_sbase.p, minlen, ctx->evraw.p, ctx->evraw.cap,
+                                                                                 ctx->events.p, ctx->events.cap, ctx->ev_off.p, ctx->d_ctr);
+            launches += 2;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_FIXUP], s));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_SCAN], s));

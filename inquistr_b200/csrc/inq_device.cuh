@@ -337,17 +337,15 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 // the lane's reference consumption (call.rs:384-392,404) and its event mask (I/D/S ops longer than
 // minlen, call.rs:388,394,400); two warp scans turn that into warp-local prefixes. Nothing in this
 // kernel depends on another CTA or on read boundaries: it writes
-//   blkpref/blkev : warp-local exclusive prefixes at every 16-word block
-//   wt_cons/wt_ev : totals per warp tile (prefix-summed afterwards by k_exclusive_scan)
+//   blk   : warp-local exclusive prefixes {consumption, events} at every 16-word block
+//   wt    : totals per warp tile (prefix-summed afterwards by k_exclusive_scan2)
 //   evraw         : {bases consumed inside the warp tile before the op, (signed len << 1) | is_S}
 //                   for every event, stored per warp tile in chunks handed out by one atomic
-// and k_read_starts / k_event_fixup turn these into per-read event lists with absolute anchors.
+// and k_read_fixup turns these into per-read event lists with absolute anchors.
 // Each CIGAR word is read from HBM exactly once.
 struct ScanParams {
-    uint32_t *blkpref;            // [ntiles * kScanThreads]
-    uint16_t *blkev;              // [ntiles * kScanThreads]
-    uint32_t *wt_cons;            // [n_wt + 1]
-    uint32_t *wt_ev;              // [n_wt + 1]
+    uint2 *blk;                   // [ntiles * kScanThreads] {warp-local exclusive consumption, event count} per 16-word block
+    uint2 *wt;                    // [n_wt + 1] {consumption, events} per warp tile (prefix-summed afterwards)
     uint32_t *wt_sbase;           // [n_wt] storage slot of the warp tile's first event
     uint2 *evraw;
     DevCounters *ctr;
@@ -457,10 +455,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint32_t excl_c = incl_c - c, excl_e = incl_e - ne;
         const uint32_t tot_e = __shfl_sync(0xffffffffu, incl_e, 31);
         const uint64_t gblk = t * kScanThreads + tid;           // global 16-word block index
-        if (!(p.debug & 16u)) {
-            p.blkpref[gblk] = excl_c;
-            p.blkev[gblk] = (uint16_t)excl_e;
-        }
+        if (!(p.debug & 16u)) p.blk[gblk] = make_uint2(excl_c, excl_e);
 
         // ---- event slots: contiguous per warp tile, taken from a warp-private chunk
         uint64_t sbase = chunk_cur;
@@ -477,8 +472,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         }
         if (lane == 31 && !(p.debug & 16u)) {
             const uint64_t gw = t * kWarpsPerScanCta + warp;    // global warp-tile index
-            p.wt_cons[gw] = incl_c;
-            p.wt_ev[gw] = incl_e;
+            p.wt[gw] = make_uint2(incl_c, incl_e);
             p.wt_sbase[gw] = (uint32_t)sbase;
         }
 
@@ -508,56 +502,56 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     }
 }
 
-// per read: index of its first event in CIGAR order and the stream-wide consumption prefix at its
-// first word. wt_cons / wt_ev hold EXCLUSIVE prefixes here (k_exclusive_scan ran in between).
+// Per read: (1) the index of its first event in CIGAR order and the stream-wide consumption prefix
+// at its first word, from the warp-tile prefixes, the block table and at most 15 CIGAR words;
+// (2) its events moved from warp-tile storage into CIGAR order with absolute anchors:
+// pos1 = ref_start + 1 + bases consumed by the read before the op (the u32 cursor of call.rs:380).
+// A warp owns 31 reads; lane 31 only supplies the first-event index of the next read.
+// `wt` holds EXCLUSIVE prefixes here (k_exclusive_scan2 ran in between).
 __global__ void __launch_bounds__(256)
-k_read_starts(const uint64_t *__restrict__ cig_off, uint64_t R, const uint32_t *__restrict__ cigar,
-              const uint32_t *__restrict__ wt_cons, const uint32_t *__restrict__ wt_ev,
-              const uint32_t *__restrict__ blkpref, const uint16_t *__restrict__ blkev, uint32_t minlen,
-              uint32_t *__restrict__ ev_off, uint32_t *__restrict__ gstart, DevCounters *__restrict__ ctr)
+k_read_fixup(const uint64_t *__restrict__ cig_off, const int32_t *__restrict__ rs, uint64_t R,
+             const uint32_t *__restrict__ cigar, const uint2 *__restrict__ wt, const uint2 *__restrict__ blk,
+             const uint32_t *__restrict__ wt_sbase, uint32_t minlen, const uint2 *__restrict__ evraw, uint64_t raw_cap,
+             uint2 *__restrict__ events, uint64_t ev_cap, uint32_t *__restrict__ ev_off, DevCounters *__restrict__ ctr)
 {
-    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (r > R) return;
-    const uint64_t g = cig_off[r];
-    const uint64_t gw = g / kWarpTileWords;
-    uint32_t e = wt_ev[gw], c = wt_cons[gw];
-    if (g % kWarpTileWords) {
-        const uint64_t blk = g / kLaneWords;
-        e += blkev[blk];
-        c += blkpref[blk];
-        for (uint64_t i = blk * kLaneWords; i < g; ++i) {
-            const uint32_t w = __ldg(cigar + i);
-            c += cig_consume(w);
-            e += cig_is_event(w, minlen) ? 1u : 0u;
+    const uint32_t lane = lane_id();
+    const uint64_t warp_global = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t r = warp_global * 31 + lane;
+    uint32_t e = 0, c = 0;
+    uint64_t g = 0;
+    if (r <= R) {
+        g = cig_off[r];
+        const uint64_t gw = g / kWarpTileWords;
+        const uint2 w0 = wt[gw];
+        c = w0.x;
+        e = w0.y;
+        if (g % kWarpTileWords) {
+            const uint64_t b = g / kLaneWords;
+            const uint2 b0 = blk[b];
+            c += b0.x;
+            e += b0.y;
+            for (uint64_t i = b * kLaneWords; i < g; ++i) {
+                const uint32_t w = __ldg(cigar + i);
+                c += cig_consume(w);
+                e += cig_is_event(w, minlen) ? 1u : 0u;
+            }
         }
     }
+    const uint32_t e_next = __shfl_down_sync(0xffffffffu, e, 1);
+    if (lane == 31 || r > R) return;
     ev_off[r] = e;
-    if (r < R) gstart[r] = c;
-    else ctr->n_events = e;
-}
-
-// per read: move its events from warp-tile storage into CIGAR order and make the anchors absolute:
-// pos1 = ref_start + 1 + bases consumed by the read before the op (the u32 cursor of call.rs:380).
-__global__ void __launch_bounds__(256)
-k_event_fixup(const uint64_t *__restrict__ cig_off, const int32_t *__restrict__ rs, uint64_t R,
-              const uint32_t *__restrict__ ev_off, const uint32_t *__restrict__ gstart,
-              const uint32_t *__restrict__ wt_cons, const uint32_t *__restrict__ wt_ev,
-              const uint32_t *__restrict__ wt_sbase, const uint2 *__restrict__ evraw, uint64_t raw_cap,
-              uint2 *__restrict__ events, uint64_t ev_cap, DevCounters *__restrict__ ctr)
-{
-    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const uint32_t e0 = ev_off[r], e1 = ev_off[r + 1];
-    if (e0 == e1) return;
-    const uint32_t base = (uint32_t)rs[r] + 1u - gstart[r];
-    uint64_t gw = cig_off[r] / kWarpTileWords;
-    uint32_t lo = wt_ev[gw], hi = wt_ev[gw + 1];
-    for (uint32_t e = e0; e < e1; ++e) {
-        while (e >= hi) { ++gw; lo = hi; hi = wt_ev[gw + 1]; }
-        const uint64_t slot = (uint64_t)wt_sbase[gw] + (e - lo);
-        if (e < ev_cap && slot < raw_cap) {
+    if (r == R) { ctr->n_events = e; return; }
+    if (e == e_next) return;
+    const uint32_t base = (uint32_t)rs[r] + 1u - c;
+    uint64_t gw = g / kWarpTileWords;
+    uint2 pre = wt[gw];
+    uint32_t hi = wt[gw + 1].y;
+    for (uint32_t k = e; k < e_next; ++k) {
+        while (k >= hi) { ++gw; pre = wt[gw]; hi = wt[gw + 1].y; }
+        const uint64_t slot = (uint64_t)wt_sbase[gw] + (k - pre.y);
+        if (k < ev_cap && slot < raw_cap) {
             const uint2 raw = evraw[slot];
-            events[e] = make_uint2(base + wt_cons[gw] + raw.x, raw.y);
+            events[k] = make_uint2(base + pre.x + raw.x, raw.y);
         } else {
             atomicOr(&ctr->flags, kFlagEventOverflow);
         }
@@ -625,6 +619,74 @@ k_exclusive_scan(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t ntiles,
     }
 }
 
+// same for pairs of u32 (both components wrap mod 2^32; `y` is checked against 2^32), in place
+__global__ void __launch_bounds__(kXsThreads)
+k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict__ desc_x, uint64_t *__restrict__ desc_y,
+                  unsigned int *__restrict__ tile_counter, unsigned int *__restrict__ overflow_flags)
+{
+    __shared__ uint32_t wsx[kXsThreads / 32], wsy[kXsThreads / 32];
+    __shared__ uint32_t tile_s;
+    __shared__ uint64_t bx_s, by_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) tile_s = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint32_t t = tile_s;
+        if (t >= ntiles) break;
+        const uint64_t i0 = (uint64_t)t * kXsTile + (uint64_t)tid * kXsItems;
+        uint2 v[kXsItems];
+        uint32_t sx = 0, sy = 0;
+#pragma unroll
+        for (int k = 0; k < kXsItems; ++k) {
+            v[k] = (i0 + k < n) ? data[i0 + k] : make_uint2(0u, 0u);
+            sx += v[k].x;
+            sy += v[k].y;
+        }
+        const uint32_t ix = warp_incl_scan(sx), iy = warp_incl_scan(sy);
+        if (lane == 31) { wsx[warp] = ix; wsy[warp] = iy; }
+        __syncthreads();
+        uint32_t wbx = 0, wby = 0, tx = 0, ty = 0;
+#pragma unroll
+        for (int w = 0; w < kXsThreads / 32; ++w) {
+            if (w < (int)warp) { wbx += wsx[w]; wby += wsy[w]; }
+            tx += wsx[w];
+            ty += wsy[w];
+        }
+        if (warp == 0) {
+            if (lane == 0) {
+                st_relaxed_u64(desc_x + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)tx);
+                st_relaxed_u64(desc_y + t, (t == 0 ? kDescPrefix : kDescAggregate) | (uint64_t)ty);
+            }
+            uint64_t bx = 0, by = 0;
+            if (t > 0) {
+                bx = lookback(desc_x, (int64_t)t);
+                by = lookback(desc_y, (int64_t)t);
+                if (lane == 0) {
+                    st_relaxed_u64(desc_x + t, kDescPrefix | ((bx + tx) & 0xFFFFFFFFull));
+                    st_relaxed_u64(desc_y + t, kDescPrefix | ((by + ty) & kDescValueMask));
+                }
+            }
+            if (lane == 0) {
+                bx_s = bx;
+                by_s = by;
+                if (t == ntiles - 1) {
+                    data[n] = make_uint2((uint32_t)(bx + tx), (uint32_t)(by + ty));
+                    if (overflow_flags && by + ty > 0xFFFFFFFFull) atomicOr(overflow_flags, kFlagCountOverflow);
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t rx = (uint32_t)bx_s + wbx + ix - sx, ry = (uint32_t)by_s + wby + iy - sy;
+#pragma unroll
+        for (int k = 0; k < kXsItems; ++k) {
+            if (i0 + k < n) data[i0 + k] = make_uint2(rx, ry);
+            rx += v[k].x;
+            ry += v[k].y;
+        }
+        __syncthreads();
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // K2b: per (read, locus) candidate: the filter (call.rs:297-300 / 350-352), the sum of the read's
 // events anchored inside the locus window (call.rs:388,394,400: start < P && P < end) and the
@@ -637,53 +699,76 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
             DevCounters *__restrict__ ctr)
 {
+    // A warp owns 32 consecutive reads; their candidates are flattened and dealt to the lanes
+    // 32 at a time (reads have 0..hundreds of candidates, a per-read loop leaves most lanes idle).
+    __shared__ uint32_t s_off[8][32];
+    __shared__ uint32_t s_joined[8];
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    int lo = 0, n = 0;
+    uint32_t n = 0, lo = 0, e0 = 0, e1 = 0, hf = 0, words = 0;
     int32_t rs = 0, re = 0;
-    uint32_t h = 0, e0 = 0, e1 = 0;
-    bool is2d = false;
     if (r < rv.R) {
-        n = (int)cand_n[r];
+        n = cand_n[r];
         if (n) {
-            lo = (int)cand_lo[r];
+            lo = cand_lo[r];
             rs = rv.rs[r];
             re = rv.re[r];
-            h = rv.hp[r];
-            is2d = (rv.flags[r] & 1u) != 0;
+            hf = (uint32_t)rv.hp[r] | ((uint32_t)(rv.flags[r] & 1u) << 8);
             // if the speculative event list overflowed the run is repeated; stay inside the allocation
             e0 = (uint32_t)min((uint64_t)ev_off[r], ev_cap);
             e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
+            words = (uint32_t)min(rv.cig_off[r + 1] - rv.cig_off[r], (uint64_t)0xFFFFFFFFu);
         }
     }
-    uint32_t npass = 0, nvisit = 0;     // bucketed pairs; pairs the reference walks (incl. HP 0)
+    const uint32_t incl = warp_incl_scan(n);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    s_off[wid][lane] = incl - n;
+    if (lane == 0) s_joined[wid] = 0u;
+    __syncwarp();
+
+    uint32_t npass = 0;                 // pairs that land in a bucket
+    uint64_t visits = 0;                // CIGAR words the reference walks: every passing pair, incl. HP 0
     bool bad_hp = false;
-    const int nmax = __reduce_max_sync(0xffffffffu, n);
-    for (int j = 0; j < nmax; ++j) {
-        if (j >= n) continue;
-        const int l = lo + j;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t k = base + lane;
+        const bool active = k < total;
+        // owning read: the last j with s_off[j] <= k
+        uint32_t j = 0;
+#pragma unroll
+        for (uint32_t step = 16; step >= 1; step >>= 1)
+            if (active && s_off[wid][j + step] <= k) j += step;
+        const uint32_t idx = k - s_off[wid][j];
+        const int32_t rs_j = __shfl_sync(0xffffffffu, rs, j), re_j = __shfl_sync(0xffffffffu, re, j);
+        const uint32_t hf_j = __shfl_sync(0xffffffffu, hf, j), lo_j = __shfl_sync(0xffffffffu, lo, j);
+        const uint32_t e0_j = __shfl_sync(0xffffffffu, e0, j), e1_j = __shfl_sync(0xffffffffu, e1, j);
+        const uint32_t words_j = __shfl_sync(0xffffffffu, words, j);
+        if (!active) continue;
+        const uint32_t l = lo_j + idx, h = hf_j & 0xFFu;
         const int32_t ls = __ldg(lv.start + l), le = __ldg(lv.end + l);
-        if (!pair_passes(unphased != 0, rs, re, ls, le)) continue;
-        ++nvisit;                                           // call.rs:357 runs before the bucket lookup
+        if (!pair_passes(unphased != 0, rs_j, re_j, ls, le)) continue;
+        visits += words_j;                                  // call.rs:357 runs before the bucket lookup
         if (!unphased) {
-            if (h > 2u) {                                    // call.rs:358 unwrap on None
+            if (h > 2u) {                                   // call.rs:358 unwrap on None
                 bad_hp = true;
                 ctr->bad_hp_value = h;
-                ctr->bad_hp_read = r;
+                ctr->bad_hp_read = r - lane + j;
                 continue;
             }
             if (h == 0u) continue;                          // HP 0 lands in the ignored bucket
         }
         ++npass;
+        atomicOr(&s_joined[wid], 1u << j);
         const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
         // first event with pos1 > start_ext
-        uint32_t a = e0, b = e1;
+        uint32_t a = e0_j, b = e1_j;
         while (a < b) {
             const uint32_t m = a + ((b - a) >> 1);
             if (events[m].x > start_ext) b = m; else a = m + 1;
         }
         int64_t call = 0;
         uint32_t clip = 0;
-        for (uint32_t e = a; e < e1; ++e) {
+        const bool is2d = (hf_j >> 8) != 0u;
+        for (uint32_t e = a; e < e1_j; ++e) {
             const uint2 ev = events[e];
             if (!(ev.x < end_ext)) break;
             const int32_t v = (int32_t)ev.y;
@@ -696,21 +781,20 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
         const bool back = !unphased && h == 2u;
         const unsigned long long old = atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
-        const uint32_t k = back ? (uint32_t)(old >> 32) : (uint32_t)old;
-        const uint64_t slot = back ? (uint64_t)seg + (cap - 1u - k) : (uint64_t)seg + k;
-        if (k < cap && slot < vals_cap) vals[slot] = key;
+        const uint32_t slot_k = back ? (uint32_t)(old >> 32) : (uint32_t)old;
+        const uint64_t slot = back ? (uint64_t)seg + (cap - 1u - slot_k) : (uint64_t)seg + slot_k;
+        if (slot_k < cap && slot < vals_cap) vals[slot] = key;
         else atomicOr(&ctr->flags, kFlagValsOverflow);
     }
+    __syncwarp();
     // statistics (one atomic per warp per counter)
-    uint64_t words = 0, nw = 0;
-    if (nvisit) nw = rv.cig_off[r + 1] - rv.cig_off[r];
-    if (npass) words = nw;
+    const bool joined = ((s_joined[wid] >> lane) & 1u) != 0u;
     const uint32_t pass_w = __reduce_add_sync(0xffffffffu, npass);
-    const uint32_t join_w = __reduce_add_sync(0xffffffffu, (uint32_t)(npass != 0));
-    const uint64_t words_w = warp_sum(words);
-    const uint64_t visits_w = warp_sum(nw * nvisit);
+    const uint32_t join_w = __popc(__ballot_sync(0xffffffffu, joined));
+    const uint64_t words_w = warp_sum(joined ? (uint64_t)words : 0ull);
+    const uint64_t visits_w = warp_sum(visits);
     const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
-    if (lane_id() == 0) {
+    if (lane == 0) {
         if (pass_w) atomicAdd(&ctr->n_pairs, (unsigned long long)pass_w);
         if (join_w) atomicAdd(&ctr->n_reads_joined, (unsigned long long)join_w);
         if (words_w) atomicAdd(&ctr->n_words_joined, (unsigned long long)words_w);
