@@ -110,6 +110,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// poll with a short sleep in between so that waiting warps do not burn issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 // same, but lets the hardware park the warp for up to ~`ns` per probe instead of spinning on issue slots
 __device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t ns)
 {
@@ -359,6 +373,10 @@ constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words 
 constexpr int kWarpTileWords = 32 * kLaneWords;         // 512
 constexpr int kCtaThreads = kScanThreads + 32;          // 16 compute warps + 1 TMA producer warp
 constexpr uint32_t kOpLut = 0x18Du | (0x16u << 16);     // bit op: consumes reference; bit 16+op: I/D/S
+// 64-bit LUT read through one wrap-mode funnel shift by 2*op: result bit 0 = op consumes the reference
+// (M,D,N,=,X: lo bit 2*op), result bit 31 = op is I, D or S (hi bit 2*op-1)
+constexpr uint32_t kOpLutLo = (1u << 0) | (1u << 4) | (1u << 6) | (1u << 14) | (1u << 16);
+constexpr uint32_t kOpLutHi = (1u << 1) | (1u << 3) | (1u << 7);
 constexpr uint32_t kEvChunk = 1024;                     // event slots a warp takes per atomic
 
 struct ScanSmem {
@@ -409,7 +427,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
                 if (t >= p.ntiles) break;
                 const uint32_t s = it % kScanStages;
                 if (it >= (uint32_t)kScanStages) {
-                    mbar_wait_parked(&sm.freeb[s], ((it / kScanStages) - 1u) & 1u, 1000u);
+                    mbar_wait_backoff(&sm.freeb[s], ((it / kScanStages) - 1u) & 1u, 256u);
                     fence_proxy_async();
                 }
                 mbar_expect_tx(&sm.full[s], kTileBytes);
@@ -429,7 +447,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint64_t t = tile_of(it);
         if (t >= p.ntiles) break;
         const uint32_t s = it % kScanStages;
-        mbar_wait(&sm.full[s], (it / kScanStages) & 1u);
+        mbar_wait_backoff(&sm.full[s], (it / kScanStages) & 1u, 32u);
         const uint32_t *stage = sm.stage[s];
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
 
@@ -443,11 +461,13 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t w = w4[k], lut = kOpLut >> (w & 15u);
-                const bool ev = ((lut & 0x10000u) != 0u) & (w > thr);
+                // one funnel shift in wrap mode indexes the 2-bit LUT by 2*op without masking the op first
+                const uint32_t w = w4[k], lut = __funnelshift_r(kOpLutLo, kOpLutHi, w + w);
+                const bool ev = ((int32_t)lut < 0) && (w > thr);
                 evmask = ev ? (evmask | (1u << (j * 4 + k))) : evmask;
                 clast = ev ? c : clast;
-                c += (lut & 1u) ? (w >> 4) : 0u;
+                // c += consumes ? len : 0 as one multiply-add (FMA pipe) instead of select + add (ALU pipe)
+                asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c) : "r"(w >> 4), "r"(lut & 1u));
             }
         }
         const uint32_t ne = __popc(evmask);
@@ -758,29 +778,48 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         }
         ++npass;
         atomicOr(&s_joined[wid], 1u << j);
-        const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
-        // first event with pos1 > start_ext
-        uint32_t a = e0_j, b = e1_j;
-        while (a < b) {
-            const uint32_t m = a + ((b - a) >> 1);
-            if (events[m].x > start_ext) b = m; else a = m + 1;
-        }
-        int64_t call = 0;
-        uint32_t clip = 0;
-        const bool is2d = (hf_j >> 8) != 0u;
-        for (uint32_t e = a; e < e1_j; ++e) {
-            const uint2 ev = events[e];
-            if (!(ev.x < end_ext)) break;
-            const int32_t v = (int32_t)ev.y;
-            const uint32_t is_s = (uint32_t)v & 1u;
-            if (is_s && is2d) continue;                     // call.rs:394 !is_accidental_2d(&r)
-            call += (int64_t)(v >> 1);
-            clip |= is_s;
-        }
-        const uint64_t key = ((uint64_t)(call + kCallBias) << 1) | clip;
-        const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
+        // slot first: the atomic's round trip overlaps the event loads below
         const bool back = !unphased && h == 2u;
         const unsigned long long old = atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
+        const uint32_t seg = __ldg(seg_off + l), cap = __ldg(seg_off + l + 1) - seg;
+        const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
+        const bool is2d = (hf_j >> 8) != 0u;
+        const uint32_t ne = e1_j - e0_j;
+        int64_t call = 0;
+        uint32_t clip = 0;
+        if (ne <= 8u) {
+            // most reads carry a handful of events: fetch them all at once (independent loads)
+            uint2 ev[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8u; ++q) ev[q] = (q < ne) ? events[e0_j + q] : make_uint2(0u, 0u);
+#pragma unroll
+            for (uint32_t q = 0; q < 8u; ++q) {
+                const int32_t v = (int32_t)ev[q].y;
+                const uint32_t is_s = (uint32_t)v & 1u;
+                // anchor 0 (padding) is never inside a window: the test is start_ext < P (call.rs:388)
+                if (ev[q].x > start_ext && ev[q].x < end_ext && !(is_s && is2d)) {   // call.rs:394 2D gate
+                    call += (int64_t)(v >> 1);
+                    clip |= is_s;
+                }
+            }
+        } else {
+            // first event with pos1 > start_ext
+            uint32_t a = e0_j, b = e1_j;
+            while (a < b) {
+                const uint32_t m = a + ((b - a) >> 1);
+                if (events[m].x > start_ext) b = m; else a = m + 1;
+            }
+            for (uint32_t e = a; e < e1_j; ++e) {
+                const uint2 ev = events[e];
+                if (!(ev.x < end_ext)) break;
+                const int32_t v = (int32_t)ev.y;
+                const uint32_t is_s = (uint32_t)v & 1u;
+                if (is_s && is2d) continue;                 // call.rs:394 !is_accidental_2d(&r)
+                call += (int64_t)(v >> 1);
+                clip |= is_s;
+            }
+        }
+        const uint64_t key = ((uint64_t)(call + kCallBias) << 1) | clip;
         const uint32_t slot_k = back ? (uint32_t)(old >> 32) : (uint32_t)old;
         const uint64_t slot = back ? (uint64_t)seg + (cap - 1u - slot_k) : (uint64_t)seg + slot_k;
         if (slot_k < cap && slot < vals_cap) vals[slot] = key;
@@ -809,9 +848,23 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
 // Phased loci set bit 63 on H2 keys so one sort orders [H1 | H2]; unphased loci split the sorted
 // run at n/2 (call.rs:314).
 
+// Key traits: 64-bit keys are ((call + 2^61) << 1) | clip with the H2 marker in bit 63; when every
+// call of a locus fits 30 bits the same layout is used in 32 bits (bias 2^29, H2 marker bit 31),
+// which halves the shuffles and compares of the sorting network.
+template <typename T> struct KeyTraits;
+template <> struct KeyTraits<uint64_t> {
+    static constexpr uint64_t hap = kKeyHapBit, inf = kKeyInf;
+    static __device__ __forceinline__ int64_t call(uint64_t k) { return (int64_t)((k & ~hap) >> 1) - kCallBias; }
+};
+template <> struct KeyTraits<uint32_t> {
+    static constexpr uint32_t hap = 1u << 31, inf = 0xFFFFFFFFu;
+    static constexpr int32_t bias = 1 << 29;
+    static __device__ __forceinline__ int64_t call(uint32_t k) { return (int64_t)((int32_t)((k & ~hap) >> 1) - bias); }
+};
+
 // all-ascending bitonic network over K striped registers per lane (element i = k*32 + lane)
-template <int K>
-__device__ __forceinline__ void warp_sort(uint64_t (&key)[K])
+template <int K, typename T>
+__device__ __forceinline__ void warp_sort(T (&key)[K])
 {
     constexpr int N = K * 32;
 #pragma unroll
@@ -819,43 +872,41 @@ __device__ __forceinline__ void warp_sort(uint64_t (&key)[K])
         // mirror step: partner = i ^ (blk - 1)
         {
             const int lane_x = (blk - 1) & 31, reg_x = (blk - 1) >> 5;
-            uint64_t other[K];
+            T other[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) other[k] = __shfl_xor_sync(0xffffffffu, key[k ^ reg_x], lane_x);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int i = k * 32 + (int)lane_id();
                 const bool lower = (i & (blk >> 1)) == 0;      // lower half of the mirrored block keeps the min
-                const uint64_t a = key[k], b = other[k];
+                const T a = key[k], b = other[k];
                 key[k] = lower ? (a < b ? a : b) : (a > b ? a : b);
             }
         }
 #pragma unroll
         for (int d = blk >> 2; d >= 1; d >>= 1) {
             const int lane_x = d & 31, reg_x = d >> 5;
-            uint64_t other[K];
+            T other[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) other[k] = __shfl_xor_sync(0xffffffffu, key[k ^ reg_x], lane_x);
+            for (int k = 0; k < K; ++k)
+                other[k] = lane_x ? __shfl_xor_sync(0xffffffffu, key[k ^ reg_x], lane_x) : key[k ^ reg_x];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int i = k * 32 + (int)lane_id();
                 const bool lower = (i & d) == 0;
-                const uint64_t a = key[k], b = other[k];
+                const T a = key[k], b = other[k];
                 key[k] = lower ? (a < b ? a : b) : (a > b ? a : b);
             }
         }
     }
 }
 
-__device__ __forceinline__ int64_t key_call(uint64_t key)
-{
-    return (int64_t)((key & ~kKeyHapBit) >> 1) - kCallBias;
-}
+__device__ __forceinline__ int64_t key_call(uint64_t key) { return KeyTraits<uint64_t>::call(key); }
 
 // median of the sorted sub-range [a, a+n) held striped across the warp. Returns validity;
 // *twice = 2 x median. call.rs:497-522.
-template <int K>
-__device__ __forceinline__ bool warp_median_part(const uint64_t (&key)[K], uint32_t a, uint32_t n, uint32_t support,
+template <int K, typename T>
+__device__ __forceinline__ bool warp_median_part(const T (&key)[K], uint32_t a, uint32_t n, uint32_t support,
                                                  int64_t *twice, bool *panicked)
 {
     *twice = 0;
@@ -866,8 +917,8 @@ __device__ __forceinline__ bool warp_median_part(const uint64_t (&key)[K], uint3
     for (int k = 0; k < K; ++k) {
         const uint32_t i = k * 32 + lane_id();
         const bool in = (i >= a) && (i < a + n);
-        span_b[k] = __ballot_sync(0xffffffffu, in && !(key[k] & 1ull));
-        clip_b[k] = __ballot_sync(0xffffffffu, in && (key[k] & 1ull));
+        span_b[k] = __ballot_sync(0xffffffffu, in && !(key[k] & 1u));
+        clip_b[k] = __ballot_sync(0xffffffffu, in && (key[k] & 1u));
         s += __popc(span_b[k]);
         c += __popc(clip_b[k]);
     }
@@ -886,7 +937,7 @@ __device__ __forceinline__ bool warp_median_part(const uint64_t (&key)[K], uint3
         const uint32_t sel_b = __ballot_sync(0xffffffffu, sel);
         const uint32_t rank = sel_before + __popc(sel_b & lanemask_lt());
         if (sel) {
-            const int64_t v = key_call(key[k]);
+            const int64_t v = KeyTraits<T>::call(key[k]);
             if (rank == t1) contrib += v;
             if (rank == t2) contrib += v;
         }
@@ -907,17 +958,37 @@ __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, ui
 {
     const uint32_t ntot = nf + nb;
     uint64_t key[K];
+    bool small = true;                      // every call fits the 32-bit key layout
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t i = k * 32 + lane_id();
         uint64_t v = kKeyInf;
         if (i < nf) v = vals[seg + i];
         else if (i < ntot) v = vals[seg + cap - nb + (i - nf)] | (phased ? kKeyHapBit : 0ull);
+        if (i < ntot) {
+            const int64_t c = key_call(v);
+            small = small && c >= -(int64_t)KeyTraits<uint32_t>::bias && c < (int64_t)KeyTraits<uint32_t>::bias;
+        }
         key[k] = v;
     }
-    warp_sort<K>(key);
-    const bool v1 = warp_median_part<K>(key, 0, n1, support, t1, panicked);
-    const bool v2 = warp_median_part<K>(key, n1, ntot - n1, support, t2, panicked);
+    bool v1, v2;
+    if (__all_sync(0xffffffffu, small)) {
+        uint32_t k32[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t i = k * 32 + lane_id();
+            const uint64_t v = key[k];
+            const uint32_t body = (uint32_t)((key_call(v) + KeyTraits<uint32_t>::bias) << 1) | (uint32_t)(v & 1ull);
+            k32[k] = (i < ntot) ? (body | ((v & kKeyHapBit) ? KeyTraits<uint32_t>::hap : 0u)) : KeyTraits<uint32_t>::inf;
+        }
+        warp_sort<K, uint32_t>(k32);
+        v1 = warp_median_part<K, uint32_t>(k32, 0, n1, support, t1, panicked);
+        v2 = warp_median_part<K, uint32_t>(k32, n1, ntot - n1, support, t2, panicked);
+    } else {
+        warp_sort<K, uint64_t>(key);
+        v1 = warp_median_part<K, uint64_t>(key, 0, n1, support, t1, panicked);
+        v2 = warp_median_part<K, uint64_t>(key, n1, ntot - n1, support, t2, panicked);
+    }
     *valid = (v1 ? 1u : 0u) | (v2 ? 2u : 0u);
 }
 
