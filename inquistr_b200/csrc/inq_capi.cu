@@ -50,7 +50,7 @@ struct inq_ctx {
     // work buffers
     DevBuf<uint32_t> cand_lo, cand_n, ev_off, delta, lcnt, seg_off, big_list;
     DevBuf<unsigned long long> cursor;
-    DevBuf<uint32_t> wt_sbase;
+    DevBuf<uint32_t> wt_sbase, wtmask;
     DevBuf<uint2> blk, wt;
     DevBuf<uint64_t> desc_scan, desc_wt, vals;
     DevBuf<uint2> evraw;
@@ -164,6 +164,8 @@ int reserve_reads(inq_ctx *ctx, uint64_t nR, uint64_t nC, double growth)
     TRY(ensure(ctx, ctx->cig_off, nR + 1, R + 1, growth));
     // CIGAR stream is padded with zero words up to a tile boundary (+1 tile of slack)
     TRY(ensure(ctx, ctx->cigar, round_up(nC, kTileWords) + kTileWords, C, growth));
+    // one mask word per 512-word warp tile: which 16-word blocks hold the first CIGAR word of a read
+    TRY(ensure(ctx, ctx->wtmask, ctx->cigar.cap / kWarpTileWords + 2, (C + kWarpTileWords - 1) / kWarpTileWords, 1.0));
     return INQ_OK;
 }
 
@@ -227,7 +229,7 @@ void inq_ctx_destroy(inq_ctx *ctx)
     release(ctx->mapq); release(ctx->hp); release(ctx->flags);
     release(ctx->cig_off); release(ctx->cigar);
     release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off);
-    release(ctx->blk); release(ctx->wt); release(ctx->wt_sbase);
+    release(ctx->blk); release(ctx->wt); release(ctx->wt_sbase); release(ctx->wtmask);
     release(ctx->desc_wt); release(ctx->evraw);
     release(ctx->delta); release(ctx->lcnt); release(ctx->seg_off); release(ctx->cursor); release(ctx->big_list);
     release(ctx->desc_scan); release(ctx->vals);
@@ -351,6 +353,14 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_
     }
     const uint64_t C1 = C0 + nw, Cpad = round_up(C1, kTileWords);
     if (Cpad > C1) CU_TRY(ctx, cudaMemsetAsync(ctx->cigar.p + C1, 0, (Cpad - C1) * sizeof(uint32_t), s));
+    {
+        // read-start mask of the warp tiles touched by this batch (k_cigar_scan writes block-table
+        // entries only where a read starts); tiles that hold only new words are cleared first
+        const uint64_t wt_lo = (C0 + kWarpTileWords - 1) / kWarpTileWords, wt_hi = Cpad / kWarpTileWords + 1;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->wtmask.p + wt_lo, 0, (wt_hi - wt_lo + 1) * sizeof(uint32_t), s));
+        k_start_mask<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p + R0, n, ctx->wtmask.p);
+        CU_TRY(ctx, cudaGetLastError());
+    }
     CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D1], s));
     CU_TRY(ctx, cudaStreamSynchronize(s));       // host arrays may be reused by the caller after return
     float ms = 0.f;
@@ -425,7 +435,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         // K2: CIGAR scan -> warp-tile tables + raw events, then prefix sums and the per-read fix-up
         if (ntiles && L) {
             ScanParams sp;
-            sp.blk = ctx->blk.p; sp.wt = ctx->wt.p;
+            sp.blk = ctx->blk.p; sp.wt = ctx->wt.p; sp.wtmask = ctx->wtmask.p;
             sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
             sp.ntiles = ntiles; sp.minlen = minlen;
             { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }

@@ -358,7 +358,9 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 // and k_read_fixup turns these into per-read event lists with absolute anchors.
 // Each CIGAR word is read from HBM exactly once.
 struct ScanParams {
-    uint2 *blk;                   // [ntiles * kScanThreads] {warp-local exclusive consumption, event count} per 16-word block
+    uint2 *blk;                   // [ntiles * kScanThreads] {warp-local exclusive consumption, event count} per 16-word block,
+                                  // written only for blocks that hold a read start (wtmask)
+    const uint32_t *wtmask;       // [n_wt] bit b: block b of the warp tile holds the first CIGAR word of a read
     uint2 *wt;                    // [n_wt + 1] {consumption, events} per warp tile (prefix-summed afterwards)
     uint32_t *wt_sbase;           // [n_wt] storage slot of the warp tile's first event
     uint2 *evraw;
@@ -447,6 +449,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint64_t t = tile_of(it);
         if (t >= p.ntiles) break;
         const uint32_t s = it % kScanStages;
+        const uint32_t wtm = __ldg(p.wtmask + t * kWarpsPerScanCta + warp);   // latency hides behind the wait
         mbar_wait_backoff(&sm.full[s], (it / kScanStages) & 1u, 32u);
         const uint32_t *stage = sm.stage[s];
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
@@ -475,7 +478,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint32_t excl_c = incl_c - c, excl_e = incl_e - ne;
         const uint32_t tot_e = __shfl_sync(0xffffffffu, incl_e, 31);
         const uint64_t gblk = t * kScanThreads + tid;           // global 16-word block index
-        if (!(p.debug & 16u)) p.blk[gblk] = make_uint2(excl_c, excl_e);
+        if ((wtm >> lane) & 1u) p.blk[gblk] = make_uint2(excl_c, excl_e);
 
         // ---- event slots: contiguous per warp tile, taken from a warp-private chunk
         uint64_t sbase = chunk_cur;
@@ -520,6 +523,17 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.freeb[s]);                // this warp is done with stage s
     }
+}
+
+// Marks, per warp tile, the 16-word blocks that hold the first CIGAR word of a read: only those
+// need an entry in the block table (3-4 % of all blocks), which saves ~10 % of the scan's DRAM traffic.
+__global__ void __launch_bounds__(256)
+k_start_mask(const uint64_t *__restrict__ cig_off, uint64_t R, uint32_t *__restrict__ wtmask)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r > R) return;
+    const uint64_t g = cig_off[r];
+    if (g % kWarpTileWords) atomicOr(wtmask + g / kWarpTileWords, 1u << ((g / kLaneWords) & 31u));
 }
 
 // Per read: (1) the index of its first event in CIGAR order and the stream-wide consumption prefix
