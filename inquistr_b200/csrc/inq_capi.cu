@@ -141,7 +141,7 @@ int make_tensor_map(inq_ctx *ctx, uint64_t n_words_padded)
     }
     const cuuint64_t gdim[2] = {32, rows};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {32, (cuuint32_t)(kTileWords / 32)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)(kWarpTileWords / 32)};    // one 2 KB warp tile
     const cuuint32_t estride[2] = {1, 1};
     CUresult r = encode(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->cigar.p, gdim, gstride, box, estride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -384,18 +384,18 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     const uint32_t ntiles = (uint32_t)((C + kTileWords - 1) / kTileWords);
     if ((C + kTileWords - 1) / kTileWords > 0x7FFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "too many CIGAR words");
     const uint32_t loc_scan_tiles = (uint32_t)(((uint64_t)L + 1 + kXsTile - 1) / kXsTile);
-    const uint64_t n_wt = (uint64_t)ntiles * kWarpsPerScanCta;                 // 512-word warp tiles
+    const uint64_t n_wt = (uint64_t)ntiles * (kTileWords / kWarpTileWords);    // 512-word warp tiles
     const uint32_t wt_scan_tiles = (uint32_t)((n_wt + kXsTile - 1) / kXsTile);
     TRY(ensure(ctx, ctx->cand_lo, R));
     TRY(ensure(ctx, ctx->cand_n, R));
     TRY(ensure(ctx, ctx->ev_off, R + 1));
-    TRY(ensure(ctx, ctx->blk, (uint64_t)ntiles * kScanThreads + 1));
+    TRY(ensure(ctx, ctx->blk, n_wt * 32 + 1));
     TRY(ensure(ctx, ctx->wt, n_wt + 2));
     TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
     TRY(ensure(ctx, ctx->desc_wt, 2 * ((uint64_t)wt_scan_tiles + 1)));
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
-    const unsigned scan_grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
-    const uint64_t raw_slack = (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kWarpsPerScanCta * kEvChunk;
+    const unsigned scan_grid = (unsigned)std::min<uint64_t>((n_wt + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
+    const uint64_t raw_slack = (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kScanWarps * kEvChunk;
     if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 16 + 4096));
     // warp-tile storage hands out kEvChunk-slot chunks: every resident warp may strand one chunk
     if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, ctx->events.cap + raw_slack));
@@ -437,7 +437,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             ScanParams sp;
             sp.blk = ctx->blk.p; sp.wt = ctx->wt.p; sp.wtmask = ctx->wtmask.p;
             sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
-            sp.ntiles = ntiles; sp.minlen = minlen;
+            sp.n_wt = n_wt; sp.minlen = minlen;
             { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
             k_cigar_scan<<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;

@@ -23,13 +23,7 @@ namespace inq {
 // ----------------------------------------------------------------------------------------------
 // constants
 constexpr int kWarp = 32;
-constexpr int kTileWords = 8192;            // CIGAR words per tile (32 KB)
-constexpr int kScanThreads = 512;           // 16 compute warps, 512 words per warp, 16 per lane
-constexpr int kScanStages = 3;              // smem ring of bulk-copied tiles
-constexpr int kQuadsPerTile = kTileWords / 4;
-constexpr int kWarpsPerScanCta = kScanThreads / kWarp;
-constexpr int kQuadsPerWarp = kQuadsPerTile / kWarpsPerScanCta;   // 128
-constexpr int kSlabs = kQuadsPerWarp / kWarp;                     // 4 x (32 lanes x uint4)
+constexpr int kTileWords = 8192;            // padding granularity of the device CIGAR stream (32 KB)
 
 constexpr uint32_t kFlagBadHp = 1u << 0;
 constexpr uint32_t kFlagMedianEmpty = 1u << 1;
@@ -345,9 +339,9 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 }
 
 // ----------------------------------------------------------------------------------------------
-// K2: CIGAR scan. Persistent CTAs stream 32 KB tiles of the flat packed-CIGAR array through a
-// 3-stage shared-memory ring filled by TMA (2-D tensor map, 128B swizzle). Every compute warp owns
-// one 512-word "warp tile" per tile, each lane 16 consecutive words. One pass over the words gives
+// K2: CIGAR scan. Persistent warps stream 2 KB "warp tiles" (512 words) of the flat packed-CIGAR array
+// through per-warp 3-stage shared-memory rings filled by TMA (2-D tensor map, 128B swizzle); each lane
+// owns 16 consecutive words. One pass over the words gives
 // the lane's reference consumption (call.rs:384-392,404) and its event mask (I/D/S ops longer than
 // minlen, call.rs:388,394,400); two warp scans turn that into warp-local prefixes. Nothing in this
 // kernel depends on another CTA or on read boundaries: it writes
@@ -358,7 +352,7 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 // and k_read_fixup turns these into per-read event lists with absolute anchors.
 // Each CIGAR word is read from HBM exactly once.
 struct ScanParams {
-    uint2 *blk;                   // [ntiles * kScanThreads] {warp-local exclusive consumption, event count} per 16-word block,
+    uint2 *blk;                   // [n_wt * 32] {warp-local exclusive consumption, event count} per 16-word block,
                                   // written only for blocks that hold a read start (wtmask)
     const uint32_t *wtmask;       // [n_wt] bit b: block b of the warp tile holds the first CIGAR word of a read
     uint2 *wt;                    // [n_wt + 1] {consumption, events} per warp tile (prefix-summed afterwards)
@@ -366,15 +360,25 @@ struct ScanParams {
     uint2 *evraw;
     DevCounters *ctr;
     uint64_t raw_cap;             // capacity of evraw (slots)
-    uint32_t ntiles;
+    uint64_t n_wt;                // warp tiles to scan
     uint32_t minlen;
     uint32_t debug;               // timing experiments only (INQ_SCAN_DEBUG): results are wrong when != 0
 };
 
-constexpr int kLaneWords = kTileWords / kScanThreads;   // 16 consecutive words per compute lane
-constexpr int kWarpTileWords = 32 * kLaneWords;         // 512
-constexpr int kCtaThreads = kScanThreads + 32;          // 16 compute warps + 1 TMA producer warp
-constexpr uint32_t kOpLut = 0x18Du | (0x16u << 16);     // bit op: consumes reference; bit 16+op: I/D/S
+constexpr int kLaneWords = 16;                          // consecutive CIGAR words per lane
+constexpr int kWarpTileWords = 32 * kLaneWords;         // 512 words = 2 KB = one TMA box
+#ifndef INQ_SCAN_WARPS
+#define INQ_SCAN_WARPS 16
+#endif
+#ifndef INQ_WARP_STAGES
+#define INQ_WARP_STAGES 3
+#endif
+#ifndef INQ_SCAN_MIN_CTAS
+#define INQ_SCAN_MIN_CTAS 2
+#endif
+constexpr int kScanWarps = INQ_SCAN_WARPS;              // warps per CTA, each fully autonomous
+constexpr int kCtaThreads = kScanWarps * 32;
+constexpr int kWarpStages = INQ_WARP_STAGES;             // per-warp ring of TMA boxes
 // 64-bit LUT read through one wrap-mode funnel shift by 2*op: result bit 0 = op consumes the reference
 // (M,D,N,=,X: lo bit 2*op), result bit 31 = op is I, D or S (hi bit 2*op-1)
 constexpr uint32_t kOpLutLo = (1u << 0) | (1u << 4) | (1u << 6) | (1u << 14) | (1u << 16);
@@ -382,13 +386,12 @@ constexpr uint32_t kOpLutHi = (1u << 1) | (1u << 3) | (1u << 7);
 constexpr uint32_t kEvChunk = 1024;                     // event slots a warp takes per atomic
 
 struct ScanSmem {
-    alignas(1024) uint32_t stage[kScanStages][kTileWords];   // 128B-swizzled by the TMA tensor map
-    alignas(8) uint64_t full[kScanStages];  // TMA landed                     (tx bytes)
-    uint64_t freeb[kScanStages];            // compute warps done with stage  (one arrival per warp)
+    alignas(1024) uint32_t stage[kScanWarps][kWarpStages][kWarpTileWords];   // 128B-swizzled by the TMA tensor map
+    alignas(8) uint64_t full[kScanWarps][kWarpStages];                        // TMA landed (tx bytes)
 };
 constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align the swizzled stages to 1 KB
 
-// word index inside a tile -> word index in the 128B-swizzled stage buffer
+// word index inside a warp tile -> word index in the 128B-swizzled stage buffer
 // (16-byte chunk index bits [2:4] ^= 128-byte row index bits [5:7])
 __device__ __forceinline__ uint32_t swz(uint32_t idx) { return idx ^ (((idx >> 5) & 7u) << 2); }
 
@@ -403,55 +406,46 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 2)
+// Every warp is an independent pipeline: it owns warp tiles gwid, gwid + W, gwid + 2W, ... (W = warps
+// in the grid), a 3-stage ring of 2 KB shared-memory boxes that it fills itself with TMA, and the
+// mbarriers of that ring. There is no block-level synchronisation and no producer warp.
+__global__ void __launch_bounds__(kCtaThreads, INQ_SCAN_MIN_CTAS)
 k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // keep the pointer in the shared address space (LDS/STS, not generic loads)
     ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr uint32_t kTileBytes = kTileWords * 4;
-    constexpr uint32_t kRowsPerTile = kTileWords / 32;          // 128-byte rows
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t kBoxBytes = kWarpTileWords * 4;
+    constexpr uint32_t kRowsPerBox = kWarpTileWords / 32;       // 128-byte rows
+    const uint64_t gwid = (uint64_t)blockIdx.x * kScanWarps + warp, stride = (uint64_t)gridDim.x * kScanWarps;
+    uint64_t *full = sm.full[warp];
 
-    if (tid == 0) {
-        for (int s = 0; s < kScanStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.freeb[s], kWarpsPerScanCta); }
+    if (lane == 0) {
+        for (int s = 0; s < kWarpStages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
-    }
-    __syncthreads();
-    const uint64_t stride = gridDim.x;
-    auto tile_of = [&](uint32_t itx) -> uint64_t { return blockIdx.x + (uint64_t)itx * stride; };
-
-    if (warp == kWarpsPerScanCta) {
-        // =============================== TMA producer warp ===============================
-        if (lane == 0) {
-            for (uint32_t it = 0;; ++it) {
-                const uint64_t t = tile_of(it);
-                if (t >= p.ntiles) break;
-                const uint32_t s = it % kScanStages;
-                if (it >= (uint32_t)kScanStages) {
-                    mbar_wait_backoff(&sm.freeb[s], ((it / kScanStages) - 1u) & 1u, 256u);
-                    fence_proxy_async();
-                }
-                mbar_expect_tx(&sm.full[s], kTileBytes);
-                tma_load_tile(sm.stage[s], &tmap, (uint32_t)t * kRowsPerTile, &sm.full[s]);
+        for (int s = 0; s < kWarpStages; ++s) {
+            const uint64_t gw = gwid + (uint64_t)s * stride;
+            if (gw < p.n_wt) {
+                mbar_expect_tx(&full[s], kBoxBytes);
+                tma_load_tile(sm.stage[warp][s], &tmap, (uint32_t)gw * kRowsPerBox, &full[s]);
             }
         }
-        return;
     }
+    __syncwarp();
 
-    // =============================== compute warps ===============================
     const uint32_t thr = (p.minlen << 4) | 15u;                 // (w >> 4) > minlen  <=>  w > thr
-    // this thread's 16 consecutive words: 128-byte row tid/2, chunks 4*(tid&1)+j, swizzled
-    const uint32_t rowq = (tid >> 1) * 8, x0 = ((tid & 1u) << 2) ^ ((tid >> 1) & 7u);
+    // this lane's 16 consecutive words: 128-byte row lane/2, chunks 4*(lane&1)+j, swizzled
+    const uint32_t rowq = (lane >> 1) * 8, x0 = ((lane & 1u) << 2) ^ ((lane >> 1) & 7u);
     uint64_t chunk_cur = 0, chunk_end = 0;                      // this warp's private range of event slots
 
     for (uint32_t it = 0;; ++it) {
-        const uint64_t t = tile_of(it);
-        if (t >= p.ntiles) break;
-        const uint32_t s = it % kScanStages;
-        const uint32_t wtm = __ldg(p.wtmask + t * kWarpsPerScanCta + warp);   // latency hides behind the wait
-        mbar_wait_backoff(&sm.full[s], (it / kScanStages) & 1u, 32u);
-        const uint32_t *stage = sm.stage[s];
+        const uint64_t gw = gwid + (uint64_t)it * stride;       // global warp-tile index
+        if (gw >= p.n_wt) break;
+        const uint32_t s = it % kWarpStages;
+        const uint32_t wtm = __ldg(p.wtmask + gw);              // latency hides behind the wait
+        mbar_wait_backoff(&full[s], (it / kWarpStages) & 1u, 32u);
+        const uint32_t *stage = sm.stage[warp][s];
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
 
         // ---- one pass over the lane's 16 words. evmask: bit i <-> word i is an event;
@@ -464,7 +458,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                // one funnel shift in wrap mode indexes the 2-bit LUT by 2*op without masking the op first
+                // one funnel shift in wrap mode indexes the LUT by 2*op without masking the op first
                 const uint32_t w = w4[k], lut = __funnelshift_r(kOpLutLo, kOpLutHi, w + w);
                 const bool ev = ((int32_t)lut < 0) && (w > thr);
                 evmask = ev ? (evmask | (1u << (j * 4 + k))) : evmask;
@@ -477,8 +471,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
         const uint32_t excl_c = incl_c - c, excl_e = incl_e - ne;
         const uint32_t tot_e = __shfl_sync(0xffffffffu, incl_e, 31);
-        const uint64_t gblk = t * kScanThreads + tid;           // global 16-word block index
-        if ((wtm >> lane) & 1u) p.blk[gblk] = make_uint2(excl_c, excl_e);
+        if ((wtm >> lane) & 1u) p.blk[gw * 32 + lane] = make_uint2(excl_c, excl_e);
 
         // ---- event slots: contiguous per warp tile, taken from a warp-private chunk
         uint64_t sbase = chunk_cur;
@@ -494,7 +487,6 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             chunk_cur += tot_e;
         }
         if (lane == 31 && !(p.debug & 16u)) {
-            const uint64_t gw = t * kWarpsPerScanCta + warp;    // global warp-tile index
             p.wt[gw] = make_uint2(incl_c, incl_e);
             p.wt_sbase[gw] = (uint32_t)sbase;
         }
@@ -505,7 +497,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             do {
                 const uint32_t bit = 31u - (uint32_t)__clz(evmask);
                 evmask ^= 1u << bit;
-                const uint32_t idx = tid * kLaneWords + bit;
+                const uint32_t idx = lane * kLaneWords + bit;
                 const uint32_t w = stage[swz(idx)];
                 uint32_t s_in = clast;                          // captured above for the last event
                 if (!first) {
@@ -520,8 +512,15 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
                 else atomicOr(&p.ctr->flags, kFlagEventOverflow);
             } while (evmask);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.freeb[s]);                // this warp is done with stage s
+        __syncwarp();                                           // every lane is done with stage s
+        if (lane == 0) {
+            const uint64_t nxt = gwid + (uint64_t)(it + kWarpStages) * stride;
+            if (nxt < p.n_wt) {
+                fence_proxy_async();
+                mbar_expect_tx(&full[s], kBoxBytes);
+                tma_load_tile(sm.stage[warp][s], &tmap, (uint32_t)nxt * kRowsPerBox, &full[s]);
+            }
+        }
     }
 }
 
