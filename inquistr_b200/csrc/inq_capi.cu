@@ -469,7 +469,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         if (work) {
             k_pair_eval<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->events.p,
                                                                    ctx->ev_off.p, ctx->events.cap, ctx->seg_off.p, ctx->cursor.p,
-                                                                   ctx->vals.p, ctx->vals.cap, ctx->d_ctr);
+                                                                   ctx->vals.p, ctx->vals.cap, ctx->d_ctr, getenv("INQ_PAIR_DEBUG") ? (uint32_t)atoi(getenv("INQ_PAIR_DEBUG")) : 0u);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_PAIRS], s));

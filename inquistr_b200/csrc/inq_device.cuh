@@ -730,7 +730,7 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             const uint32_t *__restrict__ cand_n, const uint2 *__restrict__ events,
             const uint32_t *__restrict__ ev_off, uint64_t ev_cap, const uint32_t *__restrict__ seg_off,
             unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
-            DevCounters *__restrict__ ctr)
+            DevCounters *__restrict__ ctr, uint32_t debug)
 {
     // A warp owns 32 consecutive reads; their candidates are flattened and dealt to the lanes
     // 32 at a time (reads have 0..hundreds of candidates, a per-read loop leaves most lanes idle).
@@ -793,14 +793,15 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         atomicOr(&s_joined[wid], 1u << j);
         // slot first: the atomic's round trip overlaps the event loads below
         const bool back = !unphased && h == 2u;
-        const unsigned long long old = atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
+        const unsigned long long old = (debug & 1u) ? 0ull : atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
         const uint32_t seg = __ldg(seg_off + l), cap = __ldg(seg_off + l + 1) - seg;
         const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
         const bool is2d = (hf_j >> 8) != 0u;
         const uint32_t ne = e1_j - e0_j;
         int64_t call = 0;
         uint32_t clip = 0;
-        if (ne <= 8u) {
+        if (debug & 4u) {
+        } else if (ne <= 8u) {
             // most reads carry a handful of events: fetch them all at once (independent loads)
             uint2 ev[8];
 #pragma unroll
@@ -835,7 +836,8 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         const uint64_t key = ((uint64_t)(call + kCallBias) << 1) | clip;
         const uint32_t slot_k = back ? (uint32_t)(old >> 32) : (uint32_t)old;
         const uint64_t slot = back ? (uint64_t)seg + (cap - 1u - slot_k) : (uint64_t)seg + slot_k;
-        if (slot_k < cap && slot < vals_cap) vals[slot] = key;
+        if (debug & 2u) {
+        } else if (slot_k < cap && slot < vals_cap) vals[slot] = key;
         else atomicOr(&ctr->flags, kFlagValsOverflow);
     }
     __syncwarp();
