@@ -49,6 +49,12 @@ int BamHeader::tid(const std::string &name) const
 
 BamReader::~BamReader()
 {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    if (producer_.joinable()) producer_.join();
     if (fp_) fclose(fp_);
 }
 
@@ -57,15 +63,13 @@ bool BamReader::open(const std::string &path, int threads)
     threads_ = std::max(1, threads);
     fp_ = fopen(path.c_str(), "rb");
     if (!fp_) { err_ = "cannot open " + path; return false; }
+    producer_ = std::thread(&BamReader::producer, this);
     return parse_header();
 }
 
-// read and inflate the next batch of BGZF blocks
-bool BamReader::fill()
+// read and inflate one batch of BGZF blocks (runs on the producer thread)
+bool BamReader::read_batch(Batch &out)
 {
-    buf_.clear();
-    cur_ = 0;
-    if (eof_) return false;
     constexpr size_t kBatchBlocks = 1024;          // up to 64 MB inflated per batch
     std::vector<uint8_t> comp;
     std::vector<Block> blocks;
@@ -73,23 +77,23 @@ bool BamReader::fill()
     while (blocks.size() < kBatchBlocks) {
         uint8_t h[12];
         size_t n = fread(h, 1, 12, fp_);
-        if (n == 0) { eof_ = true; break; }
-        if (n != 12 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { err_ = "not a BGZF block (bad gzip header)"; return false; }
+        if (n == 0) { out.eof = true; break; }
+        if (n != 12 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { out.err = "not a BGZF block (bad gzip header)"; return false; }
         const uint16_t xlen = rd16(h + 10);
-        std::vector<uint8_t> extra(xlen);
-        if (fread(extra.data(), 1, xlen, fp_) != xlen) { err_ = "truncated BGZF extra field"; return false; }
+        uint8_t extra[65536];
+        if (fread(extra, 1, xlen, fp_) != xlen) { out.err = "truncated BGZF extra field"; return false; }
         int bsize = -1;
-        for (size_t i = 0; i + 4 <= extra.size();) {
+        for (size_t i = 0; i + 4 <= xlen;) {
             const uint16_t slen = rd16(&extra[i + 2]);
-            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= extra.size()) bsize = rd16(&extra[i + 4]);
+            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = rd16(&extra[i + 4]);
             i += 4 + slen;
         }
-        if (bsize < 0) { err_ = "BGZF block without BC subfield"; return false; }
+        if (bsize < 0) { out.err = "BGZF block without BC subfield"; return false; }
         const long remaining = (long)bsize + 1 - 12 - xlen;     // deflate payload + crc32 + isize
-        if (remaining < 8) { err_ = "corrupt BGZF block size"; return false; }
+        if (remaining < 8) { out.err = "corrupt BGZF block size"; return false; }
         const size_t off = comp.size();
         comp.resize(off + (size_t)remaining);
-        if (fread(&comp[off], 1, (size_t)remaining, fp_) != (size_t)remaining) { err_ = "truncated BGZF block"; return false; }
+        if (fread(&comp[off], 1, (size_t)remaining, fp_) != (size_t)remaining) { out.err = "truncated BGZF block"; return false; }
         Block b;
         b.in_off = off;
         b.in_len = (size_t)remaining - 8;
@@ -99,16 +103,17 @@ bool BamReader::fill()
         out_total += b.out_len;
         blocks.push_back(b);
     }
-    if (blocks.empty()) return false;
-    buf_.resize(out_total);
+    out.data.resize(kSlack + out_total);
+    if (blocks.empty()) return true;
     std::atomic<size_t> next{0};
     std::atomic<int> bad{0};
+    uint8_t *base = out.data.data() + kSlack;
     auto work = [&]() {
         for (;;) {
             size_t i = next.fetch_add(1);
             if (i >= blocks.size()) break;
             const Block &b = blocks[i];
-            if (!inflate_block(&comp[b.in_off], b.in_len, buf_.data() + b.out_off, b.out_len, b.crc)) bad.store(1);
+            if (!inflate_block(&comp[b.in_off], b.in_len, base + b.out_off, b.out_len, b.crc)) bad.store(1);
         }
     };
     const int nt = (int)std::min<size_t>((size_t)threads_, blocks.size());
@@ -116,68 +121,107 @@ bool BamReader::fill()
     for (int t = 1; t < nt; ++t) th.emplace_back(work);
     work();
     for (auto &t : th) t.join();
-    if (bad.load()) { err_ = "BGZF inflate / CRC failure"; return false; }
-    total_out_ += out_total;
+    if (bad.load()) { out.err = "BGZF inflate / CRC failure"; return false; }
     return true;
 }
 
-bool BamReader::read_exact(void *dst, size_t n)
+void BamReader::producer()
 {
-    uint8_t *d = static_cast<uint8_t *>(dst);
-    while (n) {
-        if (cur_ == buf_.size()) {
-            if (!fill()) return false;
-            if (buf_.empty()) continue;          // empty BGZF block (EOF marker) in the middle
+    for (;;) {
+        Batch b;
+        const bool ok = read_batch(b);
+        const bool last = !ok || b.eof;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || queue_.size() < 2; });     // double buffering
+            if (stop_) return;
+            queue_.push_back(std::move(b));
         }
-        const size_t k = std::min(n, buf_.size() - cur_);
-        memcpy(d, buf_.data() + cur_, k);
-        cur_ += k;
-        d += k;
-        n -= k;
+        cv_.notify_all();
+        if (last) return;
+    }
+}
+
+// make the next batch current, keeping the unconsumed tail of the old one in front of it
+bool BamReader::next_batch()
+{
+    if (eof_) return false;
+    Batch nb;
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !queue_.empty(); });
+        nb = std::move(queue_.front());
+        queue_.pop_front();
+    }
+    cv_.notify_all();
+    if (!nb.err.empty()) { err_ = nb.err; eof_ = true; return false; }
+    const size_t tail = end_ - cur_;
+    const size_t payload = nb.data.size() - kSlack;
+    total_out_ += payload;
+    if (nb.eof) eof_ = true;
+    if (tail <= kSlack) {
+        if (tail) memcpy(nb.data.data() + kSlack - tail, cur_batch_.data.data() + cur_, tail);
+        cur_batch_ = std::move(nb);
+        cur_ = kSlack - tail;
+        end_ = cur_batch_.data.size();
+    } else {                                        // a record larger than the slack: concatenate
+        std::vector<uint8_t> joined(kSlack + tail + payload);
+        memcpy(joined.data() + kSlack, cur_batch_.data.data() + cur_, tail);
+        memcpy(joined.data() + kSlack + tail, nb.data.data() + kSlack, payload);
+        cur_batch_.data = std::move(joined);
+        cur_batch_.eof = nb.eof;
+        cur_ = kSlack;
+        end_ = cur_batch_.data.size();
+    }
+    return payload > 0 || !eof_;
+}
+
+bool BamReader::ensure_bytes(size_t n)
+{
+    while (end_ - cur_ < n) {
+        if (eof_) return false;
+        next_batch();
+        if (!err_.empty()) return false;
     }
     return true;
 }
 
 bool BamReader::parse_header()
 {
-    uint8_t magic[4];
-    if (!read_exact(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM file (bad magic)"; return false; }
-    uint8_t b4[4];
-    if (!read_exact(b4, 4)) { err_ = "truncated BAM header"; return false; }
-    const uint32_t l_text = rd32(b4);
-    header_.text.resize(l_text);
-    if (l_text && !read_exact(&header_.text[0], l_text)) { err_ = "truncated BAM header text"; return false; }
-    if (!read_exact(b4, 4)) { err_ = "truncated BAM header"; return false; }
-    const uint32_t n_ref = rd32(b4);
+    if (!ensure_bytes(12) || memcmp(cur_batch_.data.data() + cur_, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM file (bad magic)"; return false; }
+    const uint32_t l_text = rd32(cur_batch_.data.data() + cur_ + 4);
+    cur_ += 8;
+    if (!ensure_bytes((size_t)l_text + 4)) { if (err_.empty()) err_ = "truncated BAM header text"; return false; }
+    header_.text.assign((const char *)cur_batch_.data.data() + cur_, l_text);
+    cur_ += l_text;
+    const uint32_t n_ref = rd32(cur_batch_.data.data() + cur_);
+    cur_ += 4;
     for (uint32_t i = 0; i < n_ref; ++i) {
-        if (!read_exact(b4, 4)) { err_ = "truncated BAM reference list"; return false; }
-        const uint32_t l_name = rd32(b4);
-        std::string name(l_name, '\0');
-        if (l_name && !read_exact(&name[0], l_name)) { err_ = "truncated BAM reference list"; return false; }
+        if (!ensure_bytes(4)) { if (err_.empty()) err_ = "truncated BAM reference list"; return false; }
+        const uint32_t l_name = rd32(cur_batch_.data.data() + cur_);
+        cur_ += 4;
+        if (!ensure_bytes((size_t)l_name + 4)) { if (err_.empty()) err_ = "truncated BAM reference list"; return false; }
+        std::string name((const char *)cur_batch_.data.data() + cur_, l_name);
         if (!name.empty() && name.back() == '\0') name.pop_back();
-        if (!read_exact(b4, 4)) { err_ = "truncated BAM reference list"; return false; }
+        cur_ += l_name;
         header_.ref_names.push_back(name);
-        header_.ref_lens.push_back((int64_t)rd32(b4));
+        header_.ref_lens.push_back((int64_t)rd32(cur_batch_.data.data() + cur_));
+        cur_ += 4;
     }
     return true;
 }
 
 bool BamReader::next(BamRecordView &rec)
 {
-    uint8_t b4[4];
-    // EOF is only legal at a record boundary
-    if (cur_ == buf_.size()) {
-        while (true) {
-            if (!fill()) return false;
-            if (!buf_.empty()) break;
-        }
+    if (!ensure_bytes(4)) {
+        if (err_.empty() && end_ != cur_) err_ = "truncated BAM record";
+        return false;
     }
-    if (!read_exact(b4, 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
-    const uint32_t block_size = rd32(b4);
+    const uint32_t block_size = rd32(cur_batch_.data.data() + cur_);
     if (block_size < 32) { err_ = "corrupt BAM record"; return false; }
-    rec_.resize(block_size);
-    if (!read_exact(rec_.data(), block_size)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
-    const uint8_t *p = rec_.data();
+    if (!ensure_bytes((size_t)block_size + 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
+    const uint8_t *p = cur_batch_.data.data() + cur_ + 4;       // record body, parsed in place
+    cur_ += (size_t)block_size + 4;
     rec.tid = rdi32(p);
     rec.pos = rdi32(p + 4);
     const uint32_t l_read_name = p[8];
@@ -188,7 +232,7 @@ bool BamReader::next(BamRecordView &rec)
     size_t off = 32 + l_read_name;
     const size_t cigar_off = off;
     off += (size_t)n_cigar * 4;
-    off += (l_seq + 1) / 2 + l_seq;
+    off += ((size_t)l_seq + 1) / 2 + l_seq;
     if (off > block_size) { err_ = "corrupt BAM record (fields exceed block)"; return false; }
 
     // aux: HP, SA, CG

@@ -5,9 +5,13 @@
 // SEQ/QUAL are skipped, never copied.
 #pragma once
 
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace inqhost {
@@ -56,20 +60,35 @@ public:
     uint64_t bytes_inflated() const { return total_out_; }
 
 private:
-    bool fill();                                   // inflate the next batch of blocks into buf_
-    bool read_exact(void *dst, size_t n);          // from the inflated stream, across batches
+    // A batch of inflated BGZF blocks. `data` starts with kSlack unused bytes so that the unconsumed
+    // tail of the previous batch can be moved in front of it without copying the batch.
+    struct Batch {
+        std::vector<uint8_t> data;
+        bool eof = false;
+        std::string err;
+    };
+    static constexpr size_t kSlack = 8u << 20;
+    bool next_batch();                             // make the next batch current (tail preserved)
+    bool ensure_bytes(size_t n);                   // at least n unconsumed bytes are contiguous at cur_
     bool parse_header();
+    void producer();                               // background thread: read + inflate batches
+    bool read_batch(Batch &b);
 
     FILE *fp_ = nullptr;
     int threads_ = 1;
     BamHeader header_;
     std::string err_;
-    std::vector<uint8_t> buf_;                     // inflated bytes of the current batch
-    size_t cur_ = 0;
+    Batch cur_batch_;
+    size_t cur_ = 0, end_ = 0;                     // unconsumed window inside cur_batch_.data
     bool eof_ = false;
     uint64_t total_out_ = 0;
-    std::vector<uint8_t> rec_;                     // current record body
-    std::vector<uint32_t> cg_;                     // aligned copy of a CG:B,I long CIGAR
+    std::vector<uint32_t> cg_;                     // aligned copy of the record's CIGAR
+
+    std::thread producer_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Batch> queue_;
+    bool stop_ = false;
 };
 
 // call.rs:461-477

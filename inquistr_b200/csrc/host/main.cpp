@@ -10,6 +10,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cinttypes>
 #include <cmath>
 #include <cstdio>
@@ -95,6 +96,26 @@ Args parse_args(int argc, char **argv)
         exit(v.empty() ? 2 : 0);
     }
     if (v[0] == "-V" || v[0] == "--version") { printf("inquistr-b200 %s\n", inq_version()); exit(0); }
+    if (v[0] == "bamstat" && v.size() >= 2) {
+        // extension: scan a BAM with the host reader only (no GPU): record counts and inflate rate
+        BamReader rd;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!rd.open(v[1], (int)std::max(1u, std::thread::hardware_concurrency()))) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
+        BamRecordView r;
+        uint64_t n = 0, words = 0, hp = 0, sa = 0, d2 = 0;
+        while (rd.next(r)) {
+            ++n; words += r.n_cigar; hp += r.hp_type != HpType::Absent; sa += r.has_sa;
+            bool pn = false;
+            d2 += is_accidental_2d(r, &pn);
+        }
+        if (!rd.error().empty()) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("{\"refs\": %zu, \"records\": %llu, \"cigar_words\": %llu, \"hp_tagged\": %llu, \"sa_tagged\": %llu, \"accidental_2d\": %llu, "
+               "\"bytes_inflated\": %llu, \"seconds\": %.3f, \"inflate_GBps\": %.3f}\n", rd.header().ref_names.size(),
+               (unsigned long long)n, (unsigned long long)words, (unsigned long long)hp, (unsigned long long)sa, (unsigned long long)d2,
+               (unsigned long long)rd.bytes_inflated(), s, rd.bytes_inflated() / 1e9 / s);
+        exit(0);
+    }
     if (v[0] != "call") usage_error("unrecognized subcommand '" + v[0] + "' (only `call` is implemented in this build)");
     if (v.size() == 1) { fputs(kHelp, stderr); exit(2); }                 // arg_required_else_help (main.rs:27)
     bool have_bam = false;

@@ -359,3 +359,174 @@ int synth_cigars(const synth_cfg *c, uint64_t R, const uint64_t *cig_off, uint32
 }
 
 }  // extern "C"
+
+// ---- BAM writer (benchmark input for the C++ host): multi-threaded BGZF deflate -----------------
+#include <zlib.h>
+#include <cstdio>
+#include <string>
+
+namespace {
+
+struct OutBlock { std::vector<uint8_t> data; };
+
+void put32(std::vector<uint8_t> &v, uint32_t x) { for (int i = 0; i < 4; ++i) v.push_back((uint8_t)(x >> (8 * i))); }
+void put16(std::vector<uint8_t> &v, uint16_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); }
+
+int reg2bin(int64_t beg, int64_t end)
+{
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+// one BGZF block (<= 65280 payload bytes)
+void bgzf_compress(const uint8_t *src, size_t n, int level, std::vector<uint8_t> &out)
+{
+    out.resize(18 + compressBound((uLong)n) + 8);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = const_cast<Bytef *>(src);
+    zs.avail_in = (uInt)n;
+    zs.next_out = out.data() + 18;
+    zs.avail_out = (uInt)(out.size() - 18 - 8);
+    deflate(&zs, Z_FINISH);
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    const uint8_t hdr[16] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0};
+    memcpy(out.data(), hdr, 16);
+    const uint16_t bsize = (uint16_t)(clen + 25);
+    out[16] = (uint8_t)bsize;
+    out[17] = (uint8_t)(bsize >> 8);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)n);
+    uint8_t *t = out.data() + 18 + clen;
+    for (int i = 0; i < 4; ++i) t[i] = (uint8_t)(crc >> (8 * i));
+    for (int i = 0; i < 4; ++i) t[4 + i] = (uint8_t)((uint32_t)n >> (8 * i));
+    out.resize(18 + clen + 8);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Writes the SoA read set as a coordinate-sorted BAM. with_seq != 0 adds pseudo-random SEQ and constant
+// QUAL of the query length implied by the CIGAR (realistic record sizes for ingest benchmarks).
+// Reads flagged accidental-2D get an SA tag the host must classify as 2D. HP is written as type C.
+// Returns bytes written, or -1.
+int64_t synth_write_bam(const char *path, int32_t n_contigs, const char *const *names, const int64_t *lens, uint64_t R,
+                        const int32_t *contig, const int32_t *rs, const int32_t *re, const uint8_t *mapq, const uint8_t *hp,
+                        const uint8_t *flags, const uint64_t *cig_off, const uint32_t *cigar, int with_seq, int level,
+                        int threads)
+{
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return -1;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 128));
+    // header
+    std::vector<uint8_t> head;
+    std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
+    for (int c = 0; c < n_contigs; ++c) text += std::string("@SQ\tSN:") + names[c] + "\tLN:" + std::to_string(lens[c]) + "\n";
+    head.insert(head.end(), {'B', 'A', 'M', 1});
+    put32(head, (uint32_t)text.size());
+    head.insert(head.end(), text.begin(), text.end());
+    put32(head, (uint32_t)n_contigs);
+    for (int c = 0; c < n_contigs; ++c) {
+        const std::string nm = names[c];
+        put32(head, (uint32_t)nm.size() + 1);
+        head.insert(head.end(), nm.begin(), nm.end());
+        head.push_back(0);
+        put32(head, (uint32_t)lens[c]);
+    }
+    int64_t written = 0;
+    auto emit_stream = [&](const std::vector<uint8_t> &raw) {
+        // compress a raw byte stream as consecutive BGZF blocks, in parallel
+        const size_t kPay = 65280;
+        const size_t nb = (raw.size() + kPay - 1) / kPay;
+        std::vector<std::vector<uint8_t>> comp(nb);
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= nb) break;
+                const size_t off = i * kPay, n = std::min(kPay, raw.size() - off);
+                bgzf_compress(raw.data() + off, n, level, comp[i]);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        for (auto &c : comp) { fwrite(c.data(), 1, c.size(), fp); written += (int64_t)c.size(); }
+    };
+    emit_stream(head);
+    // records, in chunks of ~256 MB of raw bytes
+    std::vector<uint8_t> raw;
+    raw.reserve(300u << 20);
+    for (uint64_t i = 0; i < R; ++i) {
+        const uint64_t a = cig_off[i], b = cig_off[i + 1];
+        const uint32_t ncig = (uint32_t)(b - a);
+        uint32_t l_seq = 0;
+        if (with_seq)
+            for (uint64_t k = a; k < b; ++k) {
+                const uint32_t op = cigar[k] & 15u;
+                if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) l_seq += cigar[k] >> 4;
+            }
+        char name[32];
+        const int ln = snprintf(name, sizeof(name), "r%llu", (unsigned long long)i) + 1;
+        Rng rr(mix(0xBA11ull, i));
+        const bool rev = rr.next() & 1;
+        std::string sa;
+        if (flags[i] & 1) {
+            const int64_t mid = ((int64_t)rs[i] + re[i]) / 2 + 1;
+            sa = std::string(names[contig[i]]) + "," + std::to_string(mid) + "," + (rev ? "+" : "-") + "," +
+                 std::to_string(std::max<int64_t>(re[i] - mid, 1)) + "M10S,60,0;";
+        }
+        const bool long_cigar = ncig > 65535;
+        size_t aux_len = (hp[i] != 0xFF ? 4 : 0) + (sa.empty() ? 0 : 3 + sa.size() + 1) + (long_cigar ? 8 + (size_t)ncig * 4 : 0);
+        const uint32_t n_cig_rec = long_cigar ? 2 : ncig;
+        const size_t body = 32 + (size_t)ln + (size_t)n_cig_rec * 4 + (l_seq + 1) / 2 + l_seq + aux_len;
+        put32(raw, (uint32_t)body);
+        put32(raw, (uint32_t)contig[i]);
+        put32(raw, (uint32_t)rs[i]);
+        raw.push_back((uint8_t)ln);
+        raw.push_back(mapq[i]);
+        put16(raw, (uint16_t)reg2bin(rs[i], std::max(re[i], rs[i] + 1)));
+        put16(raw, (uint16_t)n_cig_rec);
+        put16(raw, (uint16_t)(rev ? 0x10 : 0));
+        put32(raw, l_seq);
+        put32(raw, 0xFFFFFFFFu);
+        put32(raw, 0xFFFFFFFFu);
+        put32(raw, 0);
+        raw.insert(raw.end(), name, name + ln);
+        if (long_cigar) {
+            put32(raw, (l_seq << 4) | 4u);
+            put32(raw, ((uint32_t)(re[i] - rs[i]) << 4) | 3u);
+        } else {
+            const uint8_t *cp = reinterpret_cast<const uint8_t *>(cigar + a);
+            raw.insert(raw.end(), cp, cp + (size_t)ncig * 4);
+        }
+        for (uint32_t k = 0; k < (l_seq + 1) / 2; ++k) raw.push_back((uint8_t)(0x11u << (rr.next() & 3)));   // A/C/G/T pairs
+        raw.insert(raw.end(), l_seq, (uint8_t)20);
+        if (hp[i] != 0xFF) { raw.push_back('H'); raw.push_back('P'); raw.push_back('C'); raw.push_back(hp[i]); }
+        if (!sa.empty()) { raw.push_back('S'); raw.push_back('A'); raw.push_back('Z'); raw.insert(raw.end(), sa.begin(), sa.end()); raw.push_back(0); }
+        if (long_cigar) {
+            raw.push_back('C'); raw.push_back('G'); raw.push_back('B'); raw.push_back('I');
+            put32(raw, ncig);
+            const uint8_t *cp = reinterpret_cast<const uint8_t *>(cigar + a);
+            raw.insert(raw.end(), cp, cp + (size_t)ncig * 4);
+        }
+        if (raw.size() >= (256u << 20)) { emit_stream(raw); raw.clear(); }
+    }
+    if (!raw.empty()) emit_stream(raw);
+    static const uint8_t eof_block[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    fwrite(eof_block, 1, 28, fp);
+    written += 28;
+    fclose(fp);
+    return written;
+}
+
+}  // extern "C"

@@ -55,7 +55,7 @@ def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libinqsynth.so")
     src = os.path.join(_HERE, "synth.cpp")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", so, src, "-lz"])
     return so
 
 
@@ -73,6 +73,8 @@ def lib():
         L.synth_headers.argtypes = [C.POINTER(_Cfg), C.c_uint64] + [C.c_void_p] * 7
         L.synth_cigars.restype = C.c_int
         L.synth_cigars.argtypes = [C.POINTER(_Cfg), C.c_uint64, C.c_void_p, C.c_void_p]
+        L.synth_write_bam.restype = C.c_int64
+        L.synth_write_bam.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -265,3 +267,28 @@ def make_workload(config: int, scale: float = 1.0, seed: int | None = None, thre
                     contig_locus_off=s_off, locus_start=ls_s, locus_end=le_s, delta_h1=d1_s, delta_h2=d2_s,
                     reads=reads, minlen=5, support=3, unphased=unphased, depth=d, shard=shard,
                     locus_range=(lo, hi), meta={"n_loci_global": nl, "scale": scale})
+
+
+def write_bam(w: Workload, path: str, with_seq: bool = False, level: int = 1, threads: int = 0) -> int:
+    """Coordinate-sorted BAM of the workload's reads (HP:C, SA for accidental-2D reads, CG for long
+    CIGARs); with_seq adds SEQ/QUAL of the query length so that records have realistic sizes."""
+    names = (C.c_char_p * w.n_contigs)(*[n.encode() for n in w.contig_names])
+    rd = w.reads
+    n = lib().synth_write_bam(path.encode(), w.n_contigs, names, w.contig_len.ctypes.data, rd.n, rd.contig.ctypes.data,
+                              rd.ref_start.ctypes.data, rd.ref_end.ctypes.data, rd.mapq.ctypes.data, rd.hp.ctypes.data,
+                              rd.flags.ctypes.data, rd.cigar_off.ctypes.data, rd.cigar.ctypes.data, int(with_seq), level, threads)
+    if n < 0:
+        raise OSError(f"cannot write {path}")
+    return int(n)
+
+
+def write_bed(w: Workload, path: str, shuffle_seed: int | None = None):
+    """BED of the workload's catalog; returns the loci in file order as (chrom, start, end, catalog index)."""
+    idx = np.arange(w.n_loci)
+    if shuffle_seed is not None:
+        idx = np.random.default_rng(shuffle_seed).permutation(w.n_loci)
+    lc = w.locus_contig
+    rows = [(w.contig_names[int(lc[i])], int(w.locus_start[i]), int(w.locus_end[i]), int(i)) for i in idx]
+    with open(path, "w") as f:
+        f.write("".join(f"{c}\t{s}\t{e}\n" for c, s, e, _ in rows))
+    return rows

@@ -4,6 +4,7 @@ TSV parity against the oracle with a GPU. Mirrors the reference's own call tests
 import functools
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -188,3 +189,33 @@ def test_long_cigar_cg_tag_and_bad_hp(cli, tmp_path):
     recs = [bamio.encode_record(0, 1000, 60, 0, words[:200], name=b"y", hp=1, hp_type="s", end=1300)]
     bamio.write_bam(bad, ["chr1"], [1_000_000], recs)
     assert run(cli, "call", "-r", "chr1:1100-1110", bad).returncode == 101
+
+
+def test_host_bam_reader_matches_workload(cli, tmp_path):
+    """the BGZF/BAM reader alone (no GPU): record, CIGAR-word, HP, SA and accidental-2D counts of a
+    synthetic BAM (with SEQ/QUAL, multi-batch, multi-threaded inflate) equal those of its SoA source"""
+    import json
+    from synth import synth as S
+    w = S.make_workload(3, scale=0.0008, threads=2)
+    for with_seq in (False, True):
+        bam = str(tmp_path / f"s{int(with_seq)}.bam")
+        assert S.write_bam(w, bam, with_seq=with_seq) > 0
+        r = run(cli, "bamstat", bam)
+        assert r.returncode == 0, r.stderr
+        st = json.loads(r.stdout)
+        assert st["refs"] == w.n_contigs and st["records"] == w.reads.n
+        assert st["cigar_words"] == len(w.reads.cigar)
+        assert st["hp_tagged"] == int((w.reads.hp != 0xFF).sum())
+        assert st["accidental_2d"] == int((w.reads.flags & 1).sum()) == st["sa_tagged"]
+
+
+@pytest.mark.gpu
+def test_cli_on_synthetic_bam_with_seq(cli, tmp_path):
+    """tools/bench_bam.py path: config 3 (shrunk) written as a BAM with SEQ/QUAL, shuffled BED, -t 8"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_bam.py"), "--scale", "0.003", "--with-seq",
+                          "--keep", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["tsv_identical_to_oracle"] is True
+    assert res["cli_stats"]["records"] == res["reads"]
