@@ -103,7 +103,12 @@ bool BamReader::read_batch(Batch &out)
         out_total += b.out_len;
         blocks.push_back(b);
     }
-    out.data.resize(kSlack + out_total);
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!pool_.empty()) { out.data = std::move(pool_.back()); pool_.pop_back(); }
+    }
+    out.size = kSlack + out_total;
+    if (out.data.size() < out.size) out.data.resize(out.size + (out.size >> 3));
     if (blocks.empty()) return true;
     std::atomic<size_t> next{0};
     std::atomic<int> bad{0};
@@ -156,22 +161,27 @@ bool BamReader::next_batch()
     cv_.notify_all();
     if (!nb.err.empty()) { err_ = nb.err; eof_ = true; return false; }
     const size_t tail = end_ - cur_;
-    const size_t payload = nb.data.size() - kSlack;
+    const size_t payload = nb.size - kSlack;
     total_out_ += payload;
     if (nb.eof) eof_ = true;
     if (tail <= kSlack) {
         if (tail) memcpy(nb.data.data() + kSlack - tail, cur_batch_.data.data() + cur_, tail);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!cur_batch_.data.empty() && pool_.size() < 4) pool_.push_back(std::move(cur_batch_.data));
+        }
         cur_batch_ = std::move(nb);
         cur_ = kSlack - tail;
-        end_ = cur_batch_.data.size();
+        end_ = cur_batch_.size;
     } else {                                        // a record larger than the slack: concatenate
         std::vector<uint8_t> joined(kSlack + tail + payload);
         memcpy(joined.data() + kSlack, cur_batch_.data.data() + cur_, tail);
         memcpy(joined.data() + kSlack + tail, nb.data.data() + kSlack, payload);
         cur_batch_.data = std::move(joined);
+        cur_batch_.size = cur_batch_.data.size();
         cur_batch_.eof = nb.eof;
         cur_ = kSlack;
-        end_ = cur_batch_.data.size();
+        end_ = cur_batch_.size;
     }
     return payload > 0 || !eof_;
 }

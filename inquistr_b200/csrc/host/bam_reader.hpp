@@ -63,10 +63,12 @@ private:
     // A batch of inflated BGZF blocks. `data` starts with kSlack unused bytes so that the unconsumed
     // tail of the previous batch can be moved in front of it without copying the batch.
     struct Batch {
-        std::vector<uint8_t> data;
+        std::vector<uint8_t> data;                 // capacity is recycled between batches (no re-faulting of pages)
+        size_t size = 0;                           // kSlack + inflated payload bytes
         bool eof = false;
         std::string err;
     };
+    std::vector<std::vector<uint8_t>> pool_;       // recycled buffers (guarded by mu_)
     static constexpr size_t kSlack = 8u << 20;
     bool next_batch();                             // make the next batch current (tail preserved)
     bool ensure_bytes(size_t n);                   // at least n unconsumed bytes are contiguous at cur_

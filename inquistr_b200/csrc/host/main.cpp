@@ -316,6 +316,8 @@ std::vector<Locus> parse_bed(const std::string &path, const BamHeader &h)
 
 int main(int argc, char **argv)
 {
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     const Args args = parse_args(argc, argv);
 
     // call.rs:87-90
@@ -373,12 +375,25 @@ int main(int argc, char **argv)
         for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) { m = std::max(m, lend[i]); pmax[i] = m; }
     }
 
+    // CUDA context + catalog upload + pinned staging buffers. (Doing this on a second thread next to the
+    // BAM scan was measured and is slower: driver initialisation and 16 inflate threads fight over the
+    // process' memory-map lock.)
+    const auto t_ctx0 = std::chrono::steady_clock::now();
     inq_ctx *ctx = nullptr;
     if (inq_ctx_create(args.device, &ctx) != INQ_OK) {
         fprintf(stderr, "ERROR: %s\n", inq_last_error(nullptr));
         return 1;
     }
     INQ_CHECK(ctx, inq_set_loci(ctx, n_contigs, contig_off.data(), lstart.data(), lend.data()));
+    // pinned staging for the pushes (DMA at PCIe speed instead of a staged pageable copy)
+    constexpr size_t kChunkWords = 32u << 20, kChunkReads = 4u << 20;
+    void *pin_cigar = nullptr, *pin_meta = nullptr;
+    if (inq_host_alloc(kChunkWords * 4, &pin_cigar) != INQ_OK) pin_cigar = nullptr;
+    if (inq_host_alloc(kChunkReads * 24 + 64, &pin_meta) != INQ_OK) pin_meta = nullptr;
+    const double s_ctx = since(t_ctx0);
+    auto wait_ctx = [&]() {};
+    const auto t_scan0 = std::chrono::steady_clock::now();
+    double s_push = 0;
 
     // one sequential pass over the BAM; keep the records htslib's fetch would yield for some locus:
     // pos < end+10 && endpos > start-10
@@ -389,10 +404,27 @@ int main(int argc, char **argv)
     uint64_t n_records = 0, n_kept = 0;
     auto flush = [&]() {
         if (r_contig.empty()) return;
-        INQ_CHECK(ctx, inq_push_reads(ctx, r_contig.size(), r_contig.data(), r_start.data(), r_end.data(), r_mapq.data(),
-                                      r_hp.data(), r_flags.data(), r_off.data(), r_cigar.data()));
+        wait_ctx();
+        const auto tp = std::chrono::steady_clock::now();
+        const size_t n = r_contig.size(), nw = r_cigar.size();
+        if (pin_cigar && pin_meta && nw <= kChunkWords && n <= kChunkReads) {
+            // stage through pinned memory: contig | start | end | off (8 B) | mapq | hp | flags
+            uint8_t *m = static_cast<uint8_t *>(pin_meta);
+            int32_t *pc = reinterpret_cast<int32_t *>(m), *ps = pc + kChunkReads, *pe = ps + kChunkReads;
+            uint64_t *po = reinterpret_cast<uint64_t *>(pe + kChunkReads);
+            uint8_t *pq = reinterpret_cast<uint8_t *>(po + kChunkReads + 1), *ph = pq + kChunkReads, *pf = ph + kChunkReads;
+            memcpy(pc, r_contig.data(), n * 4); memcpy(ps, r_start.data(), n * 4); memcpy(pe, r_end.data(), n * 4);
+            memcpy(po, r_off.data(), (n + 1) * 8);
+            memcpy(pq, r_mapq.data(), n); memcpy(ph, r_hp.data(), n); memcpy(pf, r_flags.data(), n);
+            memcpy(pin_cigar, r_cigar.data(), nw * 4);
+            INQ_CHECK(ctx, inq_push_reads(ctx, n, pc, ps, pe, pq, ph, pf, po, static_cast<uint32_t *>(pin_cigar)));
+        } else {
+            INQ_CHECK(ctx, inq_push_reads(ctx, n, r_contig.data(), r_start.data(), r_end.data(), r_mapq.data(),
+                                          r_hp.data(), r_flags.data(), r_off.data(), r_cigar.data()));
+        }
         r_contig.clear(); r_start.clear(); r_end.clear(); r_mapq.clear(); r_hp.clear(); r_flags.clear();
         r_off.assign(1, 0); r_cigar.clear();
+        s_push += since(tp);
     };
     BamRecordView rec;
     while (bam.next(rec)) {
@@ -428,10 +460,13 @@ int main(int argc, char **argv)
         r_cigar.insert(r_cigar.end(), rec.cigar, rec.cigar + rec.n_cigar);
         r_off.push_back(r_cigar.size());
         ++n_kept;
-        if (r_cigar.size() >= (64u << 20) || r_contig.size() >= (8u << 20)) flush();
+        if (r_cigar.size() + 70000 >= kChunkWords || r_contig.size() + 1 >= kChunkReads) flush();
     }
     if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
     flush();
+    wait_ctx();
+    const double s_scan = since(t_scan0);
+    const auto t_gen0 = std::chrono::steady_clock::now();
 
     std::vector<int64_t> t1(L), t2(L);
     std::vector<uint8_t> valid(L);
@@ -439,6 +474,7 @@ int main(int argc, char **argv)
     memset(&st, 0, sizeof(st));
     INQ_CHECK(ctx, inq_genotype(ctx, args.minlen, (uint32_t)args.support, args.unphased ? 1 : 0, t1.data(), t2.data(), valid.data(), &st));
 
+    const double s_gen = since(t_gen0);
     // output order: -t 1 BED order (call.rs:149-157); -t > 1 sorted by (human chrom, start) (call.rs:137-145)
     std::vector<uint32_t> pos_of(L);                 // BED index -> catalog position
     for (size_t i = 0; i < L; ++i) pos_of[order[i]] = (uint32_t)i;
@@ -475,12 +511,15 @@ int main(int argc, char **argv)
         if (f) {
             fprintf(f, "{\"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
                        ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
-                       ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u}\n",
+                       ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u"
+                       ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_inside_scan\": %.3f, \"s_genotype\": %.3f, \"s_total\": %.3f}\n",
                     n_records, n_kept, bam.bytes_inflated(), st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
-                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches);
+                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, s_ctx, s_scan, s_push, s_gen, since(t_begin));
             fclose(f);
         }
     }
+    inq_host_free(pin_cigar);
+    inq_host_free(pin_meta);
     inq_ctx_destroy(ctx);
     return 0;
 }
