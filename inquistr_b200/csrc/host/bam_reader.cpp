@@ -232,6 +232,11 @@ bool BamReader::next(BamRecordView &rec)
     if (!ensure_bytes((size_t)block_size + 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
     const uint8_t *p = cur_batch_.data.data() + cur_ + 4;       // record body, parsed in place
     cur_ += (size_t)block_size + 4;
+    return parse_bam_record(p, block_size, rec, cg_, err_);
+}
+
+bool parse_bam_record(const uint8_t *p, uint32_t block_size, BamRecordView &rec, std::vector<uint32_t> &cg_, std::string &err_)
+{
     rec.tid = rdi32(p);
     rec.pos = rdi32(p + 4);
     const uint32_t l_read_name = p[8];
@@ -319,6 +324,165 @@ bool BamReader::next(BamRecordView &rec)
     if (rlen == 0) rlen = 1;
     rec.end = (int32_t)(rec.pos + rlen);
     return true;
+}
+
+// ---- BamIndexedReader -----------------------------------------------------------------------------
+BamIndexedReader::~BamIndexedReader()
+{
+    if (fp_) fclose(fp_);
+}
+
+bool BamIndexedReader::load_block(uint64_t coffset)
+{
+    if (fseeko(fp_, (off_t)coffset, SEEK_SET) != 0) { err_ = "seek failed"; return false; }
+    uint8_t h[12];
+    const size_t n = fread(h, 1, 12, fp_);
+    block_.clear();
+    block_pos_ = 0;
+    block_coff_ = coffset;
+    if (n == 0) { at_eof_ = true; return false; }
+    if (n != 12 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { err_ = "not a BGZF block (bad gzip header)"; return false; }
+    const uint16_t xlen = rd16(h + 10);
+    uint8_t extra[65536];
+    if (fread(extra, 1, xlen, fp_) != xlen) { err_ = "truncated BGZF extra field"; return false; }
+    int bsize = -1;
+    for (size_t i = 0; i + 4 <= xlen;) {
+        const uint16_t slen = rd16(&extra[i + 2]);
+        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = rd16(&extra[i + 4]);
+        i += 4 + slen;
+    }
+    if (bsize < 0) { err_ = "BGZF block without BC subfield"; return false; }
+    const long remaining = (long)bsize + 1 - 12 - xlen;
+    if (remaining < 8) { err_ = "corrupt BGZF block size"; return false; }
+    comp_.resize((size_t)remaining);
+    if (fread(comp_.data(), 1, (size_t)remaining, fp_) != (size_t)remaining) { err_ = "truncated BGZF block"; return false; }
+    const uint32_t crc = rd32(&comp_[remaining - 8]), isize = rd32(&comp_[remaining - 4]);
+    block_.resize(isize);
+    if (!inflate_block(comp_.data(), (size_t)remaining - 8, block_.data(), isize, crc)) { err_ = "BGZF inflate / CRC failure"; return false; }
+    next_coff_ = coffset + (uint64_t)bsize + 1;
+    total_out_ += isize;
+    at_eof_ = false;
+    return true;
+}
+
+bool BamIndexedReader::read_bytes(void *dst, size_t n)
+{
+    uint8_t *d = static_cast<uint8_t *>(dst);
+    while (n) {
+        if (block_pos_ >= block_.size()) {
+            if (!load_block(next_coff_)) return false;
+            continue;
+        }
+        const size_t k = std::min(n, block_.size() - block_pos_);
+        memcpy(d, block_.data() + block_pos_, k);
+        block_pos_ += k;
+        d += k;
+        n -= k;
+    }
+    return true;
+}
+
+bool BamIndexedReader::open_bam(const std::string &bam_path)
+{
+    fp_ = fopen(bam_path.c_str(), "rb");
+    if (!fp_) { err_ = "cannot open " + bam_path; return false; }
+    // header through the block reader
+    if (!load_block(0)) { if (err_.empty()) err_ = "empty BAM"; return false; }
+    uint8_t b4[4], magic[4];
+    if (!read_bytes(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM file (bad magic)"; return false; }
+    if (!read_bytes(b4, 4)) { err_ = "truncated BAM header"; return false; }
+    header_.text.resize(rd32(b4));
+    if (!header_.text.empty() && !read_bytes(&header_.text[0], header_.text.size())) { err_ = "truncated BAM header"; return false; }
+    if (!read_bytes(b4, 4)) { err_ = "truncated BAM header"; return false; }
+    const uint32_t n_ref = rd32(b4);
+    for (uint32_t i = 0; i < n_ref; ++i) {
+        if (!read_bytes(b4, 4)) { err_ = "truncated BAM reference list"; return false; }
+        std::string name(rd32(b4), '\0');
+        if (!name.empty() && !read_bytes(&name[0], name.size())) { err_ = "truncated BAM reference list"; return false; }
+        if (!name.empty() && name.back() == '\0') name.pop_back();
+        if (!read_bytes(b4, 4)) { err_ = "truncated BAM reference list"; return false; }
+        header_.ref_names.push_back(name);
+        header_.ref_lens.push_back((int64_t)rd32(b4));
+    }
+    return true;
+}
+
+bool BamIndexedReader::load_index(const std::string &bai_path)
+{
+    FILE *fi = fopen(bai_path.c_str(), "rb");
+    if (!fi) { err_ = "cannot open " + bai_path; return false; }
+    std::vector<uint8_t> bai;
+    uint8_t buf[1 << 16];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof(buf), fi)) > 0) bai.insert(bai.end(), buf, buf + k);
+    fclose(fi);
+    size_t p = 0;
+    auto need = [&](size_t n) { return p + n <= bai.size(); };
+    if (!need(8) || memcmp(bai.data(), "BAI\1", 4) != 0) { err_ = "not a BAI index"; return false; }
+    const uint32_t nr = rd32(&bai[4]);
+    p = 8;
+    index_.resize(nr);
+    for (uint32_t r = 0; r < nr; ++r) {
+        if (!need(4)) { err_ = "truncated BAI"; return false; }
+        const uint32_t n_bin = rd32(&bai[p]);
+        p += 4;
+        for (uint32_t b = 0; b < n_bin; ++b) {
+            if (!need(8)) { err_ = "truncated BAI"; return false; }
+            const uint32_t bin = rd32(&bai[p]), n_chunk = rd32(&bai[p + 4]);
+            p += 8;
+            if (!need((size_t)n_chunk * 16)) { err_ = "truncated BAI"; return false; }
+            std::vector<Chunk> ch(n_chunk);
+            for (uint32_t c = 0; c < n_chunk; ++c) {
+                ch[c].beg = (uint64_t)rd32(&bai[p]) | ((uint64_t)rd32(&bai[p + 4]) << 32);
+                ch[c].end = (uint64_t)rd32(&bai[p + 8]) | ((uint64_t)rd32(&bai[p + 12]) << 32);
+                p += 16;
+            }
+            if (bin != 37450) index_[r].bins.emplace_back(bin, std::move(ch));      // 37450 = metadata pseudo-bin
+        }
+        if (!need(4)) { err_ = "truncated BAI"; return false; }
+        const uint32_t n_intv = rd32(&bai[p]);
+        p += 4;
+        if (!need((size_t)n_intv * 8)) { err_ = "truncated BAI"; return false; }
+        index_[r].linear.resize(n_intv);
+        for (uint32_t i = 0; i < n_intv; ++i) {
+            index_[r].linear[i] = (uint64_t)rd32(&bai[p]) | ((uint64_t)rd32(&bai[p + 4]) << 32);
+            p += 8;
+        }
+    }
+    return true;
+}
+
+std::vector<BamIndexedReader::Chunk> BamIndexedReader::query_chunks(int tid, int64_t beg, int64_t end) const
+{
+    const RefIndex &ri = index_[tid];
+    if (end <= beg) return {};
+    // reg2bins (SAM spec 5.3)
+    std::vector<uint32_t> want{0};
+    const int64_t e = end - 1;
+    for (int64_t k = 1 + (beg >> 26); k <= 1 + (e >> 26); ++k) want.push_back((uint32_t)k);
+    for (int64_t k = 9 + (beg >> 23); k <= 9 + (e >> 23); ++k) want.push_back((uint32_t)k);
+    for (int64_t k = 73 + (beg >> 20); k <= 73 + (e >> 20); ++k) want.push_back((uint32_t)k);
+    for (int64_t k = 585 + (beg >> 17); k <= 585 + (e >> 17); ++k) want.push_back((uint32_t)k);
+    for (int64_t k = 4681 + (beg >> 14); k <= 4681 + (e >> 14); ++k) want.push_back((uint32_t)k);
+    std::sort(want.begin(), want.end());
+    uint64_t min_off = 0;
+    if (!ri.linear.empty()) {
+        const size_t w = (size_t)(beg >> 14);
+        min_off = w < ri.linear.size() ? ri.linear[w] : ri.linear.back();
+    }
+    std::vector<Chunk> out;
+    for (const auto &b : ri.bins) {
+        if (!std::binary_search(want.begin(), want.end(), b.first)) continue;
+        for (const Chunk &c : b.second)
+            if (c.end > min_off) out.push_back(c);
+    }
+    std::sort(out.begin(), out.end(), [](const Chunk &a, const Chunk &b) { return a.beg < b.beg; });
+    std::vector<Chunk> merged;
+    for (const Chunk &c : out) {
+        if (!merged.empty() && c.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, c.end);
+        else merged.push_back(c);
+    }
+    return merged;
 }
 
 int64_t cigar_text_to_rlen(const std::string &cigar)

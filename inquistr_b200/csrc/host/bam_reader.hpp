@@ -93,6 +93,82 @@ private:
     bool stop_ = false;
 };
 
+// Parses one BAM alignment record body (the bytes after block_size) in place. `cg` receives an aligned
+// copy of the CIGAR (from the record or from the CG:B,I tag). Returns false and sets err on corruption.
+bool parse_bam_record(const uint8_t *body, uint32_t block_size, BamRecordView &rec, std::vector<uint32_t> &cg,
+                      std::string &err);
+
+// Random access through a .bai index (SAM spec 5.2) for small panels: the records htslib's
+// fetch(tid, beg, end) yields -- tid match, pos < end, endpos > beg -- in file order
+// (replaces IndexedReader::fetch, call.rs:288,338).
+class BamIndexedReader {
+public:
+    ~BamIndexedReader();
+    bool open_bam(const std::string &bam_path);        // header only
+    bool load_index(const std::string &bai_path);
+    bool has_index() const { return !index_.empty(); }
+    const BamHeader &header() const { return header_; }
+    const std::string &error() const { return err_; }
+    uint64_t bytes_inflated() const { return total_out_; }
+    // calls f(rec, virtual_offset_of_record) for every record of the query; false on error
+    template <typename F>
+    bool fetch(int tid, int64_t beg, int64_t end, F f);
+
+private:
+    struct Chunk { uint64_t beg, end; };
+    struct RefIndex {
+        std::vector<std::pair<uint32_t, std::vector<Chunk>>> bins;
+        std::vector<uint64_t> linear;
+    };
+    bool load_block(uint64_t coffset);             // inflate the block at file offset coffset
+    bool read_bytes(void *dst, size_t n);          // from the current position, across blocks
+    std::vector<Chunk> query_chunks(int tid, int64_t beg, int64_t end) const;
+    uint64_t tell() const { return (block_coff_ << 16) | (uint64_t)block_pos_; }
+
+    FILE *fp_ = nullptr;
+    BamHeader header_;
+    std::string err_;
+    std::vector<RefIndex> index_;
+    std::vector<uint8_t> block_, rec_, comp_;
+    uint64_t block_coff_ = 0, next_coff_ = 0;
+    size_t block_pos_ = 0;
+    bool at_eof_ = false;
+    uint64_t total_out_ = 0;
+    std::vector<uint32_t> cg_;
+};
+
+template <typename F>
+bool BamIndexedReader::fetch(int tid, int64_t beg, int64_t end, F f)
+{
+    if (tid < 0 || tid >= (int)index_.size()) return true;
+    if (beg < 0) beg = 0;
+    const std::vector<Chunk> chunks = query_chunks(tid, beg, end);
+    BamRecordView rec;
+    for (const Chunk &c : chunks) {
+        if (!load_block(c.beg >> 16)) return err_.empty();
+        block_pos_ = (size_t)(c.beg & 0xFFFF);
+        for (;;) {
+            // normalise the position to the start of the next block when this one is exhausted
+            while (block_pos_ >= block_.size() && !at_eof_) {
+                if (!load_block(next_coff_)) break;
+            }
+            if (at_eof_ && block_pos_ >= block_.size()) break;
+            const uint64_t v = tell();
+            if (v >= c.end) break;
+            uint8_t b4[4];
+            if (!read_bytes(b4, 4)) return err_.empty();
+            const uint32_t bs = (uint32_t)b4[0] | ((uint32_t)b4[1] << 8) | ((uint32_t)b4[2] << 16) | ((uint32_t)b4[3] << 24);
+            if (bs < 32) { err_ = "corrupt BAM record"; return false; }
+            rec_.resize(bs);
+            if (!read_bytes(rec_.data(), bs)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
+            if (!parse_bam_record(rec_.data(), bs, rec, cg_, err_)) return false;
+            if (rec.tid != tid || (int64_t)rec.pos >= end) return true;     // coordinate-sorted: nothing further
+            if ((int64_t)rec.end > beg) f(rec, v);
+        }
+    }
+    return err_.empty();
+}
+
 // call.rs:461-477
 int64_t cigar_text_to_rlen(const std::string &cigar);
 // call.rs:415-459 ; *panic set when the reference would panic (SA not a string)

@@ -20,7 +20,9 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <array>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "../../../include/inqcall.h"
@@ -97,7 +99,20 @@ Args parse_args(int argc, char **argv)
     }
     if (v[0] == "-V" || v[0] == "--version") { printf("inquistr-b200 %s\n", inq_version()); exit(0); }
     if (v[0] == "bamstat" && v.size() >= 2) {
-        // extension: scan a BAM with the host reader only (no GPU): record counts and inflate rate
+        // extension: scan a BAM with the host reader only (no GPU): record counts and inflate rate;
+        // `bamstat x.bam chr:beg-end` does the same through the .bai index for one region
+        if (v.size() >= 3) {
+            BamIndexedReader ix;
+            if (!ix.open_bam(v[1]) || !ix.load_index(v[1] + ".bai")) { fprintf(stderr, "%s\n", ix.error().c_str()); exit(1); }
+            const size_t c1 = v[2].find(':'), c2 = v[2].find('-', c1);
+            const int tid = ix.header().tid(v[2].substr(0, c1));
+            const long long b = atoll(v[2].substr(c1 + 1, c2 - c1 - 1).c_str()), e = atoll(v[2].substr(c2 + 1).c_str());
+            uint64_t n = 0, words = 0;
+            if (!ix.fetch(tid, b, e, [&](const BamRecordView &r, uint64_t) { ++n; words += r.n_cigar; })) { fprintf(stderr, "%s\n", ix.error().c_str()); exit(1); }
+            printf("{\"records\": %llu, \"cigar_words\": %llu, \"bytes_inflated\": %llu}\n", (unsigned long long)n,
+                   (unsigned long long)words, (unsigned long long)ix.bytes_inflated());
+            exit(0);
+        }
         BamReader rd;
         const auto t0 = std::chrono::steady_clock::now();
         if (!rd.open(v[1], (int)std::max(1u, std::thread::hardware_concurrency()))) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
@@ -336,9 +351,9 @@ int main(int argc, char **argv)
     const std::string sample = args.has_sample ? args.sample_name : sample_from_path(args.bam);   // call.rs:91-100
 
     const int host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    BamReader bam;
-    if (!bam.open(args.bam, host_threads)) panic("Error opening local BAM: " + bam.error());     // call.rs:242-243
-    const BamHeader &hdr = bam.header();
+    BamIndexedReader ibam;                                 // header now, random access later if a .bai is usable
+    if (!ibam.open_bam(args.bam)) panic("Error opening local BAM: " + ibam.error());             // call.rs:242-243
+    const BamHeader &hdr = ibam.header();
 
     // call.rs:182-202
     std::vector<Locus> loci;
@@ -426,15 +441,14 @@ int main(int argc, char **argv)
         r_off.assign(1, 0); r_cigar.clear();
         s_push += since(tp);
     };
-    BamRecordView rec;
-    while (bam.next(rec)) {
-        ++n_records;
-        if (rec.tid < 0 || rec.tid >= n_contigs) continue;
+    // what to do with one record htslib's fetch could return for some locus
+    auto consider = [&](const BamRecordView &rec) {
+        if (rec.tid < 0 || rec.tid >= n_contigs) return;
         const int64_t l0 = contig_off[rec.tid], l1 = contig_off[rec.tid + 1];
-        if (l0 == l1) continue;
+        if (l0 == l1) return;
         // loci with start - 10 < endpos, and among them one with end + 10 > pos
         const int64_t hi = std::lower_bound(lstart.begin() + l0, lstart.begin() + l1, (int32_t)std::min<int64_t>((int64_t)rec.end + 10, INT32_MAX)) - lstart.begin();
-        if (hi == l0 || (int64_t)pmax[hi - 1] + 10 <= (int64_t)rec.pos) continue;
+        if (hi == l0 || (int64_t)pmax[hi - 1] + 10 <= (int64_t)rec.pos) return;
         // a record the reference would fetch: its aux tags are inspected there too
         uint8_t hp = 0xFF;
         if (!args.unphased) {                                              // get_phase, call.rs:482-491
@@ -461,8 +475,49 @@ int main(int argc, char **argv)
         r_off.push_back(r_cigar.size());
         ++n_kept;
         if (r_cigar.size() + 70000 >= kChunkWords || r_contig.size() + 1 >= kChunkReads) flush();
+    };
+
+    // Small panels: seek through the .bai instead of inflating the whole file.
+    // Windows closer than 100 kb are fetched as one region; a read returned by two regions is kept once.
+    std::vector<std::array<int64_t, 3>> regions;           // tid, beg, end
+    int64_t region_span = 0, genome = 0;
+    for (int64_t len : hdr.ref_lens) genome += len;
+    for (int c = 0; c < n_contigs; ++c)
+        for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) {
+            const int64_t b = (int64_t)lstart[i] - 10, e = (int64_t)lend[i] + 10;
+            if (!regions.empty() && regions.back()[0] == c && b <= regions.back()[2] + 100000) regions.back()[2] = std::max(regions.back()[2], e);
+            else regions.push_back({(int64_t)c, b, e});
+        }
+    for (const auto &r : regions) region_span += r[2] - r[1] + 50000;     // + typical read overhang
+    std::string bai = args.bam + ".bai";
+    if (!is_file(bai) && ends_with(args.bam, ".bam")) bai = args.bam.substr(0, args.bam.size() - 4) + ".bai";
+    const char *idx_env = getenv("INQ_BAM_INDEX");
+    const bool want_index = idx_env ? atoi(idx_env) != 0 : (region_span * 10 < genome);
+    bool used_index = false;
+    uint64_t bytes_inflated = 0;
+    if (want_index && is_file(bai)) {
+        if (!ibam.load_index(bai)) panic("Error opening BAM index: " + ibam.error());
+        used_index = true;
+        std::unordered_set<uint64_t> seen;
+        for (const auto &r : regions) {
+            const bool ok = ibam.fetch((int)r[0], r[1], r[2], [&](const BamRecordView &rec, uint64_t voff) {
+                ++n_records;
+                if (seen.insert(voff).second) consider(rec);
+            });
+            if (!ok) panic("Failed to fetch region: " + ibam.error());       // call.rs:288
+        }
+        bytes_inflated = ibam.bytes_inflated();
+    } else {
+        BamReader bam;
+        if (!bam.open(args.bam, host_threads)) panic("Error opening local BAM: " + bam.error());
+        BamRecordView rec;
+        while (bam.next(rec)) {
+            ++n_records;
+            consider(rec);
+        }
+        if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
+        bytes_inflated = bam.bytes_inflated();
     }
-    if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
     flush();
     wait_ctx();
     const double s_scan = since(t_scan0);
@@ -509,11 +564,11 @@ int main(int argc, char **argv)
     if (!args.stats_json.empty()) {
         FILE *f = fopen(args.stats_json.c_str(), "w");
         if (f) {
-            fprintf(f, "{\"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
+            fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
                        ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
                        ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u"
                        ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_inside_scan\": %.3f, \"s_genotype\": %.3f, \"s_total\": %.3f}\n",
-                    n_records, n_kept, bam.bytes_inflated(), st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
+                    used_index ? 1 : 0, n_records, n_kept, bytes_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
                     st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, s_ctx, s_scan, s_push, s_gen, since(t_begin));
             fclose(f);
         }

@@ -101,3 +101,80 @@ def reads_to_bam(path, ref_names, ref_lens, reads, rng=None, sa_for_flags=True, 
         recs.append(encode_record(int(reads.contig[i]), pos, int(reads.mapq[i]), flag, cig, name=f"r{i}".encode(), hp=hp,
                                   hp_type=hp_type, sa=sa, end=end))
     write_bam(path, ref_names, ref_lens, recs)
+
+
+def index_bam(path: str) -> str:
+    """Pure-Python BAI builder (SAM spec 5.2) for coordinate-sorted BAMs written by this module or by
+    synth.write_bam: bins with merged chunks, 16 kb linear index. Returns the .bai path."""
+    data = open(path, "rb").read()
+    # pass 1: BGZF blocks -> (compressed offset, inflated bytes)
+    blocks, off = [], 0
+    while off < len(data):
+        xlen = struct.unpack_from("<H", data, off + 10)[0]
+        bsize = None
+        p = off + 12
+        while p < off + 12 + xlen:
+            si1, si2, slen = data[p], data[p + 1], struct.unpack_from("<H", data, p + 2)[0]
+            if si1 == 66 and si2 == 67:
+                bsize = struct.unpack_from("<H", data, p + 4)[0] + 1
+            p += 4 + slen
+        raw = zlib.decompress(data[off + 12 + xlen: off + bsize - 8], -15) if bsize > 12 + xlen + 8 else b""
+        blocks.append((off, raw))
+        off += bsize
+    stream = b"".join(r for _, r in blocks)
+    starts, acc = [], 0
+    for coff, raw in blocks:
+        starts.append((acc, coff, len(raw)))
+        acc += len(raw)
+
+    def voffset(pos):  # stream position -> virtual offset (first block that contains it)
+        import bisect
+        i = bisect.bisect_right([s for s, _, _ in starts], pos) - 1
+        while i + 1 < len(starts) and pos >= starts[i][0] + starts[i][2]:
+            i += 1
+        s, coff, _ = starts[i]
+        return (coff << 16) | (pos - s)
+
+    p = 4
+    l_text = struct.unpack_from("<I", stream, p)[0]; p += 4 + l_text
+    n_ref = struct.unpack_from("<I", stream, p)[0]; p += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<I", stream, p)[0]; p += 4 + l_name + 4
+    bins = [dict() for _ in range(n_ref)]
+    linear = [dict() for _ in range(n_ref)]
+    while p + 4 <= len(stream):
+        bs = struct.unpack_from("<I", stream, p)[0]
+        tid, pos, l_name, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHI", stream, p + 4)
+        cig = np.frombuffer(stream, dtype="<u4", count=n_cig, offset=p + 4 + 32 + l_name)
+        rlen = int((cig >> 4)[np.isin(cig & 15, [0, 2, 3, 7, 8])].sum()) if not (flag & 4) else 0
+        # CG long cigar: reference length is in the second op (N)
+        if n_cig == 2 and (int(cig[0]) & 15) == 4 and (int(cig[1]) & 15) == 3:
+            rlen = int(cig[1]) >> 4
+        end = pos + max(rlen, 1)
+        v0, v1 = voffset(p), voffset(p + 4 + bs)
+        if tid >= 0:
+            b = reg2bin(pos, end)
+            ch = bins[tid].setdefault(b, [])
+            if ch and ch[-1][1] == v0:
+                ch[-1][1] = v1
+            else:
+                ch.append([v0, v1])
+            for w in range(pos >> 14, ((end - 1) >> 14) + 1):
+                if w not in linear[tid]:
+                    linear[tid][w] = v0
+        p += 4 + bs
+    out = bytearray(b"BAI\1" + struct.pack("<i", n_ref))
+    for t in range(n_ref):
+        out += struct.pack("<i", len(bins[t]))
+        for b, chunks in bins[t].items():
+            out += struct.pack("<Ii", b, len(chunks))
+            for v0, v1 in chunks:
+                out += struct.pack("<QQ", v0, v1)
+        n_intv = (max(linear[t]) + 1) if linear[t] else 0
+        out += struct.pack("<i", n_intv)
+        last = 0
+        for w in range(n_intv):
+            last = linear[t].get(w, last)
+            out += struct.pack("<Q", last)
+    open(path + ".bai", "wb").write(bytes(out))
+    return path + ".bai"

@@ -219,3 +219,61 @@ def test_cli_on_synthetic_bam_with_seq(cli, tmp_path):
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["tsv_identical_to_oracle"] is True
     assert res["cli_stats"]["records"] == res["reads"]
+
+
+@pytest.fixture(scope="module")
+def panel_bam(tmp_path_factory):
+    from synth import synth as S
+    w = S.make_workload(4, threads=2)
+    d = tmp_path_factory.mktemp("panel")
+    bam = str(d / "panel.bam")
+    S.write_bam(w, bam)
+    bamio.index_bam(bam)
+    rows = S.write_bed(w, str(d / "panel.bed"), shuffle_seed=3)
+    return bam, str(d / "panel.bed"), rows, w
+
+
+def test_bai_fetch_matches_htslib_overlap_rule(cli, panel_bam):
+    """indexed random access (no GPU): records with pos < end && endpos > beg on the contig, in file order"""
+    import json
+    bam, _, _, w = panel_bam
+    rd = w.reads
+    n_cig = (rd.cigar_off[1:] - rd.cigar_off[:-1]).astype(np.int64)
+    for k in (0, 13, 41, 59):
+        c = int(w.locus_contig[k]); b = int(w.locus_start[k]) - 10; e = int(w.locus_end[k]) + 10
+        m = (rd.contig == c) & (rd.ref_start < e) & (rd.ref_end > b)
+        r = run(cli, "bamstat", bam, f"{w.contig_names[c]}:{b}-{e}")
+        assert r.returncode == 0, r.stderr
+        st = json.loads(r.stdout)
+        assert st["records"] == int(m.sum()) and st["cigar_words"] == int(n_cig[m].sum())
+        assert st["bytes_inflated"] < 0.3 * os.path.getsize(bam) * 4     # a fraction of the file, not all of it
+    r = run(cli, "bamstat", bam, "chr1:1-2")                              # nothing there
+    assert json.loads(r.stdout)["records"] == 0
+
+
+@pytest.mark.gpu
+def test_panel_with_and_without_index(cli, panel_bam, tmp_path):
+    """config 4 (expansion panel): the .bai path and the sequential scan print the same bytes"""
+    import json
+    bam, bed, rows, w = panel_bam
+    sel = np.asarray([i for *_, i in rows])
+    rc, p1, p2, _ = O.genotype_loci(w.reads, w.n_contigs, w.locus_contig[sel], w.locus_start[sel].astype(np.uint32),
+                                    w.locus_end[sel].astype(np.uint32), 5, 3, False)
+    exp = expected_tsv("panel", None, [(c, s, e) for c, s, e, _ in rows], p1, p2, 1)
+    outs = {}
+    for mode in ("1", "0"):
+        stats = str(tmp_path / f"st{mode}.json")
+        r = subprocess.run([cli, "call", "-R", bed, "--stats-json", stats, bam], capture_output=True, timeout=300,
+                           env={**os.environ, "INQ_BAM_INDEX": mode})
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == exp
+        outs[mode] = json.load(open(stats))
+    assert outs["1"]["used_index"] == 1 and outs["0"]["used_index"] == 0
+    assert outs["1"]["bytes_inflated"] <= outs["0"]["bytes_inflated"]
+    assert outs["1"]["records_pushed"] == outs["0"]["records_pushed"]
+    # single region (-r) picks the index on its own
+    stats = str(tmp_path / "st_r.json")
+    c, s, e, _ = rows[0]
+    r = run(cli, "call", "-r", f"{c}:{s}-{e}", "--stats-json", stats, bam)
+    assert r.returncode == 0 and json.load(open(stats))["used_index"] == 1
+    assert r.stdout.splitlines()[1] == exp.splitlines()[1]
