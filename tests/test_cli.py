@@ -269,7 +269,7 @@ def test_panel_with_and_without_index(cli, panel_bam, tmp_path):
         assert r.stdout == exp
         outs[mode] = json.load(open(stats))
     assert outs["1"]["used_index"] == 1 and outs["0"]["used_index"] == 0
-    assert outs["1"]["bytes_inflated"] <= outs["0"]["bytes_inflated"]
+    assert outs["1"]["records"] <= outs["0"]["records"]          # only records near the loci are decoded
     assert outs["1"]["records_pushed"] == outs["0"]["records_pushed"]
     # single region (-r) picks the index on its own
     stats = str(tmp_path / "st_r.json")
