@@ -725,6 +725,9 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
 // events anchored inside the locus window (call.rs:388,394,400: start < P && P < end) and the
 // scatter of the packed call into the locus' segment: H1 (or every unphased call) grows from the
 // front of the segment, H2 from its back; one 64-bit atomic per pair hands out the slot.
+constexpr int kPairEvCache = 8;             // events per read kept in shared memory
+constexpr int kPairLociCache = 128;         // catalog entries per warp kept in shared memory
+
 __global__ void __launch_bounds__(256)
 k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
             const uint32_t *__restrict__ cand_n, const uint2 *__restrict__ events,
@@ -734,8 +737,15 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
 {
     // A warp owns 32 consecutive reads; their candidates are flattened and dealt to the lanes
     // 32 at a time (reads have 0..hundreds of candidates, a per-read loop leaves most lanes idle).
+    // Everything the inner loop needs is staged in shared memory first (the reads' first events, the
+    // slice of the catalog the warp touches), so that the only global operations left in the loop
+    // are the slot atomic and the store of the call -- and the store is deferred by one iteration so
+    // that the atomic's round trip overlaps the next candidate.
     __shared__ uint32_t s_off[8][32];
     __shared__ uint32_t s_joined[8];
+    __shared__ uint2 s_ev[8][32][kPairEvCache];
+    __shared__ int32_t s_ls[8][kPairLociCache], s_le[8][kPairLociCache];
+    __shared__ uint32_t s_seg[8][kPairLociCache + 1];
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t n = 0, lo = 0, e0 = 0, e1 = 0, hf = 0, words = 0;
@@ -751,17 +761,52 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             e0 = (uint32_t)min((uint64_t)ev_off[r], ev_cap);
             e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
             words = (uint32_t)min(rv.cig_off[r + 1] - rv.cig_off[r], (uint64_t)0xFFFFFFFFu);
+            if (e1 - e0 <= (uint32_t)kPairEvCache) {
+#pragma unroll
+                for (uint32_t q = 0; q < (uint32_t)kPairEvCache; ++q)
+                    s_ev[wid][lane][q] = (q < e1 - e0) ? events[e0 + q] : make_uint2(0u, 0u);   // anchor 0 is never in a window
+            } else {
+                hf |= 1u << 9;                              // long event list: searched in global memory
+            }
         }
     }
     const uint32_t incl = warp_incl_scan(n);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     s_off[wid][lane] = incl - n;
     if (lane == 0) s_joined[wid] = 0u;
+    // slice of the catalog this warp touches
+    const uint32_t lo_min = __reduce_min_sync(0xffffffffu, n ? lo : 0xFFFFFFFFu);
+    const uint32_t hi_max = __reduce_max_sync(0xffffffffu, n ? lo + n : 0u);
+    const bool cached = total && (hi_max - lo_min <= (uint32_t)kPairLociCache);
+    if (cached) {
+        const uint32_t span = hi_max - lo_min;
+        for (uint32_t i = lane; i < span; i += 32) {
+            s_ls[wid][i] = __ldg(lv.start + lo_min + i);
+            s_le[wid][i] = __ldg(lv.end + lo_min + i);
+        }
+        for (uint32_t i = lane; i <= span; i += 32) s_seg[wid][i] = __ldg(seg_off + lo_min + i);
+    }
     __syncwarp();
 
     uint32_t npass = 0;                 // pairs that land in a bucket
     uint64_t visits = 0;                // CIGAR words the reference walks: every passing pair, incl. HP 0
     bool bad_hp = false;
+    // deferred store of the previous candidate
+    bool pend = false;
+    unsigned long long pend_old = 0;
+    uint64_t pend_key = 0;
+    uint32_t pend_seg = 0, pend_cap = 0;
+    bool pend_back = false;
+    auto flush_pending = [&]() {
+        if (!pend) return;
+        const uint32_t slot_k = pend_back ? (uint32_t)(pend_old >> 32) : (uint32_t)pend_old;
+        const uint64_t slot = pend_back ? (uint64_t)pend_seg + (pend_cap - 1u - slot_k) : (uint64_t)pend_seg + slot_k;
+        if (debug & 2u) {
+        } else if (slot_k < pend_cap && slot < vals_cap) vals[slot] = pend_key;
+        else atomicOr(&ctr->flags, kFlagValsOverflow);
+        pend = false;
+    };
+
     for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t k = base + lane;
         const bool active = k < total;
@@ -775,71 +820,93 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         const uint32_t hf_j = __shfl_sync(0xffffffffu, hf, j), lo_j = __shfl_sync(0xffffffffu, lo, j);
         const uint32_t e0_j = __shfl_sync(0xffffffffu, e0, j), e1_j = __shfl_sync(0xffffffffu, e1, j);
         const uint32_t words_j = __shfl_sync(0xffffffffu, words, j);
-        if (!active) continue;
-        const uint32_t l = lo_j + idx, h = hf_j & 0xFFu;
-        const int32_t ls = __ldg(lv.start + l), le = __ldg(lv.end + l);
-        if (!pair_passes(unphased != 0, rs_j, re_j, ls, le)) continue;
-        visits += words_j;                                  // call.rs:357 runs before the bucket lookup
-        if (!unphased) {
-            if (h > 2u) {                                   // call.rs:358 unwrap on None
-                bad_hp = true;
-                ctr->bad_hp_value = h;
-                ctr->bad_hp_read = r - lane + j;
-                continue;
+        bool emit = false;
+        uint32_t l = 0, h = 0, seg = 0, cap = 0;
+        int32_t ls = 0, le = 0;
+        if (active) {
+            l = lo_j + idx;
+            h = hf_j & 0xFFu;
+            if (cached) {
+                ls = s_ls[wid][l - lo_min];
+                le = s_le[wid][l - lo_min];
+                seg = s_seg[wid][l - lo_min];
+                cap = s_seg[wid][l - lo_min + 1] - seg;
+            } else {
+                ls = __ldg(lv.start + l);
+                le = __ldg(lv.end + l);
+                seg = __ldg(seg_off + l);
+                cap = __ldg(seg_off + l + 1) - seg;
             }
-            if (h == 0u) continue;                          // HP 0 lands in the ignored bucket
+            if (pair_passes(unphased != 0, rs_j, re_j, ls, le)) {
+                visits += words_j;                          // call.rs:357 runs before the bucket lookup
+                emit = true;
+                if (!unphased) {
+                    if (h > 2u) {                           // call.rs:358 unwrap on None
+                        bad_hp = true;
+                        ctr->bad_hp_value = h;
+                        ctr->bad_hp_read = r - lane + j;
+                        emit = false;
+                    } else if (h == 0u) {
+                        emit = false;                       // HP 0 lands in the ignored bucket
+                    }
+                }
+            }
         }
-        ++npass;
-        atomicOr(&s_joined[wid], 1u << j);
-        // slot first: the atomic's round trip overlaps the event loads below
+        unsigned long long old = 0;
+        uint64_t key = 0;
         const bool back = !unphased && h == 2u;
-        const unsigned long long old = (debug & 1u) ? 0ull : atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
-        const uint32_t seg = __ldg(seg_off + l), cap = __ldg(seg_off + l + 1) - seg;
-        const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
-        const bool is2d = (hf_j >> 8) != 0u;
-        const uint32_t ne = e1_j - e0_j;
-        int64_t call = 0;
-        uint32_t clip = 0;
-        if (debug & 4u) {
-        } else if (ne <= 8u) {
-            // most reads carry a handful of events: fetch them all at once (independent loads)
-            uint2 ev[8];
+        if (emit) {
+            ++npass;
+            atomicOr(&s_joined[wid], 1u << j);
+            // slot first: the atomic's round trip overlaps the rest of this iteration and the next one
+            old = (debug & 1u) ? 0ull : atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
+            const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
+            const bool is2d = ((hf_j >> 8) & 1u) != 0u;
+            int64_t call = 0;
+            uint32_t clip = 0;
+            if (debug & 4u) {
+            } else if (!(hf_j & (1u << 9))) {
 #pragma unroll
-            for (uint32_t q = 0; q < 8u; ++q) ev[q] = (q < ne) ? events[e0_j + q] : make_uint2(0u, 0u);
-#pragma unroll
-            for (uint32_t q = 0; q < 8u; ++q) {
-                const int32_t v = (int32_t)ev[q].y;
-                const uint32_t is_s = (uint32_t)v & 1u;
-                // anchor 0 (padding) is never inside a window: the test is start_ext < P (call.rs:388)
-                if (ev[q].x > start_ext && ev[q].x < end_ext && !(is_s && is2d)) {   // call.rs:394 2D gate
+                for (uint32_t q = 0; q < (uint32_t)kPairEvCache; ++q) {
+                    const uint2 ev = s_ev[wid][j][q];
+                    const int32_t v = (int32_t)ev.y;
+                    const uint32_t is_s = (uint32_t)v & 1u;
+                    // start_ext < P && P < end_ext (call.rs:388,394,400); 2D gate call.rs:394
+                    if (ev.x > start_ext && ev.x < end_ext && !(is_s && is2d)) {
+                        call += (int64_t)(v >> 1);
+                        clip |= is_s;
+                    }
+                }
+            } else {
+                // first event with pos1 > start_ext
+                uint32_t a = e0_j, b = e1_j;
+                while (a < b) {
+                    const uint32_t m = a + ((b - a) >> 1);
+                    if (events[m].x > start_ext) b = m; else a = m + 1;
+                }
+                for (uint32_t e = a; e < e1_j; ++e) {
+                    const uint2 ev = events[e];
+                    if (!(ev.x < end_ext)) break;
+                    const int32_t v = (int32_t)ev.y;
+                    const uint32_t is_s = (uint32_t)v & 1u;
+                    if (is_s && is2d) continue;             // call.rs:394 !is_accidental_2d(&r)
                     call += (int64_t)(v >> 1);
                     clip |= is_s;
                 }
             }
-        } else {
-            // first event with pos1 > start_ext
-            uint32_t a = e0_j, b = e1_j;
-            while (a < b) {
-                const uint32_t m = a + ((b - a) >> 1);
-                if (events[m].x > start_ext) b = m; else a = m + 1;
-            }
-            for (uint32_t e = a; e < e1_j; ++e) {
-                const uint2 ev = events[e];
-                if (!(ev.x < end_ext)) break;
-                const int32_t v = (int32_t)ev.y;
-                const uint32_t is_s = (uint32_t)v & 1u;
-                if (is_s && is2d) continue;                 // call.rs:394 !is_accidental_2d(&r)
-                call += (int64_t)(v >> 1);
-                clip |= is_s;
-            }
+            key = ((uint64_t)(call + kCallBias) << 1) | clip;
         }
-        const uint64_t key = ((uint64_t)(call + kCallBias) << 1) | clip;
-        const uint32_t slot_k = back ? (uint32_t)(old >> 32) : (uint32_t)old;
-        const uint64_t slot = back ? (uint64_t)seg + (cap - 1u - slot_k) : (uint64_t)seg + slot_k;
-        if (debug & 2u) {
-        } else if (slot_k < cap && slot < vals_cap) vals[slot] = key;
-        else atomicOr(&ctr->flags, kFlagValsOverflow);
+        flush_pending();                                    // store of the previous candidate
+        if (emit) {
+            pend = true;
+            pend_old = old;
+            pend_key = key;
+            pend_seg = seg;
+            pend_cap = cap;
+            pend_back = back;
+        }
     }
+    flush_pending();
     __syncwarp();
     // statistics (one atomic per warp per counter)
     const bool joined = ((s_joined[wid] >> lane) & 1u) != 0u;
