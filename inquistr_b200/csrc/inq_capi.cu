@@ -530,12 +530,13 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         stats->n_loci = (uint64_t)L;
         stats->n_reads = R;
         stats->n_cigar_words = C;
-        stats->n_cigar_words_joined = ctx->h_ctr->n_words_joined;
-        stats->n_reads_joined = ctx->h_ctr->n_reads_joined;
-        stats->n_pairs = ctx->h_ctr->n_pairs;
-        stats->n_candidates = ctx->h_ctr->n_candidates;
+        auto total = [&](int k) { uint64_t t = 0; for (int i = 0; i < kStatSlots; ++i) t += ctx->h_ctr->stat[i][k]; return t; };
+        stats->n_cigar_words_joined = total(ST_WORDS_JOINED);
+        stats->n_reads_joined = total(ST_READS_JOINED);
+        stats->n_pairs = total(ST_PAIRS);
+        stats->n_candidates = total(ST_CANDIDATES);
         stats->n_events = ctx->h_ctr->n_events;
-        stats->op_visits = ctx->h_ctr->op_visits;
+        stats->op_visits = total(ST_OP_VISITS);
         stats->n_kernel_launches = launches;
         stats->n_tiles = ntiles;
         auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };

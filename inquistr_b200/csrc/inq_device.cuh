@@ -41,12 +41,13 @@ constexpr uint64_t kKeyHapBit = 1ull << 63;
 constexpr uint64_t kKeyInf = ~0ull;
 
 // device-side counters, one struct per ctx
+// statistics are accumulated per block into one of kStatSlots copies (a single address would
+// serialise hundreds of thousands of atomics in L2); the host adds the copies up
+constexpr int kStatSlots = 32;
+enum { ST_CANDIDATES = 0, ST_PAIRS, ST_READS_JOINED, ST_WORDS_JOINED, ST_OP_VISITS, ST_COUNT = 8 };
+
 struct DevCounters {
-    unsigned long long n_candidates;
-    unsigned long long n_pairs;
-    unsigned long long n_reads_joined;
-    unsigned long long n_words_joined;
-    unsigned long long op_visits;
+    unsigned long long stat[kStatSlots][ST_COUNT];
     unsigned long long n_events;
     unsigned long long ev_alloc;      // event slots handed out to warps (chunks)
     unsigned int flags;
@@ -310,8 +311,13 @@ k_join_ranges(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ ca
         cand_lo[r] = (uint32_t)lo;
         cand_n[r] = (uint32_t)n;
     }
+    __shared__ unsigned long long s_cand;
+    if (threadIdx.x == 0) s_cand = 0ull;
+    __syncthreads();
     const uint32_t cand_w = __reduce_add_sync(0xffffffffu, (uint32_t)n);
-    if (lane_id() == 0 && cand_w) atomicAdd(&ctr->n_candidates, (unsigned long long)cand_w);
+    if (lane_id() == 0 && cand_w) atomicAdd(&s_cand, (unsigned long long)cand_w);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cand) atomicAdd(&ctr->stat[blockIdx.x % kStatSlots][ST_CANDIDATES], s_cand);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -725,7 +731,7 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
 // events anchored inside the locus window (call.rs:388,394,400: start < P && P < end) and the
 // scatter of the packed call into the locus' segment: H1 (or every unphased call) grows from the
 // front of the segment, H2 from its back; one 64-bit atomic per pair hands out the slot.
-constexpr int kPairEvCache = 8;             // events per read kept in shared memory
+constexpr int kPairEvCache = 16;            // events per read kept in shared memory
 constexpr int kPairLociCache = 128;         // catalog entries per warp kept in shared memory
 
 __global__ void __launch_bounds__(256)
@@ -764,7 +770,7 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             if (e1 - e0 <= (uint32_t)kPairEvCache) {
 #pragma unroll
                 for (uint32_t q = 0; q < (uint32_t)kPairEvCache; ++q)
-                    s_ev[wid][lane][q] = (q < e1 - e0) ? events[e0 + q] : make_uint2(0u, 0u);   // anchor 0 is never in a window
+                    if (q < e1 - e0) s_ev[wid][lane][q] = events[e0 + q];
             } else {
                 hf |= 1u << 9;                              // long event list: searched in global memory
             }
@@ -866,24 +872,31 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             uint32_t clip = 0;
             if (debug & 4u) {
             } else if (!(hf_j & (1u << 9))) {
-#pragma unroll
-                for (uint32_t q = 0; q < (uint32_t)kPairEvCache; ++q) {
+                // the read's events sit in shared memory, sorted by anchor: binary search, then a short scan
+                const uint32_t ne = e1_j - e0_j;
+                uint32_t a = 0, b = ne;
+                while (a < b) {
+                    const uint32_t m = (a + b) >> 1;
+                    if (s_ev[wid][j][m].x > start_ext) b = m; else a = m + 1;
+                }
+                for (uint32_t q = a; q < ne; ++q) {
                     const uint2 ev = s_ev[wid][j][q];
+                    if (!(ev.x < end_ext)) break;           // start_ext < P && P < end_ext (call.rs:388,394,400)
                     const int32_t v = (int32_t)ev.y;
                     const uint32_t is_s = (uint32_t)v & 1u;
-                    // start_ext < P && P < end_ext (call.rs:388,394,400); 2D gate call.rs:394
-                    if (ev.x > start_ext && ev.x < end_ext && !(is_s && is2d)) {
-                        call += (int64_t)(v >> 1);
-                        clip |= is_s;
-                    }
+                    if (is_s && is2d) continue;             // call.rs:394 !is_accidental_2d(&r)
+                    call += (int64_t)(v >> 1);
+                    clip |= is_s;
                 }
             } else {
-                // first event with pos1 > start_ext
-                uint32_t a = e0_j, b = e1_j;
-                while (a < b) {
-                    const uint32_t m = a + ((b - a) >> 1);
-                    if (events[m].x > start_ext) b = m; else a = m + 1;
-                }
+                // long event list in global memory: anchors grow roughly linearly along the read, so start
+                // from the interpolated position and walk to the first event with pos1 > start_ext
+                const uint32_t ne = e1_j - e0_j;
+                const int64_t span = max((int64_t)re_j - (int64_t)rs_j, (int64_t)1);
+                int64_t g = (int64_t)e0_j + ((int64_t)start_ext - (int64_t)rs_j) * (int64_t)ne / span;
+                uint32_t a = (uint32_t)min(max(g, (int64_t)e0_j), (int64_t)e1_j - 1);
+                while (a > e0_j && events[a - 1].x > start_ext) --a;
+                while (a < e1_j && !(events[a].x > start_ext)) ++a;
                 for (uint32_t e = a; e < e1_j; ++e) {
                     const uint2 ev = events[e];
                     if (!(ev.x < end_ext)) break;
@@ -915,13 +928,19 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     const uint64_t words_w = warp_sum(joined ? (uint64_t)words : 0ull);
     const uint64_t visits_w = warp_sum(visits);
     const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
+    __shared__ unsigned long long s_stat[4];
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
+    __syncthreads();
     if (lane == 0) {
-        if (pass_w) atomicAdd(&ctr->n_pairs, (unsigned long long)pass_w);
-        if (join_w) atomicAdd(&ctr->n_reads_joined, (unsigned long long)join_w);
-        if (words_w) atomicAdd(&ctr->n_words_joined, (unsigned long long)words_w);
-        if (visits_w) atomicAdd(&ctr->op_visits, (unsigned long long)visits_w);
+        if (pass_w) atomicAdd(&s_stat[0], (unsigned long long)pass_w);
+        if (join_w) atomicAdd(&s_stat[1], (unsigned long long)join_w);
+        if (words_w) atomicAdd(&s_stat[2], (unsigned long long)words_w);
+        if (visits_w) atomicAdd(&s_stat[3], (unsigned long long)visits_w);
         if (bad_w) atomicOr(&ctr->flags, kFlagBadHp);
     }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_stat[threadIdx.x])
+        atomicAdd(&ctr->stat[blockIdx.x % kStatSlots][ST_PAIRS + threadIdx.x], s_stat[threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------------------
