@@ -43,7 +43,7 @@ constexpr uint64_t kKeyInf = ~0ull;
 // device-side counters, one struct per ctx
 // statistics are accumulated per block into one of kStatSlots copies (a single address would
 // serialise hundreds of thousands of atomics in L2); the host adds the copies up
-constexpr int kStatSlots = 32;
+constexpr int kStatSlots = 64;
 enum { ST_CANDIDATES = 0, ST_PAIRS, ST_READS_JOINED, ST_WORDS_JOINED, ST_OP_VISITS, ST_COUNT = 8 };
 
 struct DevCounters {
@@ -311,13 +311,9 @@ k_join_ranges(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ ca
         cand_lo[r] = (uint32_t)lo;
         cand_n[r] = (uint32_t)n;
     }
-    __shared__ unsigned long long s_cand;
-    if (threadIdx.x == 0) s_cand = 0ull;
-    __syncthreads();
     const uint32_t cand_w = __reduce_add_sync(0xffffffffu, (uint32_t)n);
-    if (lane_id() == 0 && cand_w) atomicAdd(&s_cand, (unsigned long long)cand_w);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_cand) atomicAdd(&ctr->stat[blockIdx.x % kStatSlots][ST_CANDIDATES], s_cand);
+    if (lane_id() == 0 && cand_w)
+        atomicAdd(&ctr->stat[(blockIdx.x * 8u + (threadIdx.x >> 5)) % kStatSlots][ST_CANDIDATES], (unsigned long long)cand_w);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -928,19 +924,15 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     const uint64_t words_w = warp_sum(joined ? (uint64_t)words : 0ull);
     const uint64_t visits_w = warp_sum(visits);
     const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
-    __shared__ unsigned long long s_stat[4];
-    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
-    __syncthreads();
     if (lane == 0) {
-        if (pass_w) atomicAdd(&s_stat[0], (unsigned long long)pass_w);
-        if (join_w) atomicAdd(&s_stat[1], (unsigned long long)join_w);
-        if (words_w) atomicAdd(&s_stat[2], (unsigned long long)words_w);
-        if (visits_w) atomicAdd(&s_stat[3], (unsigned long long)visits_w);
+        // one of kStatSlots copies per warp: no block barrier, and no single hot address in L2
+        unsigned long long *slot = ctr->stat[(blockIdx.x * 8u + wid) % kStatSlots];
+        if (pass_w) atomicAdd(slot + ST_PAIRS, (unsigned long long)pass_w);
+        if (join_w) atomicAdd(slot + ST_READS_JOINED, (unsigned long long)join_w);
+        if (words_w) atomicAdd(slot + ST_WORDS_JOINED, (unsigned long long)words_w);
+        if (visits_w) atomicAdd(slot + ST_OP_VISITS, (unsigned long long)visits_w);
         if (bad_w) atomicOr(&ctr->flags, kFlagBadHp);
     }
-    __syncthreads();
-    if (threadIdx.x < 4 && s_stat[threadIdx.x])
-        atomicAdd(&ctr->stat[blockIdx.x % kStatSlots][ST_PAIRS + threadIdx.x], s_stat[threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------------------
