@@ -367,16 +367,19 @@ struct ScanParams {
     uint32_t debug;               // timing experiments only (INQ_SCAN_DEBUG): results are wrong when != 0
 };
 
-constexpr int kLaneWords = 16;                          // consecutive CIGAR words per lane
-constexpr int kWarpTileWords = 32 * kLaneWords;         // 512 words = 2 KB = one TMA box
+#ifndef INQ_LANE_WORDS
+#define INQ_LANE_WORDS 32
+#endif
+constexpr int kLaneWords = INQ_LANE_WORDS;               // consecutive CIGAR words per lane (16 or 32)
+constexpr int kWarpTileWords = 32 * kLaneWords;         // 1024 words = 4 KB = one TMA box
 #ifndef INQ_SCAN_WARPS
-#define INQ_SCAN_WARPS 16
+#define INQ_SCAN_WARPS 24
 #endif
 #ifndef INQ_WARP_STAGES
-#define INQ_WARP_STAGES 3
+#define INQ_WARP_STAGES 2
 #endif
 #ifndef INQ_SCAN_MIN_CTAS
-#define INQ_SCAN_MIN_CTAS 2
+#define INQ_SCAN_MIN_CTAS 1
 #endif
 constexpr int kScanWarps = INQ_SCAN_WARPS;              // warps per CTA, each fully autonomous
 constexpr int kCtaThreads = kScanWarps * 32;
@@ -437,8 +440,10 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     __syncwarp();
 
     const uint32_t thr = (p.minlen << 4) | 15u;                 // (w >> 4) > minlen  <=>  w > thr
-    // this lane's 16 consecutive words: 128-byte row lane/2, chunks 4*(lane&1)+j, swizzled
-    const uint32_t rowq = (lane >> 1) * 8, x0 = ((lane & 1u) << 2) ^ ((lane >> 1) & 7u);
+    // this lane's kLaneWords consecutive words: quads q0..q0+kLaneWords/4-1 of the box; quad q lives in
+    // 128-byte row q/8 at chunk (q%8) ^ (row%8) (128B swizzle) -> conflict-free LDS.128 across the warp
+    constexpr uint32_t kQuads = kLaneWords / 4;
+    const uint32_t q0 = lane * kQuads;
     uint64_t chunk_cur = 0, chunk_end = 0;                      // this warp's private range of event slots
 
     for (uint32_t it = 0;; ++it) {
@@ -455,8 +460,9 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         uint32_t c = 0, evmask = 0, clast = 0;
         if (!(p.debug & 8u))
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 v = st4[rowq + (x0 ^ (uint32_t)j)];
+        for (int j = 0; j < (int)kQuads; ++j) {
+            const uint32_t q = q0 + (uint32_t)j, row = q >> 3;
+            const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
