@@ -22,7 +22,6 @@ namespace inq {
 
 // ----------------------------------------------------------------------------------------------
 // constants
-constexpr int kWarp = 32;
 constexpr int kTileWords = 8192;            // padding granularity of the device CIGAR stream (32 KB)
 
 constexpr uint32_t kFlagBadHp = 1u << 0;
@@ -31,7 +30,6 @@ constexpr uint32_t kFlagEventOverflow = 1u << 2;
 constexpr uint32_t kFlagValsOverflow = 1u << 3;
 constexpr uint32_t kFlagCountOverflow = 1u << 4;
 
-constexpr uint64_t kDescInvalid = 0ull;
 constexpr uint64_t kDescAggregate = 1ull << 62;
 constexpr uint64_t kDescPrefix = 2ull << 62;
 constexpr uint64_t kDescValueMask = (1ull << 62) - 1;
@@ -83,7 +81,7 @@ __device__ __forceinline__ uint32_t lanemask_lt()
     return m;
 }
 
-// mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP)
+// mbarrier helpers for the TMA tensor loads of k_cigar_scan
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -92,18 +90,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
 }
 // poll with a short sleep in between so that waiting warps do not burn issue slots
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns)
@@ -118,25 +104,6 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
         if (done) break;
         __nanosleep(ns);
     }
-}
-// same, but lets the hardware park the warp for up to ~`ns` per probe instead of spinning on issue slots
-__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t ns)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -406,11 +373,6 @@ __device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap 
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // Every warp is an independent pipeline: it owns warp tiles gwid, gwid + W, gwid + 2W, ... (W = warps
 // in the grid), a 3-stage ring of 2 KB shared-memory boxes that it fills itself with TMA, and the
 // mbarriers of that ring. There is no block-level synchronisation and no producer warp.
