@@ -211,10 +211,11 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaMalloc(&ctx->d_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost(&ctx->h_total, 64)) != cudaSuccess) return bail("cudaMallocHost", e);
-    if ((e = cudaFuncSetAttribute(k_cigar_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_cigar_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_cigar_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_cigar_scan)", e);
     int occ = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan, kCtaThreads, kScanSmemBytes)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan<false>, kCtaThreads, kScanSmemBytes)) != cudaSuccess)
         return bail("occupancy(k_cigar_scan)", e);
     ctx->scan_ctas_per_sm = std::max(1, occ);
     *out = ctx;
@@ -430,9 +431,11 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             ScanParams sp;
             sp.blk = ctx->blk.p; sp.wt = ctx->wt.p; sp.wtmask = ctx->wtmask.p;
             sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
-            sp.n_wt = n_wt; sp.minlen = minlen;
+            sp.n_wt = n_wt; sp.neg1 = 0xFFFFFFFFu;
+            sp.thr = (std::min<uint32_t>(minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
             { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
-            k_cigar_scan<<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
+            if (sp.thr >> 31) k_cigar_scan<true><<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
+            else k_cigar_scan<false><<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;
         }
 

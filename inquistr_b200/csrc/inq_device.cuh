@@ -330,7 +330,8 @@ struct ScanParams {
     DevCounters *ctr;
     uint64_t raw_cap;             // capacity of evraw (slots)
     uint64_t n_wt;                // warp tiles to scan
-    uint32_t minlen;
+    uint32_t thr;                 // (min(minlen, 2^28 - 1) << 4) | 15: an op is longer than minlen iff its word > thr
+    uint32_t neg1;                // 0xFFFFFFFF as a run-time value (keeps thr - w a multiply-add on the FMA pipe)
     uint32_t debug;               // timing experiments only (INQ_SCAN_DEBUG): results are wrong when != 0
 };
 
@@ -376,6 +377,7 @@ __device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap 
 // Every warp is an independent pipeline: it owns warp tiles gwid, gwid + W, gwid + 2W, ... (W = warps
 // in the grid), a 3-stage ring of 2 KB shared-memory boxes that it fills itself with TMA, and the
 // mbarriers of that ring. There is no block-level synchronisation and no producer warp.
+template <bool kThrHigh>
 __global__ void __launch_bounds__(kCtaThreads, INQ_SCAN_MIN_CTAS)
 k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
 {
@@ -401,7 +403,8 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     }
     __syncwarp();
 
-    const uint32_t thr = (p.minlen << 4) | 15u;                 // (w >> 4) > minlen  <=>  w > thr
+    const uint32_t thr = p.thr;                                 // (w >> 4) > minlen  <=>  w > thr
+    const uint32_t neg1 = p.neg1;
     // this lane's kLaneWords consecutive words: quads q0..q0+kLaneWords/4-1 of the box; quad q lives in
     // 128-byte row q/8 at chunk (q%8) ^ (row%8) (128B swizzle) -> conflict-free LDS.128 across the warp
     constexpr uint32_t kQuads = kLaneWords / 4;
@@ -417,27 +420,37 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint32_t *stage = sm.stage[warp][s];
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
 
-        // ---- one pass over the lane's 16 words. evmask: bit i <-> word i is an event;
-        //      clast: bases consumed inside the block before its LAST event
-        uint32_t c = 0, evmask = 0, clast = 0;
+        // ---- one pass over the lane's words. evrev: bit (31 - i) <-> word i is an event;
+        //      snap[j]: bases consumed inside the lane's words before quad j (no instructions: live values)
+        uint32_t c = 0, evrev = 0;
+        uint32_t snap[kQuads];
         if (!(p.debug & 8u))
 #pragma unroll
         for (int j = 0; j < (int)kQuads; ++j) {
             const uint32_t q = q0 + (uint32_t)j, row = q >> 3;
             const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            snap[j] = c;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 // one funnel shift in wrap mode indexes the LUT by 2*op without masking the op first
                 const uint32_t w = w4[k], lut = __funnelshift_r(kOpLutLo, kOpLutHi, w + w);
-                const bool ev = ((int32_t)lut < 0) && (w > thr);
-                evmask = ev ? (evmask | (1u << (j * 4 + k))) : evmask;
-                clast = ev ? c : clast;
+                // borrow of thr - w (<=> w > thr) lands in the sign bit of d | w (thr < 2^31) or d & w
+                // (thr >= 2^31); the subtraction is a multiply-add by a run-time -1 so that it issues on
+                // the FMA pipe. One LOP3 ands it with the op class, one funnel shift appends the sign bit.
+                uint32_t d;
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(neg1), "r"(thr));
+                const uint32_t t = kThrHigh ? (lut & (d & w)) : (lut & (d | w));
+                evrev = __funnelshift_l(t, evrev, 1);
                 // c += consumes ? len : 0 as one multiply-add (FMA pipe) instead of select + add (ALU pipe)
                 asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c) : "r"(w >> 4), "r"(lut & 1u));
             }
         }
-        const uint32_t ne = __popc(evmask);
+        else {
+#pragma unroll
+            for (int j = 0; j < (int)kQuads; ++j) snap[j] = 0;
+        }
+        const uint32_t ne = __popc(evrev);
         const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
         const uint32_t excl_c = incl_c - c, excl_e = incl_e - ne;
         const uint32_t tot_e = __shfl_sync(0xffffffffu, incl_e, 31);
@@ -461,26 +474,35 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             p.wt_sbase[gw] = (uint32_t)sbase;
         }
 
-        // ---- emit this lane's events (about 1% of the words), last event of the block first
-        if (evmask && !(p.debug & 1u)) {
-            bool first = true;
+        // ---- emit this lane's events (about 1% of the words): reload the event's quad, start from the
+        //      quad's snapshot and add the consumption of the (at most 3) words in front of the event
+        if (evrev && !(p.debug & 1u)) {
             do {
-                const uint32_t bit = 31u - (uint32_t)__clz(evmask);
-                evmask ^= 1u << bit;
-                const uint32_t idx = lane * kLaneWords + bit;
-                const uint32_t w = stage[swz(idx)];
-                uint32_t s_in = clast;                          // captured above for the last event
-                if (!first) {
-                    s_in = 0;
-                    for (uint32_t i = idx - bit; i < idx; ++i) s_in += cig_consume(stage[swz(i)]);
+                const uint32_t rbit = (uint32_t)__ffs(evrev) - 1u;      // last remaining event of the lane
+                evrev &= evrev - 1u;
+                const uint32_t word = 31u - rbit - (32u - kLaneWords), j = word >> 2, k = word & 3u;
+                const uint32_t q = q0 + j, row = q >> 3;
+                const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
+                uint32_t s_in;
+                if constexpr (kQuads == 8) {
+                    const bool b0 = j & 1u, b1 = j & 2u, b2 = j & 4u;
+                    const uint32_t a0 = b0 ? snap[1] : snap[0], a1 = b0 ? snap[3] : snap[2];
+                    const uint32_t a2 = b0 ? snap[5] : snap[4], a3 = b0 ? snap[7] : snap[6];
+                    const uint32_t lo = b1 ? a1 : a0, hi = b1 ? a3 : a2;
+                    s_in = b2 ? hi : lo;
+                } else {
+                    s_in = snap[0];
+#pragma unroll
+                    for (int jj = 1; jj < (int)kQuads; ++jj) s_in = (j == (uint32_t)jj) ? snap[jj] : s_in;
                 }
-                first = false;
+                s_in += (k > 0u ? cig_consume(v.x) : 0u) + (k > 1u ? cig_consume(v.y) : 0u) + (k > 2u ? cig_consume(v.z) : 0u);
+                const uint32_t w = k == 0u ? v.x : k == 1u ? v.y : k == 2u ? v.z : v.w;
                 const uint32_t len = w >> 4, op = w & 15u;
                 const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
-                const uint64_t slot = sbase + excl_e + __popc(evmask);   // lower bits remain in evmask
+                const uint64_t slot = sbase + excl_e + __popc(evrev);   // earlier events remain in evrev
                 if (slot < p.raw_cap) p.evraw[slot] = make_uint2(excl_c + s_in, (uint32_t)val);
                 else atomicOr(&p.ctr->flags, kFlagEventOverflow);
-            } while (evmask);
+            } while (evrev);
         }
         __syncwarp();                                           // every lane is done with stage s
         if (lane == 0) {
