@@ -51,8 +51,8 @@ struct inq_ctx {
     // work buffers
     DevBuf<uint32_t> cand_lo, cand_n, ev_off, delta, lcnt, seg_off, big_list;
     DevBuf<unsigned long long> cursor;
-    DevBuf<uint32_t> wt_sbase, wtmask;
-    DevBuf<uint2> blk, wt;
+    DevBuf<uint32_t> wt_sbase, tile_first;
+    DevBuf<uint2> rd_pre, wt;
     DevBuf<uint64_t> desc_scan, desc_wt, vals;
     DevBuf<uint2> evraw;
     CUtensorMap tmap;                 // 2-D view of the packed CIGAR stream: rows of 32 words, 128B swizzle
@@ -165,8 +165,8 @@ int reserve_reads(inq_ctx *ctx, uint64_t nR, uint64_t nC, double growth)
     TRY(ensure(ctx, ctx->cig_off, nR + 1, R + 1, growth));
     // CIGAR stream is padded with zero words up to a tile boundary (+1 tile of slack)
     TRY(ensure(ctx, ctx->cigar, round_up(nC, kTileWords) + kTileWords, C, growth));
-    // one mask word per 512-word warp tile: which 16-word blocks hold the first CIGAR word of a read
-    TRY(ensure(ctx, ctx->wtmask, ctx->cigar.cap / kWarpTileWords + 2, (C + kWarpTileWords - 1) / kWarpTileWords, 1.0));
+    // per warp tile: the first read that starts in it (entries below C / kWarpTileWords stay valid across pushes)
+    TRY(ensure(ctx, ctx->tile_first, ctx->cigar.cap / kWarpTileWords + 2, C / kWarpTileWords, 1.0));
     return INQ_OK;
 }
 
@@ -232,7 +232,7 @@ void inq_ctx_destroy(inq_ctx *ctx)
     release(ctx->mapq); release(ctx->hp); release(ctx->flags);
     release(ctx->cig_off); release(ctx->cigar);
     release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off);
-    release(ctx->blk); release(ctx->wt); release(ctx->wt_sbase); release(ctx->wtmask);
+    release(ctx->rd_pre); release(ctx->wt); release(ctx->wt_sbase); release(ctx->tile_first);
     release(ctx->desc_wt); release(ctx->evraw);
     release(ctx->delta); release(ctx->lcnt); release(ctx->seg_off); release(ctx->cursor); release(ctx->big_list);
     release(ctx->desc_scan); release(ctx->vals);
@@ -358,11 +358,10 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_
     const uint64_t C1 = C0 + nw, Cpad = round_up(C1, kTileWords);
     if (Cpad > C1) CU_TRY(ctx, cudaMemsetAsync(ctx->cigar.p + C1, 0, (Cpad - C1) * sizeof(uint32_t), s));
     {
-        // read-start mask of the warp tiles touched by this batch (k_cigar_scan writes block-table
-        // entries only where a read starts); tiles that hold only new words are cleared first
-        const uint64_t wt_lo = (C0 + kWarpTileWords - 1) / kWarpTileWords, wt_hi = Cpad / kWarpTileWords + 1;
-        CU_TRY(ctx, cudaMemsetAsync(ctx->wtmask.p + wt_lo, 0, (wt_hi - wt_lo + 1) * sizeof(uint32_t), s));
-        k_start_mask<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p + R0, n, ctx->wtmask.p);
+        // reads starting per warp tile, for the tiles that gained words (k_cigar_scan leaves the tile-local
+        // prefix of every read start in rd_pre); cig_off[R0 + n] is the sentinel and counts as a start
+        const uint64_t t0 = C0 / kWarpTileWords, t1 = Cpad / kWarpTileWords;
+        k_tile_first<<<(unsigned)((t1 - t0 + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R0 + n + 1, t0, t1, ctx->tile_first.p);
         CU_TRY(ctx, cudaGetLastError());
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D1], s));
@@ -393,7 +392,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     TRY(ensure(ctx, ctx->cand_lo, R));
     TRY(ensure(ctx, ctx->cand_n, R));
     TRY(ensure(ctx, ctx->ev_off, R + 1));
-    TRY(ensure(ctx, ctx->blk, n_wt * 32 + 1));
+    TRY(ensure(ctx, ctx->rd_pre, R + 1));
     TRY(ensure(ctx, ctx->wt, n_wt + 2));
     TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
     TRY(ensure(ctx, ctx->desc_wt, 2 * ((uint64_t)wt_scan_tiles + 1)));
@@ -429,7 +428,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR0], s));
         if (ntiles && L) {
             ScanParams sp;
-            sp.blk = ctx->blk.p; sp.wt = ctx->wt.p; sp.wtmask = ctx->wtmask.p;
+            sp.tile_first = ctx->tile_first.p; sp.cig_off = ctx->cig_off.p; sp.rd_pre = ctx->rd_pre.p; sp.wt = ctx->wt.p;
             sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
             sp.n_wt = n_wt; sp.neg1 = 0xFFFFFFFFu;
             sp.thr = (std::min<uint32_t>(minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
@@ -469,8 +468,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             k_exclusive_scan2<<<g, kXsThreads, 0, s>>>(ctx->wt.p, n_wt, wt_scan_tiles, ctx->desc_wt.p, ctx->desc_wt.p + wt_scan_tiles + 1,
                                                        &ctx->d_ctr->scan_counter[0], &ctx->d_ctr->flags);
             const uint64_t fix_warps = (R + 1 + 30) / 31;
-            k_read_fixup<<<(unsigned)((fix_warps * 32 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->cigar.p, ctx->wt.p, ctx->blk.p,
-                                                                                 ctx->wt_sbase.p, minlen, ctx->evraw.p, ctx->evraw.cap,
+            k_read_fixup<<<(unsigned)((fix_warps * 32 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->wt.p, ctx->rd_pre.p,
+                                                                                 ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap,
                                                                                  ctx->events.p, ctx->events.cap, ctx->ev_off.p, ctx->d_ctr);
             launches += 2;
         }

@@ -308,22 +308,23 @@ __device__ __forceinline__ uint64_t lookback(const uint64_t *__restrict__ desc, 
 }
 
 // ----------------------------------------------------------------------------------------------
-// K2: CIGAR scan. Persistent warps stream 2 KB "warp tiles" (512 words) of the flat packed-CIGAR array
-// through per-warp 3-stage shared-memory rings filled by TMA (2-D tensor map, 128B swizzle); each lane
-// owns 16 consecutive words. One pass over the words gives
-// the lane's reference consumption (call.rs:384-392,404) and its event mask (I/D/S ops longer than
-// minlen, call.rs:388,394,400); two warp scans turn that into warp-local prefixes. Nothing in this
-// kernel depends on another CTA or on read boundaries: it writes
-//   blk   : warp-local exclusive prefixes {consumption, events} at every 16-word block
-//   wt    : totals per warp tile (prefix-summed afterwards by k_exclusive_scan2)
-//   evraw         : {bases consumed inside the warp tile before the op, (signed len << 1) | is_S}
-//                   for every event, stored per warp tile in chunks handed out by one atomic
+// K2: CIGAR scan. Persistent warps stream 4 KB "warp tiles" (1024 words) of the flat packed-CIGAR array
+// through per-warp 2-stage shared-memory rings filled by TMA (2-D tensor map, 128B swizzle); each lane
+// owns 32 consecutive words. One pass over the words gives the lane's reference consumption
+// (call.rs:384-392,404) and its event mask (I/D/S ops longer than minlen, call.rs:388,394,400); two warp
+// scans turn that into warp-local prefixes. Nothing in this kernel depends on another CTA or warp:
+// it writes
+//   rd_pre : warp-tile-local exclusive prefixes {consumption, events} at the first word of every read
+//            that starts inside the tile (tile_first, built when reads are pushed, names those reads)
+//   wt     : totals per warp tile (prefix-summed afterwards by k_exclusive_scan2)
+//   evraw  : {bases consumed inside the warp tile before the op, (signed len << 1) | is_S}
+//            for every event, stored per warp tile in chunks handed out by one atomic
 // and k_read_fixup turns these into per-read event lists with absolute anchors.
 // Each CIGAR word is read from HBM exactly once.
 struct ScanParams {
-    uint2 *blk;                   // [n_wt * 32] {warp-local exclusive consumption, event count} per 16-word block,
-                                  // written only for blocks that hold a read start (wtmask)
-    const uint32_t *wtmask;       // [n_wt] bit b: block b of the warp tile holds the first CIGAR word of a read
+    const uint32_t *tile_first;   // [n_wt + 1] first read (index into cig_off, sentinel R included) starting in warp tile t or later
+    const uint64_t *cig_off;      // [R + 1] first CIGAR word of every read (+ sentinel)
+    uint2 *rd_pre;                // [R + 1] {consumption, events} inside the read's warp tile before its first word
     uint2 *wt;                    // [n_wt + 1] {consumption, events} per warp tile (prefix-summed afterwards)
     uint32_t *wt_sbase;           // [n_wt] storage slot of the warp tile's first event
     uint2 *evraw;
@@ -360,6 +361,7 @@ constexpr uint32_t kEvChunk = 1024;                     // event slots a warp ta
 
 struct ScanSmem {
     alignas(1024) uint32_t stage[kScanWarps][kWarpStages][kWarpTileWords];   // 128B-swizzled by the TMA tensor map
+    uint32_t snap[kScanWarps][kLaneWords / 4][32];                            // per-quad cursor snapshots of every lane
     alignas(8) uint64_t full[kScanWarps][kWarpStages];                        // TMA landed (tx bytes)
 };
 constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align the swizzled stages to 1 KB
@@ -410,18 +412,31 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     constexpr uint32_t kQuads = kLaneWords / 4;
     const uint32_t q0 = lane * kQuads;
     uint64_t chunk_cur = 0, chunk_end = 0;                      // this warp's private range of event slots
+    // reads that start inside the current warp tile: [tf_lo, tf_hi), lane i holds the first word of read
+    // tf_lo + i. Both are fetched one iteration ahead so that their latency never shows.
+    uint32_t tf_lo = 0, tf_hi = 0;
+    uint64_t g_cur = 0;
+    if (gwid < p.n_wt) {
+        tf_lo = __ldg(p.tile_first + gwid);
+        tf_hi = __ldg(p.tile_first + gwid + 1);
+        if (tf_lo + lane < tf_hi) g_cur = __ldg(p.cig_off + tf_lo + lane);
+    }
 
     for (uint32_t it = 0;; ++it) {
         const uint64_t gw = gwid + (uint64_t)it * stride;       // global warp-tile index
         if (gw >= p.n_wt) break;
         const uint32_t s = it % kWarpStages;
-        const uint32_t wtm = __ldg(p.wtmask + gw);              // latency hides behind the wait
+        uint32_t nf_lo = 0, nf_hi = 0;
+        if (gw + stride < p.n_wt) {
+            nf_lo = __ldg(p.tile_first + gw + stride);
+            nf_hi = __ldg(p.tile_first + gw + stride + 1);
+        }
         mbar_wait_backoff(&full[s], (it / kWarpStages) & 1u, 32u);
         const uint32_t *stage = sm.stage[warp][s];
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
 
         // ---- one pass over the lane's words. evrev: bit (31 - i) <-> word i is an event;
-        //      snap[j]: bases consumed inside the lane's words before quad j (no instructions: live values)
+        //      snap[j]: bases consumed inside the lane's words before quad j (parked in shared memory below)
         uint32_t c = 0, evrev = 0;
         uint32_t snap[kQuads];
         if (!(p.debug & 8u))
@@ -454,7 +469,36 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint32_t incl_c = warp_incl_scan(c), incl_e = warp_incl_scan(ne);
         const uint32_t excl_c = incl_c - c, excl_e = incl_e - ne;
         const uint32_t tot_e = __shfl_sync(0xffffffffu, incl_e, 31);
-        if ((wtm >> lane) & 1u) p.blk[gw * 32 + lane] = make_uint2(excl_c, excl_e);
+        uint64_t g_nxt = 0;
+        if (nf_lo + lane < nf_hi) g_nxt = __ldg(p.cig_off + nf_lo + lane);
+
+        // ---- reads that start inside this warp tile: the tile-local prefix at their first word, from the
+        //      owning lane's scan values (shuffles), its quad snapshot (shared memory) and at most 3 words
+#pragma unroll
+        for (int j = 0; j < (int)kQuads; ++j) sm.snap[warp][j][lane] = snap[j];
+        __syncwarp();
+        if (tf_lo < tf_hi) {
+            for (uint32_t r0 = tf_lo; r0 < tf_hi; r0 += 32) {
+                const uint32_t rr = r0 + lane;
+                const bool act = rr < tf_hi;
+                const uint64_t g = (r0 == tf_lo) ? g_cur : (act ? __ldg(p.cig_off + rr) : 0ull);
+                const uint32_t off = act ? (uint32_t)(g - gw * kWarpTileWords) : 0u;
+                const uint32_t owner = off / kLaneWords, k = off % kLaneWords;
+                const uint32_t xc = __shfl_sync(0xffffffffu, excl_c, owner), xe = __shfl_sync(0xffffffffu, excl_e, owner);
+                const uint32_t er = __shfl_sync(0xffffffffu, evrev, owner);
+                if (act && off) {
+                    const uint32_t j = k >> 2, kk = k & 3u, q = owner * kQuads + j, row = q >> 3;
+                    const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
+                    const uint32_t c_in = sm.snap[warp][j][owner] + (kk > 0u ? cig_consume(v.x) : 0u) +
+                                          (kk > 1u ? cig_consume(v.y) : 0u) + (kk > 2u ? cig_consume(v.z) : 0u);
+                    const uint32_t e_in = k ? __popc(er >> (kLaneWords - k)) : 0u;     // word i <-> bit kLaneWords-1-i
+                    p.rd_pre[rr] = make_uint2(xc + c_in, xe + e_in);
+                }
+            }
+        }
+        tf_lo = nf_lo;
+        tf_hi = nf_hi;
+        g_cur = g_nxt;
 
         // ---- event slots: contiguous per warp tile, taken from a warp-private chunk
         uint64_t sbase = chunk_cur;
@@ -483,18 +527,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
                 const uint32_t word = 31u - rbit - (32u - kLaneWords), j = word >> 2, k = word & 3u;
                 const uint32_t q = q0 + j, row = q >> 3;
                 const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
-                uint32_t s_in;
-                if constexpr (kQuads == 8) {
-                    const bool b0 = j & 1u, b1 = j & 2u, b2 = j & 4u;
-                    const uint32_t a0 = b0 ? snap[1] : snap[0], a1 = b0 ? snap[3] : snap[2];
-                    const uint32_t a2 = b0 ? snap[5] : snap[4], a3 = b0 ? snap[7] : snap[6];
-                    const uint32_t lo = b1 ? a1 : a0, hi = b1 ? a3 : a2;
-                    s_in = b2 ? hi : lo;
-                } else {
-                    s_in = snap[0];
-#pragma unroll
-                    for (int jj = 1; jj < (int)kQuads; ++jj) s_in = (j == (uint32_t)jj) ? snap[jj] : s_in;
-                }
+                uint32_t s_in = sm.snap[warp][j][lane];
                 s_in += (k > 0u ? cig_consume(v.x) : 0u) + (k > 1u ? cig_consume(v.y) : 0u) + (k > 2u ? cig_consume(v.z) : 0u);
                 const uint32_t w = k == 0u ? v.x : k == 1u ? v.y : k == 2u ? v.z : v.w;
                 const uint32_t len = w >> 4, op = w & 15u;
@@ -516,27 +549,33 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     }
 }
 
-// Marks, per warp tile, the 16-word blocks that hold the first CIGAR word of a read: only those
-// need an entry in the block table (3-4 % of all blocks), which saves ~10 % of the scan's DRAM traffic.
+// tile_first[t] = first entry of cig_off[0, n_entries) that is >= t * kWarpTileWords (n_entries if none), for
+// warp tiles t0..t1: the reads that start inside warp tile t are [tile_first[t], tile_first[t+1]).
+// Runs when reads are pushed, not per genotyping pass.
 __global__ void __launch_bounds__(256)
-k_start_mask(const uint64_t *__restrict__ cig_off, uint64_t R, uint32_t *__restrict__ wtmask)
+k_tile_first(const uint64_t *__restrict__ cig_off, uint64_t n_entries, uint64_t t0, uint64_t t1, uint32_t *__restrict__ tile_first)
 {
-    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (r > R) return;
-    const uint64_t g = cig_off[r];
-    if (g % kWarpTileWords) atomicOr(wtmask + g / kWarpTileWords, 1u << ((g / kLaneWords) & 31u));
+    const uint64_t t = t0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t > t1) return;
+    const uint64_t target = t * kWarpTileWords;
+    uint64_t lo = 0, hi = n_entries;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(cig_off + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    tile_first[t] = (uint32_t)lo;
 }
 
 // Per read: (1) the index of its first event in CIGAR order and the stream-wide consumption prefix
-// at its first word, from the warp-tile prefixes, the block table and at most 15 CIGAR words;
+// at its first word = warp-tile prefix + the tile-local prefix k_cigar_scan left in rd_pre;
 // (2) its events moved from warp-tile storage into CIGAR order with absolute anchors:
 // pos1 = ref_start + 1 + bases consumed by the read before the op (the u32 cursor of call.rs:380).
 // A warp owns 31 reads; lane 31 only supplies the first-event index of the next read.
 // `wt` holds EXCLUSIVE prefixes here (k_exclusive_scan2 ran in between).
 __global__ void __launch_bounds__(256)
 k_read_fixup(const uint64_t *__restrict__ cig_off, const int32_t *__restrict__ rs, uint64_t R,
-             const uint32_t *__restrict__ cigar, const uint2 *__restrict__ wt, const uint2 *__restrict__ blk,
-             const uint32_t *__restrict__ wt_sbase, uint32_t minlen, const uint2 *__restrict__ evraw, uint64_t raw_cap,
+             const uint2 *__restrict__ wt, const uint2 *__restrict__ rd_pre,
+             const uint32_t *__restrict__ wt_sbase, const uint2 *__restrict__ evraw, uint64_t raw_cap,
              uint2 *__restrict__ events, uint64_t ev_cap, uint32_t *__restrict__ ev_off, DevCounters *__restrict__ ctr)
 {
     const uint32_t lane = lane_id();
@@ -546,20 +585,13 @@ k_read_fixup(const uint64_t *__restrict__ cig_off, const int32_t *__restrict__ r
     uint64_t g = 0;
     if (r <= R) {
         g = cig_off[r];
-        const uint64_t gw = g / kWarpTileWords;
-        const uint2 w0 = wt[gw];
+        const uint2 w0 = wt[g / kWarpTileWords];
         c = w0.x;
         e = w0.y;
         if (g % kWarpTileWords) {
-            const uint64_t b = g / kLaneWords;
-            const uint2 b0 = blk[b];
-            c += b0.x;
-            e += b0.y;
-            for (uint64_t i = b * kLaneWords; i < g; ++i) {
-                const uint32_t w = __ldg(cigar + i);
-                c += cig_consume(w);
-                e += cig_is_event(w, minlen) ? 1u : 0u;
-            }
+            const uint2 pre = rd_pre[r];
+            c += pre.x;
+            e += pre.y;
         }
     }
     const uint32_t e_next = __shfl_down_sync(0xffffffffu, e, 1);
@@ -717,7 +749,7 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
 // events anchored inside the locus window (call.rs:388,394,400: start < P && P < end) and the
 // scatter of the packed call into the locus' segment: H1 (or every unphased call) grows from the
 // front of the segment, H2 from its back; one 64-bit atomic per pair hands out the slot.
-constexpr int kPairEvCache = 16;            // events per read kept in shared memory
+constexpr int kPairEvPool = 512;            // events per warp (32 consecutive reads) kept in shared memory
 constexpr int kPairLociCache = 128;         // catalog entries per warp kept in shared memory
 
 __global__ void __launch_bounds__(256)
@@ -729,13 +761,14 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
 {
     // A warp owns 32 consecutive reads; their candidates are flattened and dealt to the lanes
     // 32 at a time (reads have 0..hundreds of candidates, a per-read loop leaves most lanes idle).
-    // Everything the inner loop needs is staged in shared memory first (the reads' first events, the
-    // slice of the catalog the warp touches), so that the only global operations left in the loop
-    // are the slot atomic and the store of the call -- and the store is deferred by one iteration so
-    // that the atomic's round trip overlaps the next candidate.
+    // Everything the inner loop needs is staged in shared memory first (the reads' events -- one
+    // contiguous, coalesced run of the event array --, the slice of the catalog the warp touches), so
+    // that the only global operations left in the loop are the slot atomic and the store of the call --
+    // and the store is deferred by one iteration so that the atomic's round trip overlaps the next
+    // candidate.
     __shared__ uint32_t s_off[8][32];
     __shared__ uint32_t s_joined[8];
-    __shared__ uint2 s_ev[8][32][kPairEvCache];
+    __shared__ uint2 s_ev[8][kPairEvPool];
     __shared__ int32_t s_ls[8][kPairLociCache], s_le[8][kPairLociCache];
     __shared__ uint32_t s_seg[8][kPairLociCache + 1];
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
@@ -743,25 +776,26 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     uint32_t n = 0, lo = 0, e0 = 0, e1 = 0, hf = 0, words = 0;
     int32_t rs = 0, re = 0;
     if (r < rv.R) {
+        // independent loads, all in flight together
         n = cand_n[r];
-        if (n) {
-            lo = cand_lo[r];
-            rs = rv.rs[r];
-            re = rv.re[r];
-            hf = (uint32_t)rv.hp[r] | ((uint32_t)(rv.flags[r] & 1u) << 8);
-            // if the speculative event list overflowed the run is repeated; stay inside the allocation
-            e0 = (uint32_t)min((uint64_t)ev_off[r], ev_cap);
-            e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
-            words = (uint32_t)min(rv.cig_off[r + 1] - rv.cig_off[r], (uint64_t)0xFFFFFFFFu);
-            if (e1 - e0 <= (uint32_t)kPairEvCache) {
-#pragma unroll
-                for (uint32_t q = 0; q < (uint32_t)kPairEvCache; ++q)
-                    if (q < e1 - e0) s_ev[wid][lane][q] = events[e0 + q];
-            } else {
-                hf |= 1u << 9;                              // long event list: searched in global memory
-            }
-        }
+        lo = cand_lo[r];
+        rs = rv.rs[r];
+        re = rv.re[r];
+        hf = (uint32_t)rv.hp[r] | ((uint32_t)(rv.flags[r] & 1u) << 8);
+        // if the speculative event list overflowed the run is repeated; stay inside the allocation
+        e0 = (uint32_t)min((uint64_t)ev_off[r], ev_cap);
+        e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
+        words = (uint32_t)min(rv.cig_off[r + 1] - rv.cig_off[r], (uint64_t)0xFFFFFFFFu);
     }
+    // the events of the warp's joined reads are one run [ev_lo, ev_hi) of the event array
+    const uint32_t ev_lo = __reduce_min_sync(0xffffffffu, n ? e0 : 0xFFFFFFFFu);
+    const uint32_t ev_hi = __reduce_max_sync(0xffffffffu, n ? e1 : 0u);
+    if (ev_lo < ev_hi) {
+        const uint32_t cnt = min(ev_hi - ev_lo, (uint32_t)kPairEvPool);
+        for (uint32_t i = lane; i < cnt; i += 32) s_ev[wid][i] = events[ev_lo + i];
+    }
+    if (n && e1 - ev_lo > (uint32_t)kPairEvPool) hf |= 1u << 9;      // not (entirely) staged: searched in global memory
+    const uint32_t eb = e0 - ev_lo;                                   // first staged event of the read
     const uint32_t incl = warp_incl_scan(n);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     s_off[wid][lane] = incl - n;
@@ -811,6 +845,7 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         const int32_t rs_j = __shfl_sync(0xffffffffu, rs, j), re_j = __shfl_sync(0xffffffffu, re, j);
         const uint32_t hf_j = __shfl_sync(0xffffffffu, hf, j), lo_j = __shfl_sync(0xffffffffu, lo, j);
         const uint32_t e0_j = __shfl_sync(0xffffffffu, e0, j), e1_j = __shfl_sync(0xffffffffu, e1, j);
+        const uint32_t eb_j = __shfl_sync(0xffffffffu, eb, j);
         const uint32_t words_j = __shfl_sync(0xffffffffu, words, j);
         bool emit = false;
         uint32_t l = 0, h = 0, seg = 0, cap = 0;
@@ -860,13 +895,14 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             } else if (!(hf_j & (1u << 9))) {
                 // the read's events sit in shared memory, sorted by anchor: binary search, then a short scan
                 const uint32_t ne = e1_j - e0_j;
+                const uint2 *sev = &s_ev[wid][eb_j];
                 uint32_t a = 0, b = ne;
                 while (a < b) {
                     const uint32_t m = (a + b) >> 1;
-                    if (s_ev[wid][j][m].x > start_ext) b = m; else a = m + 1;
+                    if (sev[m].x > start_ext) b = m; else a = m + 1;
                 }
                 for (uint32_t q = a; q < ne; ++q) {
-                    const uint2 ev = s_ev[wid][j][q];
+                    const uint2 ev = sev[q];
                     if (!(ev.x < end_ext)) break;           // start_ext < P && P < end_ext (call.rs:388,394,400)
                     const int32_t v = (int32_t)ev.y;
                     const uint32_t is_s = (uint32_t)v & 1u;
@@ -946,10 +982,10 @@ template <> struct KeyTraits<uint32_t> {
 };
 
 // all-ascending bitonic network over K striped registers per lane (element i = k*32 + lane)
-template <int K, typename T>
+// N < K * 32 sorts every aligned run of N elements on its own
+template <int K, typename T, int N = K * 32>
 __device__ __forceinline__ void warp_sort(T (&key)[K])
 {
-    constexpr int N = K * 32;
 #pragma unroll
     for (int blk = 2; blk <= N; blk <<= 1) {
         // mirror step: partner = i ^ (blk - 1)
@@ -1010,7 +1046,7 @@ __device__ __forceinline__ bool warp_median_part(const T (&key)[K], uint32_t a, 
     if (m == 0) { *panicked = true; return false; }                  // call.rs:516 on an empty vector
     const uint32_t t2 = m >> 1, t1 = (m & 1u) ? t2 : t2 - 1u;        // call.rs:515-521
     uint32_t clip_before = 0, sel_before = 0;
-    int64_t contrib = 0;
+    int64_t sum = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t me = 1u << lane_id();
@@ -1021,56 +1057,70 @@ __device__ __forceinline__ bool warp_median_part(const T (&key)[K], uint32_t a, 
         const uint32_t rank = sel_before + __popc(sel_b & lanemask_lt());
         if (sel) {
             const int64_t v = KeyTraits<T>::call(key[k]);
-            if (rank == t1) contrib += v;
-            if (rank == t2) contrib += v;
+            if (rank == t1) sum += v;
+            if (rank == t2) sum += v;
         }
         clip_before += __popc(clip_b[k]);
         sel_before += __popc(sel_b);
     }
-    *twice = warp_sum(contrib);
+    // (handing the two middle keys out by ballot + shuffle instead was measured: 15 % slower)
+    *twice = warp_sum(sum);
     return true;
 }
 
 // A locus' segment [seg, seg+cap) holds its H1 calls at the front and its H2 calls at the back
 // (unphased: everything at the front). nf/nb = number of front/back entries; n1 = split point of
 // the sorted run (phased: nf, unphased: (nf)/2).
-template <int K>
+// kSplit > 0 (phased only): H1 lives at positions [0, nf) and H2 at [kSplit, kSplit + nb) and the two
+// runs of kSplit elements are sorted independently (a shorter network than one sort over both).
+template <int K, int kSplit = 0>
 __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, uint32_t seg, uint32_t cap, uint32_t nf,
                                            uint32_t nb, uint32_t n1, bool phased, uint32_t support, int64_t *t1,
                                            int64_t *t2, uint32_t *valid, bool *panicked)
 {
     const uint32_t ntot = nf + nb;
+    constexpr int kSortN = kSplit ? kSplit : K * 32;
+    const uint32_t a2 = kSplit ? (uint32_t)kSplit : n1;              // first position of the second part
     uint64_t key[K];
+    bool have_k[K];
     bool small = true;                      // every call fits the 32-bit key layout
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t i = k * 32 + lane_id();
         uint64_t v = kKeyInf;
-        if (i < nf) v = vals[seg + i];
-        else if (i < ntot) v = vals[seg + cap - nb + (i - nf)] | (phased ? kKeyHapBit : 0ull);
-        if (i < ntot) {
+        bool have;
+        if constexpr (kSplit > 0) {
+            have = (i < nf) || (i >= (uint32_t)kSplit && i - (uint32_t)kSplit < nb);
+            if (i < nf) v = vals[seg + i];
+            else if (have) v = vals[seg + cap - nb + (i - (uint32_t)kSplit)];
+        } else {
+            have = i < ntot;
+            if (i < nf) v = vals[seg + i];
+            else if (have) v = vals[seg + cap - nb + (i - nf)] | (phased ? kKeyHapBit : 0ull);
+        }
+        if (have) {
             const int64_t c = key_call(v);
             small = small && c >= -(int64_t)KeyTraits<uint32_t>::bias && c < (int64_t)KeyTraits<uint32_t>::bias;
         }
         key[k] = v;
+        have_k[k] = have;
     }
     bool v1, v2;
     if (__all_sync(0xffffffffu, small)) {
         uint32_t k32[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const uint32_t i = k * 32 + lane_id();
             const uint64_t v = key[k];
             const uint32_t body = (uint32_t)((key_call(v) + KeyTraits<uint32_t>::bias) << 1) | (uint32_t)(v & 1ull);
-            k32[k] = (i < ntot) ? (body | ((v & kKeyHapBit) ? KeyTraits<uint32_t>::hap : 0u)) : KeyTraits<uint32_t>::inf;
+            k32[k] = have_k[k] ? (body | ((v & kKeyHapBit) ? KeyTraits<uint32_t>::hap : 0u)) : KeyTraits<uint32_t>::inf;
         }
-        warp_sort<K, uint32_t>(k32);
+        warp_sort<K, uint32_t, kSortN>(k32);
         v1 = warp_median_part<K, uint32_t>(k32, 0, n1, support, t1, panicked);
-        v2 = warp_median_part<K, uint32_t>(k32, n1, ntot - n1, support, t2, panicked);
+        v2 = warp_median_part<K, uint32_t>(k32, a2, ntot - n1, support, t2, panicked);
     } else {
-        warp_sort<K, uint64_t>(key);
+        warp_sort<K, uint64_t, kSortN>(key);
         v1 = warp_median_part<K, uint64_t>(key, 0, n1, support, t1, panicked);
-        v2 = warp_median_part<K, uint64_t>(key, n1, ntot - n1, support, t2, panicked);
+        v2 = warp_median_part<K, uint64_t>(key, a2, ntot - n1, support, t2, panicked);
     }
     *valid = (v1 ? 1u : 0u) | (v2 ? 2u : 0u);
 }
@@ -1097,7 +1147,9 @@ k_locus_median(uint32_t L, int unphased, uint32_t support, const uint32_t *__res
     int64_t t1 = 0, t2 = 0;
     uint32_t vm = 0;
     bool panicked = false;
-    if (ntot <= 32) warp_locus<1>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+    if (!unphased && nf <= 16 && nb <= 16) warp_locus<1, 16>(vals, seg, cap, nf, nb, n1, true, support, &t1, &t2, &vm, &panicked);
+    else if (ntot <= 32) warp_locus<1>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+    else if (!unphased && nf <= 32 && nb <= 32) warp_locus<2, 32>(vals, seg, cap, nf, nb, n1, true, support, &t1, &t2, &vm, &panicked);
     else if (ntot <= 64) warp_locus<2>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
     else if (ntot <= kMedianWarpMax) warp_locus<4>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
     else {
