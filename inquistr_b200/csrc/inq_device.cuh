@@ -358,10 +358,16 @@ constexpr int kWarpStages = INQ_WARP_STAGES;             // per-warp ring of TMA
 constexpr uint32_t kOpLutLo = (1u << 0) | (1u << 4) | (1u << 6) | (1u << 14) | (1u << 16);
 constexpr uint32_t kOpLutHi = (1u << 1) | (1u << 3) | (1u << 7);
 constexpr uint32_t kEvChunk = 1024;                     // event slots a warp takes per atomic
+// cig_consume through the LUT: branch-free, the multiply issues on the FMA pipe
+__device__ __forceinline__ uint32_t cig_consume_lut(uint32_t w)
+{
+    return (w >> 4) * (__funnelshift_r(kOpLutLo, kOpLutHi, w + w) & 1u);
+}
 
 struct ScanSmem {
     alignas(1024) uint32_t stage[kScanWarps][kWarpStages][kWarpTileWords];   // 128B-swizzled by the TMA tensor map
     uint32_t snap[kScanWarps][kLaneWords / 4][32];                            // per-quad cursor snapshots of every lane
+    uint16_t qlist[kScanWarps][32];                                           // word positions of one round of events
     alignas(8) uint64_t full[kScanWarps][kWarpStages];                        // TMA landed (tx bytes)
 };
 constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align the swizzled stages to 1 KB
@@ -472,34 +478,6 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         uint64_t g_nxt = 0;
         if (nf_lo + lane < nf_hi) g_nxt = __ldg(p.cig_off + nf_lo + lane);
 
-        // ---- reads that start inside this warp tile: the tile-local prefix at their first word, from the
-        //      owning lane's scan values (shuffles), its quad snapshot (shared memory) and at most 3 words
-#pragma unroll
-        for (int j = 0; j < (int)kQuads; ++j) sm.snap[warp][j][lane] = snap[j];
-        __syncwarp();
-        if (tf_lo < tf_hi) {
-            for (uint32_t r0 = tf_lo; r0 < tf_hi; r0 += 32) {
-                const uint32_t rr = r0 + lane;
-                const bool act = rr < tf_hi;
-                const uint64_t g = (r0 == tf_lo) ? g_cur : (act ? __ldg(p.cig_off + rr) : 0ull);
-                const uint32_t off = act ? (uint32_t)(g - gw * kWarpTileWords) : 0u;
-                const uint32_t owner = off / kLaneWords, k = off % kLaneWords;
-                const uint32_t xc = __shfl_sync(0xffffffffu, excl_c, owner), xe = __shfl_sync(0xffffffffu, excl_e, owner);
-                const uint32_t er = __shfl_sync(0xffffffffu, evrev, owner);
-                if (act && off) {
-                    const uint32_t j = k >> 2, kk = k & 3u, q = owner * kQuads + j, row = q >> 3;
-                    const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
-                    const uint32_t c_in = sm.snap[warp][j][owner] + (kk > 0u ? cig_consume(v.x) : 0u) +
-                                          (kk > 1u ? cig_consume(v.y) : 0u) + (kk > 2u ? cig_consume(v.z) : 0u);
-                    const uint32_t e_in = k ? __popc(er >> (kLaneWords - k)) : 0u;     // word i <-> bit kLaneWords-1-i
-                    p.rd_pre[rr] = make_uint2(xc + c_in, xe + e_in);
-                }
-            }
-        }
-        tf_lo = nf_lo;
-        tf_hi = nf_hi;
-        g_cur = g_nxt;
-
         // ---- event slots: contiguous per warp tile, taken from a warp-private chunk
         uint64_t sbase = chunk_cur;
         if (tot_e) {
@@ -518,25 +496,60 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             p.wt_sbase[gw] = (uint32_t)sbase;
         }
 
-        // ---- emit this lane's events (about 1% of the words): reload the event's quad, start from the
-        //      quad's snapshot and add the consumption of the (at most 3) words in front of the event
-        if (evrev && !(p.debug & 1u)) {
-            do {
-                const uint32_t rbit = (uint32_t)__ffs(evrev) - 1u;      // last remaining event of the lane
-                evrev &= evrev - 1u;
-                const uint32_t word = 31u - rbit - (32u - kLaneWords), j = word >> 2, k = word & 3u;
-                const uint32_t q = q0 + j, row = q >> 3;
+        // ---- position queries. Two things need the tile-local prefix at a word position: every event
+        //      (about 1 % of the words -> {bases consumed before the op, value}) and the first word of every
+        //      read that starts in the tile (-> rd_pre). They are dealt to the lanes 32 at a time (one round
+        //      for a typical tile): the lane that owns the word supplies its scan values by shuffle and its
+        //      per-quad snapshot through shared memory; at most 3 words are re-read from the stage.
+#pragma unroll
+        for (int j = 0; j < (int)kQuads; ++j) sm.snap[warp][j][lane] = snap[j];
+        const uint32_t n_starts = tf_hi - tf_lo;
+        const uint32_t n_q = tot_e + n_starts;                  // queries [0, tot_e) are the events in word order
+        const uint32_t off_cur = (uint32_t)(g_cur - gw * kWarpTileWords);    // lane i: first word of read tf_lo + i
+        uint32_t ev_left = evrev, ev_idx = excl_e;
+        if (!(p.debug & 1u))
+        for (uint32_t base = 0; base < n_q; base += 32) {
+            // owners list their events with index in [base, base + 32): word order = descending bits of evrev
+            while (ev_left && ev_idx < base + 32u) {
+                const uint32_t bit = 31u - (uint32_t)__clz(ev_left);
+                ev_left ^= 1u << bit;
+                sm.qlist[warp][ev_idx - base] = (uint16_t)(lane * kLaneWords + (kLaneWords - 1u - bit));
+                ++ev_idx;
+            }
+            __syncwarp();
+            const uint32_t qi = base + lane;
+            const bool is_ev = qi < tot_e, act = qi < n_q;
+            const uint32_t si = qi - tot_e;                     // index of the read start (when !is_ev)
+            const uint32_t spos = __shfl_sync(0xffffffffu, off_cur, si & 31u);
+            uint32_t pos = 0;
+            if (is_ev) pos = sm.qlist[warp][lane];
+            else if (act) pos = (si < 32u) ? spos : (uint32_t)(__ldg(p.cig_off + tf_lo + si) - gw * kWarpTileWords);
+            const uint32_t owner = pos / kLaneWords, k = pos % kLaneWords;
+            const uint32_t xc = __shfl_sync(0xffffffffu, excl_c, owner), xe = __shfl_sync(0xffffffffu, excl_e, owner);
+            const uint32_t er = __shfl_sync(0xffffffffu, evrev, owner);
+            if (act) {
+                const uint32_t j = k >> 2, kk = k & 3u, q = owner * kQuads + j, row = q >> 3;
                 const uint4 v = st4[row * 8 + ((q & 7u) ^ (row & 7u))];
-                uint32_t s_in = sm.snap[warp][j][lane];
-                s_in += (k > 0u ? cig_consume(v.x) : 0u) + (k > 1u ? cig_consume(v.y) : 0u) + (k > 2u ? cig_consume(v.z) : 0u);
-                const uint32_t w = k == 0u ? v.x : k == 1u ? v.y : k == 2u ? v.z : v.w;
-                const uint32_t len = w >> 4, op = w & 15u;
-                const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
-                const uint64_t slot = sbase + excl_e + __popc(evrev);   // earlier events remain in evrev
-                if (slot < p.raw_cap) p.evraw[slot] = make_uint2(excl_c + s_in, (uint32_t)val);
-                else atomicOr(&p.ctr->flags, kFlagEventOverflow);
-            } while (evrev);
+                // a zero word (M, length 0) consumes nothing: blank the words at and after the position
+                const uint32_t c_in = xc + sm.snap[warp][j][owner] + cig_consume_lut(kk > 0u ? v.x : 0u) +
+                                      cig_consume_lut(kk > 1u ? v.y : 0u) + cig_consume_lut(kk > 2u ? v.z : 0u);
+                if (is_ev) {
+                    const uint32_t w = kk == 0u ? v.x : kk == 1u ? v.y : kk == 2u ? v.z : v.w;
+                    const uint32_t len = w >> 4, op = w & 15u;
+                    const int32_t val = (int32_t)(((op == 2u) ? (0u - len) : len) << 1) | (int32_t)(op == 4u);
+                    const uint64_t slot = sbase + qi;
+                    if (slot < p.raw_cap) p.evraw[slot] = make_uint2(c_in, (uint32_t)val);
+                    else atomicOr(&p.ctr->flags, kFlagEventOverflow);
+                } else if (pos) {
+                    const uint32_t e_in = k ? __popc(er >> (kLaneWords - k)) : 0u;     // word i <-> bit kLaneWords-1-i
+                    p.rd_pre[tf_lo + si] = make_uint2(c_in, xe + e_in);
+                }
+            }
+            __syncwarp();                                       // qlist is rewritten in the next round
         }
+        tf_lo = nf_lo;
+        tf_hi = nf_hi;
+        g_cur = g_nxt;
         __syncwarp();                                           // every lane is done with stage s
         if (lane == 0) {
             const uint64_t nxt = gwid + (uint64_t)(it + kWarpStages) * stride;
