@@ -214,6 +214,8 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaFuncSetAttribute(k_cigar_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_cigar_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_cigar_scan)", e);
+    if ((e = cudaFuncSetAttribute(k_pair_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem))) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(k_pair_eval)", e);
     int occ = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan<false>, kCtaThreads, kScanSmemBytes)) != cudaSuccess)
         return bail("occupancy(k_cigar_scan)", e);
@@ -391,7 +393,6 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     const uint32_t wt_scan_tiles = (uint32_t)((n_wt + kXsTile - 1) / kXsTile);
     TRY(ensure(ctx, ctx->cand_lo, R));
     TRY(ensure(ctx, ctx->cand_n, R));
-    TRY(ensure(ctx, ctx->ev_off, R + 1));
     TRY(ensure(ctx, ctx->rd_pre, R + 1));
     TRY(ensure(ctx, ctx->wt, n_wt + 2));
     TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
@@ -399,9 +400,9 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
     const unsigned scan_grid = (unsigned)std::min<uint64_t>((n_wt + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
     const uint64_t raw_slack = (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kScanWarps * kEvChunk;
-    if (ctx->events.cap == 0) TRY(ensure(ctx, ctx->events, C / 16 + 4096));
-    // warp-tile storage hands out kEvChunk-slot chunks: every resident warp may strand one chunk
-    if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, ctx->events.cap + raw_slack));
+    // event storage is sized speculatively (1/16 of the words; checked and regrown after the run); it hands
+    // out kEvChunk-slot chunks, so every resident warp may strand one chunk
+    if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, C / 16 + 4096 + raw_slack));
 
     ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
     LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
@@ -418,7 +419,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s));
             CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s));
         }
-        if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->ev_off.p, 0, (R + 1) * sizeof(uint32_t), s));
+        if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->wt.p, 0, 2 * sizeof(uint2), s));      // no CIGAR words at all
         if (wt_scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, 2 * ((uint64_t)wt_scan_tiles + 1) * sizeof(uint64_t), s));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_INDEX], s));
 
@@ -467,12 +468,10 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             const unsigned g = std::min<unsigned>(wt_scan_tiles, (unsigned)ctx->sm_count * 4);
             k_exclusive_scan2<<<g, kXsThreads, 0, s>>>(ctx->wt.p, n_wt, wt_scan_tiles, ctx->desc_wt.p, ctx->desc_wt.p + wt_scan_tiles + 1,
                                                        &ctx->d_ctr->scan_counter[0], &ctx->d_ctr->flags);
-            const uint64_t fix_warps = (R + 1 + 30) / 31;
-            k_read_fixup<<<(unsigned)((fix_warps * 32 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->wt.p, ctx->rd_pre.p,
-                                                                                 ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap,
-                                                                                 ctx->events.p, ctx->events.cap, ctx->ev_off.p, ctx->d_ctr);
-            launches += 2;
+            ++launches;
         }
+        // total number of events = last entry of the exclusive scan
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 2, ctx->wt.p + n_wt, sizeof(uint2), cudaMemcpyDeviceToHost, s));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_FIXUP], s));
         CU_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_SCAN], s));
@@ -488,8 +487,9 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
 
         // K2b: filter + window sums + scatter
         if (work) {
-            k_pair_eval<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->events.p,
-                                                                   ctx->ev_off.p, ctx->events.cap, ctx->seg_off.p, ctx->cursor.p,
+            k_pair_eval<<<(unsigned)((R + 255) / 256), 256, sizeof(PairSmem), s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p,
+                                                                   EventSource{ctx->wt.p, ctx->rd_pre.p, ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap},
+                                                                   ctx->seg_off.p, ctx->cursor.p,
                                                                    ctx->vals.p, ctx->vals.cap, ctx->d_ctr, getenv("INQ_PAIR_DEBUG") ? (uint32_t)atoi(getenv("INQ_PAIR_DEBUG")) : 0u);
             ++launches;
         }
@@ -520,11 +520,8 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         bool retry = false;
         if (f & kFlagEventOverflow) {
             // the event buffers were sized speculatively; the scan still counted every event and slot
-            const uint64_t need = ctx->h_ctr->n_events + 4096;
             const uint64_t need_raw = ctx->h_ctr->ev_alloc + raw_slack;
-            release(ctx->events);
             release(ctx->evraw);
-            TRY(ensure(ctx, ctx->events, need));
             TRY(ensure(ctx, ctx->evraw, need_raw));
             retry = true;
         }
@@ -544,7 +541,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         break;
     }
     if (ctx->h_ctr->flags & kFlagEventOverflow) return fail(ctx, INQ_ERR_STATE, "internal: event list overflow persists");
-    ctx->last_n_events = ctx->h_ctr->n_events;
+    ctx->last_n_events = (ntiles && L) ? ctx->h_total[3] : 0;      // .y of wt[n_wt]
 
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -556,7 +553,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         stats->n_reads_joined = total(ST_READS_JOINED);
         stats->n_pairs = total(ST_PAIRS);
         stats->n_candidates = total(ST_CANDIDATES);
-        stats->n_events = ctx->h_ctr->n_events;
+        stats->n_events = ctx->last_n_events;
         stats->op_visits = total(ST_OP_VISITS);
         stats->n_kernel_launches = launches;
         stats->n_tiles = ntiles;
@@ -580,10 +577,24 @@ int inq_debug_events(inq_ctx *ctx, uint64_t *n_events, uint32_t *event_pos, int3
 {
     if (!ctx) return INQ_ERR_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const uint64_t E = ctx->last_n_events;
+    const uint64_t E = ctx->last_n_events, R = ctx->R;
     if (n_events) *n_events = E;
-    if (read_event_off && ctx->ev_off.p)
-        CU_TRY(ctx, cudaMemcpy(read_event_off, ctx->ev_off.p, (ctx->R + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    // the genotyping pass reads events straight from the scan kernel's warp-tile storage; the per-read
+    // lists in CIGAR order with absolute anchors are only materialised here
+    TRY(ensure(ctx, ctx->ev_off, R + 1));
+    if (ctx->events.cap < E + 1) { release(ctx->events); TRY(ensure(ctx, ctx->events, E + 1)); }
+    if (E) {
+        const uint64_t fix_warps = (R + 1 + 30) / 31;
+        k_read_fixup<<<(unsigned)((fix_warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->cig_off.p, ctx->rs.p, R, ctx->wt.p, ctx->rd_pre.p,
+                                                                                       ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap,
+                                                                                       ctx->events.p, ctx->events.cap, ctx->ev_off.p, ctx->d_ctr);
+        CU_TRY(ctx, cudaGetLastError());
+    } else {
+        CU_TRY(ctx, cudaMemsetAsync(ctx->ev_off.p, 0, (R + 1) * sizeof(uint32_t), ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (read_event_off)
+        CU_TRY(ctx, cudaMemcpy(read_event_off, ctx->ev_off.p, (R + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     const uint64_t n = std::min(E, cap);
     if (n && (event_pos || event_val)) {
         uint2 *tmp = (uint2 *)malloc(n * sizeof(uint2));

@@ -762,31 +762,77 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
 // events anchored inside the locus window (call.rs:388,394,400: start < P && P < end) and the
 // scatter of the packed call into the locus' segment: H1 (or every unphased call) grows from the
 // front of the segment, H2 from its back; one 64-bit atomic per pair hands out the slot.
+// The kernel reads the events straight from the scan kernel's warp-tile storage: event k of the stream
+// lives in warp tile t with wt[t].y <= k < wt[t+1].y at slot wt_sbase[t] + (k - wt[t].y), and its 1-based
+// anchor (the u32 cursor of call.rs:380) is ref_start + 1 + (wt[t].x + raw.x) - (consumption prefix at the
+// read's first word).
 constexpr int kPairEvPool = 512;            // events per warp (32 consecutive reads) kept in shared memory
 constexpr int kPairLociCache = 128;         // catalog entries per warp kept in shared memory
+constexpr int kPairTileCache = 64;          // warp-tile prefixes per warp kept in shared memory
+
+struct EventSource {
+    const uint2 *wt;              // [n_wt + 1] exclusive prefixes {consumption, events} per warp tile
+    const uint2 *rd_pre;          // [R + 1] tile-local prefixes at each read's first word
+    const uint32_t *wt_sbase;     // [n_wt] storage slot of the warp tile's first event
+    const uint2 *evraw;           // {consumption inside the warp tile before the op, val}
+    uint64_t raw_cap;
+};
+
+// stream-wide {consumption, events} prefix at CIGAR word g, which is the first word of read r
+__device__ __forceinline__ uint2 read_prefix(const EventSource &es, uint64_t g, uint64_t r)
+{
+    const uint2 pre = es.rd_pre[r];                          // unconditional: not behind the load of g
+    uint2 v = es.wt[g / kWarpTileWords];
+    if (g % kWarpTileWords) {                               // (rd_pre is only written for reads starting inside a tile)
+        v.x += pre.x;
+        v.y += pre.y;
+    }
+    return v;
+}
+
+// event k of a read whose words lie in warp tiles [t_lo, t_hi]: {anchor - base, val} via a search in global memory
+__device__ __forceinline__ uint2 event_at(const EventSource &es, uint32_t k, uint32_t t_lo, uint32_t t_hi)
+{
+    while (t_lo < t_hi) {
+        const uint32_t mid = (t_lo + t_hi) >> 1;
+        if (es.wt[mid + 1].y > k) t_hi = mid; else t_lo = mid + 1;
+    }
+    const uint2 w = es.wt[t_lo];
+    const uint64_t slot = (uint64_t)es.wt_sbase[t_lo] + (k - w.y);
+    uint2 raw = make_uint2(0u, 0u);
+    if (slot < es.raw_cap) raw = es.evraw[slot];            // (overflowed speculative buffer: the run is repeated)
+    return make_uint2(w.x + raw.x, raw.y);
+}
+
+struct PairSmem {                           // per CTA of 8 warps (dynamic shared memory, > 48 KB)
+    uint2 ev[8][kPairEvPool];
+    uint32_t off[8][32], e0[8][32], base[8][32];
+    uint32_t ty[8][kPairTileCache + 1], tx[8][kPairTileCache], tsb[8][kPairTileCache];
+    int32_t ls[8][kPairLociCache], le[8][kPairLociCache];
+    uint32_t seg[8][kPairLociCache + 1];
+    uint32_t joined[8];
+};
 
 __global__ void __launch_bounds__(256)
 k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
-            const uint32_t *__restrict__ cand_n, const uint2 *__restrict__ events,
-            const uint32_t *__restrict__ ev_off, uint64_t ev_cap, const uint32_t *__restrict__ seg_off,
+            const uint32_t *__restrict__ cand_n, EventSource es, const uint32_t *__restrict__ seg_off,
             unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
             DevCounters *__restrict__ ctr, uint32_t debug)
 {
     // A warp owns 32 consecutive reads; their candidates are flattened and dealt to the lanes
     // 32 at a time (reads have 0..hundreds of candidates, a per-read loop leaves most lanes idle).
     // Everything the inner loop needs is staged in shared memory first (the reads' events -- one
-    // contiguous, coalesced run of the event array --, the slice of the catalog the warp touches), so
-    // that the only global operations left in the loop are the slot atomic and the store of the call --
-    // and the store is deferred by one iteration so that the atomic's round trip overlaps the next
-    // candidate.
-    __shared__ uint32_t s_off[8][32];
-    __shared__ uint32_t s_joined[8];
-    __shared__ uint2 s_ev[8][kPairEvPool];
-    __shared__ int32_t s_ls[8][kPairLociCache], s_le[8][kPairLociCache];
-    __shared__ uint32_t s_seg[8][kPairLociCache + 1];
+    // contiguous run of the event stream, translated to absolute anchors on the way in --, the slice of
+    // the catalog the warp touches), so that the only global operations left in the loop are the slot
+    // atomic and the store of the call -- and the store is deferred by one iteration so that the atomic's
+    // round trip overlaps the next candidate.
+    extern __shared__ __align__(16) unsigned char pair_smem_raw[];
+    PairSmem &sm = *reinterpret_cast<PairSmem *>(pair_smem_raw);
+    auto &s_off = sm.off; auto &s_joined = sm.joined; auto &s_ev = sm.ev; auto &s_e0 = sm.e0; auto &s_base = sm.base;
+    auto &s_ty = sm.ty; auto &s_tx = sm.tx; auto &s_tsb = sm.tsb; auto &s_ls = sm.ls; auto &s_le = sm.le; auto &s_seg = sm.seg;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint32_t n = 0, lo = 0, e0 = 0, e1 = 0, hf = 0, words = 0;
+    uint32_t n = 0, lo = 0, e0 = 0xFFFFFFFFu, e1 = 0xFFFFFFFFu, hf = 0, words = 0, t_lo = 0, t_hi = 0, abase = 0;
     int32_t rs = 0, re = 0;
     if (r < rv.R) {
         // independent loads, all in flight together
@@ -795,17 +841,74 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         rs = rv.rs[r];
         re = rv.re[r];
         hf = (uint32_t)rv.hp[r] | ((uint32_t)(rv.flags[r] & 1u) << 8);
-        // if the speculative event list overflowed the run is repeated; stay inside the allocation
-        e0 = (uint32_t)min((uint64_t)ev_off[r], ev_cap);
-        e1 = (uint32_t)min((uint64_t)ev_off[r + 1], ev_cap);
-        words = (uint32_t)min(rv.cig_off[r + 1] - rv.cig_off[r], (uint64_t)0xFFFFFFFFu);
+        const uint64_t g0 = rv.cig_off[r], g1 = rv.cig_off[r + 1];
+        const uint2 p0 = read_prefix(es, g0, r), p1 = read_prefix(es, g1, r + 1);
+        e0 = p0.y;
+        e1 = p1.y;
+        abase = (uint32_t)rs + 1u - p0.x;                       // anchor = abase + stream-wide consumption before the op
+        t_lo = (uint32_t)(g0 / kWarpTileWords);
+        t_hi = g1 > g0 ? (uint32_t)((g1 - 1) / kWarpTileWords) : t_lo;
+        words = (uint32_t)min(g1 - g0, (uint64_t)0xFFFFFFFFu);
     }
-    // the events of the warp's joined reads are one run [ev_lo, ev_hi) of the event array
+    // the events of the warp's joined reads are one run [ev_lo, ev_hi) of the event stream, stored in the
+    // warp tiles [tile_lo, tile_hi]; the tile range only depends on cig_off, so its prefixes are fetched
+    // while the per-read prefixes are still in flight
+    const uint32_t tile_lo = __reduce_min_sync(0xffffffffu, n ? t_lo : 0xFFFFFFFFu);
+    const uint32_t tile_hi = __reduce_max_sync(0xffffffffu, n ? t_hi : 0u);
+    const uint32_t nt = tile_hi - tile_lo + 1u;
+    const bool tiles_cached = tile_lo <= tile_hi && nt <= (uint32_t)kPairTileCache;
+    if (tiles_cached) {
+        for (uint32_t i = lane; i <= nt; i += 32) {
+            const uint2 w = es.wt[tile_lo + i];
+            s_ty[wid][i] = w.y;
+            if (i < nt) {
+                s_tx[wid][i] = w.x;
+                s_tsb[wid][i] = es.wt_sbase[tile_lo + i];
+            }
+        }
+    }
     const uint32_t ev_lo = __reduce_min_sync(0xffffffffu, n ? e0 : 0xFFFFFFFFu);
     const uint32_t ev_hi = __reduce_max_sync(0xffffffffu, n ? e1 : 0u);
+    s_e0[wid][lane] = e0;
+    s_base[wid][lane] = abase;
+    __syncwarp();
     if (ev_lo < ev_hi) {
         const uint32_t cnt = min(ev_hi - ev_lo, (uint32_t)kPairEvPool);
-        for (uint32_t i = lane; i < cnt; i += 32) s_ev[wid][i] = events[ev_lo + i];
+        // pass 1: where each event lives (storage slot) and what its anchor is relative to -- parked in s_ev
+        uint32_t ta = 0;                                        // cached tiles: this lane's k only grows, so does its tile
+        for (uint32_t i = lane; i < cnt; i += 32) {
+            const uint32_t k = ev_lo + i;
+            // owning read: the last j with e0[j] <= k (e0 is non-decreasing; lanes past the last read hold ~0)
+            uint32_t j = 0;
+#pragma unroll
+            for (uint32_t step = 16; step >= 1; step >>= 1)
+                if (s_e0[wid][j + step] <= k) j += step;
+            uint32_t slot, rel;
+            if (tiles_cached) {
+                // first tile t with ty[t + 1] > k: 32 events further on is typically 2-3 tiles further on
+                while (ta + 1u < nt && s_ty[wid][ta + 1u] <= k) ++ta;
+                slot = s_tsb[wid][ta] + (k - s_ty[wid][ta]);
+                rel = s_base[wid][j] + s_tx[wid][ta];
+            } else {
+                uint32_t a = tile_lo, b = tile_hi;
+                while (a < b) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if (es.wt[mid + 1].y > k) b = mid; else a = mid + 1;
+                }
+                const uint2 w = es.wt[a];
+                slot = es.wt_sbase[a] + (k - w.y);
+                rel = s_base[wid][j] + w.x;
+            }
+            s_ev[wid][i] = make_uint2(slot, rel);
+        }
+        // pass 2: independent loads from the event storage (several in flight per lane)
+#pragma unroll 4
+        for (uint32_t i = lane; i < cnt; i += 32) {
+            const uint2 sr = s_ev[wid][i];
+            uint2 raw = make_uint2(0u, 0u);
+            if ((uint64_t)sr.x < es.raw_cap) raw = es.evraw[sr.x];   // (overflowed speculative buffer: the run is repeated)
+            s_ev[wid][i] = make_uint2(sr.y + raw.x, raw.y);
+        }
     }
     if (n && e1 - ev_lo > (uint32_t)kPairEvPool) hf |= 1u << 9;      // not (entirely) staged: searched in global memory
     const uint32_t eb = e0 - ev_lo;                                   // first staged event of the read
@@ -859,6 +962,8 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         const uint32_t hf_j = __shfl_sync(0xffffffffu, hf, j), lo_j = __shfl_sync(0xffffffffu, lo, j);
         const uint32_t e0_j = __shfl_sync(0xffffffffu, e0, j), e1_j = __shfl_sync(0xffffffffu, e1, j);
         const uint32_t eb_j = __shfl_sync(0xffffffffu, eb, j);
+        const uint32_t tlo_j = __shfl_sync(0xffffffffu, t_lo, j), thi_j = __shfl_sync(0xffffffffu, t_hi, j);
+        const uint32_t abase_j = __shfl_sync(0xffffffffu, abase, j);
         const uint32_t words_j = __shfl_sync(0xffffffffu, words, j);
         bool emit = false;
         uint32_t l = 0, h = 0, seg = 0, cap = 0;
@@ -924,17 +1029,16 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
                     clip |= is_s;
                 }
             } else {
-                // long event list in global memory: anchors grow roughly linearly along the read, so start
-                // from the interpolated position and walk to the first event with pos1 > start_ext
-                const uint32_t ne = e1_j - e0_j;
-                const int64_t span = max((int64_t)re_j - (int64_t)rs_j, (int64_t)1);
-                int64_t g = (int64_t)e0_j + ((int64_t)start_ext - (int64_t)rs_j) * (int64_t)ne / span;
-                uint32_t a = (uint32_t)min(max(g, (int64_t)e0_j), (int64_t)e1_j - 1);
-                while (a > e0_j && events[a - 1].x > start_ext) --a;
-                while (a < e1_j && !(events[a].x > start_ext)) ++a;
+                // long event list, read from the warp-tile storage: anchors increase along the read, so a
+                // binary search finds the first event with pos1 > start_ext; then a short scan
+                uint32_t a = e0_j, b = e1_j;
+                while (a < b) {
+                    const uint32_t m = (a + b) >> 1;
+                    if (abase_j + event_at(es, m, tlo_j, thi_j).x > start_ext) b = m; else a = m + 1;
+                }
                 for (uint32_t e = a; e < e1_j; ++e) {
-                    const uint2 ev = events[e];
-                    if (!(ev.x < end_ext)) break;
+                    const uint2 ev = event_at(es, e, tlo_j, thi_j);
+                    if (!(abase_j + ev.x < end_ext)) break;
                     const int32_t v = (int32_t)ev.y;
                     const uint32_t is_s = (uint32_t)v & 1u;
                     if (is_s && is2d) continue;             // call.rs:394 !is_accidental_2d(&r)
