@@ -1188,6 +1188,44 @@ __device__ __forceinline__ bool warp_median_part(const T (&key)[K], uint32_t a, 
 // A locus' segment [seg, seg+cap) holds its H1 calls at the front and its H2 calls at the back
 // (unphased: everything at the front). nf/nb = number of front/back entries; n1 = split point of
 // the sorted run (phased: nf, unphased: (nf)/2).
+// Both haplotypes of a phased locus in one pass (call.rs:497-522 twice): 32-bit keys, H1 sorted in lanes
+// 0-15 (nf of them), H2 sorted in lanes 16-31 (nb of them). Every lane works on its own half: the ballots
+// are shared, the counts are taken under the half's lane mask.
+__device__ __forceinline__ void median_halves32(uint32_t key, uint32_t nf, uint32_t nb, uint32_t support, int64_t *t1,
+                                                int64_t *t2, uint32_t *valid, bool *panicked)
+{
+    const uint32_t lane = lane_id();
+    const bool upper = lane >= 16u;
+    const uint32_t hm = upper ? 0xFFFF0000u : 0x0000FFFFu;
+    const uint32_t n = upper ? nb : nf;
+    const bool in = (lane & 15u) < n;
+    const uint32_t span_b = __ballot_sync(0xffffffffu, in && !(key & 1u));
+    const uint32_t clip_b = __ballot_sync(0xffffffffu, in && (key & 1u));
+    const uint32_t s = __popc(span_b & hm), c = __popc(clip_b & hm);
+    const bool enough = n >= support;                                // call.rs:498-500
+    const uint32_t topk = (s <= support) ? (support - s) : 0u;       // call.rs:509-513
+    const uint32_t m = s + topk;
+    const bool ok = enough && m != 0u;                               // m == 0: call.rs:516 on an empty vector
+    const uint32_t i2 = m >> 1, i1 = (m & 1u) ? i2 : i2 - 1u;        // call.rs:515-521
+    const uint32_t below = hm & lanemask_lt();
+    const bool is_span = (span_b >> lane) & 1u, is_clip = (clip_b >> lane) & 1u;
+    const bool sel = ok && (is_span || (is_clip && __popc(clip_b & below) + topk >= c));   // the topk largest clips
+    const uint32_t sel_b = __ballot_sync(0xffffffffu, sel);
+    const uint32_t rank = __popc(sel_b & below);
+    int32_t sum = 0;                                                 // |call| < 2^29: two of them fit
+    if (sel) {
+        const int32_t v = (int32_t)KeyTraits<uint32_t>::call(key);
+        sum = (rank == i1 ? v : 0) + (rank == i2 ? v : 0);
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const uint32_t ok_b = __ballot_sync(0xffffffffu, ok), bad_b = __ballot_sync(0xffffffffu, enough && m == 0u);
+    *t1 = (ok_b & 1u) ? (int64_t)__shfl_sync(0xffffffffu, sum, 0) : 0;
+    *t2 = (ok_b & 0x10000u) ? (int64_t)__shfl_sync(0xffffffffu, sum, 16) : 0;
+    *valid = ((ok_b & 1u) ? 1u : 0u) | ((ok_b & 0x10000u) ? 2u : 0u);
+    if (bad_b & 0x10001u) *panicked = true;
+}
+
 // kSplit > 0 (phased only): H1 lives at positions [0, nf) and H2 at [kSplit, kSplit + nb) and the two
 // runs of kSplit elements are sorted independently (a shorter network than one sort over both).
 template <int K, int kSplit = 0>
@@ -1232,6 +1270,10 @@ __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, ui
             k32[k] = have_k[k] ? (body | ((v & kKeyHapBit) ? KeyTraits<uint32_t>::hap : 0u)) : KeyTraits<uint32_t>::inf;
         }
         warp_sort<K, uint32_t, kSortN>(k32);
+        if constexpr (K == 1 && kSplit == 16) {
+            median_halves32(k32[0], nf, nb, support, t1, t2, valid, panicked);
+            return;
+        }
         v1 = warp_median_part<K, uint32_t>(k32, 0, n1, support, t1, panicked);
         v2 = warp_median_part<K, uint32_t>(k32, a2, ntot - n1, support, t2, panicked);
     } else {
