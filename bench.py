@@ -136,8 +136,21 @@ def cpu_reference(w, threads: int, seconds: float):
     }, (sel, p1, p2)
 
 
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else this process (or NCCL) prints to fd 1
+    was redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)               # libraries that print to stdout (e.g. "NCCL version ...") must not break the contract
     rank, local_rank, world = dist_env()
     if world != args.gpus and world > 1:
         args.gpus = world
@@ -176,7 +189,7 @@ def main():
             "e2e": {"value": v, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "cigar_op_visits_per_s": base["op_visits_per_s"], "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -344,7 +357,7 @@ def main():
             "parity": parity,
             "host": {"cores": threads, "gen_seconds": t_gen, "wall_resident_s": wall_resident},
         }
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
