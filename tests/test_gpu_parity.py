@@ -98,6 +98,28 @@ def test_long_reads_span_many_tiles(ctx):
     assert np.array_equal(off, eoff) and np.array_equal(pos, epos) and np.array_equal(val, eval_)
 
 
+def test_tiny_reads_many_starts_per_warp_tile(ctx):
+    # reads of 1-40 CIGAR words: a 1024-word warp tile holds far more than 32 read starts, and with
+    # minlen 0 most tiles hold several rounds of 32 events (the scan kernel's position-query pass loops)
+    case = make_case(51, n_contigs=2, contig_len=40_000, n_loci=300, n_reads=12_000, max_read=400)
+    assert case["reads"].n / (len(case["reads"].cigar) / 1024) > 40
+    for minlen in (0, 5):
+        run_case(ctx, case, minlen, 2, False)
+        pos, val, off = ctx.debug_events()
+        epos, eval_, eoff = expected_events(case["reads"], minlen)
+        assert np.array_equal(off, eoff) and np.array_equal(pos, epos) and np.array_equal(val, eval_)
+    run_case(ctx, case, 0, 2, True, chunks=5)
+
+
+def test_event_dense_long_reads(ctx):
+    # every second word is an event (minlen 0) in reads of tens of thousands of words: the pair kernel's
+    # shared-memory event pool overflows and its warp-tile table does not fit -> global search paths
+    case = make_case(61, n_contigs=1, contig_len=2_000_000, n_loci=600, n_reads=120, max_read=600_000)
+    res = run_case(ctx, case, 0, 1, False)
+    assert res.stats["n_events"] > 600 * 120
+    run_case(ctx, case, 0, 1, True)
+
+
 def test_empty_inputs(ctx):
     case = make_case(51, n_reads=50)
     ctx.set_loci(case["contig_off"], case["locus_start"], case["locus_end"])
