@@ -70,11 +70,11 @@ typedef struct inq_stats {
     uint32_t n_tiles;            /* CIGAR tiles scanned */
     float ms_total;              /* first kernel start -> last kernel end */
     float ms_index;              /* memsets */
-    float ms_join;               /* K1 read x locus overlap join (count) */
+    float ms_join;               /* K1 read x locus overlap join + segment offsets (second stream, under K2) */
     float ms_cigar;              /* K2 CIGAR scan (dominant kernel) */
-    float ms_fixup;              /* warp-tile prefix scans + per-read event fix-up */
-    float ms_scan;               /* bucket offset scan */
-    float ms_pairs;              /* K2b per-pair window sums + scatter into buckets */
+    float ms_fixup;              /* prefix scan over the warp-tile totals */
+    float ms_scan;               /* wait for the join stream */
+    float ms_pairs;              /* K2b event staging, per-pair window sums, scatter into buckets */
     float ms_median;             /* K3 per-locus sort / support filter / median */
     float ms_h2d;                /* host->device copies of the last inq_push_reads */
     float ms_d2h;                /* device->host copy of the results */
@@ -139,8 +139,9 @@ int inq_clear_reads(inq_ctx *ctx);
 int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased,
                  int64_t *twice_h1, int64_t *twice_h2, uint8_t *valid_mask, inq_stats *stats);
 
-/* Debug/verification hooks used by the parity tests: copy the per-read join summary and
- * the event list of the last inq_genotype back to the host. Any pointer may be NULL. */
+/* Debug/verification hook used by the parity tests: materialises the per-read event lists of the last
+ * inq_genotype (CIGAR order, 1-based anchors; the genotyping pass itself never builds them) and copies
+ * them back to the host. Any pointer may be NULL. */
 int inq_debug_events(inq_ctx *ctx, uint64_t *n_events, uint32_t *event_pos /*cap*/,
                      int32_t *event_val /*cap*/, uint64_t cap, uint32_t *read_event_off /*n_reads+1*/);
 
