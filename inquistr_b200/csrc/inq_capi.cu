@@ -32,6 +32,7 @@ struct inq_ctx {
     int sm_count = 0;
     int scan_ctas_per_sm = 1;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_chunk[kMedianChunks + 1] = {};
     cudaStream_t stream_join = nullptr;   // the join runs next to the CIGAR scan (latency-bound vs ALU-bound)
     std::string err;
 
@@ -208,6 +209,8 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream_join, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < EV_COUNT; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i <= kMedianChunks; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost(&ctx->h_total, 64)) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -244,6 +247,8 @@ void inq_ctx_destroy(inq_ctx *ctx)
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i <= kMedianChunks; ++i)
+        if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->stream_join) cudaStreamDestroy(ctx->stream_join);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -495,24 +500,33 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_PAIRS], s));
 
-        // K3: medians
+        // K3: medians, in chunks of the catalog: the result copy of one chunk (second stream, copy engine)
+        // runs under the median kernels of the next
         if (L) {
-            k_locus_median<<<(unsigned)(((uint64_t)L * 32 + 255) / 256), 256, 0, s>>>((uint32_t)L, unphased, support, ctx->seg_off.p, ctx->cursor.p,
-                                                                                     ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
-                                                                                     ctx->big_list.p, ctx->d_ctr);
-            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s>>>(unphased, support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p, ctx->vals.cap,
-                                                                                  ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
-            launches += 2;
+            const int nchunk = L >= (1 << 16) ? kMedianChunks : 1;
+            cudaStream_t sc = ctx->stream_join;
+            for (int c = 0; c < nchunk; ++c) {
+                const uint32_t l0 = (uint32_t)((uint64_t)L * c / nchunk), l1 = (uint32_t)((uint64_t)L * (c + 1) / nchunk);
+                k_locus_median<<<(unsigned)(((uint64_t)(l1 - l0) * 32 + 255) / 256), 256, 0, s>>>(l0, l1, c, unphased, support, ctx->seg_off.p, ctx->cursor.p,
+                                                                                                  ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
+                                                                                                  ctx->big_list.p, ctx->d_ctr);
+                k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s>>>(l0, c, unphased, support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
+                                                                                      ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+                launches += 2;
+                CU_TRY(ctx, cudaEventRecord(ctx->ev_chunk[c], s));
+                CU_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_chunk[c], 0));
+                const size_t n = l1 - l0;
+                CU_TRY(ctx, cudaMemcpyAsync(twice_h1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
+                CU_TRY(ctx, cudaMemcpyAsync(twice_h2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
+                CU_TRY(ctx, cudaMemcpyAsync(valid_mask + l0, ctx->valid.p + l0, n, cudaMemcpyDeviceToHost, sc));
+            }
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_chunk[kMedianChunks], sc));
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_MEDIAN], s));
         CU_TRY(ctx, cudaGetLastError());
 
         CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
-        if (L) {
-            CU_TRY(ctx, cudaMemcpyAsync(twice_h1, ctx->t1.p, (size_t)L * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            CU_TRY(ctx, cudaMemcpyAsync(twice_h2, ctx->t2.p, (size_t)L * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            CU_TRY(ctx, cudaMemcpyAsync(valid_mask, ctx->valid.p, (size_t)L, cudaMemcpyDeviceToHost, s));
-        }
+        if (L) CU_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_chunk[kMedianChunks], 0));
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_D2H], s));
         CU_TRY(ctx, cudaStreamSynchronize(s));
 

@@ -44,6 +44,7 @@ constexpr uint64_t kKeyInf = ~0ull;
 constexpr int kStatSlots = 64;
 enum { ST_CANDIDATES = 0, ST_PAIRS, ST_READS_JOINED, ST_WORDS_JOINED, ST_OP_VISITS, ST_COUNT = 8 };
 
+constexpr int kMedianChunks = 4;            // the medians run in catalog chunks so that the result copy of one overlaps the next
 struct DevCounters {
     unsigned long long stat[kStatSlots][ST_COUNT];
     unsigned long long n_events;
@@ -51,8 +52,8 @@ struct DevCounters {
     unsigned int flags;
     unsigned int tile_counter;
     unsigned int scan_counter[4];
-    unsigned int big_count;
-    unsigned int big_cursor;
+    unsigned int big_count[kMedianChunks];     // per chunk of the catalog (see inq_genotype): loci for the CTA path
+    unsigned int big_cursor[kMedianChunks];
     unsigned int bad_hp_value;        // diagnostics: HP value and read index of one offending read
     unsigned long long bad_hp_read;
 };
@@ -1287,13 +1288,14 @@ __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, ui
 constexpr int kMedianWarpMax = 128;         // loci with more calls go to the CTA kernel
 
 __global__ void __launch_bounds__(256)
-k_locus_median(uint32_t L, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
+k_locus_median(uint32_t l0, uint32_t l1, int chunk, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
                const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ vals, uint64_t vals_cap,
                int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
                uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
 {
-    const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (l >= L) return;
+    // loci [l0, l1) of the catalog; the chunk's CTA-path loci are listed in big_list[l0 ...]
+    const uint32_t l = l0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (l >= l1) return;
     const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
     if ((uint64_t)seg + cap > vals_cap) {               // speculatively sized call buffer too small: the run is repeated
         if (lane_id() == 0) atomicOr(&ctr->flags, kFlagValsOverflow);
@@ -1312,7 +1314,7 @@ k_locus_median(uint32_t L, int unphased, uint32_t support, const uint32_t *__res
     else if (ntot <= 64) warp_locus<2>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
     else if (ntot <= kMedianWarpMax) warp_locus<4>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
     else {
-        if (lane_id() == 0) big_list[atomicAdd(&ctr->big_count, 1u)] = l;
+        if (lane_id() == 0) big_list[l0 + atomicAdd(&ctr->big_count[chunk], 1u)] = l;
         return;
     }
     if (lane_id() == 0) {
@@ -1389,7 +1391,7 @@ __device__ __forceinline__ void block_part_median(volatile uint64_t *a, uint32_t
 }
 
 __global__ void __launch_bounds__(kBigThreads)
-k_locus_median_big(int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
+k_locus_median_big(uint32_t l0, int chunk, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
                    const unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
                    int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
                    const uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
@@ -1400,11 +1402,11 @@ k_locus_median_big(int unphased, uint32_t support, const uint32_t *__restrict__ 
     __shared__ unsigned long long sh_acc;
     const uint32_t tid = threadIdx.x;
     while (true) {
-        if (tid == 0) item_s = atomicAdd(&ctr->big_cursor, 1u);
+        if (tid == 0) item_s = atomicAdd(&ctr->big_cursor[chunk], 1u);
         __syncthreads();
         const uint32_t item = item_s;
-        if (item >= ctr->big_count) break;
-        const uint32_t l = big_list[item];
+        if (item >= ctr->big_count[chunk]) break;
+        const uint32_t l = big_list[l0 + item];
         const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
         if ((uint64_t)seg + cap > vals_cap) { __syncthreads(); continue; }     // see k_locus_median
         const unsigned long long cur = cursor[l];
