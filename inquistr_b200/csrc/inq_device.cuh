@@ -807,7 +807,7 @@ __device__ __forceinline__ uint2 event_at(const EventSource &es, uint32_t k, uin
 
 struct PairSmem {                           // per CTA of 8 warps (dynamic shared memory, > 48 KB)
     uint2 ev[8][kPairEvPool];
-    uint32_t off[8][32], e0[8][32], base[8][32];
+    uint32_t off[8][32];
     uint32_t ty[8][kPairTileCache + 1], tx[8][kPairTileCache], tsb[8][kPairTileCache];
     int32_t ls[8][kPairLociCache], le[8][kPairLociCache];
     uint32_t seg[8][kPairLociCache + 1];
@@ -823,13 +823,14 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     // A warp owns 32 consecutive reads; their candidates are flattened and dealt to the lanes
     // 32 at a time (reads have 0..hundreds of candidates, a per-read loop leaves most lanes idle).
     // Everything the inner loop needs is staged in shared memory first (the reads' events -- one
-    // contiguous run of the event stream, translated to absolute anchors on the way in --, the slice of
+    // contiguous run of the event stream, rebased from tile-local to stream-wide consumption on the way
+    // in: a read's anchors are its abase + that --, the slice of
     // the catalog the warp touches), so that the only global operations left in the loop are the slot
     // atomic and the store of the call -- and the store is deferred by one iteration so that the atomic's
     // round trip overlaps the next candidate.
     extern __shared__ __align__(16) unsigned char pair_smem_raw[];
     PairSmem &sm = *reinterpret_cast<PairSmem *>(pair_smem_raw);
-    auto &s_off = sm.off; auto &s_joined = sm.joined; auto &s_ev = sm.ev; auto &s_e0 = sm.e0; auto &s_base = sm.base;
+    auto &s_off = sm.off; auto &s_joined = sm.joined; auto &s_ev = sm.ev;
     auto &s_ty = sm.ty; auto &s_tx = sm.tx; auto &s_tsb = sm.tsb; auto &s_ls = sm.ls; auto &s_le = sm.le; auto &s_seg = sm.seg;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -870,26 +871,19 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     }
     const uint32_t ev_lo = __reduce_min_sync(0xffffffffu, n ? e0 : 0xFFFFFFFFu);
     const uint32_t ev_hi = __reduce_max_sync(0xffffffffu, n ? e1 : 0u);
-    s_e0[wid][lane] = e0;
-    s_base[wid][lane] = abase;
     __syncwarp();
     if (ev_lo < ev_hi) {
         const uint32_t cnt = min(ev_hi - ev_lo, (uint32_t)kPairEvPool);
-        // pass 1: where each event lives (storage slot) and what its anchor is relative to -- parked in s_ev
+        // pass 1: where each event lives (storage slot) and the consumption prefix of its tile -- parked in s_ev
         uint32_t ta = 0;                                        // cached tiles: this lane's k only grows, so does its tile
         for (uint32_t i = lane; i < cnt; i += 32) {
             const uint32_t k = ev_lo + i;
-            // owning read: the last j with e0[j] <= k (e0 is non-decreasing; lanes past the last read hold ~0)
-            uint32_t j = 0;
-#pragma unroll
-            for (uint32_t step = 16; step >= 1; step >>= 1)
-                if (s_e0[wid][j + step] <= k) j += step;
-            uint32_t slot, rel;
+            uint32_t slot, rel;                                 // rel: stream-wide consumption before the tile
             if (tiles_cached) {
                 // first tile t with ty[t + 1] > k: 32 events further on is typically 2-3 tiles further on
                 while (ta + 1u < nt && s_ty[wid][ta + 1u] <= k) ++ta;
                 slot = s_tsb[wid][ta] + (k - s_ty[wid][ta]);
-                rel = s_base[wid][j] + s_tx[wid][ta];
+                rel = s_tx[wid][ta];
             } else {
                 uint32_t a = tile_lo, b = tile_hi;
                 while (a < b) {
@@ -898,7 +892,7 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
                 }
                 const uint2 w = es.wt[a];
                 slot = es.wt_sbase[a] + (k - w.y);
-                rel = s_base[wid][j] + w.x;
+                rel = w.x;
             }
             s_ev[wid][i] = make_uint2(slot, rel);
         }
@@ -1018,11 +1012,11 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
                 uint32_t a = 0, b = ne;
                 while (a < b) {
                     const uint32_t m = (a + b) >> 1;
-                    if (sev[m].x > start_ext) b = m; else a = m + 1;
+                    if (abase_j + sev[m].x > start_ext) b = m; else a = m + 1;
                 }
                 for (uint32_t q = a; q < ne; ++q) {
                     const uint2 ev = sev[q];
-                    if (!(ev.x < end_ext)) break;           // start_ext < P && P < end_ext (call.rs:388,394,400)
+                    if (!(abase_j + ev.x < end_ext)) break; // start_ext < P && P < end_ext (call.rs:388,394,400)
                     const int32_t v = (int32_t)ev.y;
                     const uint32_t is_s = (uint32_t)v & 1u;
                     if (is_s && is2d) continue;             // call.rs:394 !is_accidental_2d(&r)
