@@ -767,7 +767,13 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
 // lives in warp tile t with wt[t].y <= k < wt[t+1].y at slot wt_sbase[t] + (k - wt[t].y), and its 1-based
 // anchor (the u32 cursor of call.rs:380) is ref_start + 1 + (wt[t].x + raw.x) - (consumption prefix at the
 // read's first word).
-constexpr int kPairEvPool = 512;            // events per warp (32 consecutive reads) kept in shared memory
+#ifndef INQ_PAIR_POOL
+#define INQ_PAIR_POOL 256
+#endif
+#ifndef INQ_PAIR_MIN_CTAS
+#define INQ_PAIR_MIN_CTAS 5
+#endif
+constexpr int kPairEvPool = INQ_PAIR_POOL;  // events per warp (32 consecutive reads) kept in shared memory
 constexpr int kPairLociCache = 128;         // catalog entries per warp kept in shared memory
 constexpr int kPairTileCache = 64;          // warp-tile prefixes per warp kept in shared memory
 
@@ -814,7 +820,7 @@ struct PairSmem {                           // per CTA of 8 warps (dynamic share
     uint32_t joined[8];
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, INQ_PAIR_MIN_CTAS)
 k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
             const uint32_t *__restrict__ cand_n, EventSource es, const uint32_t *__restrict__ seg_off,
             unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
