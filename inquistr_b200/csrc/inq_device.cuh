@@ -1287,7 +1287,10 @@ __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, ui
 
 constexpr int kMedianWarpMax = 128;         // loci with more calls go to the CTA kernel
 
-__global__ void __launch_bounds__(256)
+#ifndef INQ_MEDIAN_MIN_CTAS
+#define INQ_MEDIAN_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(256, INQ_MEDIAN_MIN_CTAS)
 k_locus_median(uint32_t l0, uint32_t l1, int chunk, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
                const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ vals, uint64_t vals_cap,
                int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
