@@ -25,10 +25,12 @@ def _stale(target: str, sources: list[str]) -> bool:
 def build_libinqcall(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     target = os.path.join(LIBDIR, "libinqcall.so")
-    sources = [os.path.join(CSRC, "inq_capi.cu"), os.path.join(CSRC, "inq_device.cuh"),
-               os.path.join(os.path.dirname(HERE), "include", "inqcall.h")]
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    units = [os.path.join(CSRC, "inq_capi.cu"), os.path.join(CSRC, "inq_cohort_capi.cu")]
+    sources = units + [os.path.join(CSRC, "inq_device.cuh"), os.path.join(CSRC, "inq_cohort.cuh"),
+                       os.path.join(inc, "inqcall.h"), os.path.join(inc, "inqcohort.h")]
     if force or _stale(target, sources):
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", target, sources[0]]
+        cmd = ["nvcc", *NVCC_FLAGS, "-o", target, *units]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)
@@ -41,8 +43,9 @@ def build_cli(force: bool = False) -> str:
     os.makedirs(bindir, exist_ok=True)
     target = os.path.join(bindir, "inquistr-b200")
     host = os.path.join(CSRC, "host")
-    sources = [os.path.join(host, "main.cpp"), os.path.join(host, "bam_reader.cpp")]
+    sources = [os.path.join(host, "main.cpp"), os.path.join(host, "bam_reader.cpp"), os.path.join(host, "cohort_cli.cpp")]
     deps = sources + [os.path.join(host, "bam_reader.hpp"), os.path.join(os.path.dirname(HERE), "include", "inqcall.h"),
+                      os.path.join(os.path.dirname(HERE), "include", "inqcohort.h"),
                       os.path.join(LIBDIR, "libinqcall.so")]
     if force or _stale(target, deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", target, *sources,

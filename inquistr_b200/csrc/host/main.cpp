@@ -28,6 +28,10 @@
 #include "../../../include/inqcall.h"
 #include "bam_reader.hpp"
 
+namespace inqhost {
+int combine_main(const std::vector<std::string> &files);                 // cohort_cli.cpp
+int outlier_main(const std::vector<std::string> &args, int device);
+}
 using namespace inqhost;
 
 namespace {
@@ -94,7 +98,8 @@ Args parse_args(int argc, char **argv)
     std::vector<std::string> v(argv + 1, argv + argc);
     if (v.empty() || v[0] == "-h" || v[0] == "--help" || v[0] == "help") {
         printf("Tool to genotype STRs from long reads (B200 build of the `call` hot path)\n\n"
-               "Usage: inquistr-b200 <COMMAND>\n\nCommands:\n  call  Call lengths\n  help  Print this message\n");
+               "Usage: inquistr-b200 <COMMAND>\n\nCommands:\n  call     Call lengths\n  combine  Combine lengths from multiple bams to a TSV\n"
+               "  outlier  Find outliers from TSV\n  help     Print this message\n");
         exit(v.empty() ? 2 : 0);
     }
     if (v[0] == "-V" || v[0] == "--version") { printf("inquistr-b200 %s\n", inq_version()); exit(0); }
@@ -131,7 +136,10 @@ Args parse_args(int argc, char **argv)
                (unsigned long long)rd.bytes_inflated(), s, rd.bytes_inflated() / 1e9 / s);
         exit(0);
     }
-    if (v[0] != "call") usage_error("unrecognized subcommand '" + v[0] + "' (only `call` is implemented in this build)");
+    // cohort follow-ons of `call`: text in, text out; cohort_cli.cpp
+    if (v[0] == "combine") exit(combine_main(std::vector<std::string>(v.begin() + 1, v.end())));
+    if (v[0] == "outlier") exit(outlier_main(std::vector<std::string>(v.begin() + 1, v.end()), a.device));
+    if (v[0] != "call") usage_error("unrecognized subcommand '" + v[0] + "' (`call`, `combine` and `outlier` are implemented in this build)");
     if (v.size() == 1) { fputs(kHelp, stderr); exit(2); }                 // arg_required_else_help (main.rs:27)
     bool have_bam = false;
     auto need = [&](size_t &i, const std::string &name) -> std::string {

@@ -1,0 +1,117 @@
+// inq_cohort_capi.cu -- extern "C" entry points of include/inqcohort.h (part of libinqcall.so)
+#include "../../include/inqcall.h"
+#include "../../include/inqcohort.h"
+#include "inq_cohort.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+thread_local std::string g_cohort_error;
+
+int cfail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_cohort_error = buf;
+    return code;
+}
+
+struct Guard {                         // frees everything on every exit path
+    void *d_m = nullptr, *d_kept = nullptr, *d_hits = nullptr, *d_ctr = nullptr;
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Guard()
+    {
+        if (d_m) cudaFree(d_m);
+        if (d_kept) cudaFree(d_kept);
+        if (d_hits) cudaFree(d_hits);
+        if (d_ctr) cudaFree(d_ctr);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (s) cudaStreamDestroy(s);
+    }
+};
+
+#define CC_TRY(call)                                                                            \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) return cfail(INQ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char *inq_cohort_last_error(void) { return g_cohort_error.c_str(); }
+
+int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const float *values, uint32_t minsize,
+                float zscore_cutoff, uint8_t *row_kept, uint64_t *n_hits, uint64_t *hits, uint64_t cap, float *ms_kernel)
+{
+    using namespace inqc;
+    if (n_hits) *n_hits = 0;
+    if (ms_kernel) *ms_kernel = 0.f;
+    if (method != INQ_OUTLIER_ZSCORE && method != INQ_OUTLIER_DBSCAN) return cfail(INQ_ERR_ARG, "inq_outlier: unknown method %d", method);
+    if (n_rows == 0) return INQ_OK;
+    if (n_cols == 0) return cfail(INQ_ERR_ARG, "inq_outlier: a row without value columns (the reference panics, outlier.rs:87-91)");
+    if (!values || !n_hits || (cap && !hits)) return cfail(INQ_ERR_ARG, "inq_outlier: NULL array");
+    if (n_rows > 0xFFFFFFFFull) return cfail(INQ_ERR_TOO_LARGE, "inq_outlier: more than 2^32-1 rows");
+    if (method == INQ_OUTLIER_DBSCAN && n_cols > 4096) return cfail(INQ_ERR_TOO_LARGE, "inq_outlier: dbscan supports at most 4096 columns");
+    CC_TRY(cudaSetDevice(device));
+    Guard g;
+    CC_TRY(cudaStreamCreateWithFlags(&g.s, cudaStreamNonBlocking));
+    CC_TRY(cudaEventCreate(&g.e0));
+    CC_TRY(cudaEventCreate(&g.e1));
+    const size_t bytes = (size_t)n_rows * n_cols * sizeof(float);
+    CC_TRY(cudaMalloc(&g.d_m, bytes));
+    CC_TRY(cudaMalloc(&g.d_kept, n_rows));
+    CC_TRY(cudaMalloc(&g.d_hits, std::max<uint64_t>(cap, 1) * sizeof(unsigned long long)));
+    CC_TRY(cudaMalloc(&g.d_ctr, sizeof(CohortCounters)));
+    CC_TRY(cudaMemcpyAsync(g.d_m, values, bytes, cudaMemcpyHostToDevice, g.s));
+    CC_TRY(cudaMemsetAsync(g.d_ctr, 0, sizeof(CohortCounters), g.s));
+    CC_TRY(cudaEventRecord(g.e0, g.s));
+    if (method == INQ_OUTLIER_ZSCORE) {
+        const unsigned grid = (unsigned)((n_rows + kZRows - 1) / kZRows);
+        k_outlier_zscore<<<grid, kZRows, 0, g.s>>>((const float *)g.d_m, n_rows, n_cols, (float)minsize, zscore_cutoff,
+                                                   (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+    } else {
+        uint32_t n2 = 32;
+        while (n2 < n_cols) n2 <<= 1;
+        const size_t smem = (size_t)n2 * (sizeof(float) + sizeof(uint32_t) + sizeof(uint16_t)) + sizeof(uint32_t);
+        uint32_t min_points = 0;                              // samples.len().ilog2(), outlier.rs:39
+        while ((2ull << min_points) <= n_cols) ++min_points;
+        int sms = 0;
+        CC_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sms * 8);
+        CC_TRY(cudaFuncSetAttribute(k_outlier_dbscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_outlier_dbscan<<<grid, kDbThreads, smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, n2, (float)minsize, min_points,
+                                                          (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+    }
+    CC_TRY(cudaGetLastError());
+    CC_TRY(cudaEventRecord(g.e1, g.s));
+    CohortCounters h;
+    CC_TRY(cudaMemcpyAsync(&h, g.d_ctr, sizeof(h), cudaMemcpyDeviceToHost, g.s));
+    if (row_kept) CC_TRY(cudaMemcpyAsync(row_kept, g.d_kept, n_rows, cudaMemcpyDeviceToHost, g.s));
+    CC_TRY(cudaStreamSynchronize(g.s));
+    if (ms_kernel) cudaEventElapsedTime(ms_kernel, g.e0, g.e1);
+    if (h.no_mode)
+        return cfail(INQ_ERR_NO_MODE, "row %llu passes the minsize test but has no positive value: no mode (the reference panics, outlier.rs:144)",
+                     ((unsigned long long)h.no_mode_row_hi << 32) | h.no_mode_row_lo);
+    *n_hits = h.n_hits;
+    const uint64_t n = std::min<uint64_t>(h.n_hits, cap);
+    if (n) {
+        CC_TRY(cudaMemcpy(hits, g.d_hits, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        std::sort(hits, hits + n);                            // (row, column) = the reference's print order
+    }
+    if (h.n_hits > cap) return cfail(INQ_ERR_HITS_CAP, "inq_outlier: %llu outliers, capacity %llu", (unsigned long long)h.n_hits, (unsigned long long)cap);
+    return INQ_OK;
+}
+
+}  // extern "C"

@@ -96,6 +96,13 @@ int orc_format_f64(double v, char *buf, size_t buflen);
 /* repeats.rs:96-115 validation. chrom_len < 0 means contig not in header. */
 int orc_validate_interval(int64_t start, int64_t end, int64_t chrom_len);
 
+/* ---- cohort `outlier` rows (src/outlier.rs); implemented in oracle_cohort.c ---- */
+int orc_repeat_lengths(const float *in, size_t n, uint32_t minsize, float *out);          /* outlier.rs:75-97 */
+void orc_std_deviation_and_mean(const float *data, size_t n, float *mean, float *sd);     /* outlier.rs:18-31 */
+void orc_zscore_outliers(const float *values, size_t n, float cutoff, uint8_t *flag);     /* outlier.rs:99-113 */
+int64_t orc_mode(const float *values, size_t n);                                           /* outlier.rs:133-145 */
+int orc_dbscan_outliers(const float *values, size_t n, size_t mincluster, uint8_t *flag); /* outlier.rs:115-131 */
+
 #ifdef __cplusplus
 }
 #endif

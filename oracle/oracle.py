@@ -47,8 +47,8 @@ class _Reads(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_cohort.c", "oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
@@ -77,6 +77,16 @@ def lib():
         L.orc_format_f64.argtypes = [C.c_double, C.c_char_p, C.c_size_t]
         L.orc_validate_interval.restype = C.c_int
         L.orc_validate_interval.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        L.orc_repeat_lengths.restype = C.c_int
+        L.orc_repeat_lengths.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+        L.orc_std_deviation_and_mean.restype = None
+        L.orc_std_deviation_and_mean.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_zscore_outliers.restype = None
+        L.orc_zscore_outliers.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]
+        L.orc_mode.restype = C.c_int64
+        L.orc_mode.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_dbscan_outliers.restype = C.c_int
+        L.orc_dbscan_outliers.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -303,3 +313,98 @@ def py_genotype_locus(reads: Reads, tid, start, end, minlen=5, support=3, unphas
         half = len(calls) // 2
         return py_median_str_length(calls[:half], support), py_median_str_length(calls[half:], support)
     return py_median_str_length(buckets[1], support), py_median_str_length(buckets[2], support)
+
+
+# --------------------------------------------------------------------------- cohort `outlier` rows (outlier.rs)
+def repeat_lengths(row, minsize: int):
+    """outlier.rs:75-97 -> (kept, cleaned f32 values)"""
+    v = np.ascontiguousarray(row, dtype=np.float32)
+    out = np.empty_like(v)
+    kept = lib().orc_repeat_lengths(v.ctypes.data, len(v), int(minsize), out.ctypes.data)
+    return bool(kept), out
+
+
+def std_deviation_and_mean(values):
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    m, sd = C.c_float(), C.c_float()
+    lib().orc_std_deviation_and_mean(v.ctypes.data, len(v), C.byref(m), C.byref(sd))
+    return np.float32(m.value), np.float32(sd.value)
+
+
+def zscore_outliers(values, cutoff: float) -> np.ndarray:
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    flag = np.zeros(len(v), np.uint8)
+    lib().orc_zscore_outliers(v.ctypes.data, len(v), float(cutoff), flag.ctypes.data)
+    return flag
+
+
+def mode(values) -> int:
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    return int(lib().orc_mode(v.ctypes.data, len(v)))
+
+
+def dbscan_outliers(values, mincluster: int):
+    """-> (rc, noise flags); rc = -1 when the row has no positive value (the reference panics)"""
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    flag = np.zeros(len(v), np.uint8)
+    rc = lib().orc_dbscan_outliers(v.ctypes.data, len(v), int(mincluster), flag.ctypes.data)
+    return rc, flag
+
+
+def outlier_matrix(matrix, minsize=10, cutoff=3.0, method="zscore"):
+    """Row loop of outlier.rs:33-72 over a rows x cols f32 matrix.
+    -> (kept[rows] u8, flags[rows, cols] u8, status[rows] i8: -1 where dbscan has no mode)"""
+    m = np.ascontiguousarray(matrix, dtype=np.float32)
+    rows, cols = m.shape
+    kept = np.zeros(rows, np.uint8)
+    flags = np.zeros((rows, cols), np.uint8)
+    status = np.zeros(rows, np.int8)
+    mincluster = int(np.log2(cols)) if cols else 0          # samples.len().ilog2(), outlier.rs:39
+    for r in range(rows):
+        k, v = repeat_lengths(m[r], minsize)
+        kept[r] = k
+        if not k:
+            continue
+        if method == "zscore":
+            flags[r] = zscore_outliers(v, cutoff)
+        else:
+            rc, f = dbscan_outliers(v, mincluster)
+            status[r] = rc
+            if rc == 0:
+                flags[r] = f
+    return kept, flags, status
+
+
+def py_zscore_outliers(values, cutoff):
+    """independent pure-Python mirror of outlier.rs:18-31,99-113 (numpy float32 scalars, sequential)"""
+    v = [np.float32(x) for x in values]
+    s = np.float32(0.0)
+    for x in v:
+        s = np.float32(s + x)
+    n = np.float32(len(v))
+    with np.errstate(all="ignore"):
+        mean = np.float32(s / n)
+        var = np.float32(0.0)
+        for x in v:
+            d = np.float32(mean - x)
+            var = np.float32(var + np.float32(d * d))
+        sd = np.float32(np.sqrt(np.float32(var / n)))
+        return np.array([1 if np.float32(np.float32(x - mean) / sd) >= np.float32(cutoff) else 0 for x in v], np.uint8)
+
+
+def py_dbscan_outliers(values, mincluster):
+    """order-independent characterisation: noise = not core and no core point within eps"""
+    v = np.asarray(values, dtype=np.float64)
+    pos = [int(x) for x in values if x > 0]
+    if not pos:
+        return -1, np.zeros(len(v), np.uint8)
+    cnt = {}
+    for x in pos:
+        cnt[x] = cnt.get(x, 0) + 1
+    best = max(cnt.values())
+    md = min(k for k, c in cnt.items() if c == best)
+    eps = float(max(2 * md, 10))
+    d = np.abs(v[:, None] - v[None, :])
+    core = (d < eps).sum(1) >= mincluster
+    near_core = ((d < eps) & core[None, :]).any(1)
+    return 0, (~core & ~near_core).astype(np.uint8)

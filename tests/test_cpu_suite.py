@@ -62,9 +62,10 @@ def test_expansion_panel_has_clip_topup_and_kb_alleles():
 def test_cabi_exports_every_declared_symbol():
     import inquistr_b200 as q
     from inquistr_b200 import api
-    hdr = open(os.path.join(ROOT, "include", "inqcall.h")).read()
+    from inquistr_b200 import cohort
+    hdr = open(os.path.join(ROOT, "include", "inqcall.h")).read() + open(os.path.join(ROOT, "include", "inqcohort.h")).read()
     declared = sorted(set(re.findall(r"\b(inq_[a-z0-9_]+)\s*\(", hdr)))
-    assert set(declared) == set(api.EXPORTS), (declared, api.EXPORTS)
+    assert set(declared) == set(api.EXPORTS) | set(cohort.EXPORTS), (declared, api.EXPORTS, cohort.EXPORTS)
     lib = q.load_library()
     for name in declared:
         assert hasattr(lib, name), name
