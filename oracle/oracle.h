@@ -13,6 +13,10 @@
  * function cites the src/call.rs / src/repeats.rs lines it follows, and the
  * known-answer vectors in tests/test_oracle_kat.py are derived by hand from
  * those lines.
+ *
+ * The cohort `outlier` rows (oracle_cohort.c) ARE pinned: the reference's unit
+ * tests outlier.rs:147-168 hold one known-answer vector per method, replayed in
+ * tests/test_cohort.py.
  */
 #ifndef INQ_ORACLE_H
 #define INQ_ORACLE_H

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/oracle.h): imported by tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.
-PARITY UNPINNED: no runnable reference and no golden `call` output exist.
+PARITY UNPINNED for `call`: no runnable reference and no golden `call` output exist.
+The `outlier` rows are pinned by the reference's unit-test vectors (outlier.rs:147-168).
 
 The pure-Python functions (`py_*`) restate the same reference lines a second
 time, independently of the C file, so the two can be cross-checked:
