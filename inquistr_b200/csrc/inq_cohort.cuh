@@ -21,22 +21,36 @@ struct CohortCounters {
 
 constexpr int kZRows = 128;            // rows (= threads) per CTA
 constexpr int kZTile = 32;             // columns per shared-memory tile
+constexpr int kZHitBuf = 1024;         // outliers buffered per CTA before they are written out
 
 __device__ __forceinline__ float clean(float v) { return (v != v) ? 0.0f : v; }   // outlier.rs:81-84
 
-// loads the tile [row0, row0 + kZRows) x [c0, c0 + kZTile) (NaN -> 0) with coalesced 128-byte row segments
-__device__ __forceinline__ void load_tile(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, uint64_t row0,
-                                          uint32_t c0, float (*tile)[kZTile + 1])
+// A CTA walks its 128 rows in tiles of 32 columns. A warp fetches 32 row segments of 128 bytes (coalesced)
+// into registers, all loads issued back to back; the registers of tile t+1 are filled while tile t is being
+// summed (software double buffering), so the global latency hides behind the sequential adds and the barriers.
+constexpr uint32_t kZWarps = kZRows / 32, kZPerWarp = kZRows / kZWarps;
+
+struct TileRegs { float v[kZPerWarp]; };
+
+__device__ __forceinline__ void fetch_tile(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, uint64_t row0,
+                                           uint32_t c0, TileRegs &t)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (uint32_t r = warp; r < (uint32_t)kZRows; r += nwarp) {
-        const uint64_t row = row0 + r;
-        const uint32_t c = c0 + lane;
-        tile[r][lane] = (row < n_rows && c < n_cols) ? clean(m[row * n_cols + c]) : 0.0f;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = c0 + lane;
+#pragma unroll
+    for (uint32_t k = 0; k < kZPerWarp; ++k) {
+        const uint64_t row = row0 + warp * kZPerWarp + k;
+        t.v[k] = (row < n_rows && c < n_cols) ? __ldg(m + row * n_cols + c) : 0.0f;
     }
 }
+__device__ __forceinline__ void store_tile(const TileRegs &t, float (*tile)[kZTile + 1])
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (uint32_t k = 0; k < kZPerWarp; ++k) tile[warp * kZPerWarp + k][lane] = clean(t.v[k]);   // NaN -> 0 (outlier.rs:81-84)
+}
 
-__global__ void __launch_bounds__(kZRows)
+__global__ void __launch_bounds__(kZRows, 4)
 k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, float minsize, float cutoff,
                  uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits, uint64_t cap,
                  CohortCounters *__restrict__ ctr)
@@ -44,13 +58,22 @@ k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
     __shared__ float tile[kZRows][kZTile + 1];
     __shared__ float s_mean[kZRows], s_sd[kZRows];
     __shared__ uint8_t s_kept[kZRows];
+    // outliers of the CTA's rows are collected here and leave with ONE global atomic; overflow falls back
+    // to one atomic per outlier
+    __shared__ unsigned long long s_hits[kZHitBuf];
+    __shared__ unsigned int s_nhits;
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_nhits = 0;
     const uint64_t row0 = (uint64_t)blockIdx.x * kZRows, row = row0 + threadIdx.x;
+    TileRegs regs;
     // pass 1: sequential f32 sum and the maximum (outlier.rs:19, 87-90)
     float sum = 0.0f, mx = 0.0f;
+    fetch_tile(m, n_rows, n_cols, row0, 0, regs);
     for (uint32_t c0 = 0; c0 < n_cols; c0 += kZTile) {
         __syncthreads();
-        load_tile(m, n_rows, n_cols, row0, c0, tile);
+        store_tile(regs, tile);
         __syncthreads();
+        if (c0 + kZTile < n_cols) fetch_tile(m, n_rows, n_cols, row0, c0 + kZTile, regs);
         const uint32_t n = min((uint32_t)kZTile, n_cols - c0);
         for (uint32_t c = 0; c < n; ++c) {
             const float v = tile[threadIdx.x][c];
@@ -63,10 +86,12 @@ k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
     const bool kept = row < n_rows && !(mx < minsize);
     // pass 2: population variance around the f32 mean (outlier.rs:22-29)
     float var = 0.0f;
+    fetch_tile(m, n_rows, n_cols, row0, 0, regs);
     for (uint32_t c0 = 0; c0 < n_cols; c0 += kZTile) {
         __syncthreads();
-        load_tile(m, n_rows, n_cols, row0, c0, tile);
+        store_tile(regs, tile);
         __syncthreads();
+        if (c0 + kZTile < n_cols) fetch_tile(m, n_rows, n_cols, row0, c0 + kZTile, regs);
         const uint32_t n = min((uint32_t)kZTile, n_cols - c0);
         for (uint32_t c = 0; c < n; ++c) {
             const float diff = __fsub_rn(mean, tile[threadIdx.x][c]);
@@ -78,22 +103,165 @@ k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
     s_sd[threadIdx.x] = sd;
     s_kept[threadIdx.x] = kept ? 1 : 0;
     if (row < n_rows && row_kept) row_kept[row] = kept ? 1 : 0;
-    // pass 3: flags, element-parallel (no order dependence): (v - mean) / sd >= cutoff (outlier.rs:109)
-    for (uint32_t c0 = 0; c0 < n_cols; c0 += kZTile) {
-        __syncthreads();
-        load_tile(m, n_rows, n_cols, row0, c0, tile);
-        __syncthreads();
-        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-        for (uint32_t r = warp; r < (uint32_t)kZRows; r += nwarp) {
+    __syncthreads();
+    // pass 3: flags, element-parallel straight from the registers (no order dependence):
+    // (v - mean) / sd >= cutoff (outlier.rs:109)
+    {
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (uint32_t c0 = 0; c0 < n_cols; c0 += kZTile) {
+            fetch_tile(m, n_rows, n_cols, row0, c0, regs);
             const uint32_t c = c0 + lane;
-            if (!s_kept[r] || c >= n_cols) continue;
-            const float z = __fdiv_rn(__fsub_rn(tile[r][lane], s_mean[r]), s_sd[r]);
-            if (z >= cutoff) {
-                const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
-                if (slot < cap) hits[slot] = ((row0 + r) << 32) | c;
+#pragma unroll
+            for (uint32_t k = 0; k < kZPerWarp; ++k) {
+                const uint32_t r = warp * kZPerWarp + k;
+                if (!s_kept[r] || c >= n_cols) continue;
+                const float z = __fdiv_rn(__fsub_rn(clean(regs.v[k]), s_mean[r]), s_sd[r]);
+                if (z >= cutoff) {
+                    const unsigned long long h = ((row0 + r) << 32) | c;
+                    const unsigned int slot_l = atomicAdd(&s_nhits, 1u);
+                    if (slot_l < (unsigned int)kZHitBuf) s_hits[slot_l] = h;
+                    else {
+                        const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                        if (slot < cap) hits[slot] = h;
+                    }
+                }
             }
         }
     }
+    __syncthreads();
+    const unsigned int nh = min(s_nhits, (unsigned int)kZHitBuf);
+    if (threadIdx.x == 0 && nh) s_base = atomicAdd(&ctr->n_hits, (unsigned long long)nh);
+    __syncthreads();
+    for (unsigned int k = threadIdx.x; k < nh; k += blockDim.x)
+        if (s_base + k < cap) hits[s_base + k] = s_hits[k];
+}
+
+// ---------------------------------------------------------------------------------------------- z-score, resident rows
+// When 32 rows fit in shared memory (n_cols <= ~1700) the matrix is read from HBM exactly once: the CTA copies
+// its 32 contiguous rows in (coalesced, all 256 threads), one warp then owns one row per lane and does the two
+// order-dependent passes out of shared memory (odd row stride: conflict-free), and all threads take the
+// element-parallel flag pass. Several CTAs per SM overlap one CTA's copy with another's sums.
+constexpr int kZResRows = 32;
+constexpr int kZResThreads = 256;
+constexpr int kZResHitBuf = 512;
+
+// (v - mean) / sd >= cutoff with the reference's f32 division (outlier.rs:109). The correctly rounded division
+// is only evaluated when the reciprocal-multiply estimate is within 1e-5 (relative) of the cutoff or not finite;
+// the estimate is off by < 2e-7 relative, so everywhere else it decides identically.
+__device__ __forceinline__ bool z_at_least(float d, float sd, float rinv, float cutoff, float margin)
+{
+    const float zp = d * rinv;
+    if (fabsf(zp - cutoff) > margin && fabsf(zp) <= 3.0e38f) return zp > cutoff;
+    return __fdiv_rn(d, sd) >= cutoff;
+}
+
+__global__ void __launch_bounds__(kZResThreads)
+k_outlier_zscore_rows(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, uint32_t stride, float minsize,
+                      float cutoff, uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits, uint64_t cap,
+                      CohortCounters *__restrict__ ctr)
+{
+    extern __shared__ float zr_rows[];                       // [kZResRows][stride], stride odd
+    __shared__ float s_mean[kZResRows], s_sd[kZResRows], s_rinv[kZResRows];
+    __shared__ uint8_t s_kept[kZResRows];
+    __shared__ unsigned long long s_hits[kZResHitBuf];
+    __shared__ unsigned int s_nhits;
+    __shared__ unsigned long long s_base;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_nhits = 0;
+    const uint64_t row0 = (uint64_t)blockIdx.x * kZResRows;
+    const uint32_t nr = (uint32_t)min((uint64_t)kZResRows, n_rows - row0);
+    const uint32_t total = nr * n_cols;
+    const float *__restrict__ src = m + row0 * n_cols;
+    // ---- copy in (NaN -> 0, outlier.rs:81-84): 8 independent loads per thread in flight before the first store
+    const float inv_cols = 1.0f / (float)n_cols;
+    auto row_of = [&](uint32_t e) {                          // e / n_cols for e < 2^24 without an integer division
+        uint32_t r = (uint32_t)((float)e * inv_cols);
+        if (r * n_cols > e) --r;
+        else if ((r + 1u) * n_cols <= e) ++r;
+        return r;
+    };
+    // 16-byte loads, 8 per thread in flight before the first store (bytes in flight bound this phase);
+    // the CTA's rows are one contiguous, 128-byte aligned block of the matrix
+    const uint32_t total4 = total / 4;
+    const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(src);
+    for (uint32_t base = 0; base < total4; base += kZResThreads * 8) {
+        float4 v[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            const uint32_t q = base + k * kZResThreads + tid;
+            v[k] = q < total4 ? __ldg(src4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            const uint32_t q = base + k * kZResThreads + tid;
+            if (q < total4) {
+                uint32_t r = row_of(4 * q), c = 4 * q - r * n_cols;
+                const float w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c == n_cols) { c = 0; ++r; }
+                    zr_rows[r * stride + c] = clean(w[j]);
+                    ++c;
+                }
+            }
+        }
+    }
+    for (uint32_t e = total4 * 4 + tid; e < total; e += kZResThreads) {     // up to 3 trailing values
+        const uint32_t r = row_of(e);
+        zr_rows[r * stride + (e - r * n_cols)] = clean(__ldg(src + e));
+    }
+    __syncthreads();
+    // ---- one lane per row: sequential f32 sum + max, then the population variance (outlier.rs:18-31,87-90)
+    if (tid < nr) {
+        const float *row = zr_rows + tid * stride;
+        float sum = 0.0f, mx = -INFINITY;
+#pragma unroll 16
+        for (uint32_t c = 0; c < n_cols; ++c) {             // unrolled: the shared-memory loads run ahead of the add chain
+            const float v = row[c];
+            sum = __fadd_rn(sum, v);
+            mx = fmaxf(mx, v);
+        }
+        const float count = (float)n_cols;
+        const float mean = __fdiv_rn(sum, count);
+        float var = 0.0f;
+#pragma unroll 16
+        for (uint32_t c = 0; c < n_cols; ++c) {
+            const float diff = __fsub_rn(mean, row[c]);
+            var = __fadd_rn(var, __fmul_rn(diff, diff));
+        }
+        const float sd = __fsqrt_rn(__fdiv_rn(var, count));
+        const bool kept = !(mx < minsize);
+        s_mean[tid] = mean;
+        s_sd[tid] = sd;
+        s_rinv[tid] = __frcp_rn(sd);
+        s_kept[tid] = kept ? 1 : 0;
+        if (row_kept) row_kept[row0 + tid] = kept ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- flags, element-parallel
+    {
+        const float margin = fabsf(cutoff) * 1e-5f + 1e-30f;
+        for (uint32_t e = tid; e < total; e += kZResThreads) {
+            const uint32_t r = row_of(e), c = e - r * n_cols;
+            if (!s_kept[r]) continue;
+            const float d = __fsub_rn(zr_rows[r * stride + c], s_mean[r]);
+            if (z_at_least(d, s_sd[r], s_rinv[r], cutoff, margin)) {
+                const unsigned long long h = ((row0 + r) << 32) | c;
+                const unsigned int k = atomicAdd(&s_nhits, 1u);
+                if (k < (unsigned int)kZResHitBuf) s_hits[k] = h;
+                else {
+                    const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                    if (slot < cap) hits[slot] = h;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int nh = min(s_nhits, (unsigned int)kZResHitBuf);
+    if (tid == 0 && nh) s_base = atomicAdd(&ctr->n_hits, (unsigned long long)nh);
+    __syncthreads();
+    for (unsigned int k = tid; k < nh; k += kZResThreads)
+        if (s_base + k < cap) hits[s_base + k] = s_hits[k];
 }
 
 // ---------------------------------------------------------------------------------------------- dbscan
@@ -247,15 +415,26 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
         if (tid == 0) pc[n2] = carry;
         __syncthreads();
         // ---- noise = not core and no core point within eps (Edge otherwise)
-        for (uint32_t i = tid; i < n_cols; i += blockDim.x) {
+        //      (flags first, then one global atomic per row reserves the slots of all its outliers)
+        uint32_t mine = 0, nmine = 0;                        // bit q: element tid + q * blockDim.x is noise (n2 <= 4096 -> q < 32)
+        for (uint32_t i = tid, q = 0; i < n_cols; i += blockDim.x, ++q) {
             uint32_t lo, hi;
             eps_range(key, n_cols, i, eps, &lo, &hi);
             const bool core = hi - lo >= min_points;
             const bool near_core = pc[hi] - pc[lo] > 0u;
-            if (!core && !near_core) {
-                const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
-                if (slot < cap) hits[slot] = (row << 32) | idx[i];
-            }
+            if (!core && !near_core) { mine |= 1u << q; ++nmine; }
+        }
+        uint32_t tot;
+        const uint32_t off = block_scan_excl(nmine, s_warp, &tot);
+        if (tid == 0 && tot) s_best = atomicAdd(&ctr->n_hits, (unsigned long long)tot);    // s_best is free again: slot base
+        __syncthreads();
+        if (tot) {
+            unsigned long long slot = s_best + off;
+            for (uint32_t q = 0; mine; ++q, mine >>= 1)
+                if (mine & 1u) {
+                    if (slot < cap) hits[slot] = (row << 32) | idx[tid + q * blockDim.x];
+                    ++slot;
+                }
         }
     }
 }

@@ -78,9 +78,19 @@ int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const 
     CC_TRY(cudaMemsetAsync(g.d_ctr, 0, sizeof(CohortCounters), g.s));
     CC_TRY(cudaEventRecord(g.e0, g.s));
     if (method == INQ_OUTLIER_ZSCORE) {
+        const uint32_t stride = n_cols | 1u;
+        const size_t res_smem = (size_t)kZResRows * stride * sizeof(float);
+        if (res_smem <= 200u * 1024u) {
+            // 32 rows fit in shared memory: the matrix is read once
+            CC_TRY(cudaFuncSetAttribute(k_outlier_zscore_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+            const unsigned grid = (unsigned)((n_rows + kZResRows - 1) / kZResRows);
+            k_outlier_zscore_rows<<<grid, kZResThreads, res_smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, stride, (float)minsize, zscore_cutoff,
+                                                                        (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+        } else {
         const unsigned grid = (unsigned)((n_rows + kZRows - 1) / kZRows);
         k_outlier_zscore<<<grid, kZRows, 0, g.s>>>((const float *)g.d_m, n_rows, n_cols, (float)minsize, zscore_cutoff,
                                                    (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+        }
     } else {
         uint32_t n2 = 32;
         while (n2 < n_cols) n2 <<= 1;

@@ -70,7 +70,7 @@ def random_matrix(seed, rows, cols):
 
 # ------------------------------------------------------------------ GPU parity through the C ABI
 @pytest.mark.gpu
-@pytest.mark.parametrize("rows,cols", [(1, 11), (300, 7), (1000, 64), (517, 536), (129, 1000)])
+@pytest.mark.parametrize("rows,cols", [(1, 11), (300, 7), (1000, 64), (517, 536), (129, 1000), (70, 2100)])   # 2100 columns: tiled z-score kernel
 @pytest.mark.parametrize("method", ["zscore", "dbscan"])
 def test_gpu_outlier_matches_oracle(rows, cols, method):
     from inquistr_b200 import cohort
