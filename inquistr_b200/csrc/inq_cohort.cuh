@@ -170,45 +170,27 @@ k_outlier_zscore_rows(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
     if (tid == 0) s_nhits = 0;
     const uint64_t row0 = (uint64_t)blockIdx.x * kZResRows;
     const uint32_t nr = (uint32_t)min((uint64_t)kZResRows, n_rows - row0);
-    const uint32_t total = nr * n_cols;
     const float *__restrict__ src = m + row0 * n_cols;
-    // ---- copy in (NaN -> 0, outlier.rs:81-84): 8 independent loads per thread in flight before the first store
-    const float inv_cols = 1.0f / (float)n_cols;
-    auto row_of = [&](uint32_t e) {                          // e / n_cols for e < 2^24 without an integer division
-        uint32_t r = (uint32_t)((float)e * inv_cols);
-        if (r * n_cols > e) --r;
-        else if ((r + 1u) * n_cols <= e) ++r;
-        return r;
-    };
-    // 16-byte loads, 8 per thread in flight before the first store (bytes in flight bound this phase);
-    // the CTA's rows are one contiguous, 128-byte aligned block of the matrix
-    const uint32_t total4 = total / 4;
-    const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(src);
-    for (uint32_t base = 0; base < total4; base += kZResThreads * 8) {
-        float4 v[8];
+    // ---- copy in (NaN -> 0, outlier.rs:81-84): a warp takes rows w, w + 8, ...; its lanes stride over the row's
+    //      columns (coalesced 128-byte requests), up to 16 loads per lane in flight before the first store
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t kWarps = kZResThreads / 32;
+    for (uint32_t r = warp; r < nr; r += kWarps) {
+        const float *__restrict__ g = src + (size_t)r * n_cols;
+        float *row = zr_rows + r * stride;
+        for (uint32_t c0 = 0; c0 < n_cols; c0 += 32 * 16) {
+            float v[16];
 #pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            const uint32_t q = base + k * kZResThreads + tid;
-            v[k] = q < total4 ? __ldg(src4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (uint32_t k = 0; k < 16; ++k) {
+                const uint32_t c = c0 + k * 32 + lane;
+                v[k] = c < n_cols ? __ldg(g + c) : 0.0f;
+            }
 #pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            const uint32_t q = base + k * kZResThreads + tid;
-            if (q < total4) {
-                uint32_t r = row_of(4 * q), c = 4 * q - r * n_cols;
-                const float w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (c == n_cols) { c = 0; ++r; }
-                    zr_rows[r * stride + c] = clean(w[j]);
-                    ++c;
-                }
+            for (uint32_t k = 0; k < 16; ++k) {
+                const uint32_t c = c0 + k * 32 + lane;
+                if (c < n_cols) row[c] = clean(v[k]);
             }
         }
-    }
-    for (uint32_t e = total4 * 4 + tid; e < total; e += kZResThreads) {     // up to 3 trailing values
-        const uint32_t r = row_of(e);
-        zr_rows[r * stride + (e - r * n_cols)] = clean(__ldg(src + e));
     }
     __syncthreads();
     // ---- one lane per row: sequential f32 sum + max, then the population variance (outlier.rs:18-31,87-90)
@@ -241,17 +223,19 @@ k_outlier_zscore_rows(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
     // ---- flags, element-parallel
     {
         const float margin = fabsf(cutoff) * 1e-5f + 1e-30f;
-        for (uint32_t e = tid; e < total; e += kZResThreads) {
-            const uint32_t r = row_of(e), c = e - r * n_cols;
+        for (uint32_t r = warp; r < nr; r += kWarps) {
             if (!s_kept[r]) continue;
-            const float d = __fsub_rn(zr_rows[r * stride + c], s_mean[r]);
-            if (z_at_least(d, s_sd[r], s_rinv[r], cutoff, margin)) {
-                const unsigned long long h = ((row0 + r) << 32) | c;
-                const unsigned int k = atomicAdd(&s_nhits, 1u);
-                if (k < (unsigned int)kZResHitBuf) s_hits[k] = h;
-                else {
-                    const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
-                    if (slot < cap) hits[slot] = h;
+            const float mean = s_mean[r], sd = s_sd[r], rinv = s_rinv[r];
+            const float *row = zr_rows + r * stride;
+            for (uint32_t c = lane; c < n_cols; c += 32) {
+                if (z_at_least(__fsub_rn(row[c], mean), sd, rinv, cutoff, margin)) {
+                    const unsigned long long h = ((row0 + r) << 32) | c;
+                    const unsigned int k = atomicAdd(&s_nhits, 1u);
+                    if (k < (unsigned int)kZResHitBuf) s_hits[k] = h;
+                    else {
+                        const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                        if (slot < cap) hits[slot] = h;
+                    }
                 }
             }
         }
