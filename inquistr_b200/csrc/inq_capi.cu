@@ -33,6 +33,7 @@ struct inq_ctx {
     int scan_ctas_per_sm = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_chunk[kMedianChunks + 1] = {};
+    uint32_t scan_debug = 0, pair_debug = 0;     // timing experiments (INQ_SCAN_DEBUG / INQ_PAIR_DEBUG, read once): results are wrong when != 0
     cudaStream_t stream_join = nullptr;   // the join runs next to the CIGAR scan (latency-bound vs ALU-bound)
     std::string err;
 
@@ -223,6 +224,8 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan<false>, kCtaThreads, kScanSmemBytes)) != cudaSuccess)
         return bail("occupancy(k_cigar_scan)", e);
     ctx->scan_ctas_per_sm = std::max(1, occ);
+    if (const char *dbg = getenv("INQ_SCAN_DEBUG")) ctx->scan_debug = (uint32_t)atoi(dbg);
+    if (const char *dbg = getenv("INQ_PAIR_DEBUG")) ctx->pair_debug = (uint32_t)atoi(dbg);
     *out = ctx;
     return INQ_OK;
 }
@@ -438,7 +441,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
             sp.n_wt = n_wt; sp.neg1 = 0xFFFFFFFFu;
             sp.thr = (std::min<uint32_t>(minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
-            { const char *dbg = getenv("INQ_SCAN_DEBUG"); sp.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
+            sp.debug = ctx->scan_debug;
             if (sp.thr >> 31) k_cigar_scan<true><<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             else k_cigar_scan<false><<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
             ++launches;
@@ -495,7 +498,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             k_pair_eval<<<(unsigned)((R + 255) / 256), 256, sizeof(PairSmem), s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p,
                                                                    EventSource{ctx->wt.p, ctx->rd_pre.p, ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap},
                                                                    ctx->seg_off.p, ctx->cursor.p,
-                                                                   ctx->vals.p, ctx->vals.cap, ctx->d_ctr, getenv("INQ_PAIR_DEBUG") ? (uint32_t)atoi(getenv("INQ_PAIR_DEBUG")) : 0u);
+                                                                   ctx->vals.p, ctx->vals.cap, ctx->d_ctr, ctx->pair_debug);
             ++launches;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_PAIRS], s));

@@ -25,9 +25,9 @@ constexpr int kZHitBuf = 1024;         // outliers buffered per CTA before they 
 
 __device__ __forceinline__ float clean(float v) { return (v != v) ? 0.0f : v; }   // outlier.rs:81-84
 
-// A CTA walks its 128 rows in tiles of 32 columns. A warp fetches 32 row segments of 128 bytes (coalesced)
-// into registers, all loads issued back to back; the registers of tile t+1 are filled while tile t is being
-// summed (software double buffering), so the global latency hides behind the sequential adds and the barriers.
+// Fallback for rows too wide for the resident kernel below: a CTA walks its 128 rows in tiles of 32 columns,
+// three passes over global memory / L2. A warp fetches 32 row segments of 128 bytes (coalesced) into
+// registers, all loads issued back to back, before the first store to shared memory.
 constexpr uint32_t kZWarps = kZRows / 32, kZPerWarp = kZRows / kZWarps;
 
 struct TileRegs { float v[kZPerWarp]; };
@@ -50,7 +50,7 @@ __device__ __forceinline__ void store_tile(const TileRegs &t, float (*tile)[kZTi
     for (uint32_t k = 0; k < kZPerWarp; ++k) tile[warp * kZPerWarp + k][lane] = clean(t.v[k]);   // NaN -> 0 (outlier.rs:81-84)
 }
 
-__global__ void __launch_bounds__(kZRows, 4)
+__global__ void __launch_bounds__(kZRows)
 k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, float minsize, float cutoff,
                  uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits, uint64_t cap,
                  CohortCounters *__restrict__ ctr)
@@ -68,12 +68,11 @@ k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
     TileRegs regs;
     // pass 1: sequential f32 sum and the maximum (outlier.rs:19, 87-90)
     float sum = 0.0f, mx = 0.0f;
-    fetch_tile(m, n_rows, n_cols, row0, 0, regs);
     for (uint32_t c0 = 0; c0 < n_cols; c0 += kZTile) {
+        fetch_tile(m, n_rows, n_cols, row0, c0, regs);
         __syncthreads();
         store_tile(regs, tile);
         __syncthreads();
-        if (c0 + kZTile < n_cols) fetch_tile(m, n_rows, n_cols, row0, c0 + kZTile, regs);
         const uint32_t n = min((uint32_t)kZTile, n_cols - c0);
         for (uint32_t c = 0; c < n; ++c) {
             const float v = tile[threadIdx.x][c];
@@ -86,12 +85,11 @@ k_outlier_zscore(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
     const bool kept = row < n_rows && !(mx < minsize);
     // pass 2: population variance around the f32 mean (outlier.rs:22-29)
     float var = 0.0f;
-    fetch_tile(m, n_rows, n_cols, row0, 0, regs);
     for (uint32_t c0 = 0; c0 < n_cols; c0 += kZTile) {
+        fetch_tile(m, n_rows, n_cols, row0, c0, regs);
         __syncthreads();
         store_tile(regs, tile);
         __syncthreads();
-        if (c0 + kZTile < n_cols) fetch_tile(m, n_rows, n_cols, row0, c0 + kZTile, regs);
         const uint32_t n = min((uint32_t)kZTile, n_cols - c0);
         for (uint32_t c = 0; c < n; ++c) {
             const float diff = __fsub_rn(mean, tile[threadIdx.x][c]);
