@@ -231,3 +231,19 @@ def test_cli_outlier_tsv_matches_oracle(cli, cohort_files, tmp_path):
     sub.write_text("sample1\nsample20\n")
     r = run(cli, "outlier", "-S", str(sub), "--method", "dbscan", str(cpath))
     assert r.returncode == 0 and r.stdout.decode() == expected_outlier_tsv(combined, 10, 3.0, "dbscan", {"sample1", "sample20"})
+
+
+def test_outlier_fails_loudly_without_gpu(cli, cohort_files, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from inquistr_b200 import cohort
+    from inquistr_b200.api import InqError
+    with pytest.raises(InqError) as e:
+        cohort.outlier(np.asarray([REF_VALUES], np.float32), 10, 2.0, "zscore")
+    assert e.value.code == -1                                            # INQ_ERR_CUDA: no CPU implementation behind the ABI
+    d, texts, paths = cohort_files
+    c = tmp_path / "c.tsv"
+    c.write_text(py_combine(texts))
+    r = run(cli, "outlier", str(c))
+    assert r.returncode == 1 and r.stdout == b"chrom\tbegin\tend\toutliers\n" and b"inquistr-b200:" in r.stderr
