@@ -36,6 +36,11 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome and catalog (tests)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pack-filter", action="store_true",
+                    help="ship every generated read (also the ones with mapq <= 10 / without HP that can never pair)")
+    ap.add_argument("--ranges", type=int, default=None, help="inq_set_option('ranges') (default: automatic)")
+    ap.add_argument("--no-graph", action="store_true", help="inq_set_option('graph', 0)")
+    ap.add_argument("--parity-seconds", type=float, default=6.0, help="budget of the per-rank oracle check at N > 1")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -163,13 +168,16 @@ def main():
         "sharding": f"locus catalog range-sharded over {world} rank(s), no collective",
         "l2": "inputs (packed CIGAR stream) are far larger than the 126 MB L2; no flush needed",
         "data_seed": args.config,
+        "pack_filter": (not args.no_pack_filter),
+        "pack_filter_note": "the host packer drops reads that fail the per-read part of call.rs:297-300/350-352 for every "
+                            "locus (mapq <= 10; phased: no HP tag), like `inquistr-b200 call` does; both arms get the same reads",
     }
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        w = make_workload(args.config, scale=args.scale, threads=threads)
+        w = make_workload(args.config, scale=args.scale, threads=threads, pack_filter=not args.no_pack_filter)
         config_desc["workload"] = w.name
         config_desc["unphased"] = bool(w.unphased)
         vals = []
@@ -225,13 +233,17 @@ def main():
 
     t_gen = time.perf_counter()
     w = make_workload(args.config, scale=args.scale, threads=max(1, threads // max(1, world)), pinned=True,
-                      shard=(rank, world))
+                      shard=(rank, world), pack_filter=not args.no_pack_filter)
     t_gen = time.perf_counter() - t_gen
     rd = w.reads
     config_desc["workload"] = w.name
     config_desc["unphased"] = bool(w.unphased)
 
     ctx = q.Context(local_rank)
+    if args.ranges is not None:
+        ctx.set_option("ranges", args.ranges)
+    if args.no_graph:
+        ctx.set_option("graph", 0)
     ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
     ctx.reserve_reads(rd.n, len(rd.cigar))
     ctx.push(rd)
@@ -305,32 +317,51 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get(f"config{args.config}_scale{args.scale:g}_gpus{world}")
+        key = f"config{args.config}_scale{args.scale:g}_gpus{world}" + ("" if not args.no_pack_filter else "_nofilter")
+        ent = tj.get(key)
         if ent:
             traffic = ent["k_cigar_scan_dram_bytes_per_launch"]
     except Exception:
         pass
+    step_ms = sec_per_step * 1e3
     roofline = {
         "kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "formula": "achieved = (4*C_j + 12*R_j) / ms_per_launch: the packed CIGAR words of reads joined to >= 1 locus, once, "
+                   "plus cig_off (8 B) and ref_start (4 B) of those reads; the other 12 B of SURVEY 8(d)'s 24 B read record "
+                   "are read by k_join_ranges / k_pair_eval and count in pipeline_* only",
         "algorithmic_bytes_per_launch": ab["cigar_scan"], "ms_per_launch": ms_cigar,
+        "launches_per_step": int(st["n_ranges"]),
+        "ms_note": "one launch per range of the pass; ms_per_launch is the SUM over the ranges of a step (CUDA events on "
+                   "the launching stream), i.e. the time to scan the whole stream once, while k_pair_eval / k_locus_median "
+                   "of the previous range share the SMs",
         "bytes_streamed_per_launch": 4 * st["n_cigar_words"],
         "streamed_GBps": 4 * st["n_cigar_words"] / (ms_cigar * 1e-3) / 1e9 if ms_cigar > 0 else 0.0,
         "pipeline_algorithmic_bytes": ab["pipeline"],
-        "pipeline_GBps": ab["pipeline"] / (st["ms_total"] * 1e-3) / 1e9 if st["ms_total"] > 0 else 0.0,
-        "pipeline_frac": (ab["pipeline"] / (st["ms_total"] * 1e-3) / 1e9 / peak) if st["ms_total"] > 0 else 0.0,
+        "pipeline_formula": "4*C_j + 24*R + 12*L + 16*P + 17*L (SURVEY 8d) / ms_per_step (the driver-timed step, not the device time)",
+        "pipeline_GBps": ab["pipeline"] / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0,
+        "pipeline_frac": (ab["pipeline"] / (step_ms * 1e-3) / 1e9 / peak) if step_ms > 0 else 0.0,
         "frac_of_nominal_8TBps": achieved / 8000.0,
     }
 
-    # ---- CPU baseline (rank 0, N=1 only) + sampled parity check of the GPU result
+    # ---- CPU baseline (rank 0, N=1 only) + parity check of the GPU result against the oracle (every rank, every N)
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
         cpu, (sel, p1, p2) = cpu_reference(w, threads, args.cpu_seconds)
         g1, g2 = res.phase1[sel], res.phase2[sel]
         ok = bool(np.array_equal(g1, p1, equal_nan=True) and np.array_equal(g2, p2, equal_nan=True))
-        parity = {"loci_checked": int(len(sel)), "bit_exact_vs_oracle": ok}
+        parity = {"loci_checked": int(len(sel)), "bit_exact_vs_oracle": ok, "ranks_checked": 1}
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "op_visits_per_s")}
+    elif world > 1:
+        # every rank checks a bounded sample of ITS shard's GPU output against the oracle on its shard's reads
+        _, (sel, p1, p2) = cpu_reference(w, max(1, threads // world), args.parity_seconds)
+        g1, g2 = res.phase1[sel], res.phase2[sel]
+        ok = bool(np.array_equal(g1, p1, equal_nan=True) and np.array_equal(g2, p2, equal_nan=True))
+        n_bad = sum_over_ranks(0.0 if ok else 1.0)
+        n_chk = sum_over_ranks(float(len(sel)))
+        parity = {"loci_checked": int(n_chk), "bit_exact_vs_oracle": bool(n_bad == 0), "ranks_checked": world,
+                  "note": "each rank: evenly spaced sample of its catalog shard, oracle on the shard's reads"}
 
     if rank == 0:
         line = {
@@ -345,6 +376,9 @@ def main():
                        "events_rank0": int(st["n_events"]), "tiles_rank0": int(st["n_tiles"])},
             "device_ms_per_step": dev_sec_per_step * 1e3,
             "stage_ms_rank0": stage_ms,
+            "pipeline": {"ranges": int(st["n_ranges"]), "median_chunks": int(st["n_median_chunks"]),
+                         "cuda_graph": bool(st["used_graph"]), "reads_sorted": bool(st["reads_sorted"]),
+                         "note": "stage_ms are per-stage sums under overlap (they add up to more than the step)"},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": None if e2e is None else {

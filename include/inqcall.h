@@ -66,18 +66,22 @@ typedef struct inq_stats {
     uint64_t n_candidates;       /* (read, locus) candidates examined by the join */
     uint64_t n_events;           /* I/D/S ops longer than minlen found by the CIGAR scan */
     uint64_t op_visits;          /* sum over pairs of n_cigar(read): what call.rs:382 executes */
-    uint32_t n_kernel_launches;  /* kernels launched by the call */
+    uint32_t n_kernel_launches;  /* kernels launched by the call (direct or replayed from the CUDA graph) */
     uint32_t n_tiles;            /* CIGAR tiles scanned */
-    float ms_total;              /* first kernel start -> last kernel end */
+    float ms_total;              /* start of the pass -> everything done, results in host memory */
     float ms_index;              /* memsets */
     float ms_join;               /* K1 read x locus overlap join + segment offsets (second stream, under K2) */
-    float ms_cigar;              /* K2 CIGAR scan (dominant kernel) */
-    float ms_fixup;              /* prefix scan over the warp-tile totals */
-    float ms_scan;               /* wait for the join stream */
-    float ms_pairs;              /* K2b event staging, per-pair window sums, scatter into buckets */
-    float ms_median;             /* K3 per-locus sort / support filter / median */
+    float ms_cigar;              /* K2 CIGAR scan (dominant kernel), summed over the ranges of the pass */
+    float ms_fixup;              /* prefix scans over the warp-tile totals, summed over the ranges */
+    float ms_scan;               /* tail: last range scanned -> end of the pass (what the overlap does not hide) */
+    float ms_pairs;              /* K2b event staging, per-pair window sums, scatter into buckets (runs under K2 of the next range) */
+    float ms_median;             /* K3 per-locus sort / support filter / median: first chunk start -> last chunk end */
     float ms_h2d;                /* host->device copies of the last inq_push_reads */
-    float ms_d2h;                /* device->host copy of the results */
+    float ms_d2h;                /* last median chunk done -> last result copy done */
+    uint32_t n_ranges;           /* ranges the CIGAR stream was scanned in (pair/median work of range k runs under scan k+1) */
+    uint32_t used_graph;         /* 1: the pass was replayed from a captured CUDA graph */
+    uint32_t reads_sorted;       /* 1: reads were pushed in (contig, ref_start) order: finished loci are reduced and copied early */
+    uint32_t n_median_chunks;
 } inq_stats;
 
 /* Create / destroy a context bound to CUDA device `device`. */
@@ -85,6 +89,17 @@ int inq_ctx_create(int device, inq_ctx **out);
 void inq_ctx_destroy(inq_ctx *ctx);
 const char *inq_last_error(const inq_ctx *ctx);   /* ctx may be NULL: message of a failed create */
 const char *inq_version(void);
+
+/*
+ * Tuning knobs (all optional; the defaults are what bench.py measures). Returns INQ_ERR_ARG for an
+ * unknown name or a value out of range.
+ *   "ranges"          number of ranges the CIGAR stream is scanned in (0 = automatic, max 16)
+ *   "max_ranges"      upper bound of the automatic choice (default 8)
+ *   "min_range_tiles" automatic choice: at least this many 4 KB warp tiles per range (default 65536)
+ *   "graph"           1 (default): replay the steady state from a CUDA graph; 0: always launch directly
+ *   "timing"          1 (default): record the CUDA events behind inq_stats.ms_*; 0: none
+ */
+int inq_set_option(inq_ctx *ctx, const char *name, int64_t value);
 
 /* Pinned host memory for the caller's staging buffers (optional). */
 int inq_host_alloc(size_t bytes, void **out);
@@ -134,7 +149,8 @@ int inq_clear_reads(inq_ctx *ctx);
  *                      prints is twice/2.0, call.rs:515-521); undefined where not valid
  *   valid_mask       : n_loci bytes of INQ_VALID_H1 | INQ_VALID_H2 (0 bit => NaN)
  *   stats            : nullable
- * Output order is catalog order. Outputs are host pointers.
+ * Output order is catalog order. Outputs are host pointers; when they come from inq_host_alloc the
+ * results are copied straight into them, chunk by chunk, while later loci are still being reduced.
  */
 int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased,
                  int64_t *twice_h1, int64_t *twice_h2, uint8_t *valid_mask, inq_stats *stats);

@@ -20,7 +20,7 @@ ERR_NAMES = {
 EXPORTS = [
     "inq_ctx_create", "inq_ctx_destroy", "inq_last_error", "inq_version", "inq_host_alloc",
     "inq_host_free", "inq_set_loci", "inq_push_reads", "inq_reserve_reads", "inq_clear_reads",
-    "inq_genotype", "inq_debug_events",
+    "inq_genotype", "inq_debug_events", "inq_set_option",
 ]
 
 
@@ -39,6 +39,8 @@ class Stats(C.Structure):
         ("ms_total", C.c_float), ("ms_index", C.c_float), ("ms_join", C.c_float),
         ("ms_cigar", C.c_float), ("ms_fixup", C.c_float), ("ms_scan", C.c_float), ("ms_pairs", C.c_float),
         ("ms_median", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+        ("n_ranges", C.c_uint32), ("used_graph", C.c_uint32), ("reads_sorted", C.c_uint32),
+        ("n_median_chunks", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -77,6 +79,8 @@ def load_library(path: str | None = None):
     L.inq_clear_reads.argtypes = [vp]
     L.inq_genotype.restype = C.c_int
     L.inq_genotype.argtypes = [vp, u32, u32, C.c_int, vp, vp, vp, C.POINTER(Stats)]
+    L.inq_set_option.restype = C.c_int
+    L.inq_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.inq_debug_events.restype = C.c_int
     L.inq_debug_events.argtypes = [vp, C.POINTER(u64), vp, vp, u64, vp]
     if path is None:
@@ -132,8 +136,8 @@ class GenotypeResult:
 class Context:
     """One GPU context (inq_ctx). Mirrors the call order of the C ABI."""
 
-    def __init__(self, device: int = 0):
-        self._lib = load_library()
+    def __init__(self, device: int = 0, lib=None):
+        self._lib = lib if lib is not None else load_library()   # `lib`: a load_library(path) handle (tools/ sweeps)
         h = C.c_void_p()
         rc = self._lib.inq_ctx_create(int(device), C.byref(h))
         if rc != INQ_OK:
@@ -170,6 +174,10 @@ class Context:
         assert len(s) == len(e) == int(off[-1])
         self._check(self._lib.inq_set_loci(self._h, len(off) - 1, off.ctypes.data, s.ctypes.data, e.ctypes.data))
         self.n_loci = len(s)
+
+    def set_option(self, name: str, value: int):
+        """inq_set_option: "ranges", "max_ranges", "min_range_tiles", "graph", "timing"."""
+        self._check(self._lib.inq_set_option(self._h, name.encode(), int(value)))
 
     def reserve_reads(self, n_reads, n_words):
         self._check(self._lib.inq_reserve_reads(self._h, int(n_reads), int(n_words)))

@@ -437,7 +437,11 @@ bool BamIndexedReader::load_index(const std::string &bai_path)
                 ch[c].end = (uint64_t)rd32(&bai[p + 8]) | ((uint64_t)rd32(&bai[p + 12]) << 32);
                 p += 16;
             }
-            if (bin != 37450) index_[r].bins.emplace_back(bin, std::move(ch));      // 37450 = metadata pseudo-bin
+            if (bin != 37450) index_[r].bins.emplace_back(bin, std::move(ch));
+            else if (n_chunk >= 2) {                                                // 37450 = metadata pseudo-bin (SAM spec 5.2)
+                index_[r].n_mapped = (int64_t)ch[1].beg;
+                index_[r].n_unmapped = (int64_t)ch[1].end;
+            }
         }
         if (!need(4)) { err_ = "truncated BAI"; return false; }
         const uint32_t n_intv = rd32(&bai[p]);
@@ -449,7 +453,16 @@ bool BamIndexedReader::load_index(const std::string &bai_path)
             p += 8;
         }
     }
+    if (need(8)) n_no_coor_ = (uint64_t)rd32(&bai[p]) | ((uint64_t)rd32(&bai[p + 4]) << 32);   // optional trailer
     return true;
+}
+
+std::vector<std::pair<uint64_t, uint64_t>> BamIndexedReader::chunks_for(int tid, int64_t beg, int64_t end) const
+{
+    std::vector<std::pair<uint64_t, uint64_t>> out;
+    if (tid < 0 || tid >= (int)index_.size()) return out;
+    for (const Chunk &c : query_chunks(tid, std::max<int64_t>(beg, 0), end)) out.emplace_back(c.beg, c.end);
+    return out;
 }
 
 std::vector<BamIndexedReader::Chunk> BamIndexedReader::query_chunks(int tid, int64_t beg, int64_t end) const

@@ -107,6 +107,13 @@ public:
     bool open_bam(const std::string &bam_path);        // header only
     bool load_index(const std::string &bai_path);
     bool has_index() const { return !index_.empty(); }
+    // what the index itself says (no BAM needed): references, the metadata pseudo-bin's mapped / unmapped read
+    // counts of a reference (-1 when the pseudo-bin is absent), and the merged chunk list fetch() would read
+    size_t n_refs() const { return index_.size(); }
+    int64_t n_mapped(int tid) const { return tid >= 0 && tid < (int)index_.size() ? index_[tid].n_mapped : -1; }
+    int64_t n_unmapped(int tid) const { return tid >= 0 && tid < (int)index_.size() ? index_[tid].n_unmapped : -1; }
+    uint64_t n_no_coor() const { return n_no_coor_; }
+    std::vector<std::pair<uint64_t, uint64_t>> chunks_for(int tid, int64_t beg, int64_t end) const;
     const BamHeader &header() const { return header_; }
     const std::string &error() const { return err_; }
     uint64_t bytes_inflated() const { return total_out_; }
@@ -119,6 +126,7 @@ private:
     struct RefIndex {
         std::vector<std::pair<uint32_t, std::vector<Chunk>>> bins;
         std::vector<uint64_t> linear;
+        int64_t n_mapped = -1, n_unmapped = -1;
     };
     bool load_block(uint64_t coffset);             // inflate the block at file offset coffset
     bool read_bytes(void *dst, size_t n);          // from the current position, across blocks
@@ -129,6 +137,7 @@ private:
     BamHeader header_;
     std::string err_;
     std::vector<RefIndex> index_;
+    uint64_t n_no_coor_ = 0;
     std::vector<uint8_t> block_, rec_, comp_;
     uint64_t block_coff_ = 0, next_coff_ = 0;
     size_t block_pos_ = 0;

@@ -103,6 +103,33 @@ Args parse_args(int argc, char **argv)
         exit(v.empty() ? 2 : 0);
     }
     if (v[0] == "-V" || v[0] == "--version") { printf("inquistr-b200 %s\n", inq_version()); exit(0); }
+    if (v[0] == "baistat" && v.size() >= 2) {
+        // extension: what a .bai says on its own (no BAM, no GPU): `baistat x.bam.bai [tid:beg-end]`
+        BamIndexedReader ix;
+        if (!ix.load_index(v[1])) { fprintf(stderr, "%s\n", ix.error().c_str()); exit(1); }
+        printf("{\"refs\": %zu, \"n_no_coor\": %llu, \"mapped\": {", ix.n_refs(), (unsigned long long)ix.n_no_coor());
+        bool first = true;
+        for (size_t t = 0; t < ix.n_refs(); ++t)
+            if (ix.n_mapped((int)t) >= 0) {
+                printf("%s\"%zu\": [%lld, %lld]", first ? "" : ", ", t, (long long)ix.n_mapped((int)t), (long long)ix.n_unmapped((int)t));
+                first = false;
+            }
+        printf("}");
+        if (v.size() >= 3) {
+            const size_t c1 = v[2].find(':'), c2 = v[2].find('-', c1);
+            const int tid = atoi(v[2].substr(0, c1).c_str());
+            const long long b = atoll(v[2].substr(c1 + 1, c2 - c1 - 1).c_str()), e = atoll(v[2].substr(c2 + 1).c_str());
+            printf(", \"chunks\": [");
+            first = true;
+            for (const auto &c : ix.chunks_for(tid, b, e)) {
+                printf("%s[%llu, %llu]", first ? "" : ", ", (unsigned long long)c.first, (unsigned long long)c.second);
+                first = false;
+            }
+            printf("]");
+        }
+        printf("}\n");
+        exit(0);
+    }
     if (v[0] == "bamstat" && v.size() >= 2) {
         // extension: scan a BAM with the host reader only (no GPU): record counts and inflate rate;
         // `bamstat x.bam chr:beg-end` does the same through the .bai index for one region

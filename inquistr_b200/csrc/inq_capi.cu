@@ -1,6 +1,15 @@
 // inq_capi.cu -- extern "C" boundary of libinqcall.so (see include/inqcall.h).
 // Host-side orchestration only: device memory, H2D/D2H copies, kernel launches and timing.
 // No CPU implementation of the hot path lives here: without a CUDA device every entry fails.
+//
+// One genotyping pass is a small DAG over four streams:
+//   S0  memsets, then per range k of the CIGAR stream: k_cigar_scan(k) -> k_exclusive_scan2(k)
+//   S1  k_join_ranges + two scans (under scan(0)), then k_pair_eval(k) as soon as range k is scanned
+//   S2  k_locus_median(+big) over the catalog chunk that became complete with pair(k)
+//   S3  device->host copies of finished chunks
+// so that the latency-bound pair/median kernels and the result copy run under the HBM-bound scan of
+// the next range. The steady state (same reads, same parameters, pinned outputs) is replayed from a
+// CUDA graph; the first call of a shape and every regrow retry launch the same DAG directly.
 #include "../../include/inqcall.h"
 #include "inq_device.cuh"
 
@@ -10,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 using namespace inq;
 
@@ -23,7 +33,119 @@ struct DevBuf {
     uint64_t cap = 0;   // elements
 };
 
-enum { EV_START = 0, EV_INDEX, EV_JOIN0, EV_JOIN, EV_CIGAR0, EV_CIGAR, EV_FIXUP, EV_SCAN, EV_PAIRS, EV_MEDIAN, EV_D2H, EV_H2D0, EV_H2D1, EV_COUNT };
+// driver entry points (libcuda is not linked; they are fetched through the runtime)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*mem_reserve_fn)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+typedef CUresult (*mem_create_fn)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
+typedef CUresult (*mem_map_fn)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+typedef CUresult (*mem_access_fn)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+typedef CUresult (*mem_unmap_fn)(CUdeviceptr, size_t);
+typedef CUresult (*mem_release_fn)(CUmemGenericAllocationHandle);
+typedef CUresult (*mem_free_fn)(CUdeviceptr, size_t);
+typedef CUresult (*mem_gran_fn)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags);
+
+struct DriverApi {
+    tmap_encode_fn tmap_encode = nullptr;
+    mem_reserve_fn reserve = nullptr;
+    mem_create_fn create = nullptr;
+    mem_map_fn map = nullptr;
+    mem_access_fn set_access = nullptr;
+    mem_unmap_fn unmap = nullptr;
+    mem_release_fn release = nullptr;
+    mem_free_fn addr_free = nullptr;
+    mem_gran_fn granularity = nullptr;
+    bool vmm = false;
+};
+
+void *driver_symbol(const char *name)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    return fn;
+}
+
+const DriverApi &driver()
+{
+    static DriverApi d = [] {
+        DriverApi a;
+        a.tmap_encode = (tmap_encode_fn)driver_symbol("cuTensorMapEncodeTiled");
+        a.reserve = (mem_reserve_fn)driver_symbol("cuMemAddressReserve");
+        a.create = (mem_create_fn)driver_symbol("cuMemCreate");
+        a.map = (mem_map_fn)driver_symbol("cuMemMap");
+        a.set_access = (mem_access_fn)driver_symbol("cuMemSetAccess");
+        a.unmap = (mem_unmap_fn)driver_symbol("cuMemUnmap");
+        a.release = (mem_release_fn)driver_symbol("cuMemRelease");
+        a.addr_free = (mem_free_fn)driver_symbol("cuMemAddressFree");
+        a.granularity = (mem_gran_fn)driver_symbol("cuMemGetAllocationGranularity");
+        a.vmm = a.reserve && a.create && a.map && a.set_access && a.unmap && a.release && a.addr_free && a.granularity;
+        return a;
+    }();
+    return d;
+}
+
+// The packed CIGAR stream (the one multi-GB buffer) lives in a reserved virtual address range that is
+// backed by physical chunks as reads arrive: growing it neither copies the stream nor moves its base
+// address (the TMA tensor map and a captured graph stay valid).
+struct VmStream {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+};
+
+enum {
+    EV_START = 0, EV_END, EV_INDEX, EV_JOIN0, EV_JOIN, EV_MED0, EV_MED1, EV_D2H, EV_H2D0, EV_H2D1,
+    EV_SCAN0,                                   // + 2k, 2k+1: start / end of k_cigar_scan(k)
+    EV_XS0 = EV_SCAN0 + 2 * kMaxRanges,         // + k: end of k_exclusive_scan2(k)
+    EV_PAIR0 = EV_XS0 + kMaxRanges,             // + 2k, 2k+1: start / end of k_pair_eval(k)
+    EV_COUNT = EV_PAIR0 + 2 * kMaxRanges
+};
+// dependency-only events (no timing)
+enum {
+    DEP_FORK = 0, DEP_JOIN_DONE, DEP_S1_DONE, DEP_S2_DONE, DEP_S3_DONE,
+    DEP_SCANNED,                                // + k: range k scanned and prefix-summed
+    DEP_PAIRED = DEP_SCANNED + kMaxRanges,      // + k: pair(k) done
+    DEP_CHUNK = DEP_PAIRED + kMaxRanges,        // + c: median chunk c done
+    DEP_COUNT = DEP_CHUNK + kMaxMedianChunks
+};
+
+struct MedianChunk {
+    uint32_t l0, l1;
+    int after_range;                            // runs once pair(after_range) is done
+};
+
+// How the pass is cut up; rebuilt whenever the reads or the catalog change.
+struct Plan {
+    bool valid = false;
+    uint64_t data_gen = 0;
+    int K = 1;
+    uint64_t tile_end[kMaxRanges + 1] = {};     // warp-tile boundaries, tile_end[0] = 0
+    uint64_t read_end[kMaxRanges + 1] = {};     // reads [read_end[k], read_end[k+1]) are evaluated after range k
+    int n_chunks = 0;
+    MedianChunk chunk[kMaxMedianChunks];
+    bool reads_sorted = false;
+};
+
+struct GraphKey {
+    uint64_t data_gen = 0, buf_gen = 0;
+    uint32_t minlen = 0, support = 0;
+    int unphased = 0, timing = 0;
+    const void *o1 = nullptr, *o2 = nullptr, *ov = nullptr;
+    bool operator==(const GraphKey &o) const
+    {
+        return data_gen == o.data_gen && buf_gen == o.buf_gen && minlen == o.minlen && support == o.support &&
+               unphased == o.unphased && timing == o.timing && o1 == o.o1 && o2 == o.o2 && ov == o.ov;
+    }
+};
+
+struct ProbeOut {                               // k_plan_probe result per range boundary
+    uint32_t read_end;
+    uint32_t contig;                            // of read `read_end` (0xFFFFFFFF if none)
+    int32_t ref_start;
+    uint32_t pad;
+};
 
 }  // namespace
 
@@ -31,30 +153,42 @@ struct inq_ctx {
     int device = 0;
     int sm_count = 0;
     int scan_ctas_per_sm = 1;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_chunk[kMedianChunks + 1] = {};
-    uint32_t scan_debug = 0, pair_debug = 0;     // timing experiments (INQ_SCAN_DEBUG / INQ_PAIR_DEBUG, read once): results are wrong when != 0
-    cudaStream_t stream_join = nullptr;   // the join runs next to the CIGAR scan (latency-bound vs ALU-bound)
+    cudaStream_t stream = nullptr;        // S0
+    cudaStream_t stream_join = nullptr;   // S1: join, pair evaluation
+    cudaStream_t stream_med = nullptr;    // S2: medians
+    cudaStream_t stream_copy = nullptr;   // S3: result copies
+    uint32_t scan_debug = 0, pair_debug = 0;     // only honoured by builds with -DINQ_TIMING_EXPERIMENTS
     std::string err;
+
+    // options (inq_set_option)
+    int opt_ranges = 0;                   // 0 = automatic
+    int64_t opt_min_range_tiles = 64 * 1024;
+    int opt_max_ranges = 8;
+    int opt_graph = 1;
+    int opt_timing = 1;
 
     // locus catalog
     int32_t n_contigs = 0;
     int64_t L = 0;
     DevBuf<int64_t> contig_off;
     DevBuf<int32_t> lstart, lend, lpmax;
+    std::vector<int64_t> h_contig_off;    // host copies for the plan (which loci are complete after which read)
+    std::vector<int32_t> h_pmax;
 
     // reads
     uint64_t R = 0, C = 0;
     DevBuf<int32_t> contig, rs, re;
     DevBuf<uint8_t> mapq, hp, flags;
     DevBuf<uint64_t> cig_off;
-    DevBuf<uint32_t> cigar;
+    DevBuf<uint32_t> cigar;               // cudaMalloc'ed fallback when the driver has no VMM API
+    VmStream vm;
+    uint32_t *d_unsorted = nullptr;       // != 0: the pushed reads are not sorted by (contig, ref_start)
 
     // work buffers
     DevBuf<uint32_t> cand_lo, cand_n, ev_off, delta, lcnt, seg_off, big_list;
     DevBuf<unsigned long long> cursor;
     DevBuf<uint32_t> wt_sbase, tile_first;
-    DevBuf<uint2> rd_pre, wt;
+    DevBuf<uint2> rd_pre, wt, wtot;
     DevBuf<uint64_t> desc_scan, desc_wt, vals;
     DevBuf<uint2> evraw;
     CUtensorMap tmap;                 // 2-D view of the packed CIGAR stream: rows of 32 words, 128B swizzle
@@ -66,10 +200,22 @@ struct inq_ctx {
     DevCounters *d_ctr = nullptr;
     DevCounters *h_ctr = nullptr;     // pinned
     uint32_t *h_total = nullptr;      // pinned
+    ProbeOut *d_probe = nullptr, *h_probe = nullptr;
+    uint64_t *d_probe_tiles = nullptr;
+    void *h_stage = nullptr;          // pinned staging of the results when the caller's arrays are pageable
+    size_t h_stage_bytes = 0;
 
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t dep[DEP_COUNT] = {};
     float ms_h2d = 0.f;
     uint64_t last_n_events = 0;
+
+    uint64_t data_gen = 1, buf_gen = 1;
+    Plan plan;
+    cudaGraphExec_t graph = nullptr;
+    GraphKey graph_key, last_key;
+    bool have_last_key = false;
+    uint32_t graph_launches = 0;
 };
 
 namespace {
@@ -93,6 +239,12 @@ int fail(inq_ctx *ctx, int code, const char *fmt, ...)
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+void drop_graph(inq_ctx *ctx)
+{
+    if (ctx->graph) cudaGraphExecDestroy(ctx->graph);
+    ctx->graph = nullptr;
+}
+
 // grow-only device buffer; keeps the first `keep` elements
 template <typename T>
 int ensure(inq_ctx *ctx, DevBuf<T> &b, uint64_t need, uint64_t keep = 0, double growth = 1.0)
@@ -102,13 +254,14 @@ int ensure(inq_ctx *ctx, DevBuf<T> &b, uint64_t need, uint64_t keep = 0, double 
     T *np = nullptr;
     CU_TRY(ctx, cudaMalloc(&np, std::max<uint64_t>(cap, 1) * sizeof(T)));
     if (keep && b.p) {
-        cudaError_t e = cudaMemcpyAsync(np, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(np, b.p, std::min<uint64_t>(keep, b.cap) * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { cudaFree(np); return fail(ctx, INQ_ERR_CUDA, "device copy failed: %s", cudaGetErrorString(e)); }
     }
     if (b.p) cudaFree(b.p);
     b.p = np;
     b.cap = cap;
+    ++ctx->buf_gen;                   // a captured graph holds the old pointer
     return INQ_OK;
 }
 
@@ -124,34 +277,83 @@ void release(DevBuf<T> &b)
 
 uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
-typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void vm_release(VmStream &vm)
+{
+    const DriverApi &d = driver();
+    size_t off = 0;
+    for (auto &c : vm.chunks) {
+        d.unmap(vm.base + off, c.second);
+        d.release(c.first);
+        off += c.second;
+    }
+    vm.chunks.clear();
+    if (vm.base) d.addr_free(vm.base, vm.reserved);
+    vm = VmStream();
+}
 
-// (re)build the TMA descriptor of the CIGAR stream: uint32 [rows][32], box = one 16 KB tile, 128B swizzle
+// make sure the first `bytes` of the stream are backed by device memory
+int vm_ensure(inq_ctx *ctx, size_t bytes)
+{
+    VmStream &vm = ctx->vm;
+    const DriverApi &d = driver();
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = ctx->device;
+    if (!vm.base) {
+        if (d.granularity(&vm.gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !vm.gran)
+            return fail(ctx, INQ_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+        size_t total = 0, free_b = 0;
+        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total));
+        vm.reserved = round_up(total, vm.gran);              // address space only: the whole device, nothing committed
+        if (d.reserve(&vm.base, vm.reserved, 1u << 21, 0, 0) != CUDA_SUCCESS) { vm.base = 0; return fail(ctx, INQ_ERR_NOMEM, "cuMemAddressReserve(%zu) failed", vm.reserved); }
+    }
+    if (bytes <= vm.mapped) return INQ_OK;
+    if (bytes > vm.reserved) return fail(ctx, INQ_ERR_NOMEM, "CIGAR stream of %zu bytes exceeds the device", bytes);
+    // geometric chunk sizes keep the number of mappings small (64 MB .. 2 GB)
+    size_t want = std::max<size_t>(bytes - vm.mapped, std::min<size_t>(std::max<size_t>(vm.mapped / 2, 64u << 20), 2048ull << 20));
+    want = std::min(round_up(want, vm.gran), vm.reserved - vm.mapped);
+    CUmemGenericAllocationHandle h;
+    if (d.create(&h, want, &prop, 0) != CUDA_SUCCESS) {
+        want = round_up(bytes - vm.mapped, vm.gran);         // no room for the slack: take exactly what is needed
+        if (d.create(&h, want, &prop, 0) != CUDA_SUCCESS) return fail(ctx, INQ_ERR_NOMEM, "cuMemCreate(%zu) failed", want);
+    }
+    if (d.map(vm.base + vm.mapped, want, 0, h, 0) != CUDA_SUCCESS) { d.release(h); return fail(ctx, INQ_ERR_CUDA, "cuMemMap failed"); }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (d.set_access(vm.base + vm.mapped, want, &acc, 1) != CUDA_SUCCESS) {
+        d.unmap(vm.base + vm.mapped, want);
+        d.release(h);
+        return fail(ctx, INQ_ERR_CUDA, "cuMemSetAccess failed");
+    }
+    vm.chunks.emplace_back(h, want);
+    vm.mapped += want;
+    return INQ_OK;
+}
+
+uint32_t *cigar_ptr(inq_ctx *ctx) { return driver().vmm ? reinterpret_cast<uint32_t *>(ctx->vm.base) : ctx->cigar.p; }
+uint64_t cigar_cap_words(inq_ctx *ctx) { return driver().vmm ? ctx->vm.mapped / 4 : ctx->cigar.cap; }
+
+// (re)build the TMA descriptor of the CIGAR stream: uint32 [rows][32], box = one 4 KB warp tile, 128B swizzle
 int make_tensor_map(inq_ctx *ctx, uint64_t n_words_padded)
 {
     const uint64_t rows = n_words_padded / 32;
-    if (ctx->tmap_base == ctx->cigar.p && ctx->tmap_rows == rows) return INQ_OK;
-    static tmap_encode_fn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-            return fail(ctx, INQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-        encode = (tmap_encode_fn)fn;
-    }
+    if (ctx->tmap_base == cigar_ptr(ctx) && ctx->tmap_rows == rows) return INQ_OK;
+    if (!driver().tmap_encode) return fail(ctx, INQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t gdim[2] = {32, rows};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {32, (cuuint32_t)(kWarpTileWords / 32)};    // one 2 KB warp tile
+    const cuuint32_t box[2] = {32, (cuuint32_t)(kWarpTileWords / 32)};    // one warp tile
     const cuuint32_t estride[2] = {1, 1};
-    CUresult r = encode(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->cigar.p, gdim, gstride, box, estride,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = driver().tmap_encode(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, cigar_ptr(ctx), gdim, gstride, box, estride,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, INQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-    ctx->tmap_base = ctx->cigar.p;
+    ctx->tmap_base = cigar_ptr(ctx);
     ctx->tmap_rows = rows;
+    ++ctx->buf_gen;                   // the tensor map is a kernel argument of a captured graph
     return INQ_OK;
 }
 
@@ -165,18 +367,290 @@ int reserve_reads(inq_ctx *ctx, uint64_t nR, uint64_t nC, double growth)
     TRY(ensure(ctx, ctx->hp, nR, R, growth));
     TRY(ensure(ctx, ctx->flags, nR, R, growth));
     TRY(ensure(ctx, ctx->cig_off, nR + 1, R + 1, growth));
-    // CIGAR stream is padded with zero words up to a tile boundary (+1 tile of slack)
-    TRY(ensure(ctx, ctx->cigar, round_up(nC, kTileWords) + kTileWords, C, growth));
-    // per warp tile: the first read that starts in it (entries below C / kWarpTileWords stay valid across pushes)
-    TRY(ensure(ctx, ctx->tile_first, ctx->cigar.cap / kWarpTileWords + 2, C / kWarpTileWords, 1.0));
+    // CIGAR stream is padded with zero words up to a tile boundary (+1 tile of slack). What must survive a
+    // regrow is everything inq_push_reads left behind: the words, their zero padding, and the tile_first
+    // entries of every warp tile up to the padded end plus the sentinel slot.
+    const uint64_t Cpad = R ? round_up(C, kTileWords) : 0;
+    const uint64_t need_words = round_up(nC, kTileWords) + kTileWords;
+    if (driver().vmm) TRY(vm_ensure(ctx, need_words * sizeof(uint32_t)));
+    else TRY(ensure(ctx, ctx->cigar, need_words, Cpad, growth));
+    TRY(ensure(ctx, ctx->tile_first, std::max(cigar_cap_words(ctx), need_words) / kWarpTileWords + 2, R ? Cpad / kWarpTileWords + 1 : 0, 1.0));
     return INQ_OK;
+}
+
+// ---- small kernels of the orchestration layer ---------------------------------------------------
+
+// reads [r0, r0 + n) continue a (contig, ref_start)-sorted sequence? contig compares unsigned so that
+// unmapped reads (tid -1) sort last, as in a coordinate-sorted BAM
+__global__ void k_check_sorted(const int32_t *__restrict__ contig, const int32_t *__restrict__ rs, uint64_t r0, uint64_t n,
+                               uint32_t *__restrict__ unsorted)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = r0 + i;
+        if (r == 0) continue;
+        const uint32_t ca = (uint32_t)contig[r - 1], cb = (uint32_t)contig[r];
+        if (ca > cb || (ca == cb && rs[r - 1] > rs[r])) *unsorted = 1u;
+    }
+}
+
+// per range boundary k: the first read that is NOT entirely inside warp tiles [0, tile_end[k]) and where it starts
+__global__ void k_plan_probe(const uint32_t *__restrict__ tile_first, const uint64_t *__restrict__ tile_end, int K, uint64_t R,
+                             const int32_t *__restrict__ contig, const int32_t *__restrict__ rs, ProbeOut *__restrict__ out)
+{
+    const int k = threadIdx.x;
+    if (k >= K) return;
+    // tile_first[t] = first entry of cig_off[0, R] that is >= t * kWarpTileWords: every read before entry f - 1 has
+    // its end (= the next read's start) below the boundary
+    const uint32_t f = tile_first[tile_end[k]];
+    uint64_t b = f ? f - 1u : 0u;
+    if (b > R) b = R;
+    ProbeOut o;
+    o.read_end = (uint32_t)b;
+    o.contig = b < R ? (uint32_t)contig[b] : 0xFFFFFFFFu;
+    o.ref_start = b < R ? rs[b] : 0;
+    o.pad = 0;
+    out[k] = o;
+}
+
+struct RunParams {
+    uint32_t minlen, support;
+    int unphased;
+    int64_t *o1, *o2;
+    uint8_t *ov;
+    bool timing;
+};
+
+// Cut the pass into ranges (see the file header). Needs one small device read-back, so it is cached until
+// the reads or the catalog change.
+int build_plan(inq_ctx *ctx, uint64_t n_wt)
+{
+    Plan &pl = ctx->plan;
+    if (pl.valid && pl.data_gen == ctx->data_gen) return INQ_OK;
+    pl = Plan();
+    const uint64_t R = ctx->R;
+    const int64_t L = ctx->L;
+    int K = ctx->opt_ranges > 0 ? ctx->opt_ranges
+                                : (int)std::min<uint64_t>((uint64_t)ctx->opt_max_ranges, n_wt / (uint64_t)std::max<int64_t>(1, ctx->opt_min_range_tiles));
+    K = std::max(1, std::min(K, kMaxRanges));
+    if ((uint64_t)K > n_wt) K = (int)std::max<uint64_t>(1, n_wt);
+    pl.K = K;
+    for (int k = 0; k <= K; ++k) pl.tile_end[k] = n_wt * (uint64_t)k / (uint64_t)K;
+    pl.read_end[0] = 0;
+    pl.read_end[K] = R;
+    std::vector<int64_t> done(K + 1, 0);
+    done[K] = L;
+    if (K > 1 && R && L) {
+        cudaStream_t s = ctx->stream;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_tiles, pl.tile_end + 1, (K - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        k_plan_probe<<<1, 32, 0, s>>>(ctx->tile_first.p, ctx->d_probe_tiles, K - 1, R, ctx->contig.p, ctx->rs.p, ctx->d_probe);
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_probe, ctx->d_probe, (K - 1) * sizeof(ProbeOut), cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 8, ctx->d_unsorted, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+        pl.reads_sorted = ctx->h_total[8] == 0;
+        for (int k = 1; k < K; ++k) {
+            const ProbeOut &o = ctx->h_probe[k - 1];
+            pl.read_end[k] = std::max<uint64_t>(pl.read_end[k - 1], std::min<uint64_t>(o.read_end, R));
+            // Sorted reads: every read from read_end[k] on starts at (o.contig, o.ref_start) or later, so a locus whose
+            // running max of end (+10) lies at or before that start cannot be a candidate of any of them
+            // (k_join_ranges / candidate_range): its calls are complete once pair(k - 1) is done.
+            int64_t d = 0;
+            if (pl.reads_sorted) {
+                if (o.contig >= (uint32_t)ctx->n_contigs) d = L;
+                else {
+                    const int64_t a = ctx->h_contig_off[o.contig], b = ctx->h_contig_off[o.contig + 1];
+                    d = std::upper_bound(ctx->h_pmax.begin() + a, ctx->h_pmax.begin() + b, (int64_t)o.ref_start - 10,
+                                         [](int64_t v, int32_t p) { return v < (int64_t)p; }) - ctx->h_pmax.begin();
+                }
+            }
+            done[k] = std::max(done[k - 1], std::min<int64_t>(d, L));
+        }
+    } else if (K > 1) {
+        for (int k = 1; k < K; ++k) pl.read_end[k] = 0;
+        pl.read_end[K] = R;
+    }
+    // median chunks: the loci that became complete with pair(k - 1), cut into pieces so that the copy of one piece
+    // runs under the medians of the next
+    const int64_t piece = std::max<int64_t>(1 << 16, (L + 7) / 8);
+    for (int k = 1; k <= K; ++k) {
+        int64_t a = done[k - 1], b = done[k];
+        if (k == K && L == 0) break;
+        while (a < b) {
+            int64_t e = std::min(b, a + piece);
+            if (b - e < piece / 4) e = b;                     // no tiny trailing piece
+            if (k == K && b - a > (1 << 16) && e == b && pl.n_chunks + 1 < kMaxMedianChunks && b - a > piece / 2) e = a + (b - a) / 2;   // halve the exposed tail
+            if (pl.n_chunks == kMaxMedianChunks - 1) e = b;
+            pl.chunk[pl.n_chunks++] = MedianChunk{(uint32_t)a, (uint32_t)e, k - 1};
+            a = e;
+        }
+    }
+    pl.valid = true;
+    pl.data_gen = ctx->data_gen;
+    return INQ_OK;
+}
+
+// Enqueue one whole pass on the four streams, starting and ending on S0. `capturing`: inside a stream
+// capture (timing events are recorded as external event nodes).
+int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_launches)
+{
+    const Plan &pl = ctx->plan;
+    const int64_t L = ctx->L;
+    const uint64_t R = ctx->R, C = ctx->C;
+    cudaStream_t s0 = ctx->stream, s1 = ctx->stream_join, s2 = ctx->stream_med, s3 = ctx->stream_copy;
+    const uint32_t ntiles = (uint32_t)((C + kTileWords - 1) / kTileWords);
+    const uint64_t n_wt = (uint64_t)ntiles * (kTileWords / kWarpTileWords);
+    const uint32_t loc_scan_tiles = (uint32_t)(((uint64_t)L + 1 + kXsTile - 1) / kXsTile);
+    const bool work = R && L;
+    uint32_t launches = 0;
+    auto stamp = [&](int e, cudaStream_t s) -> cudaError_t {
+        if (!rp.timing) return cudaSuccess;
+        return cudaEventRecordWithFlags(ctx->ev[e], s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+    };
+    ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
+    LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
+
+    CU_TRY(ctx, stamp(EV_START, s0));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s0));
+    if (L) {
+        CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s0));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->seg_off.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s0));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s0));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s0));
+    }
+    if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->wt.p, 0, 2 * sizeof(uint2), s0));      // no CIGAR words at all
+    if (n_wt) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, ctx->desc_wt.cap * sizeof(uint64_t), s0));
+    CU_TRY(ctx, stamp(EV_INDEX, s0));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));
+
+    // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
+    CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_FORK], 0));
+    CU_TRY(ctx, stamp(EV_JOIN0, s1));
+    if (work) {
+        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+        const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
+        // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
+        k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
+                                                   &ctx->d_ctr->scan_counter[2], nullptr);
+        k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->lcnt.p + 1, ctx->seg_off.p, (uint64_t)L, loc_scan_tiles,
+                                                   ctx->desc_scan.p + loc_scan_tiles + 1, &ctx->d_ctr->scan_counter[3], &ctx->d_ctr->flags);
+        launches += 3;
+        CU_TRY(ctx, cudaGetLastError());
+        // the call buffer holds one slot per candidate; its size is only known on the device (checked after the pass)
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s1));
+    }
+    CU_TRY(ctx, stamp(EV_JOIN, s1));
+
+    // ---- S0: K2 per range, each followed by the prefix sum over its warp-tile totals
+    uint64_t desc_base = 0;
+    for (int k = 0; k < pl.K; ++k) {
+        const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
+        CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k, s0));
+        if (t1 > t0 && L) {
+            ScanParams sp;
+            sp.tile_first = ctx->tile_first.p; sp.cig_off = ctx->cig_off.p; sp.rd_pre = ctx->rd_pre.p; sp.wt = ctx->wtot.p;
+            sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
+            sp.wt_begin = t0; sp.n_wt = t1; sp.neg1 = 0xFFFFFFFFu;
+            sp.thr = (std::min<uint32_t>(rp.minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
+            sp.debug = ctx->scan_debug;
+            const unsigned grid = (unsigned)std::min<uint64_t>((t1 - t0 + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
+            if (sp.thr >> 31) k_cigar_scan<true><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
+            else k_cigar_scan<false><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
+            ++launches;
+        }
+        CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0));
+        if (t1 > t0 && L) {
+            const uint64_t n = t1 - t0;
+            const uint32_t xt = (uint32_t)((n + kXsTile - 1) / kXsTile);
+            const unsigned g = std::min<unsigned>(xt, (unsigned)ctx->sm_count * 4);
+            uint64_t *dx = ctx->desc_wt.p + desc_base, *dy = dx + xt + 1;
+            desc_base += 2 * ((uint64_t)xt + 1);
+            k_exclusive_scan2<<<g, kXsThreads, 0, s0>>>(ctx->wtot.p + t0, ctx->wt.p + t0, n, xt, dx, dy, &ctx->d_ctr->wt_scan_counter[k],
+                                                        ctx->d_ctr->wt_carry[k], ctx->d_ctr->wt_carry[k + 1], &ctx->d_ctr->flags);
+            ++launches;
+        }
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, stamp(EV_XS0 + k, s0));
+        CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
+    }
+    // total number of events = the last prefix
+    if (n_wt && L) CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 2, ctx->wt.p + n_wt, sizeof(uint2), cudaMemcpyDeviceToHost, s0));
+
+    // ---- S1: K2b per range ; S2: K3 per finished catalog chunk ; S3: result copies
+    int c = 0;
+    int64_t *o1 = rp.o1, *o2 = rp.o2;
+    uint8_t *ov = rp.ov;
+    for (int k = 0; k < pl.K; ++k) {
+        const uint64_t r0 = pl.read_end[k], r1 = pl.read_end[k + 1];
+        CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_SCANNED + k], 0));
+        CU_TRY(ctx, stamp(EV_PAIR0 + 2 * k, s1));
+        if (work && r1 > r0) {
+            const unsigned threads = kPairWarps * 32;
+            k_pair_eval<<<(unsigned)((r1 - r0 + threads - 1) / threads), threads, sizeof(PairSmem), s1>>>(
+                rv, r0, r1, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p,
+                EventSource{ctx->wt.p, ctx->rd_pre.p, ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap}, ctx->seg_off.p, ctx->cursor.p,
+                ctx->vals.p, ctx->vals.cap, ctx->d_ctr, ctx->pair_debug);
+            ++launches;
+            CU_TRY(ctx, cudaGetLastError());
+        }
+        CU_TRY(ctx, stamp(EV_PAIR0 + 2 * k + 1, s1));
+        CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_PAIRED + k], s1));
+        bool waited = false;
+        for (; c < pl.n_chunks && pl.chunk[c].after_range == k; ++c) {
+            const uint32_t l0 = pl.chunk[c].l0, l1 = pl.chunk[c].l1;
+            if (!waited) {
+                CU_TRY(ctx, cudaStreamWaitEvent(s2, ctx->dep[DEP_PAIRED + k], 0));
+                // the first chunk also needs the (empty) segments of loci without reads: wait for the join if nothing was paired
+                waited = true;
+            }
+            if (c == 0) CU_TRY(ctx, stamp(EV_MED0, s2));
+            k_locus_median<<<(unsigned)(((uint64_t)(l1 - l0) * 32 + 255) / 256), 256, 0, s2>>>(l0, l1, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p,
+                                                                                              ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
+                                                                                              ctx->big_list.p, ctx->d_ctr);
+            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s2>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
+                                                                                  ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+            launches += 2;
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
+            CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
+            const size_t n = l1 - l0;
+            CU_TRY(ctx, cudaMemcpyAsync(o1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
+            CU_TRY(ctx, cudaMemcpyAsync(o2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
+            CU_TRY(ctx, cudaMemcpyAsync(ov + l0, ctx->valid.p + l0, n, cudaMemcpyDeviceToHost, s3));
+        }
+    }
+    if (pl.n_chunks == 0) {                                   // nothing to do on S2/S3: keep them in the DAG for the join below
+        CU_TRY(ctx, cudaStreamWaitEvent(s2, ctx->dep[DEP_FORK], 0));
+        CU_TRY(ctx, stamp(EV_MED0, s2));
+        CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_FORK], 0));
+    }
+    CU_TRY(ctx, stamp(EV_MED1, s2));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S2_DONE], s2));
+    CU_TRY(ctx, stamp(EV_D2H, s3));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S3_DONE], s3));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S1_DONE], s1));
+
+    // ---- join everything on S0
+    CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S1_DONE], 0));
+    CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S2_DONE], 0));
+    CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S3_DONE], 0));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s0));
+    CU_TRY(ctx, stamp(EV_END, s0));
+    *n_launches = launches;
+    return INQ_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 }  // namespace
 
 extern "C" {
 
-const char *inq_version(void) { return "inquistr-b200 0.1.0 (sm_100a)"; }
+const char *inq_version(void) { return "inquistr-b200 0.2.0 (sm_100a)"; }
 
 const char *inq_last_error(const inq_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -206,15 +680,25 @@ int inq_ctx_create(int device, inq_ctx **out)
         return INQ_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream_join, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    // the HBM-bound scan gets the SMs first; pair / median CTAs fill what its one CTA per SM leaves free
+    int prio_lo = 0, prio_hi = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return bail("cudaDeviceGetStreamPriorityRange", e);
+    cudaStream_t *streams[4] = {&ctx->stream, &ctx->stream_join, &ctx->stream_med, &ctx->stream_copy};
+    for (int i = 0; i < 4; ++i)
+        if ((e = cudaStreamCreateWithPriority(streams[i], cudaStreamNonBlocking, i == 0 ? prio_hi : prio_lo)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < EV_COUNT; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
-    for (int i = 0; i <= kMedianChunks; ++i)
-        if ((e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < DEP_COUNT; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->dep[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_unsorted, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMemset(ctx->d_unsorted, 0, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+    if ((e = cudaMalloc(&ctx->d_probe, kMaxRanges * sizeof(ProbeOut))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_probe_tiles, kMaxRanges * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost(&ctx->h_total, 64)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost(&ctx->h_probe, kMaxRanges * sizeof(ProbeOut))) != cudaSuccess) return bail("cudaMallocHost", e);
+    memset(ctx->h_ctr, 0, sizeof(DevCounters));
     if ((e = cudaFuncSetAttribute(k_cigar_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_cigar_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_cigar_scan)", e);
@@ -224,8 +708,10 @@ int inq_ctx_create(int device, inq_ctx **out)
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cigar_scan<false>, kCtaThreads, kScanSmemBytes)) != cudaSuccess)
         return bail("occupancy(k_cigar_scan)", e);
     ctx->scan_ctas_per_sm = std::max(1, occ);
+#ifdef INQ_TIMING_EXPERIMENTS
     if (const char *dbg = getenv("INQ_SCAN_DEBUG")) ctx->scan_debug = (uint32_t)atoi(dbg);
     if (const char *dbg = getenv("INQ_PAIR_DEBUG")) ctx->pair_debug = (uint32_t)atoi(dbg);
+#endif
     *out = ctx;
     return INQ_OK;
 }
@@ -235,26 +721,56 @@ void inq_ctx_destroy(inq_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drop_graph(ctx);
     release(ctx->contig_off); release(ctx->lstart); release(ctx->lend); release(ctx->lpmax);
     release(ctx->contig); release(ctx->rs); release(ctx->re);
     release(ctx->mapq); release(ctx->hp); release(ctx->flags);
     release(ctx->cig_off); release(ctx->cigar);
+    if (ctx->vm.base) vm_release(ctx->vm);
     release(ctx->cand_lo); release(ctx->cand_n); release(ctx->ev_off);
-    release(ctx->rd_pre); release(ctx->wt); release(ctx->wt_sbase); release(ctx->tile_first);
+    release(ctx->rd_pre); release(ctx->wt); release(ctx->wtot); release(ctx->wt_sbase); release(ctx->tile_first);
     release(ctx->desc_wt); release(ctx->evraw);
     release(ctx->delta); release(ctx->lcnt); release(ctx->seg_off); release(ctx->cursor); release(ctx->big_list);
     release(ctx->desc_scan); release(ctx->vals);
     release(ctx->events); release(ctx->t1); release(ctx->t2); release(ctx->valid);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->d_unsorted) cudaFree(ctx->d_unsorted);
+    if (ctx->d_probe) cudaFree(ctx->d_probe);
+    if (ctx->d_probe_tiles) cudaFree(ctx->d_probe_tiles);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
+    if (ctx->h_probe) cudaFreeHost(ctx->h_probe);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i <= kMedianChunks; ++i)
-        if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
-    if (ctx->stream_join) cudaStreamDestroy(ctx->stream_join);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < DEP_COUNT; ++i)
+        if (ctx->dep[i]) cudaEventDestroy(ctx->dep[i]);
+    cudaStream_t streams[4] = {ctx->stream_copy, ctx->stream_med, ctx->stream_join, ctx->stream};
+    for (auto s : streams)
+        if (s) cudaStreamDestroy(s);
     delete ctx;
+}
+
+int inq_set_option(inq_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return INQ_ERR_ARG;
+    const std::string n(name);
+    if (n == "ranges") {
+        if (value < 0 || value > kMaxRanges) return fail(ctx, INQ_ERR_ARG, "ranges must be in [0, %d]", kMaxRanges);
+        ctx->opt_ranges = (int)value;
+    } else if (n == "max_ranges") {
+        if (value < 1 || value > kMaxRanges) return fail(ctx, INQ_ERR_ARG, "max_ranges must be in [1, %d]", kMaxRanges);
+        ctx->opt_max_ranges = (int)value;
+    } else if (n == "min_range_tiles") {
+        if (value < 1) return fail(ctx, INQ_ERR_ARG, "min_range_tiles must be positive");
+        ctx->opt_min_range_tiles = value;
+    } else if (n == "graph") ctx->opt_graph = value != 0;
+    else if (n == "timing") ctx->opt_timing = value != 0;
+    else return fail(ctx, INQ_ERR_ARG, "unknown option '%s'", name);
+    ctx->plan.valid = false;
+    drop_graph(ctx);
+    ctx->have_last_key = false;
+    return INQ_OK;
 }
 
 int inq_host_alloc(size_t bytes, void **out)
@@ -285,6 +801,7 @@ int inq_set_loci(inq_ctx *ctx, int32_t n_contigs, const int64_t *contig_locus_of
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->n_contigs = 0;
     ctx->L = 0;
+    ++ctx->data_gen;
     TRY(ensure(ctx, ctx->contig_off, (uint64_t)n_contigs + 1));
     TRY(ensure(ctx, ctx->lstart, (uint64_t)L));
     TRY(ensure(ctx, ctx->lend, (uint64_t)L));
@@ -309,6 +826,13 @@ int inq_set_loci(inq_ctx *ctx, int32_t n_contigs, const int64_t *contig_locus_of
         CU_TRY(ctx, cudaGetLastError());
         CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
     }
+    // host copy of the running max of `end` per contig (the plan's "which loci are complete" test); overlaps the copies above
+    ctx->h_contig_off.assign(contig_locus_offsets, contig_locus_offsets + n_contigs + 1);
+    ctx->h_pmax.resize((size_t)L);
+    for (int32_t c = 0; c < n_contigs; ++c) {
+        int32_t m = INT32_MIN;
+        for (int64_t i = contig_locus_offsets[c]; i < contig_locus_offsets[c + 1]; ++i) { m = std::max(m, end[i]); ctx->h_pmax[(size_t)i] = m; }
+    }
     CU_TRY(ctx, cudaStreamSynchronize(s));
     if (L) {
         const unsigned f = ctx->h_ctr->flags;
@@ -331,8 +855,11 @@ int inq_reserve_reads(inq_ctx *ctx, uint64_t n_reads, uint64_t n_cigar_words)
 int inq_clear_reads(inq_ctx *ctx)
 {
     if (!ctx) return INQ_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->R = 0;
     ctx->C = 0;
+    ++ctx->data_gen;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_unsorted, 0, sizeof(uint32_t), ctx->stream));
     return INQ_OK;
 }
 
@@ -350,8 +877,10 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_
     if (ctx->R + n >= 0xFFFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "inq_push_reads: more than 2^32-2 reads");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(reserve_reads(ctx, ctx->R + n, ctx->C + nw, 1.5));
+    ++ctx->data_gen;
     cudaStream_t s = ctx->stream;
     const uint64_t R0 = ctx->R, C0 = ctx->C;
+    uint32_t *cig = cigar_ptr(ctx);
     CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D0], s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->contig.p + R0, contig, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->rs.p + R0, ref_start, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -360,13 +889,15 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_
     CU_TRY(ctx, cudaMemcpyAsync(ctx->hp.p + R0, hp, n, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p + R0, flags, n, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cig_off.p + R0, cigar_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    if (nw) CU_TRY(ctx, cudaMemcpyAsync(ctx->cigar.p + C0, cigar_words, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (nw) CU_TRY(ctx, cudaMemcpyAsync(cig + C0, cigar_words, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     if (C0) {
         k_rebase_offsets<<<(unsigned)std::min<uint64_t>((n + 1 + 255) / 256, 8192), 256, 0, s>>>(ctx->cig_off.p + R0, n + 1, C0);
         CU_TRY(ctx, cudaGetLastError());
     }
+    k_check_sorted<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, s>>>(ctx->contig.p, ctx->rs.p, R0, n, ctx->d_unsorted);
+    CU_TRY(ctx, cudaGetLastError());
     const uint64_t C1 = C0 + nw, Cpad = round_up(C1, kTileWords);
-    if (Cpad > C1) CU_TRY(ctx, cudaMemsetAsync(ctx->cigar.p + C1, 0, (Cpad - C1) * sizeof(uint32_t), s));
+    if (Cpad > C1) CU_TRY(ctx, cudaMemsetAsync(cig + C1, 0, (Cpad - C1) * sizeof(uint32_t), s));
     {
         // reads starting per warp tile, for the tiles that gained words (k_cigar_scan leaves the tile-local
         // prefix of every read start in rd_pre); cig_off[R0 + n] is the sentinel and counts as a start
@@ -392,145 +923,93 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     const uint64_t R = ctx->R, C = ctx->C;
     if (L > 0 && (!twice_h1 || !twice_h2 || !valid_mask)) return fail(ctx, INQ_ERR_ARG, "inq_genotype: NULL output array");
     if (minlen >= (1u << 28)) minlen = (1u << 28) - 1;       // BAM op lengths have 28 bits: nothing is longer
+    unphased = unphased != 0;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const uint32_t ntiles = (uint32_t)((C + kTileWords - 1) / kTileWords);
     if ((C + kTileWords - 1) / kTileWords > 0x7FFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "too many CIGAR words");
-    const uint32_t loc_scan_tiles = (uint32_t)(((uint64_t)L + 1 + kXsTile - 1) / kXsTile);
-    const uint64_t n_wt = (uint64_t)ntiles * (kTileWords / kWarpTileWords);    // 512-word warp tiles
-    const uint32_t wt_scan_tiles = (uint32_t)((n_wt + kXsTile - 1) / kXsTile);
+    const uint64_t n_wt = (uint64_t)ntiles * (kTileWords / kWarpTileWords);
+    const bool work = R && L;
     TRY(ensure(ctx, ctx->cand_lo, R));
     TRY(ensure(ctx, ctx->cand_n, R));
     TRY(ensure(ctx, ctx->rd_pre, R + 1));
     TRY(ensure(ctx, ctx->wt, n_wt + 2));
+    TRY(ensure(ctx, ctx->wtot, n_wt + 2));
     TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
-    TRY(ensure(ctx, ctx->desc_wt, 2 * ((uint64_t)wt_scan_tiles + 1)));
+    TRY(ensure(ctx, ctx->desc_wt, 2 * ((n_wt + kXsTile - 1) / kXsTile + 2 * kMaxRanges + 1)));
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
-    const unsigned scan_grid = (unsigned)std::min<uint64_t>((n_wt + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
     const uint64_t raw_slack = (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kScanWarps * kEvChunk;
-    // event storage is sized speculatively (1/16 of the words; checked and regrown after the run); it hands
-    // out kEvChunk-slot chunks, so every resident warp may strand one chunk
+    // event storage is sized speculatively (1/16 of the words; checked and regrown after the run); it hands out
+    // kEvChunk-slot chunks and a warp strands the remainder of its chunk whenever a tile does not fit any more
     if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, C / 16 + 4096 + raw_slack));
+    TRY(build_plan(ctx, n_wt));
 
-    ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
-    LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
-    uint32_t launches = 0;
-    const bool work = R && L;
+    // results go straight to the caller's arrays when those are pinned, otherwise through a pinned staging buffer
+    const bool direct_out = L == 0 || (is_pinned(twice_h1) && is_pinned(twice_h2) && is_pinned(valid_mask));
+    RunParams rp{minlen, support, unphased, twice_h1, twice_h2, valid_mask, ctx->opt_timing != 0};
+    if (!direct_out) {
+        const size_t need = (size_t)L * 17 + 64;
+        if (need > ctx->h_stage_bytes) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr;
+            ctx->h_stage_bytes = 0;
+            CU_TRY(ctx, cudaMallocHost(&ctx->h_stage, need));
+            ctx->h_stage_bytes = need;
+        }
+        rp.o1 = static_cast<int64_t *>(ctx->h_stage);
+        rp.o2 = rp.o1 + L;
+        rp.ov = reinterpret_cast<uint8_t *>(rp.o2 + L);
+    }
 
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        launches = 0;
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_START], s));
+    // the call buffer holds one slot per candidate; on the first call of a context its size is read back from a
+    // join-only pre-pass, afterwards it is sized from the previous run and checked after the pass
+    if (work && ctx->vals.cap == 0) {
+        const uint32_t loc_scan_tiles = (uint32_t)(((uint64_t)L + 1 + kXsTile - 1) / kXsTile);
+        ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
+        LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
-        if (L) {
-            CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
-            CU_TRY(ctx, cudaMemsetAsync(ctx->seg_off.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
-            CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s));
-            CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s));
-        }
-        if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->wt.p, 0, 2 * sizeof(uint2), s));      // no CIGAR words at all
-        if (wt_scan_tiles) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, 2 * ((uint64_t)wt_scan_tiles + 1) * sizeof(uint64_t), s));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_INDEX], s));
-
-        auto launch_scan = [&]() -> int {
-        // K2 first: the persistent scan kernel takes its one CTA per SM (and nearly all of its registers);
-        // the join (K1), on a second stream, fills SMs as scan CTAs retire and overlaps the scan's tail
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR0], s));
-        if (ntiles && L) {
-            ScanParams sp;
-            sp.tile_first = ctx->tile_first.p; sp.cig_off = ctx->cig_off.p; sp.rd_pre = ctx->rd_pre.p; sp.wt = ctx->wt.p;
-            sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
-            sp.n_wt = n_wt; sp.neg1 = 0xFFFFFFFFu;
-            sp.thr = (std::min<uint32_t>(minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
-            sp.debug = ctx->scan_debug;
-            if (sp.thr >> 31) k_cigar_scan<true><<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
-            else k_cigar_scan<false><<<scan_grid, kCtaThreads, kScanSmemBytes, s>>>(ctx->tmap, sp);
-            ++launches;
-        }
-
-            return INQ_OK;
-        };
-        auto launch_join = [&]() -> int {
-        // K1: candidate ranges + difference array, then the per-locus segment offsets (second stream)
-        cudaStream_t sj = ctx->stream_join;
-        CU_TRY(ctx, cudaStreamWaitEvent(sj, ctx->ev[EV_INDEX], 0));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_JOIN0], sj));
-        if (work) {
-            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, sj>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
-            const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
-            // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
-            k_exclusive_scan<<<g, kXsThreads, 0, sj>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
-                                                       &ctx->d_ctr->scan_counter[2], nullptr);
-            k_exclusive_scan<<<g, kXsThreads, 0, sj>>>(ctx->lcnt.p + 1, ctx->seg_off.p, (uint64_t)L, loc_scan_tiles,
-                                                       ctx->desc_scan.p + loc_scan_tiles + 1, &ctx->d_ctr->scan_counter[3], &ctx->d_ctr->flags);
-            launches += 3;
-        }
-            return INQ_OK;
-        };
-        // measured: scan first 4.35 ms/step, join first 4.39 (the join's CTAs delay the scan's), serial 4.41
-        TRY(launch_scan());
-        TRY(launch_join());
-        cudaStream_t sj = ctx->stream_join;
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_JOIN], sj));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_CIGAR], s));
-        if (ntiles && L) {
-            const unsigned g = std::min<unsigned>(wt_scan_tiles, (unsigned)ctx->sm_count * 4);
-            k_exclusive_scan2<<<g, kXsThreads, 0, s>>>(ctx->wt.p, n_wt, wt_scan_tiles, ctx->desc_wt.p, ctx->desc_wt.p + wt_scan_tiles + 1,
-                                                       &ctx->d_ctr->scan_counter[0], &ctx->d_ctr->flags);
-            ++launches;
-        }
-        // total number of events = last entry of the exclusive scan
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 2, ctx->wt.p + n_wt, sizeof(uint2), cudaMemcpyDeviceToHost, s));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_FIXUP], s));
-        CU_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_SCAN], s));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s));
+        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+        const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
+        k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
+                                                  &ctx->d_ctr->scan_counter[2], nullptr);
+        k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->lcnt.p + 1, ctx->seg_off.p, (uint64_t)L, loc_scan_tiles,
+                                                  ctx->desc_scan.p + loc_scan_tiles + 1, &ctx->d_ctr->scan_counter[3], &ctx->d_ctr->flags);
         CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+        TRY(ensure(ctx, ctx->vals, (uint64_t)*ctx->h_total + 1));
+    }
 
-        // the call buffer holds one slot per candidate; its size is only known on the device. It is
-        // sized from the previous run when there was one (checked afterwards), otherwise read back now.
-        if (work) CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (work && ctx->vals.cap == 0) {
-            CU_TRY(ctx, cudaStreamSynchronize(s));
-            TRY(ensure(ctx, ctx->vals, (uint64_t)*ctx->h_total + 1));
+    uint32_t launches = 0;
+    bool used_graph = false, done = false;
+    for (int attempt = 0; attempt < 4 && !done; ++attempt) {
+        const GraphKey key{ctx->data_gen, ctx->buf_gen, minlen, support, unphased, rp.timing ? 1 : 0, rp.o1, rp.o2, rp.ov};
+        used_graph = false;
+        if (ctx->graph && !(ctx->graph_key == key)) drop_graph(ctx);
+        if (ctx->opt_graph && !ctx->graph && ctx->have_last_key && ctx->last_key == key) {
+            // second call with the same shape: capture the DAG once, replay it from now on
+            cudaGraph_t g = nullptr;
+            CU_TRY(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_pass(ctx, rp, true, &ctx->graph_launches);
+            cudaError_t e = cudaStreamEndCapture(s, &g);
+            if (rc != INQ_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return fail(ctx, INQ_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&ctx->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { ctx->graph = nullptr; return fail(ctx, INQ_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+            ctx->graph_key = key;
         }
-
-        // K2b: filter + window sums + scatter
-        if (work) {
-            k_pair_eval<<<(unsigned)((R + 255) / 256), 256, sizeof(PairSmem), s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p,
-                                                                   EventSource{ctx->wt.p, ctx->rd_pre.p, ctx->wt_sbase.p, ctx->evraw.p, ctx->evraw.cap},
-                                                                   ctx->seg_off.p, ctx->cursor.p,
-                                                                   ctx->vals.p, ctx->vals.cap, ctx->d_ctr, ctx->pair_debug);
-            ++launches;
+        if (ctx->graph) {
+            CU_TRY(ctx, cudaGraphLaunch(ctx->graph, s));
+            launches = ctx->graph_launches;
+            used_graph = true;
+        } else {
+            TRY(enqueue_pass(ctx, rp, false, &launches));
         }
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_PAIRS], s));
-
-        // K3: medians, in chunks of the catalog: the result copy of one chunk (second stream, copy engine)
-        // runs under the median kernels of the next
-        if (L) {
-            const int nchunk = L >= (1 << 16) ? kMedianChunks : 1;
-            cudaStream_t sc = ctx->stream_join;
-            for (int c = 0; c < nchunk; ++c) {
-                const uint32_t l0 = (uint32_t)((uint64_t)L * c / nchunk), l1 = (uint32_t)((uint64_t)L * (c + 1) / nchunk);
-                k_locus_median<<<(unsigned)(((uint64_t)(l1 - l0) * 32 + 255) / 256), 256, 0, s>>>(l0, l1, c, unphased, support, ctx->seg_off.p, ctx->cursor.p,
-                                                                                                  ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
-                                                                                                  ctx->big_list.p, ctx->d_ctr);
-                k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s>>>(l0, c, unphased, support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
-                                                                                      ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
-                launches += 2;
-                CU_TRY(ctx, cudaEventRecord(ctx->ev_chunk[c], s));
-                CU_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_chunk[c], 0));
-                const size_t n = l1 - l0;
-                CU_TRY(ctx, cudaMemcpyAsync(twice_h1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
-                CU_TRY(ctx, cudaMemcpyAsync(twice_h2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
-                CU_TRY(ctx, cudaMemcpyAsync(valid_mask + l0, ctx->valid.p + l0, n, cudaMemcpyDeviceToHost, sc));
-            }
-            CU_TRY(ctx, cudaEventRecord(ctx->ev_chunk[kMedianChunks], sc));
-        }
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_MEDIAN], s));
-        CU_TRY(ctx, cudaGetLastError());
-
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
-        if (L) CU_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_chunk[kMedianChunks], 0));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_D2H], s));
+        ctx->last_key = key;
+        ctx->have_last_key = true;
         CU_TRY(ctx, cudaStreamSynchronize(s));
 
         const unsigned f = ctx->h_ctr->flags;
@@ -547,7 +1026,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             TRY(ensure(ctx, ctx->vals, (uint64_t)*ctx->h_total + 1));
             retry = true;
         }
-        if (retry) continue;
+        if (retry) { ctx->have_last_key = false; continue; }       // buffers moved: the next attempt launches directly
         if (f & kFlagCountOverflow) return fail(ctx, INQ_ERR_TOO_LARGE, "pair or event count exceeds 2^32");
         if (f & kFlagValsOverflow) return fail(ctx, INQ_ERR_STATE, "internal: call buffer overflow");
         if (f & kFlagBadHp)
@@ -555,10 +1034,15 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
                         (unsigned long long)ctx->h_ctr->bad_hp_read, ctx->h_ctr->bad_hp_value);
         if (f & kFlagMedianEmpty)
             return fail(ctx, INQ_ERR_MEDIAN_EMPTY, "support == 0 with a bucket without usable calls (the reference panics, call.rs:516)");
-        break;
+        done = true;
     }
-    if (ctx->h_ctr->flags & kFlagEventOverflow) return fail(ctx, INQ_ERR_STATE, "internal: event list overflow persists");
+    if (!done) return fail(ctx, INQ_ERR_STATE, "internal: speculative buffers still too small after 4 attempts");
     ctx->last_n_events = (ntiles && L) ? ctx->h_total[3] : 0;      // .y of wt[n_wt]
+    if (!direct_out && L) {
+        memcpy(twice_h1, rp.o1, (size_t)L * sizeof(int64_t));
+        memcpy(twice_h2, rp.o2, (size_t)L * sizeof(int64_t));
+        memcpy(valid_mask, rp.ov, (size_t)L);
+    }
 
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -574,16 +1058,24 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         stats->op_visits = total(ST_OP_VISITS);
         stats->n_kernel_launches = launches;
         stats->n_tiles = ntiles;
-        auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
-        stats->ms_total = el(EV_START, EV_MEDIAN);
-        stats->ms_index = el(EV_START, EV_INDEX);
-        stats->ms_join = el(EV_JOIN0, EV_JOIN);          // runs concurrently with the CIGAR scan
-        stats->ms_cigar = el(EV_CIGAR0, EV_CIGAR);
-        stats->ms_fixup = el(EV_CIGAR, EV_FIXUP);
-        stats->ms_scan = el(EV_FIXUP, EV_SCAN);
-        stats->ms_pairs = el(EV_SCAN, EV_PAIRS);
-        stats->ms_median = el(EV_PAIRS, EV_MEDIAN);
-        stats->ms_d2h = el(EV_MEDIAN, EV_D2H);
+        stats->n_ranges = (uint32_t)ctx->plan.K;
+        stats->used_graph = used_graph ? 1u : 0u;
+        stats->reads_sorted = ctx->plan.reads_sorted ? 1u : 0u;
+        stats->n_median_chunks = (uint32_t)ctx->plan.n_chunks;
+        if (rp.timing) {
+            auto el = [&](int a, int b) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; } return ms; };
+            stats->ms_total = el(EV_START, EV_END);
+            stats->ms_index = el(EV_START, EV_INDEX);
+            stats->ms_join = el(EV_JOIN0, EV_JOIN);          // runs concurrently with the CIGAR scan
+            for (int k = 0; k < ctx->plan.K; ++k) {
+                stats->ms_cigar += el(EV_SCAN0 + 2 * k, EV_SCAN0 + 2 * k + 1);
+                stats->ms_fixup += el(EV_SCAN0 + 2 * k + 1, EV_XS0 + k);
+                stats->ms_pairs += el(EV_PAIR0 + 2 * k, EV_PAIR0 + 2 * k + 1);
+            }
+            stats->ms_scan = el(EV_XS0 + ctx->plan.K - 1, EV_END);      // what is left exposed after the last range is scanned
+            stats->ms_median = el(EV_MED0, EV_MED1);
+            stats->ms_d2h = el(EV_MED1, EV_D2H);
+        }
         stats->ms_h2d = ctx->ms_h2d;
     }
     return INQ_OK;

@@ -44,16 +44,19 @@ constexpr uint64_t kKeyInf = ~0ull;
 constexpr int kStatSlots = 64;
 enum { ST_CANDIDATES = 0, ST_PAIRS, ST_READS_JOINED, ST_WORDS_JOINED, ST_OP_VISITS, ST_COUNT = 8 };
 
-constexpr int kMedianChunks = 4;            // the medians run in catalog chunks so that the result copy of one overlaps the next
+constexpr int kMaxRanges = 16;              // the CIGAR stream is scanned in up to this many ranges of warp tiles (see inq_genotype)
+constexpr int kMaxMedianChunks = 48;        // the medians run in catalog chunks so that the result copy of one overlaps the next
 struct DevCounters {
     unsigned long long stat[kStatSlots][ST_COUNT];
     unsigned long long n_events;
     unsigned long long ev_alloc;      // event slots handed out to warps (chunks)
+    unsigned long long wt_carry[kMaxRanges + 1][2];   // warp-tile prefix {consumption, events} at the start of every scanned range
     unsigned int flags;
     unsigned int tile_counter;
     unsigned int scan_counter[4];
-    unsigned int big_count[kMedianChunks];     // per chunk of the catalog (see inq_genotype): loci for the CTA path
-    unsigned int big_cursor[kMedianChunks];
+    unsigned int wt_scan_counter[kMaxRanges];  // dynamic tile ids of k_exclusive_scan2, one per range
+    unsigned int big_count[kMaxMedianChunks];  // per chunk of the catalog (see inq_genotype): loci for the CTA path
+    unsigned int big_cursor[kMaxMedianChunks];
     unsigned int bad_hp_value;        // diagnostics: HP value and read index of one offending read
     unsigned long long bad_hp_read;
 };
@@ -326,16 +329,22 @@ struct ScanParams {
     const uint32_t *tile_first;   // [n_wt + 1] first read (index into cig_off, sentinel R included) starting in warp tile t or later
     const uint64_t *cig_off;      // [R + 1] first CIGAR word of every read (+ sentinel)
     uint2 *rd_pre;                // [R + 1] {consumption, events} inside the read's warp tile before its first word
-    uint2 *wt;                    // [n_wt + 1] {consumption, events} per warp tile (prefix-summed afterwards)
+    uint2 *wt;                    // [n_wt] {consumption, events} totals per warp tile (prefix-summed by k_exclusive_scan2 into a second array)
     uint32_t *wt_sbase;           // [n_wt] storage slot of the warp tile's first event
     uint2 *evraw;
     DevCounters *ctr;
     uint64_t raw_cap;             // capacity of evraw (slots)
-    uint64_t n_wt;                // warp tiles to scan
+    uint64_t wt_begin;            // this launch scans warp tiles [wt_begin, n_wt)
+    uint64_t n_wt;
     uint32_t thr;                 // (min(minlen, 2^28 - 1) << 4) | 15: an op is longer than minlen iff its word > thr
     uint32_t neg1;                // 0xFFFFFFFF as a run-time value (keeps thr - w a multiply-add on the FMA pipe)
-    uint32_t debug;               // timing experiments only (INQ_SCAN_DEBUG): results are wrong when != 0
+    uint32_t debug;               // timing experiments only, compiled in with -DINQ_TIMING_EXPERIMENTS: results are wrong when != 0
 };
+#ifdef INQ_TIMING_EXPERIMENTS
+#define INQ_DBG(x) (x)
+#else
+#define INQ_DBG(x) 0u             // the shipped library cannot be switched into a wrong-answer mode
+#endif
 
 #ifndef INQ_LANE_WORDS
 #define INQ_LANE_WORDS 32
@@ -396,7 +405,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr uint32_t kBoxBytes = kWarpTileWords * 4;
     constexpr uint32_t kRowsPerBox = kWarpTileWords / 32;       // 128-byte rows
-    const uint64_t gwid = (uint64_t)blockIdx.x * kScanWarps + warp, stride = (uint64_t)gridDim.x * kScanWarps;
+    const uint64_t gwid = p.wt_begin + (uint64_t)blockIdx.x * kScanWarps + warp, stride = (uint64_t)gridDim.x * kScanWarps;
     uint64_t *full = sm.full[warp];
 
     if (lane == 0) {
@@ -446,7 +455,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         //      snap[j]: bases consumed inside the lane's words before quad j (parked in shared memory below)
         uint32_t c = 0, evrev = 0;
         uint32_t snap[kQuads];
-        if (!(p.debug & 8u))
+        if (!(INQ_DBG(p.debug) & 8u))
 #pragma unroll
         for (int j = 0; j < (int)kQuads; ++j) {
             const uint32_t q = q0 + (uint32_t)j, row = q >> 3;
@@ -485,14 +494,18 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             if (chunk_end - chunk_cur < tot_e) {
                 unsigned long long base = 0;
                 const uint32_t n = max(kEvChunk, tot_e);
-                if (lane == 0) base = atomicAdd(&p.ctr->ev_alloc, (unsigned long long)n);
+                if (lane == 0) {
+                    base = atomicAdd(&p.ctr->ev_alloc, (unsigned long long)n);
+                    // wt_sbase holds 32-bit slots: more than 2^32 slots handed out (stranded chunk remainders included) is an error
+                    if (base + n > 0xFFFFFFFFull) atomicOr(&p.ctr->flags, kFlagCountOverflow);
+                }
                 chunk_cur = __shfl_sync(0xffffffffu, base, 0);
                 chunk_end = chunk_cur + n;
                 sbase = chunk_cur;
             }
             chunk_cur += tot_e;
         }
-        if (lane == 31 && !(p.debug & 16u)) {
+        if (lane == 31 && !(INQ_DBG(p.debug) & 16u)) {
             p.wt[gw] = make_uint2(incl_c, incl_e);
             p.wt_sbase[gw] = (uint32_t)sbase;
         }
@@ -508,7 +521,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
         const uint32_t n_q = tot_e + n_starts;                  // queries [0, tot_e) are the events in word order
         const uint32_t off_cur = (uint32_t)(g_cur - gw * kWarpTileWords);    // lane i: first word of read tf_lo + i
         uint32_t ev_left = evrev, ev_idx = excl_e;
-        if (!(p.debug & 1u))
+        if (!(INQ_DBG(p.debug) & 1u))
         for (uint32_t base = 0; base < n_q; base += 32) {
             // owners list their events with index in [base, base + 32): word order = descending bits of evrev
             while (ev_left && ev_idx < base + 32u) {
@@ -690,15 +703,21 @@ k_exclusive_scan(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t ntiles,
     }
 }
 
-// same for pairs of u32 (both components wrap mod 2^32; `y` is checked against 2^32), in place
+// same for pairs of u32 (both components wrap mod 2^32; `y` is checked against 2^32): totals `in[0, n)` ->
+// exclusive prefixes `out[0, n]`. The CIGAR stream is scanned in ranges of warp tiles (inq_genotype); every
+// range continues from the prefix the previous one left in carry_in and leaves its own end in carry_out
+// (out[n], the end sentinel of this range, is the value the next range writes to the same slot again).
 __global__ void __launch_bounds__(kXsThreads)
-k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict__ desc_x, uint64_t *__restrict__ desc_y,
-                  unsigned int *__restrict__ tile_counter, unsigned int *__restrict__ overflow_flags)
+k_exclusive_scan2(const uint2 *__restrict__ in, uint2 *__restrict__ out, uint64_t n, uint32_t ntiles,
+                  uint64_t *__restrict__ desc_x, uint64_t *__restrict__ desc_y, unsigned int *__restrict__ tile_counter,
+                  const unsigned long long *__restrict__ carry_in, unsigned long long *__restrict__ carry_out,
+                  unsigned int *__restrict__ overflow_flags)
 {
     __shared__ uint32_t wsx[kXsThreads / 32], wsy[kXsThreads / 32];
     __shared__ uint32_t tile_s;
     __shared__ uint64_t bx_s, by_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t cx = carry_in[0], cy = carry_in[1];
     while (true) {
         if (tid == 0) tile_s = atomicAdd(tile_counter, 1u);
         __syncthreads();
@@ -709,7 +728,7 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
         uint32_t sx = 0, sy = 0;
 #pragma unroll
         for (int k = 0; k < kXsItems; ++k) {
-            v[k] = (i0 + k < n) ? data[i0 + k] : make_uint2(0u, 0u);
+            v[k] = (i0 + k < n) ? in[i0 + k] : make_uint2(0u, 0u);
             sx += v[k].x;
             sy += v[k].y;
         }
@@ -738,11 +757,13 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
                 }
             }
             if (lane == 0) {
-                bx_s = bx;
-                by_s = by;
+                bx_s = bx + cx;
+                by_s = by + cy;
                 if (t == ntiles - 1) {
-                    data[n] = make_uint2((uint32_t)(bx + tx), (uint32_t)(by + ty));
-                    if (overflow_flags && by + ty > 0xFFFFFFFFull) atomicOr(overflow_flags, kFlagCountOverflow);
+                    out[n] = make_uint2((uint32_t)(cx + bx + tx), (uint32_t)(cy + by + ty));
+                    carry_out[0] = (cx + bx + tx) & 0xFFFFFFFFull;
+                    carry_out[1] = cy + by + ty;
+                    if (overflow_flags && cy + by + ty > 0xFFFFFFFFull) atomicOr(overflow_flags, kFlagCountOverflow);
                 }
             }
         }
@@ -750,7 +771,7 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
         uint32_t rx = (uint32_t)bx_s + wbx + ix - sx, ry = (uint32_t)by_s + wby + iy - sy;
 #pragma unroll
         for (int k = 0; k < kXsItems; ++k) {
-            if (i0 + k < n) data[i0 + k] = make_uint2(rx, ry);
+            if (i0 + k < n) out[i0 + k] = make_uint2(rx, ry);
             rx += v[k].x;
             ry += v[k].y;
         }
@@ -770,9 +791,13 @@ k_exclusive_scan2(uint2 *data, uint64_t n, uint32_t ntiles, uint64_t *__restrict
 #ifndef INQ_PAIR_POOL
 #define INQ_PAIR_POOL 256
 #endif
-#ifndef INQ_PAIR_MIN_CTAS
-#define INQ_PAIR_MIN_CTAS 5
+#ifndef INQ_PAIR_WARPS
+#define INQ_PAIR_WARPS 8
 #endif
+#ifndef INQ_PAIR_MIN_CTAS
+#define INQ_PAIR_MIN_CTAS (40 / INQ_PAIR_WARPS)
+#endif
+constexpr int kPairWarps = INQ_PAIR_WARPS;  // warps per CTA of k_pair_eval (each warp works alone: no block-level sync)
 constexpr int kPairEvPool = INQ_PAIR_POOL;  // events per warp (32 consecutive reads) kept in shared memory
 constexpr int kPairLociCache = 128;         // catalog entries per warp kept in shared memory
 constexpr int kPairTileCache = 64;          // warp-tile prefixes per warp kept in shared memory
@@ -811,17 +836,19 @@ __device__ __forceinline__ uint2 event_at(const EventSource &es, uint32_t k, uin
     return make_uint2(w.x + raw.x, raw.y);
 }
 
-struct PairSmem {                           // per CTA of 8 warps (dynamic shared memory, > 48 KB)
-    uint2 ev[8][kPairEvPool];
-    uint32_t off[8][32];
-    uint32_t ty[8][kPairTileCache + 1], tx[8][kPairTileCache], tsb[8][kPairTileCache];
-    int32_t ls[8][kPairLociCache], le[8][kPairLociCache];
-    uint32_t seg[8][kPairLociCache + 1];
-    uint32_t joined[8];
+struct PairSmem {                           // per CTA of kPairWarps warps (dynamic shared memory)
+    uint2 ev[kPairWarps][kPairEvPool];
+    uint32_t off[kPairWarps][32];
+    uint32_t ty[kPairWarps][kPairTileCache + 1], tx[kPairWarps][kPairTileCache], tsb[kPairWarps][kPairTileCache];
+    int32_t ls[kPairWarps][kPairLociCache], le[kPairWarps][kPairLociCache];
+    uint32_t seg[kPairWarps][kPairLociCache + 1];
+    uint32_t joined[kPairWarps];
 };
 
-__global__ void __launch_bounds__(256, INQ_PAIR_MIN_CTAS)
-k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
+// reads [r_begin, r_end): the CIGAR stream is scanned in ranges of warp tiles and every range's reads are
+// evaluated as soon as their last word has been scanned (inq_genotype)
+__global__ void __launch_bounds__(kPairWarps * 32, INQ_PAIR_MIN_CTAS)
+k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unphased, const uint32_t *__restrict__ cand_lo,
             const uint32_t *__restrict__ cand_n, EventSource es, const uint32_t *__restrict__ seg_off,
             unsigned long long *__restrict__ cursor, uint64_t *__restrict__ vals, uint64_t vals_cap,
             DevCounters *__restrict__ ctr, uint32_t debug)
@@ -839,10 +866,10 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     auto &s_off = sm.off; auto &s_joined = sm.joined; auto &s_ev = sm.ev;
     auto &s_ty = sm.ty; auto &s_tx = sm.tx; auto &s_tsb = sm.tsb; auto &s_ls = sm.ls; auto &s_le = sm.le; auto &s_seg = sm.seg;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
-    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t r = r_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t n = 0, lo = 0, e0 = 0xFFFFFFFFu, e1 = 0xFFFFFFFFu, hf = 0, words = 0, t_lo = 0, t_hi = 0, abase = 0;
     int32_t rs = 0, re = 0;
-    if (r < rv.R) {
+    if (r < r_end) {
         // independent loads, all in flight together
         n = cand_n[r];
         lo = cand_lo[r];
@@ -944,7 +971,7 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
         if (!pend) return;
         const uint32_t slot_k = pend_back ? (uint32_t)(pend_old >> 32) : (uint32_t)pend_old;
         const uint64_t slot = pend_back ? (uint64_t)pend_seg + (pend_cap - 1u - slot_k) : (uint64_t)pend_seg + slot_k;
-        if (debug & 2u) {
+        if (INQ_DBG(debug) & 2u) {
         } else if (slot_k < pend_cap && slot < vals_cap) vals[slot] = pend_key;
         else atomicOr(&ctr->flags, kFlagValsOverflow);
         pend = false;
@@ -1005,12 +1032,12 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
             ++npass;
             atomicOr(&s_joined[wid], 1u << j);
             // slot first: the atomic's round trip overlaps the rest of this iteration and the next one
-            old = (debug & 1u) ? 0ull : atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
+            old = (INQ_DBG(debug) & 1u) ? 0ull : atomicAdd(cursor + l, back ? (1ull << 32) : 1ull);
             const uint32_t start_ext = (uint32_t)ls - 10u, end_ext = (uint32_t)le + 10u;
             const bool is2d = ((hf_j >> 8) & 1u) != 0u;
             int64_t call = 0;
             uint32_t clip = 0;
-            if (debug & 4u) {
+            if (INQ_DBG(debug) & 4u) {
             } else if (!(hf_j & (1u << 9))) {
                 // the read's events sit in shared memory, sorted by anchor: binary search, then a short scan
                 const uint32_t ne = e1_j - e0_j;
@@ -1070,7 +1097,7 @@ k_pair_eval(ReadView rv, LocusView lv, int unphased, const uint32_t *__restrict_
     const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
     if (lane == 0) {
         // one of kStatSlots copies per warp: no block barrier, and no single hot address in L2
-        unsigned long long *slot = ctr->stat[(blockIdx.x * 8u + wid) % kStatSlots];
+        unsigned long long *slot = ctr->stat[(blockIdx.x * (uint32_t)kPairWarps + wid) % kStatSlots];
         if (pass_w) atomicAdd(slot + ST_PAIRS, (unsigned long long)pass_w);
         if (join_w) atomicAdd(slot + ST_READS_JOINED, (unsigned long long)join_w);
         if (words_w) atomicAdd(slot + ST_WORDS_JOINED, (unsigned long long)words_w);
@@ -1296,7 +1323,7 @@ k_locus_median(uint32_t l0, uint32_t l1, int chunk, int unphased, uint32_t suppo
                int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
                uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
 {
-    // loci [l0, l1) of the catalog; the chunk's CTA-path loci are listed in big_list[l0 ...]
+    // loci [l0, l1) of the catalog (chunk < kMaxMedianChunks); the chunk's CTA-path loci are listed in big_list[l0 ...]
     const uint32_t l = l0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (l >= l1) return;
     const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;

@@ -358,6 +358,26 @@ int synth_cigars(const synth_cfg *c, uint64_t R, const uint64_t *cig_off, uint32
     return bad.load() ? -2 : 0;
 }
 
+// pass 2 for a packed subset: only reads with keep[i] != 0 are written, read i at cigar + dst_off[i]
+// (the host packer's pre-filter, see synth.py: the random stream of every read is the same as without it)
+int synth_cigars_sel(const synth_cfg *c, uint64_t R, const uint64_t *cig_off, const uint8_t *keep, const uint64_t *dst_off,
+                     uint32_t *cigar)
+{
+    ensure_luts(c);
+    std::vector<uint64_t> per(c->n_regions), base(c->n_regions);
+    synth_plan(c, per.data());
+    if (synth_selected(c) != R) return -1;
+    uint64_t acc = 0;
+    for (int64_t g = 0; g < c->n_regions; ++g) { base[g] = acc; acc += per[g]; }
+    std::atomic<int> bad{0};
+    parallel_regions(c, per, base, [&](int64_t g, uint64_t j, uint64_t n, uint64_t gi, uint64_t i) {
+        if (!keep[i]) return;
+        ReadOut h = gen_read(c, g, j, n, gi, cigar + dst_off[i]);
+        if (h.n_cigar != cig_off[i + 1] - cig_off[i]) bad.store(1);
+    });
+    return bad.load() ? -2 : 0;
+}
+
 }  // extern "C"
 
 // ---- BAM writer (benchmark input for the C++ host): multi-threaded BGZF deflate -----------------

@@ -73,6 +73,8 @@ def lib():
         L.synth_headers.argtypes = [C.POINTER(_Cfg), C.c_uint64] + [C.c_void_p] * 7
         L.synth_cigars.restype = C.c_int
         L.synth_cigars.argtypes = [C.POINTER(_Cfg), C.c_uint64, C.c_void_p, C.c_void_p]
+        L.synth_cigars_sel.restype = C.c_int
+        L.synth_cigars_sel.argtypes = [C.POINTER(_Cfg), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.synth_write_bam.restype = C.c_int64
         L.synth_write_bam.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int]
         _LIB = L
@@ -140,11 +142,24 @@ def _alloc(n, dtype, pinned):
     return np.empty(int(n), dtype=dtype)
 
 
+def pack_keep_mask(mapq, hp, unphased: bool) -> np.ndarray:
+    """The host packer's per-read predicate (`consider()` in csrc/host/main.cpp): a read with mapq <= 10
+    fails both filters (call.rs:297-300,350-352), and without an HP tag it fails the phased one, for
+    every locus -- such a read can never pair, so the host does not ship it. HP 0 and HP > 2 reads are
+    kept: they pass the filter (the reference walks them / panics on them)."""
+    keep = np.asarray(mapq) > 10
+    if not unphased:
+        keep &= np.asarray(hp) != 0xFF
+    return keep
+
+
 def make_workload(config: int, scale: float = 1.0, seed: int | None = None, threads: int = 0,
                   pinned: bool = False, shard: tuple = (0, 1), depth: float | None = None,
-                  n_loci: int | None = None) -> Workload:
+                  n_loci: int | None = None, pack_filter: bool = False) -> Workload:
     """Build one of the BASELINE.json configurations. `shard=(rank, world)` keeps only the loci of
-    the rank's contiguous slice of the sorted catalog and the reads that can overlap them."""
+    the rank's contiguous slice of the sorted catalog and the reads that can overlap them.
+    `pack_filter` applies the host packer's per-read predicate (pack_keep_mask) while packing: the same
+    reads are drawn, the ones that can never pair are not emitted."""
     L = lib()
     seed = config if seed is None else seed
     p_tagged, p_big_trunc, mode, unphased = 0.85, 0.0, 0, False
@@ -245,16 +260,42 @@ def make_workload(config: int, scale: float = 1.0, seed: int | None = None, thre
         cfg.sel_lo, cfg.sel_hi = sel_lo.ctypes.data, sel_hi.ctypes.data
     R = int(L.synth_selected(C.byref(cfg)))
 
-    contig = _alloc(R, np.int32, pinned); rs = _alloc(R, np.int32, pinned); re_ = _alloc(R, np.int32, pinned)
-    mapq = _alloc(R, np.uint8, pinned); hp = _alloc(R, np.uint8, pinned); fl = _alloc(R, np.uint8, pinned)
-    coff = _alloc(R + 1, np.uint64, pinned)
+    hdr_pinned = pinned and not pack_filter
+    contig = _alloc(R, np.int32, hdr_pinned); rs = _alloc(R, np.int32, hdr_pinned); re_ = _alloc(R, np.int32, hdr_pinned)
+    mapq = _alloc(R, np.uint8, hdr_pinned); hp = _alloc(R, np.uint8, hdr_pinned); fl = _alloc(R, np.uint8, hdr_pinned)
+    coff = _alloc(R + 1, np.uint64, hdr_pinned)
     rc = L.synth_headers(C.byref(cfg), R, contig.ctypes.data, rs.ctypes.data, re_.ctypes.data, mapq.ctypes.data,
                          hp.ctypes.data, fl.ctypes.data, coff.ctypes.data)
     assert rc == 0, rc
-    ncig = int(coff[R]) if R else 0
-    cigar = _alloc(ncig, np.uint32, pinned)
-    rc = L.synth_cigars(C.byref(cfg), R, coff.ctypes.data, cigar.ctypes.data)
-    assert rc == 0, rc
+    n_generated, words_generated = R, (int(coff[R]) if R else 0)
+    if pack_filter:
+        keep = pack_keep_mask(mapq, hp, unphased)
+        idx = np.flatnonzero(keep)
+        ncw = (coff[1:] - coff[:-1])[idx]
+        Rk = len(idx)
+        dst = np.zeros(R, np.uint64)
+        koff = _alloc(Rk + 1, np.uint64, pinned)
+        koff[0] = 0
+        np.cumsum(ncw, out=koff[1:])
+        dst[idx] = koff[:-1]
+        ncig = int(koff[Rk]) if Rk else 0
+        cigar = _alloc(ncig, np.uint32, pinned)
+        keep8 = np.ascontiguousarray(keep, np.uint8)
+        rc = L.synth_cigars_sel(C.byref(cfg), R, coff.ctypes.data, keep8.ctypes.data, dst.ctypes.data, cigar.ctypes.data)
+        assert rc == 0, rc
+
+        def take(a, dt):
+            out = _alloc(Rk, dt, pinned)
+            out[:] = a[idx]
+            return out
+        contig, rs, re_ = take(contig, np.int32), take(rs, np.int32), take(re_, np.int32)
+        mapq, hp, fl = take(mapq, np.uint8), take(hp, np.uint8), take(fl, np.uint8)
+        coff = koff
+    else:
+        ncig = int(coff[R]) if R else 0
+        cigar = _alloc(ncig, np.uint32, pinned)
+        rc = L.synth_cigars(C.byref(cfg), R, coff.ctypes.data, cigar.ctypes.data)
+        assert rc == 0, rc
     reads = ReadSet(contig, rs, re_, mapq, hp, fl, coff, cigar)
 
     # shard view of the catalog (offsets rebuilt for the slice)
@@ -266,7 +307,8 @@ def make_workload(config: int, scale: float = 1.0, seed: int | None = None, thre
     return Workload(config=config, name=name, seed=seed, contig_names=names, contig_len=contig_len,
                     contig_locus_off=s_off, locus_start=ls_s, locus_end=le_s, delta_h1=d1_s, delta_h2=d2_s,
                     reads=reads, minlen=5, support=3, unphased=unphased, depth=d, shard=shard,
-                    locus_range=(lo, hi), meta={"n_loci_global": nl, "scale": scale})
+                    locus_range=(lo, hi), meta={"n_loci_global": nl, "scale": scale, "pack_filter": bool(pack_filter),
+                                                "reads_generated": n_generated, "cigar_words_generated": words_generated})
 
 
 def write_bam(w: Workload, path: str, with_seq: bool = False, level: int = 1, threads: int = 0) -> int:

@@ -214,3 +214,113 @@ def test_size_independent_properties(ctx):
     assert same(a.phase1, c.phase1) and same(a.phase2, c.phase2)
     d = ctx.genotype(5, 6, False)
     assert np.all((d.valid & ~a.valid) == 0)
+
+
+# ------------------------------------------------------------------ range pipeline + CUDA graph
+def _pinned_out(n):
+    import inquistr_b200 as q
+    return (q.pinned_empty(n, np.int64), q.pinned_empty(n, np.int64), q.pinned_empty(n, np.uint8))
+
+
+@pytest.mark.parametrize("sort_reads", [True, False])
+@pytest.mark.parametrize("ranges", [2, 3, 7, 16])
+def test_range_pipeline_and_graph_replay(sort_reads, ranges):
+    """the pass cut into `ranges` ranges of warp tiles (pair / median work of range k under the scan of
+    range k+1), launched directly, captured, and replayed from the CUDA graph: same bits every time"""
+    import inquistr_b200 as q
+    case = make_case(70 + ranges, n_contigs=3, contig_len=200_000, n_loci=700, n_reads=5000, sort_reads=sort_reads)
+    rd = case["reads"]
+    assert len(rd.cigar) // 1024 >= 3 * ranges
+    rc, p1, p2, visits = O.genotype_loci(rd, case["n_contigs"], case["locus_contig"], case["locus_start"],
+                                         case["locus_end"], 5, 3, False, threads=4)
+    assert rc == 0
+    with q.Context(0) as c:
+        c.set_option("ranges", ranges)
+        c.set_loci(case["contig_off"], case["locus_start"], case["locus_end"])
+        c.push(rd)
+        out = _pinned_out(len(case["locus_start"]))
+        graphs = 0
+        for it in range(4):
+            out[0][:] = -1; out[1][:] = -1; out[2][:] = 0xFF
+            res = c.genotype(5, 3, False, out=out)
+            assert same(res.phase1, p1) and same(res.phase2, p2), (it, res.stats)
+            assert res.stats["op_visits"] == visits
+            assert res.stats["n_ranges"] == ranges
+            assert res.stats["reads_sorted"] == int(sort_reads)
+            graphs += res.stats["used_graph"]
+        assert graphs == 3                                  # first call direct, then capture + replay
+        # other parameters: new key -> direct again, still right; unphased too
+        rc, u1, u2, _ = O.genotype_loci(rd, case["n_contigs"], case["locus_contig"], case["locus_start"],
+                                        case["locus_end"], 0, 2, True, threads=4)
+        for it in range(3):
+            res = c.genotype(0, 2, True, out=out)          # minlen 0: the event buffer regrows on the first of these
+            assert same(res.phase1, u1) and same(res.phase2, u2)
+        assert res.stats["used_graph"] == 1
+        # pageable outputs: staged through the library's pinned buffer, no graph requirement on the caller
+        res = c.genotype(5, 3, False)
+        assert same(res.phase1, p1) and same(res.phase2, p2)
+        # graph off
+        c.set_option("graph", 0)
+        for it in range(2):
+            res = c.genotype(5, 3, False, out=out)
+            assert res.stats["used_graph"] == 0 and same(res.phase1, p1) and same(res.phase2, p2)
+        for a in out:
+            q.free_pinned(a)
+
+
+def test_sorted_reads_finish_loci_early():
+    """coordinate-sorted reads: catalog chunks are reduced as soon as no later read can reach them"""
+    import inquistr_b200 as q
+    from synth.synth import make_workload
+    w = make_workload(3, scale=0.02, threads=4, pack_filter=True)
+    with q.Context(0) as c:
+        c.set_option("ranges", 4)
+        c.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
+        c.push(w.reads)
+        res = c.genotype(w.minlen, w.support, w.unphased)
+        assert res.stats["reads_sorted"] == 1 and res.stats["n_median_chunks"] >= 4
+        rc, p1, p2, visits = O.genotype_loci(w.reads, w.n_contigs, w.locus_contig, w.locus_start.astype(np.uint32),
+                                             w.locus_end.astype(np.uint32), w.minlen, w.support, w.unphased, threads=8)
+        assert rc == 0 and same(res.phase1, p1) and same(res.phase2, p2) and res.stats["op_visits"] == visits
+
+
+def test_reserve_after_push_keeps_padding_and_tile_table(ctx):
+    """inq_reserve_reads between the last push and inq_genotype must not lose the zero padding of the
+    CIGAR stream nor the tile_first entries of the last partial tiles"""
+    case = make_case(81, n_reads=700)
+    rd = case["reads"]
+    ctx.set_loci(case["contig_off"], case["locus_start"], case["locus_end"])
+    ctx.clear_reads()
+    ctx.push(rd)
+    a = ctx.genotype(5, 3, False)
+    ctx.clear_reads()
+    ctx.push(rd)
+    ctx.reserve_reads(rd.n * 40, len(rd.cigar) * 40)        # grows every read buffer
+    b = ctx.genotype(5, 3, False)
+    assert same(a.phase1, b.phase1) and same(a.phase2, b.phase2)
+    rc, p1, p2, _ = O.genotype_loci(rd, case["n_contigs"], case["locus_contig"], case["locus_start"], case["locus_end"], 5, 3, False)
+    assert rc == 0 and same(b.phase1, p1) and same(b.phase2, p2)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("cfg,scale", [(3, 0.01), (4, 1.0)])
+def test_sharded_gpu_output_equals_unsharded_oracle(ctx, world, cfg, scale):
+    """contiguous catalog ranges, each shard's reads through the GPU, ordered concatenation
+    == the oracle on the whole input"""
+    from inquistr_b200 import shard as S
+    from synth.synth import make_workload
+    w = make_workload(cfg, scale=scale, threads=4)
+    rc, p1, p2, visits = O.genotype_loci(w.reads, w.n_contigs, w.locus_contig, w.locus_start.astype(np.uint32),
+                                         w.locus_end.astype(np.uint32), w.minlen, w.support, w.unphased, threads=8)
+    assert rc == 0
+    g1, g2, tot_visits = [], [], 0
+    for lo, hi in S.split_catalog(w.n_loci, world):
+        s_off, s_start, s_end = S.shard_catalog(w.contig_locus_off, w.locus_start, w.locus_end, lo, hi)
+        sub = S.take_reads(w.reads, S.reads_for_shard(w.reads.contig, w.reads.ref_start, w.reads.ref_end, s_off, s_start, s_end))
+        ctx.set_loci(s_off, s_start, s_end)
+        ctx.clear_reads()
+        ctx.push_reads(**sub)
+        res = ctx.genotype(w.minlen, w.support, w.unphased)
+        g1.append(res.phase1); g2.append(res.phase2); tot_visits += res.stats["op_visits"]
+    assert same(S.concat_ordered(g1), p1) and same(S.concat_ordered(g2), p2)
+    assert tot_visits == visits
