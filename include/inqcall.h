@@ -45,9 +45,14 @@ extern "C" {
 #define INQ_ERR_LOCUS_ORDER (-13)    /* loci not sorted by start within a contig, or end < start
                                         (repeats.rs:102-104) */
 #define INQ_ERR_TOO_LARGE (-14)      /* a count exceeds an internal 32-bit index */
+#define INQ_ERR_BAD_SA (-17)         /* a read passing the filter carries INQ_FLAG_SA_PANIC: the reference panics
+                                        inside is_accidental_2d (call.rs:431,439-450) */
 
 #define INQ_HP_ABSENT 0xFFu          /* hp[] value for a read without an HP tag (call.rs:482-491) */
 #define INQ_FLAG_ACCIDENTAL_2D 0x1u  /* flags[] bit0: is_accidental_2d(read) (call.rs:415-459) */
+#define INQ_FLAG_SA_PANIC 0x2u       /* flags[] bit1: the read has an S op and an SA tag that is not a string or that
+                                        is_accidental_2d cannot split/parse: the reference panics when (and only
+                                        when) such a read passes the filter of some locus (call.rs:394,431) */
 
 #define INQ_VALID_H1 0x1u            /* valid_mask bit0: phase1 is a number (else NaN) */
 #define INQ_VALID_H2 0x2u            /* valid_mask bit1: phase2 is a number (else NaN) */
@@ -94,7 +99,8 @@ const char *inq_version(void);
  * Tuning knobs (all optional; the defaults are what bench.py measures). Returns INQ_ERR_ARG for an
  * unknown name or a value out of range.
  *   "ranges"          number of ranges the CIGAR stream is scanned in (0 = automatic, max 16)
- *   "max_ranges"      upper bound of the automatic choice (default 8)
+ *   "max_ranges"      upper bound of the automatic choice (default 1: one scan launch; ranges > 1 let the
+ *                     pair / median kernels of a range run next to the scan of the following one)
  *   "min_range_tiles" automatic choice: at least this many 4 KB warp tiles per range (default 65536)
  *   "graph"           1 (default): replay the steady state from a CUDA graph; 0: always launch directly
  *   "timing"          1 (default): record the CUDA events behind inq_stats.ms_*; 0: none

@@ -15,7 +15,7 @@ INQ_OK = 0
 ERR_NAMES = {
     -1: "INQ_ERR_CUDA", -2: "INQ_ERR_ARG", -3: "INQ_ERR_NOMEM", -4: "INQ_ERR_STATE",
     -10: "INQ_ERR_BAD_HP", -11: "INQ_ERR_MEDIAN_EMPTY", -12: "INQ_ERR_LOCUS_START",
-    -13: "INQ_ERR_LOCUS_ORDER", -14: "INQ_ERR_TOO_LARGE", -15: "INQ_ERR_NO_MODE", -16: "INQ_ERR_HITS_CAP",
+    -13: "INQ_ERR_LOCUS_ORDER", -14: "INQ_ERR_TOO_LARGE", -15: "INQ_ERR_NO_MODE", -16: "INQ_ERR_HITS_CAP", -17: "INQ_ERR_BAD_SA",
 }
 EXPORTS = [
     "inq_ctx_create", "inq_ctx_destroy", "inq_last_error", "inq_version", "inq_host_alloc",

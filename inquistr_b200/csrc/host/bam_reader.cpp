@@ -535,8 +535,9 @@ bool is_accidental_2d(const BamRecordView &rec, bool *panic)
         f.push_back(e.substr(a, b - a));
         a = b + 1;
     }
-    if (f.size() < 4 || f[2].empty()) { *panic = true; return false; }
+    if (f.size() < 3 || f[2].empty()) { *panic = true; return false; }   // sa_entry[2] / .next().unwrap()
     if (strand == f[2][0]) return false;                             // call.rs:441-443
+    if (f.size() < 4) { *panic = true; return false; }               // sa_entry[3] is only touched after the strand test
     char *endp = nullptr;
     const long long sa_start = strtoll(f[1].c_str(), &endp, 10);     // call.rs:450 (1-based POS used as is)
     if (endp == f[1].c_str() || *endp) { *panic = true; return false; }

@@ -355,7 +355,7 @@ std::vector<Locus> parse_bed(const std::string &path, const BamHeader &h)
         int rc_ = (call);                                                                           \
         if (rc_ != INQ_OK) {                                                                        \
             const char *m_ = inq_last_error(ctx);                                                   \
-            if (rc_ == INQ_ERR_BAD_HP || rc_ == INQ_ERR_MEDIAN_EMPTY || rc_ == INQ_ERR_LOCUS_START) \
+            if (rc_ == INQ_ERR_BAD_HP || rc_ == INQ_ERR_BAD_SA || rc_ == INQ_ERR_MEDIAN_EMPTY || rc_ == INQ_ERR_LOCUS_START) \
                 panic(m_);                                                                          \
             fprintf(stderr, "ERROR: %s (code %d)\n", m_, rc_);                                      \
             exit(1);                                                                                \
@@ -451,7 +451,7 @@ int main(int argc, char **argv)
     std::vector<uint8_t> r_mapq, r_hp, r_flags;
     std::vector<uint64_t> r_off{0};
     std::vector<uint32_t> r_cigar;
-    uint64_t n_records = 0, n_kept = 0;
+    uint64_t n_records = 0, n_kept = 0, n_unpairable = 0;
     auto flush = [&]() {
         if (r_contig.empty()) return;
         wait_ctx();
@@ -484,28 +484,35 @@ int main(int argc, char **argv)
         // loci with start - 10 < endpos, and among them one with end + 10 > pos
         const int64_t hi = std::lower_bound(lstart.begin() + l0, lstart.begin() + l1, (int32_t)std::min<int64_t>((int64_t)rec.end + 10, INT32_MAX)) - lstart.begin();
         if (hi == l0 || (int64_t)pmax[hi - 1] + 10 <= (int64_t)rec.pos) return;
-        // a record the reference would fetch: its aux tags are inspected there too
+        // a record the reference would fetch. Phased mode reads its HP tag first, whatever the filter says later
+        // (get_phase, call.rs:349,482-491): an unexpected integer width panics for every fetched record.
         uint8_t hp = 0xFF;
-        if (!args.unphased) {                                              // get_phase, call.rs:482-491
+        if (!args.unphased) {
             switch (rec.hp_type) {
             case HpType::Absent: break;
             case HpType::U8: hp = (uint8_t)rec.hp_value; break;
             case HpType::I32: hp = (uint8_t)rec.hp_value; break;           // `v as u8`
             default: panic("Unexpected type of Aux for HP (call.rs:487)");
             }
-            if (hp == 0xFF && rec.hp_type != HpType::Absent) panic("HP value 255 cannot be represented (reserved for 'no tag')");
+            // 0xFF is the ABI's "no tag"; a real value of 255 only matters through the HP-not-in-{0,1,2} panic of a
+            // read that passes the filter (call.rs:358), which 254 raises just the same
+            if (hp == 0xFF && rec.hp_type != HpType::Absent) hp = 0xFE;
         }
+        // The per-read half of both filters (call.rs:297-300,350-352): such a read is skipped at every locus, before
+        // its CIGAR or SA tag are looked at, so it is not shipped to the GPU at all.
+        if (rec.mapq <= 10 || (!args.unphased && hp == 0xFF)) { ++n_unpairable; return; }
+        // is_accidental_2d is only consulted on S ops of reads that passed the filter (call.rs:394): what it would
+        // panic on travels as a flag and is raised by the GPU only if the read really pairs with a locus
         bool sa_panic = false;
         bool has_clip = false;
         for (uint32_t i = 0; i < rec.n_cigar && !has_clip; ++i) has_clip = (rec.cigar[i] & 0xF) == 4;
-        const bool two_d = has_clip ? is_accidental_2d(rec, &sa_panic) : false;   // only consulted on S ops (call.rs:394)
-        if (sa_panic) panic("Unexpected type of Aux for SA (call.rs:431)");
+        const bool two_d = has_clip ? is_accidental_2d(rec, &sa_panic) : false;
         r_contig.push_back(rec.tid);
         r_start.push_back(rec.pos);
         r_end.push_back(rec.end);
         r_mapq.push_back(rec.mapq);
         r_hp.push_back(hp);
-        r_flags.push_back(two_d ? INQ_FLAG_ACCIDENTAL_2D : 0);
+        r_flags.push_back((two_d ? INQ_FLAG_ACCIDENTAL_2D : 0) | (sa_panic ? INQ_FLAG_SA_PANIC : 0));
         r_cigar.insert(r_cigar.end(), rec.cigar, rec.cigar + rec.n_cigar);
         r_off.push_back(r_cigar.size());
         ++n_kept;
@@ -599,11 +606,11 @@ int main(int argc, char **argv)
     if (!args.stats_json.empty()) {
         FILE *f = fopen(args.stats_json.c_str(), "w");
         if (f) {
-            fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
+            fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"records_unpairable\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
                        ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
                        ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u"
                        ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_inside_scan\": %.3f, \"s_genotype\": %.3f, \"s_total\": %.3f}\n",
-                    used_index ? 1 : 0, n_records, n_kept, bytes_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
+                    used_index ? 1 : 0, n_records, n_kept, n_unpairable, bytes_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
                     st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, s_ctx, s_scan, s_push, s_gen, since(t_begin));
             fclose(f);
         }

@@ -98,14 +98,14 @@ struct VmStream {
 enum {
     EV_START = 0, EV_END, EV_INDEX, EV_JOIN0, EV_JOIN, EV_MED0, EV_MED1, EV_D2H, EV_H2D0, EV_H2D1,
     EV_SCAN0,                                   // + 2k, 2k+1: start / end of k_cigar_scan(k)
-    EV_XS0 = EV_SCAN0 + 2 * kMaxRanges,         // + k: end of k_exclusive_scan2(k)
-    EV_PAIR0 = EV_XS0 + kMaxRanges,             // + 2k, 2k+1: start / end of k_pair_eval(k)
+    EV_XS0 = EV_SCAN0 + 2 * kMaxRanges,         // + 2k, 2k+1: start / end of k_exclusive_scan2(k)
+    EV_PAIR0 = EV_XS0 + 2 * kMaxRanges,         // + 2k, 2k+1: start / end of k_pair_eval(k)
     EV_COUNT = EV_PAIR0 + 2 * kMaxRanges
 };
 // dependency-only events (no timing)
 enum {
     DEP_FORK = 0, DEP_JOIN_DONE, DEP_S1_DONE, DEP_S2_DONE, DEP_S3_DONE,
-    DEP_SCANNED,                                // + k: range k scanned and prefix-summed
+    DEP_SCANNED,                                // + k: range k scanned
     DEP_PAIRED = DEP_SCANNED + kMaxRanges,      // + k: pair(k) done
     DEP_CHUNK = DEP_PAIRED + kMaxRanges,        // + c: median chunk c done
     DEP_COUNT = DEP_CHUNK + kMaxMedianChunks
@@ -163,7 +163,7 @@ struct inq_ctx {
     // options (inq_set_option)
     int opt_ranges = 0;                   // 0 = automatic
     int64_t opt_min_range_tiles = 64 * 1024;
-    int opt_max_ranges = 8;
+    int opt_max_ranges = 1;               // measured (profiles/README.md, r2 sweeps): co-scheduling pair/median CTAs under the scan is zero-sum on B200
     int opt_graph = 1;
     int opt_timing = 1;
 
@@ -509,22 +509,22 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
     LocusView lv{ctx->contig_off.p, ctx->lstart.p, ctx->lend.p, ctx->lpmax.p, ctx->n_contigs};
 
-    CU_TRY(ctx, stamp(EV_START, s0));
+    // S0 only needs the counters zeroed before the scan starts; everything the join / pair / median kernels need
+    // zeroed is cleared on S1, off the scan's critical path
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s0));
-    if (L) {
-        CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s0));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->seg_off.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s0));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s0));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s0));
-    }
-    if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->wt.p, 0, 2 * sizeof(uint2), s0));      // no CIGAR words at all
-    if (n_wt) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, ctx->desc_wt.cap * sizeof(uint64_t), s0));
-    CU_TRY(ctx, stamp(EV_INDEX, s0));
+    CU_TRY(ctx, stamp(EV_START, s0));
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));
 
     // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
     CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_FORK], 0));
-    CU_TRY(ctx, stamp(EV_JOIN0, s1));
+    if (L) {
+        CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s1));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->seg_off.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s1));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s1));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s1));
+    }
+    if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->wt.p, 0, 2 * sizeof(uint2), s1));      // no CIGAR words at all
+    if (n_wt) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, ctx->desc_wt.cap * sizeof(uint64_t), s1));
     if (work) {
         k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
         const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
@@ -540,8 +540,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     }
     CU_TRY(ctx, stamp(EV_JOIN, s1));
 
-    // ---- S0: K2 per range, each followed by the prefix sum over its warp-tile totals
-    uint64_t desc_base = 0;
+    // ---- S0: K2, range after range, nothing in between (the scan of a range depends on nothing but the reads)
     for (int k = 0; k < pl.K; ++k) {
         const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
         CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k, s0));
@@ -556,32 +555,32 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
             if (sp.thr >> 31) k_cigar_scan<true><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
             else k_cigar_scan<false><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
             ++launches;
+            CU_TRY(ctx, cudaGetLastError());
         }
         CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0));
+        CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
+    }
+
+    // ---- S1: prefix sum over the range's warp-tile totals, then K2b ; S2: K3 per finished catalog chunk ; S3: result copies
+    int c = 0;
+    int64_t *o1 = rp.o1, *o2 = rp.o2;
+    uint8_t *ov = rp.ov;
+    uint64_t desc_base = 0;
+    for (int k = 0; k < pl.K; ++k) {
+        const uint64_t r0 = pl.read_end[k], r1 = pl.read_end[k + 1];
+        const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
+        CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_SCANNED + k], 0));
         if (t1 > t0 && L) {
             const uint64_t n = t1 - t0;
             const uint32_t xt = (uint32_t)((n + kXsTile - 1) / kXsTile);
             const unsigned g = std::min<unsigned>(xt, (unsigned)ctx->sm_count * 4);
             uint64_t *dx = ctx->desc_wt.p + desc_base, *dy = dx + xt + 1;
             desc_base += 2 * ((uint64_t)xt + 1);
-            k_exclusive_scan2<<<g, kXsThreads, 0, s0>>>(ctx->wtot.p + t0, ctx->wt.p + t0, n, xt, dx, dy, &ctx->d_ctr->wt_scan_counter[k],
+            k_exclusive_scan2<<<g, kXsThreads, 0, s1>>>(ctx->wtot.p + t0, ctx->wt.p + t0, n, xt, dx, dy, &ctx->d_ctr->wt_scan_counter[k],
                                                         ctx->d_ctr->wt_carry[k], ctx->d_ctr->wt_carry[k + 1], &ctx->d_ctr->flags);
             ++launches;
+            CU_TRY(ctx, cudaGetLastError());
         }
-        CU_TRY(ctx, cudaGetLastError());
-        CU_TRY(ctx, stamp(EV_XS0 + k, s0));
-        CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
-    }
-    // total number of events = the last prefix
-    if (n_wt && L) CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 2, ctx->wt.p + n_wt, sizeof(uint2), cudaMemcpyDeviceToHost, s0));
-
-    // ---- S1: K2b per range ; S2: K3 per finished catalog chunk ; S3: result copies
-    int c = 0;
-    int64_t *o1 = rp.o1, *o2 = rp.o2;
-    uint8_t *ov = rp.ov;
-    for (int k = 0; k < pl.K; ++k) {
-        const uint64_t r0 = pl.read_end[k], r1 = pl.read_end[k + 1];
-        CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_SCANNED + k], 0));
         CU_TRY(ctx, stamp(EV_PAIR0 + 2 * k, s1));
         if (work && r1 > r0) {
             const unsigned threads = kPairWarps * 32;
@@ -627,6 +626,8 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S2_DONE], s2));
     CU_TRY(ctx, stamp(EV_D2H, s3));
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S3_DONE], s3));
+    // total number of events = the last prefix
+    if (n_wt && L) CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 2, ctx->wt.p + n_wt, sizeof(uint2), cudaMemcpyDeviceToHost, s1));
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S1_DONE], s1));
 
     // ---- join everything on S0
@@ -1029,6 +1030,9 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         if (retry) { ctx->have_last_key = false; continue; }       // buffers moved: the next attempt launches directly
         if (f & kFlagCountOverflow) return fail(ctx, INQ_ERR_TOO_LARGE, "pair or event count exceeds 2^32");
         if (f & kFlagValsOverflow) return fail(ctx, INQ_ERR_STATE, "internal: call buffer overflow");
+        if (f & kFlagBadSa)
+            return fail(ctx, INQ_ERR_BAD_SA, "read %llu passes the filter and has a soft clip, but its SA tag is not a string or cannot be split/parsed "
+                        "(the reference panics in is_accidental_2d, call.rs:431,439-450)", (unsigned long long)ctx->h_ctr->bad_sa_read);
         if (f & kFlagBadHp)
             return fail(ctx, INQ_ERR_BAD_HP, "read %llu passes the phased filter but carries HP %u, outside {0,1,2} (the reference panics, call.rs:358)",
                         (unsigned long long)ctx->h_ctr->bad_hp_read, ctx->h_ctr->bad_hp_value);
@@ -1065,14 +1069,15 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         if (rp.timing) {
             auto el = [&](int a, int b) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; } return ms; };
             stats->ms_total = el(EV_START, EV_END);
-            stats->ms_index = el(EV_START, EV_INDEX);
-            stats->ms_join = el(EV_JOIN0, EV_JOIN);          // runs concurrently with the CIGAR scan
+            stats->ms_index = 0.f;
+            stats->ms_join = el(EV_START, EV_JOIN);          // memsets + join + segment offsets, under the CIGAR scan
             for (int k = 0; k < ctx->plan.K; ++k) {
                 stats->ms_cigar += el(EV_SCAN0 + 2 * k, EV_SCAN0 + 2 * k + 1);
-                stats->ms_fixup += el(EV_SCAN0 + 2 * k + 1, EV_XS0 + k);
                 stats->ms_pairs += el(EV_PAIR0 + 2 * k, EV_PAIR0 + 2 * k + 1);
             }
-            stats->ms_scan = el(EV_XS0 + ctx->plan.K - 1, EV_END);      // what is left exposed after the last range is scanned
+            // prefix scan over the last range's warp-tile totals (incl. waiting for the join stream)
+            stats->ms_fixup = el(EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1, EV_PAIR0 + 2 * (ctx->plan.K - 1));
+            stats->ms_scan = el(EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1, EV_END);      // what is left exposed after the last range is scanned
             stats->ms_median = el(EV_MED0, EV_MED1);
             stats->ms_d2h = el(EV_MED1, EV_D2H);
         }

@@ -29,6 +29,7 @@ constexpr uint32_t kFlagMedianEmpty = 1u << 1;
 constexpr uint32_t kFlagEventOverflow = 1u << 2;
 constexpr uint32_t kFlagValsOverflow = 1u << 3;
 constexpr uint32_t kFlagCountOverflow = 1u << 4;
+constexpr uint32_t kFlagBadSa = 1u << 5;
 
 constexpr uint64_t kDescAggregate = 1ull << 62;
 constexpr uint64_t kDescPrefix = 2ull << 62;
@@ -59,6 +60,7 @@ struct DevCounters {
     unsigned int big_cursor[kMaxMedianChunks];
     unsigned int bad_hp_value;        // diagnostics: HP value and read index of one offending read
     unsigned long long bad_hp_read;
+    unsigned long long bad_sa_read;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -792,7 +794,7 @@ k_exclusive_scan2(const uint2 *__restrict__ in, uint2 *__restrict__ out, uint64_
 #define INQ_PAIR_POOL 256
 #endif
 #ifndef INQ_PAIR_WARPS
-#define INQ_PAIR_WARPS 8
+#define INQ_PAIR_WARPS 4
 #endif
 #ifndef INQ_PAIR_MIN_CTAS
 #define INQ_PAIR_MIN_CTAS (40 / INQ_PAIR_WARPS)
@@ -875,7 +877,7 @@ k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unp
         lo = cand_lo[r];
         rs = rv.rs[r];
         re = rv.re[r];
-        hf = (uint32_t)rv.hp[r] | ((uint32_t)(rv.flags[r] & 1u) << 8);
+        hf = (uint32_t)rv.hp[r] | ((uint32_t)(rv.flags[r] & 1u) << 8) | ((uint32_t)(rv.flags[r] & 2u) << 9);   // bit 10: SA panic
         const uint64_t g0 = rv.cig_off[r], g1 = rv.cig_off[r + 1];
         const uint2 p0 = read_prefix(es, g0, r), p1 = read_prefix(es, g1, r + 1);
         e0 = p0.y;
@@ -960,7 +962,7 @@ k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unp
 
     uint32_t npass = 0;                 // pairs that land in a bucket
     uint64_t visits = 0;                // CIGAR words the reference walks: every passing pair, incl. HP 0
-    bool bad_hp = false;
+    bool bad_hp = false, bad_sa = false;
     // deferred store of the previous candidate
     bool pend = false;
     unsigned long long pend_old = 0;
@@ -1013,7 +1015,11 @@ k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unp
             if (pair_passes(unphased != 0, rs_j, re_j, ls, le)) {
                 visits += words_j;                          // call.rs:357 runs before the bucket lookup
                 emit = true;
-                if (!unphased) {
+                if (hf_j & (1u << 10)) {                    // call.rs:394 -> 431: the walk panics inside is_accidental_2d
+                    bad_sa = true;
+                    ctr->bad_sa_read = r - lane + j;
+                    emit = false;
+                } else if (!unphased) {
                     if (h > 2u) {                           // call.rs:358 unwrap on None
                         bad_hp = true;
                         ctr->bad_hp_value = h;
@@ -1094,7 +1100,7 @@ k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unp
     const uint32_t join_w = __popc(__ballot_sync(0xffffffffu, joined));
     const uint64_t words_w = warp_sum(joined ? (uint64_t)words : 0ull);
     const uint64_t visits_w = warp_sum(visits);
-    const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp);
+    const uint32_t bad_w = __any_sync(0xffffffffu, bad_hp), bad_sa_w = __any_sync(0xffffffffu, bad_sa);
     if (lane == 0) {
         // one of kStatSlots copies per warp: no block barrier, and no single hot address in L2
         unsigned long long *slot = ctr->stat[(blockIdx.x * (uint32_t)kPairWarps + wid) % kStatSlots];
@@ -1103,6 +1109,7 @@ k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unp
         if (words_w) atomicAdd(slot + ST_WORDS_JOINED, (unsigned long long)words_w);
         if (visits_w) atomicAdd(slot + ST_OP_VISITS, (unsigned long long)visits_w);
         if (bad_w) atomicOr(&ctr->flags, kFlagBadHp);
+        if (bad_sa_w) atomicOr(&ctr->flags, kFlagBadSa);
     }
 }
 

@@ -316,6 +316,9 @@ int orc_genotype_locus(const orc_reads *rd, const orc_index *ix, int32_t tid,
         }
         int clip = 0;
         uint64_t c0 = rd->cigar_off[r], c1 = rd->cigar_off[r + 1];
+        /* call.rs:303/357 -> 394: the walk evaluates is_accidental_2d on the first S op, which panics
+           on a non-string / malformed SA tag (call.rs:431,439-450) -- only for reads that got this far */
+        if (rd->flags[r] & 2) { rc = ORC_PANIC_BAD_SA; break; }
         int64_t v = orc_call_from_cigar(rd->ref_start[r], rd->cigar + c0, c1 - c0, minlen,
                                         start_ext, end_ext, rd->flags[r] & 1, &clip);
         visits += c1 - c0;

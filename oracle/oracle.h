@@ -34,6 +34,7 @@ extern "C" {
 #define ORC_PANIC_MEDIAN_EMPTY (-2)   /* call.rs:516  support==0 and no values -> index underflow */
 #define ORC_PANIC_START_LT_10 (-3)    /* call.rs:285  u32 underflow of start-10 (treated as rejected input) */
 #define ORC_PANIC_BAD_INTERVAL (-4)   /* repeats.rs:102-114 */
+#define ORC_PANIC_BAD_SA (-5)         /* call.rs:431,439-450  is_accidental_2d on an SA tag it cannot digest */
 #define ORC_ERR_ARG (-5)
 
 /* SoA view of aligned reads: exactly what the reference reads off each
@@ -45,7 +46,8 @@ typedef struct {
     const int32_t *ref_end;     /* bam_endpos (reference_end) */
     const uint8_t *mapq;
     const uint8_t *hp;          /* HP tag value, 0xFF = tag absent (call.rs:482-491) */
-    const uint8_t *flags;       /* bit0: is_accidental_2d(read) (call.rs:415-459) */
+    const uint8_t *flags;       /* bit0: is_accidental_2d(read) (call.rs:415-459); bit1: the read has an S op and
+                                   an SA tag on which is_accidental_2d panics (call.rs:431,439-450) */
     const uint64_t *cigar_off;  /* n_reads+1 */
     const uint32_t *cigar;      /* BAM packed words: len<<4 | op, ops MIDNSHP=X */
 } orc_reads;

@@ -28,6 +28,7 @@ ORC_PANIC_BAD_HP = -1
 ORC_PANIC_MEDIAN_EMPTY = -2
 ORC_PANIC_START_LT_10 = -3
 ORC_PANIC_BAD_INTERVAL = -4
+ORC_PANIC_BAD_SA = -5
 
 OPS = "MIDNSHP=X"
 
@@ -301,6 +302,8 @@ def py_genotype_locus(reads: Reads, tid, start, end, minlen=5, support=3, unphas
             if hp == 0xFF or (start_ext < rs and re_ < end_ext) or mq <= 10:
                 continue
         a, b = int(reads.cigar_off[r]), int(reads.cigar_off[r + 1])
+        if reads.flags[r] & 2:
+            raise ValueError("is_accidental_2d panics on this read's SA tag (call.rs:431,439-450)")
         call = py_call_from_cigar(rs, reads.cigar[a:b], minlen, start_ext, end_ext,
                                   bool(reads.flags[r] & 1))
         if unphased:

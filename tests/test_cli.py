@@ -277,3 +277,45 @@ def test_panel_with_and_without_index(cli, panel_bam, tmp_path):
     r = run(cli, "call", "-r", f"{c}:{s}-{e}", "--stats-json", stats, bam)
     assert r.returncode == 0 and json.load(open(stats))["used_index"] == 1
     assert r.stdout.splitlines()[1] == exp.splitlines()[1]
+
+
+@pytest.mark.gpu
+def test_aux_panics_fire_only_for_reads_that_pair(cli, tmp_path):
+    """is_accidental_2d (SA) and the HP bucket lookup only run for reads that passed the filter of some locus
+    (call.rs:350-358,394,431): a low-mapq or untagged read with a malformed SA / HP 255 is skipped silently,
+    the same tags on a read that pairs abort with a panic (exit 101)"""
+    import struct
+    M, S, I = 0, 4, 1
+    spanning = np.asarray([(20 << 4) | S, (500 << 4) | M, (8 << 4) | I, (500 << 4) | M], np.uint32)
+    noclip = np.asarray([(500 << 4) | M, (8 << 4) | I, (500 << 4) | M], np.uint32)
+    sa_int = b"SAi" + struct.pack("<i", 7)                      # SA present but not a string: Aux::I32 -> panic at call.rs:431
+
+    def bam_of(recs, name):
+        p = str(tmp_path / name)
+        bamio.write_bam(p, ["chr1"], [1_000_000], recs)
+        return p
+
+    good = [bamio.encode_record(0, 1000, 60, 0, spanning, name=b"g%d" % i, hp=1 + i % 2, end=2000) for i in range(6)]
+    region = ["-r", "chr1:1490-1510", "-s", "2"]
+    # harmless carriers: mapq 10, no HP tag (phased), or no soft clip at all
+    quiet = [bamio.encode_record(0, 1000, 10, 0, spanning, name=b"q1", hp=1, end=2000, extra_aux=sa_int),
+             bamio.encode_record(0, 1000, 60, 0, spanning, name=b"q2", end=2000, sa="chr1,100"),
+             bamio.encode_record(0, 1000, 60, 0, noclip, name=b"q3", hp=2, end=2000, extra_aux=sa_int),
+             bamio.encode_record(0, 1000, 5, 0, spanning, name=b"q4", hp=255, end=2000)]
+    r = run(cli, "call", *region, bam_of(good + quiet, "quiet.bam"))
+    assert r.returncode == 0, r.stderr
+    base = run(cli, "call", *region, bam_of(good + quiet[2:3], "base.bam"))
+    assert base.returncode == 0 and r.stdout.splitlines()[1] == base.stdout.splitlines()[1]
+    # the same tags on reads that pair
+    for k, bad in enumerate([bamio.encode_record(0, 1000, 60, 0, spanning, name=b"b1", hp=1, end=2000, extra_aux=sa_int),
+                             bamio.encode_record(0, 1000, 60, 0, spanning, name=b"b2", hp=1, end=2000, sa="chr1,100"),
+                             bamio.encode_record(0, 1000, 60, 16, spanning, name=b"b3", hp=1, end=2000, sa="chr1,100,+"),
+                             bamio.encode_record(0, 1000, 60, 0, spanning, name=b"b4", hp=255, end=2000)]):
+        r = run(cli, "call", *region, bam_of(good + [bad], f"bad{k}.bam"))
+        assert r.returncode == 101, (k, r.stderr)
+    # same strand: sa_entry[3] is never touched (call.rs:441-443), no panic although the entry has only 3 fields
+    ok = bamio.encode_record(0, 1000, 60, 0, spanning, name=b"ok", hp=1, end=2000, sa="chr1,100,+")
+    assert run(cli, "call", *region, bam_of(good + [ok], "ok.bam")).returncode == 0
+    # unphased: q2 (no HP) now pairs and its SA panics; q4 (HP 255, mapq 5) stays quiet
+    assert run(cli, "call", *region, "-u", bam_of(good + quiet[1:2], "u1.bam")).returncode == 101
+    assert run(cli, "call", *region, "-u", bam_of(good + quiet[3:4], "u2.bam")).returncode == 0

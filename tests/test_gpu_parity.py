@@ -324,3 +324,44 @@ def test_sharded_gpu_output_equals_unsharded_oracle(ctx, world, cfg, scale):
         g1.append(res.phase1); g2.append(res.phase2); tot_visits += res.stats["op_visits"]
     assert same(S.concat_ordered(g1), p1) and same(S.concat_ordered(g2), p2)
     assert tot_visits == visits
+
+
+def test_sa_panic_flag_only_fires_when_the_read_pairs(ctx):
+    """flags bit1 (INQ_FLAG_SA_PANIC): INQ_ERR_BAD_SA iff the oracle's walk would hit is_accidental_2d's panic"""
+    import inquistr_b200 as q
+    case = make_case(91, n_reads=600)
+    rd = case["reads"]
+    args = (case["n_contigs"], case["locus_contig"], case["locus_start"], case["locus_end"], 5, 3)
+    ctx.set_loci(case["contig_off"], case["locus_start"], case["locus_end"])
+    # flag only reads that can never pair in phased mode (mapq <= 10 or no HP): no error, same result
+    quiet = (rd.mapq <= 10) | (rd.hp == 0xFF)
+    assert quiet.sum() > 20
+    fl = rd.flags.copy(); fl[quiet] |= 2
+    rd2 = O.Reads(rd.contig, rd.ref_start, rd.ref_end, rd.mapq, rd.hp, fl, rd.cigar_off, rd.cigar)
+    ctx.clear_reads(); ctx.push(rd2)
+    res = ctx.genotype(5, 3, False)
+    rc, p1, p2, _ = O.genotype_loci(rd2, *args, False)
+    assert rc == 0 and same(res.phase1, p1) and same(res.phase2, p2)
+    # unphased: the untagged ones now pair -> both sides report the SA panic
+    rc, *_ = O.genotype_loci(rd2, *args, True)
+    assert rc == O.ORC_PANIC_BAD_SA
+    with pytest.raises(q.InqError) as ei:
+        ctx.genotype(5, 3, True)
+    assert ei.value.code == -17
+    # flag one read that pairs in phased mode
+    rc0, p1, p2, _ = O.genotype_loci(rd, *args, False)
+    fl = rd.flags.copy()
+    cand = np.flatnonzero((rd.mapq > 10) & (rd.hp != 0xFF) & (rd.hp <= 2))
+    for r in cand[:50]:
+        fl[:] = rd.flags; fl[r] |= 2
+        rd3 = O.Reads(rd.contig, rd.ref_start, rd.ref_end, rd.mapq, rd.hp, fl, rd.cigar_off, rd.cigar)
+        rc, *_ = O.genotype_loci(rd3, *args, False)
+        ctx.clear_reads(); ctx.push(rd3)
+        if rc == O.ORC_PANIC_BAD_SA:
+            with pytest.raises(q.InqError) as ei:
+                ctx.genotype(5, 3, False)
+            assert ei.value.code == -17
+        else:
+            assert rc == 0
+            res = ctx.genotype(5, 3, False)
+            assert same(res.phase1, p1) and same(res.phase2, p2)
