@@ -43,8 +43,9 @@ def build_cli(force: bool = False) -> str:
     os.makedirs(bindir, exist_ok=True)
     target = os.path.join(bindir, "inquistr-b200")
     host = os.path.join(CSRC, "host")
-    sources = [os.path.join(host, "main.cpp"), os.path.join(host, "bam_reader.cpp"), os.path.join(host, "cohort_cli.cpp")]
-    deps = sources + [os.path.join(host, "bam_reader.hpp"), os.path.join(os.path.dirname(HERE), "include", "inqcall.h"),
+    sources = [os.path.join(host, "main.cpp"), os.path.join(host, "bam_reader.cpp"), os.path.join(host, "cohort_cli.cpp"),
+               os.path.join(host, "shard_driver.cpp")]
+    deps = sources + [os.path.join(host, "bam_reader.hpp"), os.path.join(host, "shard_driver.hpp"), os.path.join(os.path.dirname(HERE), "include", "inqcall.h"),
                       os.path.join(os.path.dirname(HERE), "include", "inqcohort.h"),
                       os.path.join(LIBDIR, "libinqcall.so")]
     if force or _stale(target, deps):

@@ -457,6 +457,16 @@ bool BamIndexedReader::load_index(const std::string &bai_path)
     return true;
 }
 
+double BamIndexedReader::window_weight(int tid, int64_t beg, int64_t end) const
+{
+    if (tid < 0 || tid >= (int)index_.size() || index_[tid].linear.empty()) return 1.0;
+    const std::vector<uint64_t> &lin = index_[tid].linear;
+    const size_t n = lin.size();
+    const size_t a = std::min<size_t>((size_t)(std::max<int64_t>(beg, 0) >> 14), n - 1), b = std::min<size_t>((size_t)(std::max<int64_t>(end, 0) >> 14) + 1, n - 1);
+    const uint64_t ca = lin[a] >> 16, cb = lin[b] >> 16;
+    return 1.0 + (cb > ca ? (double)(cb - ca) : 0.0);
+}
+
 std::vector<std::pair<uint64_t, uint64_t>> BamIndexedReader::chunks_for(int tid, int64_t beg, int64_t end) const
 {
     std::vector<std::pair<uint64_t, uint64_t>> out;

@@ -114,6 +114,9 @@ public:
     int64_t n_unmapped(int tid) const { return tid >= 0 && tid < (int)index_.size() ? index_[tid].n_unmapped : -1; }
     uint64_t n_no_coor() const { return n_no_coor_; }
     std::vector<std::pair<uint64_t, uint64_t>> chunks_for(int tid, int64_t beg, int64_t end) const;
+    // 1 + compressed BAM bytes between the linear-index entries of the 16 kb windows around [beg, end): a cheap
+    // proxy of the reads piled up there (used to balance catalog shards)
+    double window_weight(int tid, int64_t beg, int64_t end) const;
     const BamHeader &header() const { return header_; }
     const std::string &error() const { return err_; }
     uint64_t bytes_inflated() const { return total_out_; }

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <array>
@@ -27,6 +28,7 @@
 
 #include "../../../include/inqcall.h"
 #include "bam_reader.hpp"
+#include "shard_driver.hpp"
 
 namespace inqhost {
 int combine_main(const std::vector<std::string> &files);                 // cohort_cli.cpp
@@ -44,7 +46,7 @@ struct Args {
     uint64_t support = 3;
     uint64_t threads = 1;
     bool unphased = false;
-    int device = 0;               // extension: CUDA device (also INQ_DEVICE)
+    std::vector<int> devices;     // extension: CUDA devices, one catalog shard + context each (also INQ_DEVICE / INQ_DEVICES)
     std::string stats_json;       // extension: timing side file
 };
 
@@ -63,6 +65,7 @@ const char *kHelp =
     "      --sample-name <SAMPLE_NAME>  sample name to use in output\n"
     "      --reference <REFERENCE>      reference fasta for cram decoding\n"
     "      --device <N>                 (extension) CUDA device to run on [default: 0]\n"
+    "      --devices <A,B,...>          (extension) shard the locus catalog over these CUDA devices (a device may repeat)\n"
     "      --stats-json <FILE>          (extension) write counters and device timings as JSON\n"
     "  -h, --help                       Print help\n";
 
@@ -94,7 +97,22 @@ bool parse_u64(const std::string &s, uint64_t *out)
 Args parse_args(int argc, char **argv)
 {
     Args a;
-    if (const char *d = getenv("INQ_DEVICE")) a.device = atoi(d);
+    auto parse_devices = [](const std::string &v, std::vector<int> *out) {
+        out->clear();
+        size_t p0 = 0;
+        while (p0 <= v.size()) {
+            size_t p1 = v.find(',', p0);
+            if (p1 == std::string::npos) p1 = v.size();
+            uint64_t n = 0;
+            if (!parse_u64(v.substr(p0, p1 - p0), &n) || n > 1023) return false;
+            out->push_back((int)n);
+            p0 = p1 + 1;
+        }
+        return !out->empty() && out->size() <= 64;
+    };
+    if (const char *d = getenv("INQ_DEVICES")) { if (!parse_devices(d, &a.devices)) a.devices.clear(); }
+    else if (const char *d = getenv("INQ_DEVICE")) a.devices.assign(1, atoi(d));
+    if (a.devices.empty()) a.devices.assign(1, 0);
     std::vector<std::string> v(argv + 1, argv + argc);
     if (v.empty() || v[0] == "-h" || v[0] == "--help" || v[0] == "help") {
         printf("Tool to genotype STRs from long reads (B200 build of the `call` hot path)\n\n"
@@ -165,7 +183,7 @@ Args parse_args(int argc, char **argv)
     }
     // cohort follow-ons of `call`: text in, text out; cohort_cli.cpp
     if (v[0] == "combine") exit(combine_main(std::vector<std::string>(v.begin() + 1, v.end())));
-    if (v[0] == "outlier") exit(outlier_main(std::vector<std::string>(v.begin() + 1, v.end()), a.device));
+    if (v[0] == "outlier") exit(outlier_main(std::vector<std::string>(v.begin() + 1, v.end()), a.devices[0]));
     if (v[0] != "call") usage_error("unrecognized subcommand '" + v[0] + "' (`call`, `combine` and `outlier` are implemented in this build)");
     if (v.size() == 1) { fputs(kHelp, stderr); exit(2); }                 // arg_required_else_help (main.rs:27)
     bool have_bam = false;
@@ -182,7 +200,8 @@ Args parse_args(int argc, char **argv)
         else if (name == "threads") { if (!parse_u64(val, &n)) usage_error("invalid value '" + val + "' for '--threads <THREADS>'"); a.threads = n; }
         else if (name == "sample-name") { a.sample_name = val; a.has_sample = true; }
         else if (name == "reference") { a.reference = val; a.has_reference = true; }
-        else if (name == "device") { if (!parse_u64(val, &n)) usage_error("invalid value for '--device'"); a.device = (int)n; }
+        else if (name == "device") { if (!parse_u64(val, &n)) usage_error("invalid value for '--device'"); a.devices.assign(1, (int)n); }
+        else if (name == "devices") { if (!parse_devices(val, &a.devices)) usage_error("invalid value '" + val + "' for '--devices <A,B,...>'"); }
         else if (name == "stats-json") a.stats_json = val;
         else usage_error("unexpected argument '--" + name + "' found");
     };
@@ -425,65 +444,56 @@ int main(int argc, char **argv)
         for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) { m = std::max(m, lend[i]); pmax[i] = m; }
     }
 
-    // CUDA context + catalog upload + pinned staging buffers. (Doing this on a second thread next to the
-    // BAM scan was measured and is slower: driver initialisation and 16 inflate threads fight over the
-    // process' memory-map lock.)
-    const auto t_ctx0 = std::chrono::steady_clock::now();
-    inq_ctx *ctx = nullptr;
-    if (inq_ctx_create(args.device, &ctx) != INQ_OK) {
-        fprintf(stderr, "ERROR: %s\n", inq_last_error(nullptr));
-        return 1;
-    }
-    INQ_CHECK(ctx, inq_set_loci(ctx, n_contigs, contig_off.data(), lstart.data(), lend.data()));
-    // pinned staging for the pushes (DMA at PCIe speed instead of a staged pageable copy)
-    constexpr size_t kChunkWords = 32u << 20, kChunkReads = 4u << 20;
-    void *pin_cigar = nullptr, *pin_meta = nullptr;
-    if (inq_host_alloc(kChunkWords * 4, &pin_cigar) != INQ_OK) pin_cigar = nullptr;
-    if (inq_host_alloc(kChunkReads * 24 + 64, &pin_meta) != INQ_OK) pin_meta = nullptr;
-    const double s_ctx = since(t_ctx0);
-    auto wait_ctx = [&]() {};
-    const auto t_scan0 = std::chrono::steady_clock::now();
-    double s_push = 0;
-
-    // one sequential pass over the BAM; keep the records htslib's fetch would yield for some locus:
-    // pos < end+10 && endpos > start-10
-    std::vector<int32_t> r_contig, r_start, r_end;
-    std::vector<uint8_t> r_mapq, r_hp, r_flags;
-    std::vector<uint64_t> r_off{0};
-    std::vector<uint32_t> r_cigar;
-    uint64_t n_records = 0, n_kept = 0, n_unpairable = 0;
-    auto flush = [&]() {
-        if (r_contig.empty()) return;
-        wait_ctx();
-        const auto tp = std::chrono::steady_clock::now();
-        const size_t n = r_contig.size(), nw = r_cigar.size();
-        if (pin_cigar && pin_meta && nw <= kChunkWords && n <= kChunkReads) {
-            // stage through pinned memory: contig | start | end | off (8 B) | mapq | hp | flags
-            uint8_t *m = static_cast<uint8_t *>(pin_meta);
-            int32_t *pc = reinterpret_cast<int32_t *>(m), *ps = pc + kChunkReads, *pe = ps + kChunkReads;
-            uint64_t *po = reinterpret_cast<uint64_t *>(pe + kChunkReads);
-            uint8_t *pq = reinterpret_cast<uint8_t *>(po + kChunkReads + 1), *ph = pq + kChunkReads, *pf = ph + kChunkReads;
-            memcpy(pc, r_contig.data(), n * 4); memcpy(ps, r_start.data(), n * 4); memcpy(pe, r_end.data(), n * 4);
-            memcpy(po, r_off.data(), (n + 1) * 8);
-            memcpy(pq, r_mapq.data(), n); memcpy(ph, r_hp.data(), n); memcpy(pf, r_flags.data(), n);
-            memcpy(pin_cigar, r_cigar.data(), nw * 4);
-            INQ_CHECK(ctx, inq_push_reads(ctx, n, pc, ps, pe, pq, ph, pf, po, static_cast<uint32_t *>(pin_cigar)));
-        } else {
-            INQ_CHECK(ctx, inq_push_reads(ctx, n, r_contig.data(), r_start.data(), r_end.data(), r_mapq.data(),
-                                          r_hp.data(), r_flags.data(), r_off.data(), r_cigar.data()));
+    // Small panels: seek through the .bai instead of inflating the whole file (SURVEY 8f rank 2).
+    // Windows closer than 100 kb are fetched as one region; a read returned by two regions is kept once.
+    std::vector<std::array<int64_t, 3>> regions;           // tid, beg, end
+    int64_t region_span = 0, genome = 0;
+    for (int64_t len : hdr.ref_lens) genome += len;
+    for (int c = 0; c < n_contigs; ++c)
+        for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) {
+            const int64_t b = (int64_t)lstart[i] - 10, e = (int64_t)lend[i] + 10;
+            if (!regions.empty() && regions.back()[0] == c && b <= regions.back()[2] + 100000) regions.back()[2] = std::max(regions.back()[2], e);
+            else regions.push_back({(int64_t)c, b, e});
         }
-        r_contig.clear(); r_start.clear(); r_end.clear(); r_mapq.clear(); r_hp.clear(); r_flags.clear();
-        r_off.assign(1, 0); r_cigar.clear();
-        s_push += since(tp);
-    };
+    for (const auto &r : regions) region_span += r[2] - r[1] + 50000;     // + typical read overhang
+    std::string bai = args.bam + ".bai";
+    if (!is_file(bai) && ends_with(args.bam, ".bam")) bai = args.bam.substr(0, args.bam.size() - 4) + ".bai";
+    const char *idx_env = getenv("INQ_BAM_INDEX");
+    const bool want_index = idx_env ? atoi(idx_env) != 0 : (region_span * 10 < genome);
+    const bool used_index = want_index && is_file(bai);
+    if (used_index && !ibam.load_index(bai)) panic("Error opening BAM index: " + ibam.error());
+
+    // ---- shards: contiguous ranges of the sorted catalog, one device context + host thread each (SURVEY 8e,
+    // replaces the rayon fan-out of call.rs:103-145). Cuts balance the expected work: with an index, the BAM
+    // bytes its linear index places around each locus (pile-up depth x read length); otherwise the locus count.
+    const int n_shards = (int)std::max<size_t>(1, std::min(args.devices.size(), std::max<size_t>(L, 1)));
+    std::vector<double> weight;
+    if (used_index && n_shards > 1) {
+        weight.resize(L);
+        for (int c = 0; c < n_contigs; ++c)
+            for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) weight[i] = ibam.window_weight(c, (int64_t)lstart[i] - 10, (int64_t)lend[i] + 10);
+    }
+    const std::vector<size_t> cuts = balanced_cuts(L, n_shards, weight.empty() ? nullptr : weight.data());
+    const auto t_ctx0 = std::chrono::steady_clock::now();
+    std::vector<std::unique_ptr<ShardWorker>> shards;
+    for (int g = 0; g < n_shards; ++g)
+        shards.emplace_back(new ShardWorker(args.devices[g], cuts[g], cuts[g + 1], n_contigs, contig_off, lstart.data(), lend.data(),
+                                            args.minlen, (uint32_t)args.support, args.unphased));
+    const auto t_scan0 = std::chrono::steady_clock::now();
+
+    // one pass over the BAM; every record goes to the shards for which htslib's fetch would return it for some
+    // locus: pos < end+10 && endpos > start-10. Reads at a cut are duplicated.
+    uint64_t n_records = 0, n_kept = 0, n_unpairable = 0, n_routed = 0;
+    std::vector<int> hit;
     // what to do with one record htslib's fetch could return for some locus
     auto consider = [&](const BamRecordView &rec) {
         if (rec.tid < 0 || rec.tid >= n_contigs) return;
         const int64_t l0 = contig_off[rec.tid], l1 = contig_off[rec.tid + 1];
         if (l0 == l1) return;
-        // loci with start - 10 < endpos, and among them one with end + 10 > pos
-        const int64_t hi = std::lower_bound(lstart.begin() + l0, lstart.begin() + l1, (int32_t)std::min<int64_t>((int64_t)rec.end + 10, INT32_MAX)) - lstart.begin();
-        if (hi == l0 || (int64_t)pmax[hi - 1] + 10 <= (int64_t)rec.pos) return;
+        hit.clear();
+        for (int g = 0; g < n_shards; ++g)
+            if (shards[g]->reaches(rec.tid, rec.pos, rec.end)) hit.push_back(g);
+        if (hit.empty()) return;
         // a record the reference would fetch. Phased mode reads its HP tag first, whatever the filter says later
         // (get_phase, call.rs:349,482-491): an unexpected integer width panics for every fetched record.
         uint8_t hp = 0xFF;
@@ -507,39 +517,14 @@ int main(int argc, char **argv)
         bool has_clip = false;
         for (uint32_t i = 0; i < rec.n_cigar && !has_clip; ++i) has_clip = (rec.cigar[i] & 0xF) == 4;
         const bool two_d = has_clip ? is_accidental_2d(rec, &sa_panic) : false;
-        r_contig.push_back(rec.tid);
-        r_start.push_back(rec.pos);
-        r_end.push_back(rec.end);
-        r_mapq.push_back(rec.mapq);
-        r_hp.push_back(hp);
-        r_flags.push_back((two_d ? INQ_FLAG_ACCIDENTAL_2D : 0) | (sa_panic ? INQ_FLAG_SA_PANIC : 0));
-        r_cigar.insert(r_cigar.end(), rec.cigar, rec.cigar + rec.n_cigar);
-        r_off.push_back(r_cigar.size());
+        const uint8_t fl = (uint8_t)((two_d ? INQ_FLAG_ACCIDENTAL_2D : 0) | (sa_panic ? INQ_FLAG_SA_PANIC : 0));
+        for (int g : hit) shards[g]->add(rec.tid, rec.pos, rec.end, rec.mapq, hp, fl, rec.cigar, rec.n_cigar);
         ++n_kept;
-        if (r_cigar.size() + 70000 >= kChunkWords || r_contig.size() + 1 >= kChunkReads) flush();
+        n_routed += hit.size();
     };
 
-    // Small panels: seek through the .bai instead of inflating the whole file (SURVEY 8f rank 2).
-    // Windows closer than 100 kb are fetched as one region; a read returned by two regions is kept once.
-    std::vector<std::array<int64_t, 3>> regions;           // tid, beg, end
-    int64_t region_span = 0, genome = 0;
-    for (int64_t len : hdr.ref_lens) genome += len;
-    for (int c = 0; c < n_contigs; ++c)
-        for (int64_t i = contig_off[c]; i < contig_off[c + 1]; ++i) {
-            const int64_t b = (int64_t)lstart[i] - 10, e = (int64_t)lend[i] + 10;
-            if (!regions.empty() && regions.back()[0] == c && b <= regions.back()[2] + 100000) regions.back()[2] = std::max(regions.back()[2], e);
-            else regions.push_back({(int64_t)c, b, e});
-        }
-    for (const auto &r : regions) region_span += r[2] - r[1] + 50000;     // + typical read overhang
-    std::string bai = args.bam + ".bai";
-    if (!is_file(bai) && ends_with(args.bam, ".bam")) bai = args.bam.substr(0, args.bam.size() - 4) + ".bai";
-    const char *idx_env = getenv("INQ_BAM_INDEX");
-    const bool want_index = idx_env ? atoi(idx_env) != 0 : (region_span * 10 < genome);
-    bool used_index = false;
     uint64_t bytes_inflated = 0;
-    if (want_index && is_file(bai)) {
-        if (!ibam.load_index(bai)) panic("Error opening BAM index: " + ibam.error());
-        used_index = true;
+    if (used_index) {
         std::unordered_set<uint64_t> seen;
         for (const auto &r : regions) {
             const bool ok = ibam.fetch((int)r[0], r[1], r[2], [&](const BamRecordView &rec, uint64_t voff) {
@@ -556,20 +541,44 @@ int main(int argc, char **argv)
         while (bam.next(rec)) {
             ++n_records;
             consider(rec);
+            if ((n_records & 0xFFFF) == 0) {                 // a shard that died (no device, out of memory) ends the scan early
+                bool dead = false;
+                for (auto &sh : shards) dead = dead || sh->failed();
+                if (dead) break;
+            }
         }
         if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
         bytes_inflated = bam.bytes_inflated();
     }
-    flush();
-    wait_ctx();
     const double s_scan = since(t_scan0);
     const auto t_gen0 = std::chrono::steady_clock::now();
 
+    // end of input: every shard flushes, genotypes its range (concurrently) and joins; ordered concatenation
+    std::vector<std::thread> closers;
+    for (auto &sh : shards) closers.emplace_back([&sh] { sh->finish(); });
+    for (auto &t : closers) t.join();
     std::vector<int64_t> t1(L), t2(L);
     std::vector<uint8_t> valid(L);
     inq_stats st;
     memset(&st, 0, sizeof(st));
-    INQ_CHECK(ctx, inq_genotype(ctx, args.minlen, (uint32_t)args.support, args.unphased ? 1 : 0, t1.data(), t2.data(), valid.data(), &st));
+    double s_ctx = 0, s_push = 0;
+    (void)t_ctx0;
+    for (auto &sh : shards) {
+        ShardResult &r = sh->result();
+        if (r.rc != INQ_OK) {
+            if (r.rc == INQ_ERR_BAD_HP || r.rc == INQ_ERR_BAD_SA || r.rc == INQ_ERR_MEDIAN_EMPTY || r.rc == INQ_ERR_LOCUS_START) panic(r.error);
+            fprintf(stderr, "ERROR: %s (code %d)\n", r.error.c_str(), r.rc);
+            return 1;
+        }
+        std::copy(r.t1.begin(), r.t1.end(), t1.begin() + sh->lo());
+        std::copy(r.t2.begin(), r.t2.end(), t2.begin() + sh->lo());
+        std::copy(r.valid.begin(), r.valid.end(), valid.begin() + sh->lo());
+        st.n_loci += r.stats.n_loci; st.n_reads += r.stats.n_reads; st.n_cigar_words += r.stats.n_cigar_words;
+        st.n_pairs += r.stats.n_pairs; st.n_events += r.stats.n_events; st.n_kernel_launches += r.stats.n_kernel_launches;
+        st.ms_total = std::max(st.ms_total, r.stats.ms_total); st.ms_cigar = std::max(st.ms_cigar, r.stats.ms_cigar);
+        st.ms_h2d = std::max(st.ms_h2d, r.stats.ms_h2d);
+        s_ctx = std::max(s_ctx, r.s_ctx); s_push = std::max(s_push, r.s_push);
+    }
 
     const double s_gen = since(t_gen0);
     // output order: -t 1 BED order (call.rs:149-157); -t > 1 sorted by (human chrom, start) (call.rs:137-145)
@@ -609,14 +618,11 @@ int main(int argc, char **argv)
             fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"records_unpairable\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
                        ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
                        ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u"
-                       ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_inside_scan\": %.3f, \"s_genotype\": %.3f, \"s_total\": %.3f}\n",
+                       ", \"n_shards\": %d, \"records_routed\": %" PRIu64 ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_under_scan\": %.3f, \"s_flush_genotype\": %.3f, \"s_total\": %.3f}\n",
                     used_index ? 1 : 0, n_records, n_kept, n_unpairable, bytes_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
-                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, s_ctx, s_scan, s_push, s_gen, since(t_begin));
+                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, n_shards, n_routed, s_ctx, s_scan, s_push, s_gen, since(t_begin));
             fclose(f);
         }
     }
-    inq_host_free(pin_cigar);
-    inq_host_free(pin_meta);
-    inq_ctx_destroy(ctx);
     return 0;
 }

@@ -319,3 +319,40 @@ def test_aux_panics_fire_only_for_reads_that_pair(cli, tmp_path):
     # unphased: q2 (no HP) now pairs and its SA panics; q4 (HP 255, mapq 5) stays quiet
     assert run(cli, "call", *region, "-u", bam_of(good + quiet[1:2], "u1.bam")).returncode == 101
     assert run(cli, "call", *region, "-u", bam_of(good + quiet[3:4], "u2.bam")).returncode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,scale", [(3, 0.004), (4, 1.0)])
+def test_devices_sharding_prints_the_same_bytes(cli, tmp_path, cfg, scale):
+    """`--devices 0,0,0`: the catalog cut into three contiguous shards, three contexts on three host threads
+    (here all on GPU 0), reads routed to every shard they can reach, ordered concatenation -- byte-identical TSV
+    to one context, for the genome-wide config and the expansion panel, with and without the .bai"""
+    import json
+    from synth import synth as S
+    w = S.make_workload(cfg, scale=scale, threads=4)
+    bam = str(tmp_path / "in.bam")
+    S.write_bam(w, bam)
+    bamio.index_bam(bam)
+    rows = S.write_bed(w, str(tmp_path / "loci.bed"), shuffle_seed=9)
+    sel = np.asarray([i for *_, i in rows])
+    rc, p1, p2, _ = O.genotype_loci(w.reads, w.n_contigs, w.locus_contig[sel], w.locus_start[sel].astype(np.uint32),
+                                    w.locus_end[sel].astype(np.uint32), 5, 3, w.unphased)
+    assert rc == 0
+    for threads in (1, 4):
+        exp = expected_tsv("in", None, [(c, s, e) for c, s, e, _ in rows], p1, p2, threads)
+        for idx_mode in ("0", "1"):
+            outs = {}
+            for devs in ("0", "0,0,0", "0,0,0,0,0,0,0"):
+                stats = str(tmp_path / f"st_{devs.count(',')}.json")
+                r = subprocess.run([cli, "call", "-R", str(tmp_path / "loci.bed"), "-t", str(threads), "--devices", devs,
+                                    "--stats-json", stats, *(["-u"] if w.unphased else []), bam],
+                                   capture_output=True, timeout=600, env={**os.environ, "INQ_BAM_INDEX": idx_mode})
+                assert r.returncode == 0, r.stderr
+                assert r.stdout == exp, (devs, idx_mode, threads)
+                outs[devs] = json.load(open(stats))
+            assert outs["0"]["n_shards"] == 1 and outs["0,0,0"]["n_shards"] == 3
+            assert outs["0,0,0"]["records_routed"] >= outs["0,0,0"]["records_pushed"]      # reads at a cut go to both sides
+            assert outs["0,0,0"]["n_loci"] == w.n_loci
+    # errors raised inside a shard keep the reference's exit behaviour: HP 3 on a read that pairs -> panic, exit 101
+    r = run(cli, "call", "-r", "chr1:5-100", "--devices", "0,0", bam)
+    assert r.returncode == 101
