@@ -140,6 +140,29 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n_reads, const int32_t *contig,
                    const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off,
                    const uint32_t *cigar_words);
 
+/*
+ * Routed push: like inq_push_reads, but keeps only the reads of the batch that htslib's fetch would return for
+ * some locus of THIS context's catalog (pos < end+10 && endpos > start-10, call.rs:285-288) and that survive
+ * `filter`. With N contexts holding N contiguous shards of the sorted catalog, handing every batch to
+ * every context routes the reads -- a read that reaches two shards is taken by both -- without the caller
+ * knowing the cuts. The selection runs on `host_threads` host threads (0 = all cores). Coordinate-sorted
+ * batches are copied straight from the caller's arrays (a few contiguous runs); scattered ones are gathered
+ * through a pinned staging buffer. Reads inside a short gap (<= 256 reads) between two kept reads are shipped as
+ * well: they cannot pair with anything and bridging is cheaper than gathering. *n_taken (nullable) receives the
+ * number of reads pushed.
+ *   INQ_ROUTE_DROP_LOW_MAPQ  drop reads with mapq <= 10: they fail both filters at every locus (call.rs:297-300,350-352)
+ *   INQ_ROUTE_DROP_NO_HP     drop reads without an HP tag: they fail the phased filter at every locus (call.rs:350);
+ *                            must not be set for an unphased (-u) run
+ * Neither flag changes any output (TSV, op_visits): such reads never reach call_from_cigar in the reference.
+ */
+#define INQ_ROUTE_DROP_LOW_MAPQ 0x1u
+#define INQ_ROUTE_DROP_NO_HP 0x2u
+int inq_push_reads_routed(inq_ctx *ctx, uint64_t n_reads, const int32_t *contig,
+                          const int32_t *ref_start, const int32_t *ref_end, const uint8_t *mapq,
+                          const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off,
+                          const uint32_t *cigar_words, uint32_t filter, int host_threads,
+                          uint64_t *n_taken);
+
 /* Optional: size the device buffers once before a series of pushes. */
 int inq_reserve_reads(inq_ctx *ctx, uint64_t n_reads, uint64_t n_cigar_words);
 

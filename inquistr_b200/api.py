@@ -20,7 +20,7 @@ ERR_NAMES = {
 EXPORTS = [
     "inq_ctx_create", "inq_ctx_destroy", "inq_last_error", "inq_version", "inq_host_alloc",
     "inq_host_free", "inq_set_loci", "inq_push_reads", "inq_reserve_reads", "inq_clear_reads",
-    "inq_genotype", "inq_debug_events", "inq_set_option",
+    "inq_genotype", "inq_debug_events", "inq_set_option", "inq_push_reads_routed",
 ]
 
 
@@ -73,6 +73,8 @@ def load_library(path: str | None = None):
     L.inq_set_loci.argtypes = [vp, i32, vp, vp, vp]
     L.inq_push_reads.restype = C.c_int
     L.inq_push_reads.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.inq_push_reads_routed.restype = C.c_int
+    L.inq_push_reads_routed.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, u32, C.c_int, C.POINTER(u64)]
     L.inq_reserve_reads.restype = C.c_int
     L.inq_reserve_reads.argtypes = [vp, u64, u64]
     L.inq_clear_reads.restype = C.c_int
@@ -199,6 +201,20 @@ class Context:
                                              ref_end.ctypes.data, mapq.ctypes.data, hp.ctypes.data,
                                              flags.ctypes.data, cigar_off.ctypes.data, cigar.ctypes.data))
         self.n_reads += n
+
+    def push_routed(self, reads, drop_low_mapq=False, drop_no_hp=False, host_threads=0) -> int:
+        """inq_push_reads_routed: keep only the reads that can reach this context's catalog; returns how many"""
+        def chk(a, dt):
+            return np.ascontiguousarray(a, dtype=dt)
+        contig, rs, re_ = chk(reads.contig, np.int32), chk(reads.ref_start, np.int32), chk(reads.ref_end, np.int32)
+        mapq, hp, fl = chk(reads.mapq, np.uint8), chk(reads.hp, np.uint8), chk(reads.flags, np.uint8)
+        off, cig = chk(reads.cigar_off, np.uint64), chk(reads.cigar, np.uint32)
+        taken = C.c_uint64(0)
+        self._check(self._lib.inq_push_reads_routed(self._h, len(contig), contig.ctypes.data, rs.ctypes.data, re_.ctypes.data,
+                                                    mapq.ctypes.data, hp.ctypes.data, fl.ctypes.data, off.ctypes.data, cig.ctypes.data,
+                                                    (1 if drop_low_mapq else 0) | (2 if drop_no_hp else 0), int(host_threads), C.byref(taken)))
+        self.n_reads += int(taken.value)
+        return int(taken.value)
 
     def push(self, reads):
         """reads: any object carrying the SoA attributes of include/inqcall.h:inq_push_reads."""

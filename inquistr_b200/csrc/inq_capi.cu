@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace inq;
@@ -173,7 +174,8 @@ struct inq_ctx {
     DevBuf<int64_t> contig_off;
     DevBuf<int32_t> lstart, lend, lpmax;
     std::vector<int64_t> h_contig_off;    // host copies for the plan (which loci are complete after which read)
-    std::vector<int32_t> h_pmax;
+    std::vector<int32_t> h_pmax, h_lstart;
+    void *h_route_stage = nullptr;        // pinned staging of inq_push_reads_routed when the kept reads are scattered
 
     // reads
     uint64_t R = 0, C = 0;
@@ -742,6 +744,7 @@ void inq_ctx_destroy(inq_ctx *ctx)
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->h_probe) cudaFreeHost(ctx->h_probe);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_route_stage) cudaFreeHost(ctx->h_route_stage);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < DEP_COUNT; ++i)
@@ -830,6 +833,7 @@ int inq_set_loci(inq_ctx *ctx, int32_t n_contigs, const int64_t *contig_locus_of
     // host copy of the running max of `end` per contig (the plan's "which loci are complete" test); overlaps the copies above
     ctx->h_contig_off.assign(contig_locus_offsets, contig_locus_offsets + n_contigs + 1);
     ctx->h_pmax.resize((size_t)L);
+    ctx->h_lstart.assign(start, start + (L ? L : 0));
     for (int32_t c = 0; c < n_contigs; ++c) {
         int32_t m = INT32_MIN;
         for (int64_t i = contig_locus_offsets[c]; i < contig_locus_offsets[c + 1]; ++i) { m = std::max(m, end[i]); ctx->h_pmax[(size_t)i] = m; }
@@ -864,25 +868,18 @@ int inq_clear_reads(inq_ctx *ctx)
     return INQ_OK;
 }
 
-int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_t *ref_start, const int32_t *ref_end,
-                   const uint8_t *mapq, const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off,
-                   const uint32_t *cigar_words)
+// Appends n reads whose CIGAR words are words[cigar_off[0] .. cigar_off[n]) (cigar_off need not start at 0).
+// The copies are asynchronous; the caller synchronises ctx->stream before the host arrays may change.
+static int push_impl(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_t *ref_start, const int32_t *ref_end,
+                     const uint8_t *mapq, const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off, const uint32_t *words)
 {
-    if (!ctx) return INQ_ERR_ARG;
-    if (n == 0) return INQ_OK;
-    if (!contig || !ref_start || !ref_end || !mapq || !hp || !flags || !cigar_off)
-        return fail(ctx, INQ_ERR_ARG, "inq_push_reads: NULL array");
-    if (cigar_off[0] != 0) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: cigar_off[0] must be 0");
-    const uint64_t nw = cigar_off[n];
-    if (nw && !cigar_words) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: cigar_words is NULL");
+    const uint64_t w0 = cigar_off[0], nw = cigar_off[n] - w0;
     if (ctx->R + n >= 0xFFFFFFFFull) return fail(ctx, INQ_ERR_TOO_LARGE, "inq_push_reads: more than 2^32-2 reads");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(reserve_reads(ctx, ctx->R + n, ctx->C + nw, 1.5));
     ++ctx->data_gen;
     cudaStream_t s = ctx->stream;
     const uint64_t R0 = ctx->R, C0 = ctx->C;
     uint32_t *cig = cigar_ptr(ctx);
-    CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D0], s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->contig.p + R0, contig, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->rs.p + R0, ref_start, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->re.p + R0, ref_end, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -890,9 +887,9 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_
     CU_TRY(ctx, cudaMemcpyAsync(ctx->hp.p + R0, hp, n, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p + R0, flags, n, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cig_off.p + R0, cigar_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    if (nw) CU_TRY(ctx, cudaMemcpyAsync(cig + C0, cigar_words, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    if (C0) {
-        k_rebase_offsets<<<(unsigned)std::min<uint64_t>((n + 1 + 255) / 256, 8192), 256, 0, s>>>(ctx->cig_off.p + R0, n + 1, C0);
+    if (nw) CU_TRY(ctx, cudaMemcpyAsync(cig + C0, words + w0, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (C0 != w0) {                                              // batch-local offsets -> offsets into the device stream (mod 2^64)
+        k_rebase_offsets<<<(unsigned)std::min<uint64_t>((n + 1 + 255) / 256, 8192), 256, 0, s>>>(ctx->cig_off.p + R0, n + 1, C0 - w0);
         CU_TRY(ctx, cudaGetLastError());
     }
     k_check_sorted<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, s>>>(ctx->contig.p, ctx->rs.p, R0, n, ctx->d_unsorted);
@@ -906,13 +903,156 @@ int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_
         k_tile_first<<<(unsigned)((t1 - t0 + 1 + 255) / 256), 256, 0, s>>>(ctx->cig_off.p, R0 + n + 1, t0, t1, ctx->tile_first.p);
         CU_TRY(ctx, cudaGetLastError());
     }
+    ctx->R = R0 + n;
+    ctx->C = C1;
+    return INQ_OK;
+}
+
+static int check_push_args(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_t *ref_start, const int32_t *ref_end,
+                           const uint8_t *mapq, const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off, const uint32_t *cigar_words)
+{
+    if (!contig || !ref_start || !ref_end || !mapq || !hp || !flags || !cigar_off) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: NULL array");
+    if (cigar_off[0] != 0) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: cigar_off[0] must be 0");
+    if (cigar_off[n] && !cigar_words) return fail(ctx, INQ_ERR_ARG, "inq_push_reads: cigar_words is NULL");
+    return INQ_OK;
+}
+
+int inq_push_reads(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_t *ref_start, const int32_t *ref_end,
+                   const uint8_t *mapq, const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off,
+                   const uint32_t *cigar_words)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    if (n == 0) return INQ_OK;
+    TRY(check_push_args(ctx, n, contig, ref_start, ref_end, mapq, hp, flags, cigar_off, cigar_words));
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool first = ctx->R == 0;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D0], s));
+    TRY(push_impl(ctx, n, contig, ref_start, ref_end, mapq, hp, flags, cigar_off, cigar_words));
     CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D1], s));
     CU_TRY(ctx, cudaStreamSynchronize(s));       // host arrays may be reused by the caller after return
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[EV_H2D0], ctx->ev[EV_H2D1]);
-    ctx->ms_h2d = (R0 == 0 ? 0.f : ctx->ms_h2d) + ms;
-    ctx->R = R0 + n;
-    ctx->C = C1;
+    ctx->ms_h2d = (first ? 0.f : ctx->ms_h2d) + ms;
+    return INQ_OK;
+}
+
+// Push only the reads of a batch that can matter to THIS context's catalog (see include/inqcall.h). With N contexts
+// holding N contiguous catalog shards, handing every batch to every context routes the reads (reads at a cut go to
+// both sides) without the caller knowing the cuts -- the host-side half of SURVEY 8e.
+int inq_push_reads_routed(inq_ctx *ctx, uint64_t n, const int32_t *contig, const int32_t *ref_start, const int32_t *ref_end,
+                          const uint8_t *mapq, const uint8_t *hp, const uint8_t *flags, const uint64_t *cigar_off,
+                          const uint32_t *cigar_words, uint32_t filter, int host_threads, uint64_t *n_taken)
+{
+    if (!ctx) return INQ_ERR_ARG;
+    if (n_taken) *n_taken = 0;
+    if (n == 0) return INQ_OK;
+    TRY(check_push_args(ctx, n, contig, ref_start, ref_end, mapq, hp, flags, cigar_off, cigar_words));
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int nt = std::max(1, std::min(host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency(), 256));
+    // 1. which reads would htslib's fetch return for some locus of this catalog (pos < end+10 && endpos > start-10,
+    //    call.rs:285-288), minus the ones the per-read half of the filters rejects everywhere (call.rs:297-300,350-352)
+    std::vector<uint8_t> keep(n);
+    const int64_t *coff = ctx->h_contig_off.data();
+    const int32_t *ls = ctx->h_lstart.data(), *pm = ctx->h_pmax.data();
+    const int32_t n_contigs = ctx->n_contigs;
+    auto mark = [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; ++i) {
+            uint8_t k = 0;
+            const int32_t c = contig[i];
+            if (c >= 0 && c < n_contigs && coff[c] != coff[c + 1] && !((filter & INQ_ROUTE_DROP_LOW_MAPQ) && mapq[i] <= 10) &&
+                !((filter & INQ_ROUTE_DROP_NO_HP) && hp[i] == INQ_HP_ABSENT)) {
+                const int32_t *b0 = ls + coff[c], *b1 = ls + coff[c + 1];
+                const int64_t hi = std::lower_bound(b0, b1, (int32_t)std::min<int64_t>((int64_t)ref_end[i] + 10, INT32_MAX)) - ls;
+                k = hi != coff[c] && (int64_t)pm[hi - 1] + 10 > (int64_t)ref_start[i];
+            }
+            keep[i] = k;
+        }
+    };
+    auto parallel = [&](uint64_t total, auto fn) {
+        const uint64_t per = (total + nt - 1) / nt;
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t)
+            if ((uint64_t)t * per < total) th.emplace_back([&, t] { fn((uint64_t)t * per, std::min(total, (uint64_t)(t + 1) * per)); });
+        fn(0, std::min(total, per));
+        for (auto &x : th) x.join();
+    };
+    parallel(n, mark);
+    // 2. runs of kept reads. Short gaps are bridged (a read that reaches nothing is harmless on the device: the join
+    //    gives it no candidates, and shipping it is cheaper than gathering around it): coordinate-sorted input and a
+    //    contiguous catalog range give one run per contig
+    constexpr uint64_t kBridge = 256;
+    std::vector<std::pair<uint64_t, uint64_t>> runs;
+    uint64_t taken = 0;
+    for (uint64_t i = 0; i < n;) {
+        if (!keep[i]) { ++i; continue; }
+        uint64_t j = i + 1;
+        while (j < n && keep[j]) ++j;
+        if (!runs.empty() && i - runs.back().second <= kBridge) runs.back().second = j;
+        else runs.emplace_back(i, j);
+        i = j;
+    }
+    for (const auto &r : runs) taken += r.second - r.first;
+    if (n_taken) *n_taken = taken;
+    if (!taken) return INQ_OK;
+    cudaStream_t s = ctx->stream;
+    const bool first = ctx->R == 0;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D0], s));
+    if (runs.size() <= 1024) {
+        // coordinate-sorted input and a contiguous catalog range: a handful of runs, copied straight from the caller's arrays
+        for (const auto &r : runs)
+            TRY(push_impl(ctx, r.second - r.first, contig + r.first, ref_start + r.first, ref_end + r.first, mapq + r.first, hp + r.first,
+                          flags + r.first, cigar_off + r.first, cigar_words));
+    } else {
+        // scattered: gather into pinned staging chunks (all host threads), one push per chunk
+        constexpr uint64_t kStageWords = 16u << 20, kStageReads = 1u << 20;
+        const size_t meta_bytes = kStageReads * 12 + (kStageReads + 1) * 8 + kStageReads * 3;
+        if (!ctx->h_route_stage) CU_TRY(ctx, cudaMallocHost(&ctx->h_route_stage, kStageWords * 4 + meta_bytes + 64));
+        uint32_t *sw = static_cast<uint32_t *>(ctx->h_route_stage);
+        uint8_t *m = reinterpret_cast<uint8_t *>(sw + kStageWords);
+        uint64_t *so = reinterpret_cast<uint64_t *>(m); m += (kStageReads + 1) * 8;
+        int32_t *sc = reinterpret_cast<int32_t *>(m); m += kStageReads * 4;
+        int32_t *ss = reinterpret_cast<int32_t *>(m); m += kStageReads * 4;
+        int32_t *se = reinterpret_cast<int32_t *>(m); m += kStageReads * 4;
+        uint8_t *sq = m; m += kStageReads;
+        uint8_t *sh = m; m += kStageReads;
+        uint8_t *sf = m;
+        std::vector<uint64_t> idx;
+        idx.reserve(kStageReads);
+        size_t ri = 0;
+        uint64_t pos_in_run = 0;
+        while (ri < runs.size()) {
+            idx.clear();
+            uint64_t words = 0;
+            so[0] = 0;
+            while (ri < runs.size() && idx.size() < kStageReads) {
+                const uint64_t i = runs[ri].first + pos_in_run;
+                const uint64_t nw = cigar_off[i + 1] - cigar_off[i];
+                if (nw > kStageWords) return fail(ctx, INQ_ERR_TOO_LARGE, "inq_push_reads_routed: a read has more CIGAR words than the staging buffer");
+                if (words + nw > kStageWords) break;
+                so[idx.size() + 1] = words + nw;
+                idx.push_back(i);
+                words += nw;
+                if (++pos_in_run == runs[ri].second - runs[ri].first) { ++ri; pos_in_run = 0; }
+            }
+            const uint64_t cnt = idx.size();
+            parallel(cnt, [&](uint64_t a, uint64_t b) {
+                for (uint64_t k = a; k < b; ++k) {
+                    const uint64_t i = idx[k];
+                    sc[k] = contig[i]; ss[k] = ref_start[i]; se[k] = ref_end[i];
+                    sq[k] = mapq[i]; sh[k] = hp[i]; sf[k] = flags[i];
+                    memcpy(sw + so[k], cigar_words + cigar_off[i], (size_t)(cigar_off[i + 1] - cigar_off[i]) * 4);
+                }
+            });
+            TRY(push_impl(ctx, cnt, sc, ss, se, sq, sh, sf, so, sw));
+            CU_TRY(ctx, cudaStreamSynchronize(s));               // the staging buffer is refilled next
+        }
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_H2D1], s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[EV_H2D0], ctx->ev[EV_H2D1]);
+    ctx->ms_h2d = (first ? 0.f : ctx->ms_h2d) + ms;
     return INQ_OK;
 }
 

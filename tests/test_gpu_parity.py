@@ -365,3 +365,36 @@ def test_sa_panic_flag_only_fires_when_the_read_pairs(ctx):
             assert rc == 0
             res = ctx.genotype(5, 3, False)
             assert same(res.phase1, p1) and same(res.phase2, p2)
+
+
+@pytest.mark.parametrize("sort_reads", [True, False])
+def test_routed_push_over_catalog_shards(sort_reads):
+    """inq_push_reads_routed: three contexts holding three contiguous catalog shards are each handed the WHOLE read
+    set (in two batches) and keep what can reach them; concatenated output == oracle on the unsharded input.
+    Sorted input takes the run path, shuffled input the gather path; the filter flags change nothing."""
+    import inquistr_b200 as q
+    from inquistr_b200 import shard as S
+    case = make_case(95, n_contigs=3, contig_len=300_000, n_loci=400, n_reads=4000, sort_reads=sort_reads, max_read=6000)
+    rd = case["reads"]
+    n_loci = len(case["locus_start"])
+    rc, p1, p2, visits = O.genotype_loci(rd, case["n_contigs"], case["locus_contig"], case["locus_start"], case["locus_end"], 5, 3, False, threads=4)
+    assert rc == 0
+    half = rd.n // 2
+    parts = []
+    for a, b in ((0, half), (half, rd.n)):
+        base = rd.cigar_off[a]
+        parts.append(O.Reads(rd.contig[a:b], rd.ref_start[a:b], rd.ref_end[a:b], rd.mapq[a:b], rd.hp[a:b], rd.flags[a:b],
+                             rd.cigar_off[a:b + 1] - base, rd.cigar[int(base):int(rd.cigar_off[b])]))
+    for drop in (False, True):
+        g1, g2, tot_visits, tot_taken = [], [], 0, 0
+        for lo, hi in S.split_catalog(n_loci, 3):
+            s_off, s_start, s_end = S.shard_catalog(case["contig_off"], case["locus_start"], case["locus_end"], lo, hi)
+            with q.Context(0) as c:
+                c.set_loci(s_off, s_start, s_end)
+                for p in parts:
+                    tot_taken += c.push_routed(p, drop_low_mapq=drop, drop_no_hp=drop, host_threads=3)
+                res = c.genotype(5, 3, False)
+                g1.append(res.phase1); g2.append(res.phase2); tot_visits += res.stats["op_visits"]
+        assert same(np.concatenate(g1), p1) and same(np.concatenate(g2), p2)
+        assert tot_visits == visits
+        assert tot_taken < 3 * rd.n                      # nobody takes everything
