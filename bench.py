@@ -40,6 +40,8 @@ def parse_args():
                     help="ship every generated read (also the ones with mapq <= 10 / without HP that can never pair)")
     ap.add_argument("--ranges", type=int, default=None, help="inq_set_option('ranges') (default: automatic)")
     ap.add_argument("--no-graph", action="store_true", help="inq_set_option('graph', 0)")
+    ap.add_argument("--bam-scale", type=float, default=0.1,
+                    help="e2e_bam: `inquistr-b200 call` on a synthetic BAM with SEQ/QUAL of config 3 at this scale (0 = skip)")
     ap.add_argument("--parity-seconds", type=float, default=6.0, help="budget of the per-rank oracle check at N > 1")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -246,7 +248,17 @@ def main():
         ctx.set_option("graph", 0)
     ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
     ctx.reserve_reads(rd.n, len(rd.cigar))
-    ctx.push(rd)
+
+    def push_all():
+        # N > 1: every rank hands its host-side slice of the input (a superset of what its shard needs: everything
+        # that starts within one maximal read length of the shard) to the routed push, which keeps what htslib's
+        # fetch would return for some locus of the shard -- the routing cost is inside the e2e timed region
+        if world > 1:
+            return ctx.push_routed(rd, host_threads=max(1, threads // world))
+        ctx.push(rd)
+        return rd.n
+
+    n_pushed = push_all()
     # results land in pinned host memory (the D2H read of every step's result is inside both timed regions)
     out = (q.pinned_empty(w.n_loci, np.int64), q.pinned_empty(w.n_loci, np.int64), q.pinned_empty(w.n_loci, np.uint8))
 
@@ -283,7 +295,7 @@ def main():
         for _ in range(args.steps):
             ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
             ctx.clear_reads()
-            ctx.push(rd)
+            push_all()
             res2 = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t1)
@@ -363,6 +375,26 @@ def main():
         parity = {"loci_checked": int(n_chk), "bit_exact_vs_oracle": bool(n_bad == 0), "ranks_checked": world,
                   "note": "each rank: evenly spaced sample of its catalog shard, oracle on the shard's reads"}
 
+    # ---- BAM -> TSV through the product CLI (rank 0; the other ranks idle at the barrier below)
+    e2e_bam = None
+    if rank == 0 and args.bam_scale > 0 and not args.no_e2e:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_bam.py"), "--config", "3", "--scale", str(args.bam_scale),
+                                "--with-seq", "-t", str(threads), "--devices", ",".join(str(i) for i in range(world))],
+                               capture_output=True, text=True, timeout=900)
+            if r.returncode == 0:
+                e2e_bam = json.loads(r.stdout.strip().splitlines()[-1])
+                e2e_bam.pop("cli_stats", None)
+                e2e_bam["note"] = ("inquistr-b200 call -R loci.bed -t N --devices ... sample.bam: BGZF inflate (own decoder, zlib fallback) + "
+                                   "record parse + routing + pinned pushes + kernels + TSV, one process, page-cache-warm file; "
+                                   "loci_per_s is over the whole process wall time incl. CUDA context creation")
+            else:
+                e2e_bam = {"error": r.stderr[-400:]}
+        except Exception as ex:          # the headline numbers do not depend on this leg
+            e2e_bam = {"error": repr(ex)}
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         line = {
             "metric": "str_loci_genotyped_per_s", "value": value, "unit": "loci/s", "n_gpus": world,
@@ -386,10 +418,13 @@ def main():
                 "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
                 "seconds_per_step": e2e["seconds_per_step"], "ms_h2d_rank0": e2e["ms_h2d_last"],
                 "cigar_ops_per_s": tot_words_j / e2e["seconds_per_step"]},
+            "e2e_bam": e2e_bam,
             "gpu_launches": int(st["n_kernel_launches"]) * args.steps,
             "clocks": clk,
             "parity": parity,
-            "host": {"cores": threads, "gen_seconds": t_gen, "wall_resident_s": wall_resident},
+            "host": {"cores": threads, "gen_seconds": t_gen, "wall_resident_s": wall_resident,
+                     "reads_host_rank0": int(rd.n), "reads_pushed_rank0": int(n_pushed),
+                     "push": "inq_push_reads_routed" if world > 1 else "inq_push_reads"},
         }
         emit(line)
     ctx.close()

@@ -1,10 +1,13 @@
 // bam_reader.cpp -- see bam_reader.hpp. SAM/BAM spec v1 section 4 (BGZF 4.1, BAM 4.2).
 #include "bam_reader.hpp"
+#include "inflate_fast.hpp"
 
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -16,15 +19,21 @@ inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); 
 inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
 
-struct Block {
-    size_t in_off, in_len;     // raw deflate payload inside the batch's compressed buffer
-    size_t out_off, out_len;
-    uint32_t crc;
-};
+std::atomic<uint64_t> g_fast_blocks{0}, g_zlib_blocks{0};
 
 bool inflate_block(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len, uint32_t crc)
 {
     if (out_len == 0) return true;
+    // own one-shot decoder first (inflate_fast.hpp); zlib when it declines or the CRC disagrees
+    static const bool use_fast = [] { const char *e = getenv("INQ_FAST_INFLATE"); return !e || atoi(e) != 0; }();
+    if (use_fast) {
+        thread_local FastInflater fi;
+        if (fi.inflate(in, in_len, out, out_len) && crc32(crc32(0L, Z_NULL, 0), out, (uInt)out_len) == crc) {
+            g_fast_blocks.fetch_add(1, std::memory_order_relaxed);
+            return true;
+        }
+    }
+    g_zlib_blocks.fetch_add(1, std::memory_order_relaxed);
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) return false;
@@ -40,6 +49,65 @@ bool inflate_block(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_le
 
 }  // namespace
 
+void inflate_counters(uint64_t *fast, uint64_t *zlib_fallback)
+{
+    *fast = g_fast_blocks.load();
+    *zlib_fallback = g_zlib_blocks.load();
+}
+
+// single-threaded differential check + timing of the two decoders on every block of a BGZF file
+bool bgzf_selfcheck(const std::string &path, std::string *report)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) { *report = "cannot open " + path; return false; }
+    std::vector<uint8_t> file;
+    uint8_t buf[1 << 16];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof(buf), fp)) > 0) file.insert(file.end(), buf, buf + k);
+    fclose(fp);
+    file.resize(file.size() + 16);
+    size_t p = 0, blocks = 0, mism = 0, declined = 0;
+    uint64_t out_bytes = 0;
+    double t_fast = 0, t_zlib = 0, t_crc = 0;
+    FastInflater fi;
+    std::vector<uint8_t> a(1 << 16), b(1 << 16);
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    while (p + 28 <= file.size() - 16) {
+        const uint16_t xlen = rd16(&file[p + 10]);
+        const size_t bsize = (size_t)rd16(&file[p + 16]) + 1;
+        const uint8_t *pay = &file[p + 12 + xlen];
+        const size_t in_len = bsize - 12 - xlen - 8;
+        const uint32_t crc = rd32(&file[p + bsize - 8]), isize = rd32(&file[p + bsize - 4]);
+        if (isize) {
+            double t0 = now();
+            const bool okf = fi.inflate(pay, in_len, a.data(), isize);
+            t_fast += now() - t0;
+            t0 = now();
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            inflateInit2(&zs, -15);
+            zs.next_in = const_cast<Bytef *>(pay); zs.avail_in = (uInt)in_len; zs.next_out = b.data(); zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            t_zlib += now() - t0;
+            t0 = now();
+            const bool crc_ok = crc32(crc32(0L, Z_NULL, 0), b.data(), isize) == crc;
+            t_crc += now() - t0;
+            if (rc != Z_STREAM_END || !crc_ok) ++mism;
+            else if (!okf) ++declined;
+            else if (memcmp(a.data(), b.data(), isize) != 0) ++mism;
+            out_bytes += isize;
+        }
+        ++blocks;
+        p += bsize;
+    }
+    char line[512];
+    snprintf(line, sizeof(line), "{\"blocks\": %zu, \"bytes\": %llu, \"mismatch\": %zu, \"fast_declined\": %zu, \"fast_MBps\": %.1f, \"zlib_MBps\": %.1f, \"crc_MBps\": %.1f}",
+             blocks, (unsigned long long)out_bytes, mism, declined, out_bytes / 1e6 / t_fast, out_bytes / 1e6 / t_zlib, out_bytes / 1e6 / t_crc);
+    *report = line;
+    return mism == 0;
+}
+
 int BamHeader::tid(const std::string &name) const
 {
     for (size_t i = 0; i < ref_names.size(); ++i)
@@ -54,7 +122,9 @@ BamReader::~BamReader()
         stop_ = true;
     }
     cv_.notify_all();
+    cv_work_.notify_all();
     if (producer_.joinable()) producer_.join();
+    for (auto &t : workers_) t.join();
     if (fp_) fclose(fp_);
 }
 
@@ -63,18 +133,25 @@ bool BamReader::open(const std::string &path, int threads)
     threads_ = std::max(1, threads);
     fp_ = fopen(path.c_str(), "rb");
     if (!fp_) { err_ = "cannot open " + path; return false; }
+    setvbuf(fp_, nullptr, _IOFBF, 8u << 20);
+    cur_batch_.reset(new Batch());
     producer_ = std::thread(&BamReader::producer, this);
+    for (int t = 0; t < threads_; ++t) workers_.emplace_back(&BamReader::inflater, this);
     return parse_header();
 }
 
-// read and inflate one batch of BGZF blocks (runs on the producer thread)
+// read the raw bytes of one batch of BGZF blocks (I/O thread; nothing is inflated here)
 bool BamReader::read_batch(Batch &out)
 {
     constexpr size_t kBatchBlocks = 1024;          // up to 64 MB inflated per batch
-    std::vector<uint8_t> comp;
-    std::vector<Block> blocks;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!pool_.empty()) { out.data = std::move(pool_.back().data); out.comp = std::move(pool_.back().comp); pool_.pop_back(); }
+    }
+    std::vector<uint8_t> &comp = out.comp;
+    comp.clear();
     size_t out_total = 0;
-    while (blocks.size() < kBatchBlocks) {
+    while (out.blocks.size() < kBatchBlocks) {
         uint8_t h[12];
         size_t n = fread(h, 1, 12, fp_);
         if (n == 0) { out.eof = true; break; }
@@ -94,56 +171,64 @@ bool BamReader::read_batch(Batch &out)
         const size_t off = comp.size();
         comp.resize(off + (size_t)remaining);
         if (fread(&comp[off], 1, (size_t)remaining, fp_) != (size_t)remaining) { out.err = "truncated BGZF block"; return false; }
-        Block b;
+        BlockRef b;
         b.in_off = off;
         b.in_len = (size_t)remaining - 8;
         b.crc = rd32(&comp[off + remaining - 8]);
         b.out_len = rd32(&comp[off + remaining - 4]);
         b.out_off = out_total;
         out_total += b.out_len;
-        blocks.push_back(b);
-    }
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (!pool_.empty()) { out.data = std::move(pool_.back()); pool_.pop_back(); }
+        out.blocks.push_back(b);
     }
     out.size = kSlack + out_total;
     if (out.data.size() < out.size) out.data.resize(out.size + (out.size >> 3));
-    if (blocks.empty()) return true;
-    std::atomic<size_t> next{0};
-    std::atomic<int> bad{0};
-    uint8_t *base = out.data.data() + kSlack;
-    auto work = [&]() {
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= blocks.size()) break;
-            const Block &b = blocks[i];
-            if (!inflate_block(&comp[b.in_off], b.in_len, base + b.out_off, b.out_len, b.crc)) bad.store(1);
-        }
-    };
-    const int nt = (int)std::min<size_t>((size_t)threads_, blocks.size());
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
-    if (bad.load()) { out.err = "BGZF inflate / CRC failure"; return false; }
     return true;
 }
 
 void BamReader::producer()
 {
     for (;;) {
-        Batch b;
-        const bool ok = read_batch(b);
-        const bool last = !ok || b.eof;
+        std::unique_ptr<Batch> b(new Batch());
+        const bool ok = read_batch(*b);
+        if (!ok) { b->bad = true; b->blocks.clear(); }
+        const bool last = !ok || b->eof;
         {
             std::unique_lock<std::mutex> lk(mu_);
-            cv_.wait(lk, [&] { return stop_ || queue_.size() < 2; });     // double buffering
+            cv_.wait(lk, [&] { return stop_ || queue_.size() < kInFlight; });
             if (stop_) return;
             queue_.push_back(std::move(b));
+            if (last) producer_done_ = true;
         }
+        cv_work_.notify_all();
         cv_.notify_all();
         if (last) return;
+    }
+}
+
+// worker: take the next block of the oldest batch that still has blocks to hand out
+void BamReader::inflater()
+{
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        Batch *b = nullptr;
+        size_t i = 0;
+        for (auto &q : queue_)
+            if (q->next_block < q->blocks.size()) { b = q.get(); i = q->next_block++; break; }
+        if (!b) {
+            if (stop_ || producer_done_) {
+                bool pending = false;
+                for (auto &q : queue_) pending = pending || q->next_block < q->blocks.size();
+                if (stop_ || !pending) return;
+            }
+            cv_work_.wait(lk);
+            continue;
+        }
+        lk.unlock();
+        const BlockRef &r = b->blocks[i];
+        const bool ok = inflate_block(&b->comp[r.in_off], r.in_len, b->data.data() + kSlack + r.out_off, r.out_len, r.crc);
+        lk.lock();
+        if (!ok) { b->bad = true; if (b->err.empty()) b->err = "BGZF inflate / CRC failure"; }
+        if (++b->done_blocks == b->blocks.size()) cv_.notify_all();
     }
 }
 
@@ -151,37 +236,39 @@ void BamReader::producer()
 bool BamReader::next_batch()
 {
     if (eof_) return false;
-    Batch nb;
+    std::unique_ptr<Batch> nb;
     {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return !queue_.empty(); });
+        cv_.wait(lk, [&] { return !queue_.empty() && queue_.front()->done_blocks == queue_.front()->blocks.size(); });
         nb = std::move(queue_.front());
         queue_.pop_front();
     }
     cv_.notify_all();
-    if (!nb.err.empty()) { err_ = nb.err; eof_ = true; return false; }
+    if (nb->bad || !nb->err.empty()) { err_ = nb->err.empty() ? "BGZF read failure" : nb->err; eof_ = true; return false; }
     const size_t tail = end_ - cur_;
-    const size_t payload = nb.size - kSlack;
+    const size_t payload = nb->size - kSlack;
     total_out_ += payload;
-    if (nb.eof) eof_ = true;
+    if (nb->eof) eof_ = true;
     if (tail <= kSlack) {
-        if (tail) memcpy(nb.data.data() + kSlack - tail, cur_batch_.data.data() + cur_, tail);
+        if (tail) memcpy(nb->data.data() + kSlack - tail, cur_batch_->data.data() + cur_, tail);
         {
             std::lock_guard<std::mutex> lk(mu_);
-            if (!cur_batch_.data.empty() && pool_.size() < 4) pool_.push_back(std::move(cur_batch_.data));
+            if (!cur_batch_->data.empty() && pool_.size() < kInFlight + 1) pool_.push_back(Buffers{std::move(cur_batch_->data), std::move(cur_batch_->comp)});
         }
         cur_batch_ = std::move(nb);
         cur_ = kSlack - tail;
-        end_ = cur_batch_.size;
+        end_ = cur_batch_->size;
     } else {                                        // a record larger than the slack: concatenate
         std::vector<uint8_t> joined(kSlack + tail + payload);
-        memcpy(joined.data() + kSlack, cur_batch_.data.data() + cur_, tail);
-        memcpy(joined.data() + kSlack + tail, nb.data.data() + kSlack, payload);
-        cur_batch_.data = std::move(joined);
-        cur_batch_.size = cur_batch_.data.size();
-        cur_batch_.eof = nb.eof;
+        memcpy(joined.data() + kSlack, cur_batch_->data.data() + cur_, tail);
+        memcpy(joined.data() + kSlack + tail, nb->data.data() + kSlack, payload);
+        const bool was_eof = nb->eof;
+        cur_batch_.reset(new Batch());
+        cur_batch_->data = std::move(joined);
+        cur_batch_->size = cur_batch_->data.size();
+        cur_batch_->eof = was_eof;
         cur_ = kSlack;
-        end_ = cur_batch_.size;
+        end_ = cur_batch_->size;
     }
     return payload > 0 || !eof_;
 }
@@ -198,24 +285,24 @@ bool BamReader::ensure_bytes(size_t n)
 
 bool BamReader::parse_header()
 {
-    if (!ensure_bytes(12) || memcmp(cur_batch_.data.data() + cur_, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM file (bad magic)"; return false; }
-    const uint32_t l_text = rd32(cur_batch_.data.data() + cur_ + 4);
+    if (!ensure_bytes(12) || memcmp(cur_batch_->data.data() + cur_, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM file (bad magic)"; return false; }
+    const uint32_t l_text = rd32(cur_batch_->data.data() + cur_ + 4);
     cur_ += 8;
     if (!ensure_bytes((size_t)l_text + 4)) { if (err_.empty()) err_ = "truncated BAM header text"; return false; }
-    header_.text.assign((const char *)cur_batch_.data.data() + cur_, l_text);
+    header_.text.assign((const char *)cur_batch_->data.data() + cur_, l_text);
     cur_ += l_text;
-    const uint32_t n_ref = rd32(cur_batch_.data.data() + cur_);
+    const uint32_t n_ref = rd32(cur_batch_->data.data() + cur_);
     cur_ += 4;
     for (uint32_t i = 0; i < n_ref; ++i) {
         if (!ensure_bytes(4)) { if (err_.empty()) err_ = "truncated BAM reference list"; return false; }
-        const uint32_t l_name = rd32(cur_batch_.data.data() + cur_);
+        const uint32_t l_name = rd32(cur_batch_->data.data() + cur_);
         cur_ += 4;
         if (!ensure_bytes((size_t)l_name + 4)) { if (err_.empty()) err_ = "truncated BAM reference list"; return false; }
-        std::string name((const char *)cur_batch_.data.data() + cur_, l_name);
+        std::string name((const char *)cur_batch_->data.data() + cur_, l_name);
         if (!name.empty() && name.back() == '\0') name.pop_back();
         cur_ += l_name;
         header_.ref_names.push_back(name);
-        header_.ref_lens.push_back((int64_t)rd32(cur_batch_.data.data() + cur_));
+        header_.ref_lens.push_back((int64_t)rd32(cur_batch_->data.data() + cur_));
         cur_ += 4;
     }
     return true;
@@ -227,10 +314,10 @@ bool BamReader::next(BamRecordView &rec)
         if (err_.empty() && end_ != cur_) err_ = "truncated BAM record";
         return false;
     }
-    const uint32_t block_size = rd32(cur_batch_.data.data() + cur_);
+    const uint32_t block_size = rd32(cur_batch_->data.data() + cur_);
     if (block_size < 32) { err_ = "corrupt BAM record"; return false; }
     if (!ensure_bytes((size_t)block_size + 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
-    const uint8_t *p = cur_batch_.data.data() + cur_ + 4;       // record body, parsed in place
+    const uint8_t *p = cur_batch_->data.data() + cur_ + 4;       // record body, parsed in place
     cur_ += (size_t)block_size + 4;
     return parse_bam_record(p, block_size, rec, cg_, err_);
 }

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -60,37 +61,51 @@ public:
     uint64_t bytes_inflated() const { return total_out_; }
 
 private:
-    // A batch of inflated BGZF blocks. `data` starts with kSlack unused bytes so that the unconsumed
-    // tail of the previous batch can be moved in front of it without copying the batch.
+    // A batch of BGZF blocks: read raw by the I/O thread, inflated block by block by the worker pool, parsed by
+    // the caller. `data` starts with kSlack unused bytes so that the unconsumed tail of the previous batch can
+    // be moved in front of it without copying the batch.
+    struct BlockRef {
+        size_t in_off, in_len;                     // raw deflate payload inside `comp`
+        size_t out_off, out_len;
+        uint32_t crc;
+    };
     struct Batch {
         std::vector<uint8_t> data;                 // capacity is recycled between batches (no re-faulting of pages)
+        std::vector<uint8_t> comp;
+        std::vector<BlockRef> blocks;
         size_t size = 0;                           // kSlack + inflated payload bytes
-        bool eof = false;
+        size_t next_block = 0, done_blocks = 0;    // guarded by mu_
+        bool eof = false, bad = false;
         std::string err;
     };
-    std::vector<std::vector<uint8_t>> pool_;       // recycled buffers (guarded by mu_)
+    struct Buffers { std::vector<uint8_t> data, comp; };
+    std::vector<Buffers> pool_;                    // recycled buffers (guarded by mu_)
     static constexpr size_t kSlack = 8u << 20;
+    static constexpr size_t kInFlight = 4;         // batches read ahead of the parser
     bool next_batch();                             // make the next batch current (tail preserved)
     bool ensure_bytes(size_t n);                   // at least n unconsumed bytes are contiguous at cur_
     bool parse_header();
-    void producer();                               // background thread: read + inflate batches
+    void producer();                               // I/O thread: reads raw batches ahead of the inflaters
+    void inflater();                               // worker: inflates blocks of the oldest unfinished batch
     bool read_batch(Batch &b);
 
     FILE *fp_ = nullptr;
     int threads_ = 1;
     BamHeader header_;
     std::string err_;
-    Batch cur_batch_;
-    size_t cur_ = 0, end_ = 0;                     // unconsumed window inside cur_batch_.data
+    std::unique_ptr<Batch> cur_batch_;
+    size_t cur_ = 0, end_ = 0;                     // unconsumed window inside cur_batch_->data
     bool eof_ = false;
     uint64_t total_out_ = 0;
     std::vector<uint32_t> cg_;                     // aligned copy of the record's CIGAR
 
     std::thread producer_;
+    std::vector<std::thread> workers_;
     std::mutex mu_;
-    std::condition_variable cv_;
-    std::deque<Batch> queue_;
-    bool stop_ = false;
+    std::condition_variable cv_;                   // consumer + producer
+    std::condition_variable cv_work_;              // inflaters
+    std::deque<std::unique_ptr<Batch>> queue_;     // in file order; the head is handed to the parser once complete
+    bool stop_ = false, producer_done_ = false;
 };
 
 // Parses one BAM alignment record body (the bytes after block_size) in place. `cg` receives an aligned
@@ -180,6 +195,11 @@ bool BamIndexedReader::fetch(int tid, int64_t beg, int64_t end, F f)
     }
     return err_.empty();
 }
+
+// BGZF blocks inflated by the own decoder (inflate_fast.hpp) / by zlib (fallback), process-wide
+void inflate_counters(uint64_t *fast, uint64_t *zlib_fallback);
+// every BGZF block of a file through both decoders, single-threaded: byte comparison + MB/s of each (JSON in *report)
+bool bgzf_selfcheck(const std::string &path, std::string *report);
 
 // call.rs:461-477
 int64_t cigar_text_to_rlen(const std::string &cigar);

@@ -1,0 +1,402 @@
+// inflate_fast.hpp -- one-shot raw DEFLATE (RFC 1951) decoder for BGZF blocks: the whole compressed block
+// and the exact output size are known up front, so there is no streaming state, no window copy and no
+// per-byte bounds bookkeeping in the hot loop. Written for the host ingest of `inquistr-b200 call`
+// (SURVEY 8f rank 1), where zlib's inflate is the bottleneck: 64-bit bit buffer refilled once per symbol
+// group, two-level decode tables (11-bit litlen, 8-bit distance primary tables), word-wise match copies.
+// Anything unexpected (invalid code, overrun, size mismatch) returns false and the caller falls back to
+// zlib; the caller also verifies the block's CRC32, so a decoder bug can never corrupt the output silently.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+
+namespace inqhost {
+
+class FastInflater {
+public:
+    // decodes exactly out_len bytes from in[0, in_len); in must be readable up to in + in_len + 8
+    // (a BGZF payload is followed by its 8-byte CRC32/ISIZE trailer)
+    bool inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+
+private:
+    static constexpr int kLitBits = 11, kDistBits = 8;
+    static constexpr uint32_t kTypeLiteral = 0, kTypeBase = 1, kTypeEob = 2, kTypeSub = 3;
+    // entry: bits 0-3 code bits to consume at this level, 4-7 extra bits (type base) or sub-table index bits
+    // (type sub), 8-9 type, 16-31 literal / base value / sub-table offset. 0 = invalid.
+    static uint32_t make(uint32_t type, uint32_t bits, uint32_t extra, uint32_t value)
+    {
+        return bits | (extra << 4) | (type << 8) | (value << 16);
+    }
+    bool build(const uint8_t *lens, int n, int primary_bits, uint32_t *table, int table_cap, bool is_dist);
+    bool read_dynamic_header();
+    void load_fixed();
+
+    uint32_t lit_[(1 << kLitBits) + 2048];
+    uint32_t dist_[(1 << kDistBits) + 1024];
+    uint32_t lit2_[1 << kLitBits];                     // two literals at once: bits 0-3 total code bits (<= 11), 4-7 unused, 16-31 the two bytes; 0 = no pair
+    void build_pairs();
+    bool fixed_loaded_ = false;
+
+    // bit reader
+    const uint8_t *in_ = nullptr, *in_end_ = nullptr;   // in_end_: end of the payload
+    uint64_t bitbuf_ = 0;
+    int bitcnt_ = 0;
+    const uint8_t *in_begin_ = nullptr;
+    // Loads whole bytes until the buffer holds >= 56 bits. The 8 trailer bytes after the payload are readable, so a
+    // load may pull in bytes that are not payload; consuming them is detected at the end (consumed_ok). Once the
+    // pointer has passed the payload nothing more is loaded: the buffer runs dry into zero bits, bitcnt_ goes negative.
+    inline void refill()
+    {
+        if (in_ <= in_end_ && bitcnt_ >= 0) {
+            uint64_t w;
+            memcpy(&w, in_, 8);
+            bitbuf_ |= w << bitcnt_;
+            in_ += (63 - bitcnt_) >> 3;
+            bitcnt_ |= 56;
+        }
+    }
+    inline bool consumed_ok() const { return (int64_t)(in_ - in_begin_) * 8 - bitcnt_ <= (int64_t)(in_end_ - in_begin_) * 8; }
+    inline uint32_t peek(int n) const { return (uint32_t)(bitbuf_ & ((1ull << n) - 1)); }
+    inline void consume(int n) { bitbuf_ >>= n; bitcnt_ -= n; }
+};
+
+namespace inflate_detail {
+static const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+static const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+inline uint32_t bitrev(uint32_t v, int n)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
+    return r;
+}
+}  // namespace inflate_detail
+
+// canonical Huffman code lengths -> two-level decode table indexed by the next bits of the (LSB-first) stream
+inline bool FastInflater::build(const uint8_t *lens, int n, int P, uint32_t *table, int table_cap, bool is_dist)
+{
+    using namespace inflate_detail;
+    int count[16] = {0};
+    for (int i = 0; i < n; ++i) count[lens[i]]++;
+    count[0] = 0;
+    // over-subscription check; incomplete codes are tolerated (unfilled entries stay invalid)
+    int left = 1;
+    for (int l = 1; l <= 15; ++l) {
+        left <<= 1;
+        left -= count[l];
+        if (left < 0) return false;
+    }
+    uint32_t next_code[16];
+    uint32_t code = 0;
+    for (int l = 1; l <= 15; ++l) {
+        code = (code + (uint32_t)count[l - 1]) << 1;
+        next_code[l] = code;
+    }
+    const int psize = 1 << P;
+    memset(table, 0, (size_t)psize * sizeof(uint32_t));
+    // pass 1 for long codes: deepest code below every primary prefix
+    uint8_t sub_bits[1 << kLitBits];
+    bool any_long = false;
+    for (int l = P + 1; l <= 15; ++l) any_long = any_long || count[l] != 0;
+    if (any_long) {
+        memset(sub_bits, 0, (size_t)psize);
+        uint32_t nc[16];
+        memcpy(nc, next_code, sizeof(nc));
+        for (int s = 0; s < n; ++s) {
+            const int l = lens[s];
+            if (l <= P) { if (l) nc[l]++; continue; }
+            const uint32_t rev = bitrev(nc[l]++, l);
+            const uint32_t prefix = rev & (uint32_t)(psize - 1);
+            if (l - P > sub_bits[prefix]) sub_bits[prefix] = (uint8_t)(l - P);
+        }
+        int off = psize;
+        for (int p = 0; p < psize; ++p)
+            if (sub_bits[p]) {
+                const int sz = 1 << sub_bits[p];
+                if (off + sz > table_cap) return false;
+                memset(table + off, 0, (size_t)sz * sizeof(uint32_t));
+                table[p] = make(kTypeSub, (uint32_t)P, sub_bits[p], (uint32_t)off);
+                off += sz;
+            }
+    }
+    for (int s = 0; s < n; ++s) {
+        const int l = lens[s];
+        if (!l) continue;
+        const uint32_t rev = bitrev(next_code[l]++, l);
+        uint32_t type, extra = 0, value;
+        if (is_dist) {
+            if (s >= 30) continue;                        // distance codes 30/31 never occur in valid data: entries stay invalid
+            type = kTypeBase; extra = kDistExtra[s]; value = kDistBase[s];
+        } else if (s < 256) {
+            type = kTypeLiteral; value = (uint32_t)s;
+        } else if (s == 256) {
+            type = kTypeEob; value = 0;
+        } else {
+            if (s > 285) continue;                        // 286/287 take part in the fixed code's construction only
+            type = kTypeBase; extra = kLenExtra[s - 257]; value = kLenBase[s - 257];
+        }
+        if (l <= P) {
+            const uint32_t e = make(type, (uint32_t)l, extra, value);
+            for (uint32_t i = rev; i < (uint32_t)psize; i += 1u << l) table[i] = e;
+        } else {
+            const uint32_t prefix = rev & (uint32_t)(psize - 1);
+            const uint32_t pe = table[prefix];
+            const uint32_t sb = (pe >> 4) & 15u, off = pe >> 16;
+            const uint32_t e = make(type, (uint32_t)(l - P), extra, value);
+            for (uint32_t i = rev >> P; i < (1u << sb); i += 1u << (l - P)) table[off + i] = e;
+        }
+    }
+    return true;
+}
+
+// lit2_[i]: when the next 11 bits hold two complete literal codes, both bytes and the bits they take
+inline void FastInflater::build_pairs()
+{
+    for (uint32_t i = 0; i < (1u << kLitBits); ++i) {
+        uint32_t v = 0;
+        const uint32_t e1 = lit_[i];
+        if (e1 && ((e1 >> 8) & 3u) == kTypeLiteral) {
+            const uint32_t l1 = e1 & 15u;
+            if (l1 < (uint32_t)kLitBits) {
+                // the entry at (i >> l1) was filled for every value of the bits above its own code, so it is the right
+                // one exactly when its code fits in the 11 - l1 bits that are known
+                const uint32_t e2 = lit_[i >> l1];
+                const uint32_t l2 = e2 & 15u;
+                if (e2 && ((e2 >> 8) & 3u) == kTypeLiteral && l1 + l2 <= (uint32_t)kLitBits)
+                    v = (l1 + l2) | ((e1 >> 16) << 16) | ((e2 >> 16) << 24);
+            }
+        }
+        lit2_[i] = v;
+    }
+}
+
+inline void FastInflater::load_fixed()
+{
+    // RFC 1951 3.2.6; symbols 286/287 and distance codes 30/31 exist only to complete the codes
+    uint8_t lens[288];
+    for (int i = 0; i < 144; ++i) lens[i] = 8;
+    for (int i = 144; i < 256; ++i) lens[i] = 9;
+    for (int i = 256; i < 280; ++i) lens[i] = 7;
+    for (int i = 280; i < 288; ++i) lens[i] = 8;
+    build(lens, 288, kLitBits, lit_, (int)(sizeof(lit_) / sizeof(lit_[0])), false);
+    uint8_t dl[32];
+    for (int i = 0; i < 32; ++i) dl[i] = 5;
+    build(dl, 32, kDistBits, dist_, (int)(sizeof(dist_) / sizeof(dist_[0])), true);
+    build_pairs();
+}
+
+inline bool FastInflater::read_dynamic_header()
+{
+    using namespace inflate_detail;
+    refill();
+    const int hlit = (int)peek(5) + 257; consume(5);
+    const int hdist = (int)peek(5) + 1; consume(5);
+    const int hclen = (int)peek(4) + 4; consume(4);
+    if (hlit > 286 || hdist > 30) return false;
+    uint8_t cl[19] = {0};
+    for (int i = 0; i < hclen; ++i) {
+        if (bitcnt_ < 3) refill();
+        cl[kClOrder[i]] = (uint8_t)peek(3);
+        consume(3);
+    }
+    uint32_t cltab[1 << 7];
+    if (!build(cl, 19, 7, cltab, 1 << 7, false)) return false;      // symbols 0..18 decode as "literals"
+    uint8_t lens[286 + 30 + 138];
+    int i = 0;
+    const int total = hlit + hdist;
+    while (i < total) {
+        if (bitcnt_ < 7 + 7) refill();
+        const uint32_t e = cltab[peek(7)];
+        if (!e || ((e >> 8) & 3u) != kTypeLiteral) return false;
+        consume((int)(e & 15u));
+        const uint32_t sym = e >> 16;
+        if (sym < 16) { lens[i++] = (uint8_t)sym; continue; }
+        int rep;
+        uint8_t v = 0;
+        if (sym == 16) {
+            if (i == 0) return false;
+            v = lens[i - 1];
+            rep = 3 + (int)peek(2); consume(2);
+        } else if (sym == 17) {
+            rep = 3 + (int)peek(3); consume(3);
+        } else {
+            rep = 11 + (int)peek(7); consume(7);
+        }
+        if (i + rep > total) return false;
+        memset(lens + i, v, (size_t)rep);
+        i += rep;
+    }
+    if (lens[256] == 0) return false;                     // no end-of-block code
+    if (!build(lens, hlit, kLitBits, lit_, (int)(sizeof(lit_) / sizeof(lit_[0])), false)) return false;
+    if (!build(lens + hlit, hdist, kDistBits, dist_, (int)(sizeof(dist_) / sizeof(dist_[0])), true)) return false;
+    fixed_loaded_ = false;
+    build_pairs();
+    return true;
+}
+
+inline bool FastInflater::inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
+{
+    in_ = in_begin_ = in;
+    in_end_ = in + in_len;
+    bitbuf_ = 0;
+    bitcnt_ = 0;
+    uint8_t *const out_begin = out, *const out_end = out + out_len;
+    for (;;) {
+        refill();
+        const uint32_t bfinal = peek(1), btype = (uint32_t)(bitbuf_ >> 1) & 3u;
+        consume(3);
+        if (btype == 0) {
+            // stored: skip to the byte boundary, LEN / NLEN, raw bytes
+            if (bitcnt_ < 0) return false;
+            consume(bitcnt_ & 7);
+            // unread bytes sit in the bit buffer: step the input pointer back to the first unconsumed byte
+            const uint8_t *p = in_ - (bitcnt_ >> 3);
+            if (p + 4 > in_end_) return false;
+            const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8), nlen = (uint32_t)p[2] | ((uint32_t)p[3] << 8);
+            if ((len ^ 0xFFFFu) != nlen) return false;
+            p += 4;
+            if (p + len > in_end_ || out + len > out_end) return false;
+            memcpy(out, p, len);
+            out += len;
+            in_ = p + len;
+            bitbuf_ = 0;
+            bitcnt_ = 0;
+        } else if (btype == 1 || btype == 2) {
+            if (btype == 1) {
+                if (!fixed_loaded_) { load_fixed(); fixed_loaded_ = true; }
+            } else if (!read_dynamic_header()) {
+                return false;
+            }
+            // fast loop: far enough from the end of the output (a symbol writes at most 258 + 7 bytes, three
+            // literals 3) that nothing needs a bounds check; the checked loop below finishes the block
+            bool eob = false;
+            if (out_len > 320) {
+                uint8_t *const fast_end = out_end - 320;
+                while (out < fast_end) {
+                    refill();
+                    // literal pairs first: up to 5 lookups (55 bits) per refill, two bytes each
+                    {
+                        uint32_t p2 = lit2_[peek(kLitBits)];
+                        if (p2) {
+                            int budget = bitcnt_ < 56 ? 0 : 5;
+                            do {
+                                consume((int)(p2 & 15u));
+                                const uint16_t two = (uint16_t)(p2 >> 16);
+                                memcpy(out, &two, 2);
+                                out += 2;
+                                if (--budget <= 0) break;
+                                p2 = lit2_[peek(kLitBits)];
+                            } while (p2);
+                            continue;
+                        }
+                    }
+                    uint32_t e = lit_[peek(kLitBits)];
+                    if (__builtin_expect(((e >> 8) & 3u) == kTypeLiteral && e, 1)) {
+                    lit1:
+                        // single literals (codes too long to pair up): up to three per refill (3 x 15 <= 56 bits)
+                        consume((int)(e & 15u));
+                        *out++ = (uint8_t)(e >> 16);
+                        if (bitcnt_ >= 30) {
+                            e = lit_[peek(kLitBits)];
+                            if (((e >> 8) & 3u) == kTypeLiteral && e) {
+                                consume((int)(e & 15u));
+                                *out++ = (uint8_t)(e >> 16);
+                                e = lit_[peek(kLitBits)];
+                                if (((e >> 8) & 3u) == kTypeLiteral && e) {
+                                    consume((int)(e & 15u));
+                                    *out++ = (uint8_t)(e >> 16);
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    if (((e >> 8) & 3u) == kTypeSub) {
+                        consume(kLitBits);
+                        e = lit_[(e >> 16) + peek((int)((e >> 4) & 15u))];
+                        if (((e >> 8) & 3u) == kTypeLiteral && e) goto lit1;
+                    }
+                    if (!e) return false;
+                    consume((int)(e & 15u));
+                    if (((e >> 8) & 3u) == kTypeEob) { eob = true; break; }
+                    const uint32_t xl = (e >> 4) & 15u;
+                    const uint32_t len = (e >> 16) + peek((int)xl);
+                    consume((int)xl);
+                    uint32_t d = dist_[peek(kDistBits)];
+                    if (((d >> 8) & 3u) == kTypeSub) {
+                        consume(kDistBits);
+                        d = dist_[(d >> 16) + peek((int)((d >> 4) & 15u))];
+                    }
+                    if (!d || ((d >> 8) & 3u) != kTypeBase) return false;
+                    consume((int)(d & 15u));
+                    const uint32_t xd = (d >> 4) & 15u;
+                    const uint32_t dist = (d >> 16) + peek((int)xd);
+                    consume((int)xd);
+                    if (dist > (size_t)(out - out_begin)) return false;
+                    const uint8_t *src = out - dist;
+                    uint8_t *dst = out;
+                    out += len;
+                    if (dist >= 8) {
+                        do {
+                            uint64_t w;
+                            memcpy(&w, src, 8);
+                            memcpy(dst, &w, 8);
+                            src += 8;
+                            dst += 8;
+                        } while (dst < out);
+                    } else if (dist == 1) {
+                        memset(dst, *src, len);
+                    } else {
+                        // short period: replicate the pattern until the copy distance is at least a word
+                        uint32_t done = 0;
+                        while (done < len && done < 8) { dst[done] = src[done]; ++done; }
+                        // from here on source and destination are >= dist * k apart; grow by copying what is already written
+                        while (done < len) { dst[done] = dst[done - dist]; ++done; }
+                    }
+                }
+            }
+            while (!eob) {
+                refill();                                            // >= 56 bits: enough for one length/distance pair (48)
+                uint32_t e = lit_[peek(kLitBits)];
+                if (((e >> 8) & 3u) == kTypeSub) {
+                    consume(kLitBits);
+                    e = lit_[(e >> 16) + peek((int)((e >> 4) & 15u))];
+                }
+                if (!e) return false;
+                consume((int)(e & 15u));
+                const uint32_t type = (e >> 8) & 3u;
+                if (type == kTypeLiteral) {
+                    if (out >= out_end) return false;
+                    *out++ = (uint8_t)(e >> 16);
+                    continue;
+                }
+                if (type == kTypeEob) break;
+                const uint32_t xl = (e >> 4) & 15u;
+                const uint32_t len = (e >> 16) + peek((int)xl);
+                consume((int)xl);
+                uint32_t d = dist_[peek(kDistBits)];
+                if (((d >> 8) & 3u) == kTypeSub) {
+                    consume(kDistBits);
+                    d = dist_[(d >> 16) + peek((int)((d >> 4) & 15u))];
+                }
+                if (!d || ((d >> 8) & 3u) != kTypeBase) return false;
+                consume((int)(d & 15u));
+                const uint32_t xd = (d >> 4) & 15u;
+                const uint32_t dist = (d >> 16) + peek((int)xd);
+                consume((int)xd);
+                if (dist > (size_t)(out - out_begin) || len > (size_t)(out_end - out)) return false;
+                const uint8_t *src = out - dist;
+                for (uint32_t k = 0; k < len; ++k) out[k] = src[k];
+                out += len;
+            }
+        } else {
+            return false;
+        }
+        if (!consumed_ok()) return false;
+        if (bfinal) break;
+    }
+    return out == out_end;
+}
+
+}  // namespace inqhost

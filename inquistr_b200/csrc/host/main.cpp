@@ -121,6 +121,13 @@ Args parse_args(int argc, char **argv)
         exit(v.empty() ? 2 : 0);
     }
     if (v[0] == "-V" || v[0] == "--version") { printf("inquistr-b200 %s\n", inq_version()); exit(0); }
+    if (v[0] == "bgzf-check" && v.size() >= 2) {
+        // extension: own DEFLATE decoder vs zlib on every block of a BGZF file (bytes compared, MB/s of each)
+        std::string rep;
+        const bool ok = bgzf_selfcheck(v[1], &rep);
+        printf("%s\n", rep.c_str());
+        exit(ok ? 0 : 1);
+    }
     if (v[0] == "baistat" && v.size() >= 2) {
         // extension: what a .bai says on its own (no BAM, no GPU): `baistat x.bam.bai [tid:beg-end]`
         BamIndexedReader ix;
@@ -175,10 +182,12 @@ Args parse_args(int argc, char **argv)
         }
         if (!rd.error().empty()) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        uint64_t nf = 0, nz = 0;
+        inflate_counters(&nf, &nz);
         printf("{\"refs\": %zu, \"records\": %llu, \"cigar_words\": %llu, \"hp_tagged\": %llu, \"sa_tagged\": %llu, \"accidental_2d\": %llu, "
-               "\"bytes_inflated\": %llu, \"seconds\": %.3f, \"inflate_GBps\": %.3f}\n", rd.header().ref_names.size(),
+               "\"bytes_inflated\": %llu, \"seconds\": %.3f, \"inflate_GBps\": %.3f, \"blocks_fast\": %llu, \"blocks_zlib\": %llu}\n", rd.header().ref_names.size(),
                (unsigned long long)n, (unsigned long long)words, (unsigned long long)hp, (unsigned long long)sa, (unsigned long long)d2,
-               (unsigned long long)rd.bytes_inflated(), s, rd.bytes_inflated() / 1e9 / s);
+               (unsigned long long)rd.bytes_inflated(), s, rd.bytes_inflated() / 1e9 / s, (unsigned long long)nf, (unsigned long long)nz);
         exit(0);
     }
     // cohort follow-ons of `call`: text in, text out; cohort_cli.cpp

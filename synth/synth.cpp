@@ -483,10 +483,9 @@ int64_t synth_write_bam(const char *path, int32_t n_contigs, const char *const *
         for (auto &c : comp) { fwrite(c.data(), 1, c.size(), fp); written += (int64_t)c.size(); }
     };
     emit_stream(head);
-    // records, in chunks of ~256 MB of raw bytes
-    std::vector<uint8_t> raw;
-    raw.reserve(300u << 20);
-    for (uint64_t i = 0; i < R; ++i) {
+    // records: chunks of 2048 reads are serialised AND compressed by the worker threads (every chunk is its own run
+    // of BGZF blocks); a wave of chunks is written in order before the next wave starts
+    auto put_record = [&](std::vector<uint8_t> &raw, uint64_t i) {
         const uint64_t a = cig_off[i], b = cig_off[i + 1];
         const uint32_t ncig = (uint32_t)(b - a);
         uint32_t l_seq = 0;
@@ -529,8 +528,24 @@ int64_t synth_write_bam(const char *path, int32_t n_contigs, const char *const *
             const uint8_t *cp = reinterpret_cast<const uint8_t *>(cigar + a);
             raw.insert(raw.end(), cp, cp + (size_t)ncig * 4);
         }
-        for (uint32_t k = 0; k < (l_seq + 1) / 2; ++k) raw.push_back((uint8_t)(0x11u << (rr.next() & 3)));   // A/C/G/T pairs
-        raw.insert(raw.end(), l_seq, (uint8_t)20);
+        {
+            // SEQ: pseudo-random A/C/G/T pairs (8 bases per draw) ; QUAL: pseudo-random Phred 10..41 (two-level mix, so that
+            // the compressed stream is a mix of literals and matches as in real ONT BAMs, not one long run)
+            const size_t ns = (l_seq + 1) / 2, base = raw.size();
+            raw.resize(base + ns + l_seq);
+            uint8_t *ps = raw.data() + base;
+            for (size_t k = 0; k < ns; k += 8) {
+                uint64_t r8 = rr.next();
+                for (size_t j = k; j < std::min(ns, k + 8); ++j, r8 >>= 8) ps[j] = (uint8_t)((0x1u << (r8 & 3)) | (0x10u << ((r8 >> 2) & 3)));
+            }
+            uint8_t *pq = ps + ns;
+            for (size_t k = 0; k < l_seq; k += 16) {
+                uint64_t r8 = rr.next();
+                const uint8_t level = (uint8_t)(18 + (r8 & 15));             // a local quality level, 16 bases long
+                r8 >>= 4;
+                for (size_t j = k; j < std::min<size_t>(l_seq, k + 16); ++j, r8 >>= 3) pq[j] = (uint8_t)(level + (r8 & 7) - 3);
+            }
+        }
         if (hp[i] != 0xFF) { raw.push_back('H'); raw.push_back('P'); raw.push_back('C'); raw.push_back(hp[i]); }
         if (!sa.empty()) { raw.push_back('S'); raw.push_back('A'); raw.push_back('Z'); raw.insert(raw.end(), sa.begin(), sa.end()); raw.push_back(0); }
         if (long_cigar) {
@@ -539,9 +554,35 @@ int64_t synth_write_bam(const char *path, int32_t n_contigs, const char *const *
             const uint8_t *cp = reinterpret_cast<const uint8_t *>(cigar + a);
             raw.insert(raw.end(), cp, cp + (size_t)ncig * 4);
         }
-        if (raw.size() >= (256u << 20)) { emit_stream(raw); raw.clear(); }
+    };
+    const uint64_t kChunk = 2048;
+    const uint64_t n_chunks = (R + kChunk - 1) / kChunk;
+    const uint64_t wave = (uint64_t)nt * 4;
+    for (uint64_t c0 = 0; c0 < n_chunks; c0 += wave) {
+        const uint64_t c1 = std::min(n_chunks, c0 + wave);
+        std::vector<std::vector<uint8_t>> comp(c1 - c0);
+        std::atomic<uint64_t> next{c0};
+        auto work = [&]() {
+            std::vector<uint8_t> raw, blk;
+            for (;;) {
+                const uint64_t c = next.fetch_add(1);
+                if (c >= c1) break;
+                raw.clear();
+                for (uint64_t i = c * kChunk; i < std::min(R, (c + 1) * kChunk); ++i) put_record(raw, i);
+                const size_t kPay = 65280;
+                std::vector<uint8_t> &out = comp[c - c0];
+                for (size_t off = 0; off < raw.size(); off += kPay) {
+                    bgzf_compress(raw.data() + off, std::min(kPay, raw.size() - off), level, blk);
+                    out.insert(out.end(), blk.begin(), blk.end());
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        for (auto &c : comp) { fwrite(c.data(), 1, c.size(), fp); written += (int64_t)c.size(); }
     }
-    if (!raw.empty()) emit_stream(raw);
     static const uint8_t eof_block[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     fwrite(eof_block, 1, 28, fp);
     written += 28;

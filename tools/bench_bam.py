@@ -16,20 +16,22 @@ ap.add_argument("--with-seq", action="store_true")
 ap.add_argument("-t", "--threads", type=int, default=8)
 ap.add_argument("--keep", default=None)
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--devices", default="0", help="passed to `inquistr-b200 call --devices`")
+ap.add_argument("--gen-threads", type=int, default=0)
 a = ap.parse_args()
 
 from inquistr_b200 import build
 cli = build.build_cli()
-w = S.make_workload(a.config, scale=a.scale)
+w = S.make_workload(a.config, scale=a.scale, threads=a.gen_threads)
 d = a.keep or tempfile.mkdtemp(prefix="inqbam")
 os.makedirs(d, exist_ok=True)
 bam, bed = os.path.join(d, "sample.bam"), os.path.join(d, "loci.bed")
 t0 = time.perf_counter()
-nbytes = S.write_bam(w, bam, with_seq=a.with_seq)
+nbytes = S.write_bam(w, bam, with_seq=a.with_seq, threads=a.gen_threads)
 t_write = time.perf_counter() - t0
 rows = S.write_bed(w, bed, shuffle_seed=1)
 stats = os.path.join(d, "stats.json")
-args = [cli, "call", "-R", bed, "-t", str(a.threads), "--stats-json", stats] + (["-u"] if w.unphased else []) + [bam]
+args = [cli, "call", "-R", bed, "-t", str(a.threads), "--devices", a.devices, "--stats-json", stats] + (["-u"] if w.unphased else []) + [bam]
 t0 = time.perf_counter()
 r = subprocess.run(args, capture_output=True)
 wall = time.perf_counter() - t0
@@ -49,7 +51,19 @@ if not a.no_check:
     exp = "chromosome\tbegin\tend\tsample_H1\tsample_H2\n" + "".join(
         O.format_row(rows[i][0], rows[i][1], rows[i][2], p1[i], p2[i]) + "\n" for i in idx)
     ok = r.stdout == exp.encode()
+scan_s = max(st["s_bam_scan"], 1e-9)
 print(json.dumps({"workload": w.name, "with_seq": a.with_seq, "bam_bytes": nbytes, "bam_write_s": round(t_write, 2),
-                  "cli_wall_s": round(wall, 3), "loci": w.n_loci, "reads": w.reads.n, "loci_per_s": w.n_loci / wall,
+                  "devices": a.devices, "cli_wall_s": round(wall, 3), "loci": w.n_loci, "reads": w.reads.n, "loci_per_s": w.n_loci / wall,
                   "inflated_GB": st["bytes_inflated"] / 1e9, "inflate_GBps": st["bytes_inflated"] / 1e9 / wall,
+                  "inflate_GBps_during_scan": st["bytes_inflated"] / 1e9 / scan_s,
+                  "phases_s": {"cuda_ctx_create+set_loci (under the scan)": st["s_ctx_create_set_loci"],
+                               "bam_scan (read + inflate + parse + route; pushes overlap it)": st["s_bam_scan"],
+                               "h2d_push (worker threads, under the scan)": st["s_push_under_scan"],
+                               "flush + genotype + join": st["s_flush_genotype"],
+                               "tsv + exit": max(0.0, st["s_total"] - st["s_bam_scan"] - st["s_flush_genotype"]),
+                               "total_in_process": st["s_total"]},
+                  "gpu_busy_ms": st["ms_total"], "gpu_idle_s": max(0.0, st["s_total"] - st["ms_total"] / 1e3 - st["ms_h2d"] / 1e3),
                   "tsv_identical_to_oracle": ok, "cli_stats": st}))
+if not a.keep:
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
