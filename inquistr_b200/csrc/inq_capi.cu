@@ -395,6 +395,19 @@ __global__ void k_check_sorted(const int32_t *__restrict__ contig, const int32_t
     }
 }
 
+// everything a pass needs zeroed besides the counters, in one launch (six small memsets cost ~15 us of launch latency
+// on the critical path of a small workload)
+struct ZeroJob { void *p; uint64_t bytes; };
+struct ZeroJobs { ZeroJob j[6]; int n; };
+__global__ void k_zero(ZeroJobs jobs)
+{
+    for (int k = 0; k < jobs.n; ++k) {
+        uint4 *p = static_cast<uint4 *>(jobs.j[k].p);
+        const uint64_t n16 = jobs.j[k].bytes / 16;
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // per range boundary k: the first read that is NOT entirely inside warp tiles [0, tile_end[k]) and where it starts
 __global__ void k_plan_probe(const uint32_t *__restrict__ tile_first, const uint64_t *__restrict__ tile_end, int K, uint64_t R,
                              const int32_t *__restrict__ contig, const int32_t *__restrict__ rs, ProbeOut *__restrict__ out)
@@ -441,12 +454,14 @@ int build_plan(inq_ctx *ctx, uint64_t n_wt)
     pl.read_end[K] = R;
     std::vector<int64_t> done(K + 1, 0);
     done[K] = L;
-    if (K > 1 && R && L) {
+    if (R && L) {
         cudaStream_t s = ctx->stream;
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_tiles, pl.tile_end + 1, (K - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        k_plan_probe<<<1, 32, 0, s>>>(ctx->tile_first.p, ctx->d_probe_tiles, K - 1, R, ctx->contig.p, ctx->rs.p, ctx->d_probe);
-        CU_TRY(ctx, cudaGetLastError());
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_probe, ctx->d_probe, (K - 1) * sizeof(ProbeOut), cudaMemcpyDeviceToHost, s));
+        if (K > 1) {
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_tiles, pl.tile_end + 1, (K - 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            k_plan_probe<<<1, 32, 0, s>>>(ctx->tile_first.p, ctx->d_probe_tiles, K - 1, R, ctx->contig.p, ctx->rs.p, ctx->d_probe);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_probe, ctx->d_probe, (K - 1) * sizeof(ProbeOut), cudaMemcpyDeviceToHost, s));
+        }
         CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 8, ctx->d_unsorted, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(ctx, cudaStreamSynchronize(s));
         pl.reads_sorted = ctx->h_total[8] == 0;
@@ -467,9 +482,6 @@ int build_plan(inq_ctx *ctx, uint64_t n_wt)
             }
             done[k] = std::max(done[k - 1], std::min<int64_t>(d, L));
         }
-    } else if (K > 1) {
-        for (int k = 1; k < K; ++k) pl.read_end[k] = 0;
-        pl.read_end[K] = R;
     }
     // median chunks: the loci that became complete with pair(k - 1), cut into pieces so that the copy of one piece
     // runs under the medians of the next
@@ -519,14 +531,27 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
 
     // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
     CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_FORK], 0));
-    if (L) {
-        CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s1));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->seg_off.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s1));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((uint64_t)L + 1) * sizeof(unsigned long long), s1));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s1));
+    {
+        // (buffers come from cudaMalloc: 256-byte aligned; the sizes are rounded up to 16 bytes inside their capacity)
+        ZeroJobs z;
+        z.n = 0;
+        auto add = [&](void *p, uint64_t bytes, uint64_t cap_bytes) { if (p && bytes) z.j[z.n++] = ZeroJob{p, std::min((bytes + 15) / 16 * 16, cap_bytes / 16 * 16)}; };
+        uint64_t biggest = 0;
+        if (L) {
+            add(ctx->delta.p, ((uint64_t)L + 2) * sizeof(uint32_t), ctx->delta.cap * sizeof(uint32_t));
+            add(ctx->seg_off.p, ((uint64_t)L + 2) * sizeof(uint32_t), ctx->seg_off.cap * sizeof(uint32_t));
+            add(ctx->cursor.p, ((uint64_t)L + 1) * sizeof(unsigned long long), ctx->cursor.cap * sizeof(unsigned long long));
+            add(ctx->desc_scan.p, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), ctx->desc_scan.cap * sizeof(uint64_t));
+            biggest = ((uint64_t)L + 1) * sizeof(unsigned long long);
+        }
+        if (!ntiles) add(ctx->wt.p, 2 * sizeof(uint2), ctx->wt.cap * sizeof(uint2));      // no CIGAR words at all
+        if (n_wt) add(ctx->desc_wt.p, ctx->desc_wt.cap * sizeof(uint64_t), ctx->desc_wt.cap * sizeof(uint64_t));
+        if (z.n) {
+            const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((std::max<uint64_t>(biggest, 4096) / 16 + 255) / 256, (uint64_t)ctx->sm_count * 4));
+            k_zero<<<g, 256, 0, s1>>>(z);
+            CU_TRY(ctx, cudaGetLastError());
+        }
     }
-    if (!ntiles) CU_TRY(ctx, cudaMemsetAsync(ctx->wt.p, 0, 2 * sizeof(uint2), s1));      // no CIGAR words at all
-    if (n_wt) CU_TRY(ctx, cudaMemsetAsync(ctx->desc_wt.p, 0, ctx->desc_wt.cap * sizeof(uint64_t), s1));
     if (work) {
         k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
         const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
@@ -604,15 +629,18 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 waited = true;
             }
             if (c == 0) CU_TRY(ctx, stamp(EV_MED0, s2));
+            // S2 runs the warp-per-locus kernels of all chunks back to back; the CTA path for the (rare) deep loci of a
+            // chunk and the chunk's result copy follow on S3, so that neither drains the SMs between two chunks
             k_locus_median<<<(unsigned)(((uint64_t)(l1 - l0) * 32 + 255) / 256), 256, 0, s2>>>(l0, l1, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p,
                                                                                               ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
                                                                                               ctx->big_list.p, ctx->d_ctr);
-            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s2>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
-                                                                                  ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
-            launches += 2;
             CU_TRY(ctx, cudaGetLastError());
             CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
             CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
+            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s3>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
+                                                                                  ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+            launches += 2;
+            CU_TRY(ctx, cudaGetLastError());
             const size_t n = l1 - l0;
             CU_TRY(ctx, cudaMemcpyAsync(o1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
             CU_TRY(ctx, cudaMemcpyAsync(o2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
@@ -687,8 +715,11 @@ int inq_ctx_create(int device, inq_ctx **out)
     int prio_lo = 0, prio_hi = 0;
     if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return bail("cudaDeviceGetStreamPriorityRange", e);
     cudaStream_t *streams[4] = {&ctx->stream, &ctx->stream_join, &ctx->stream_med, &ctx->stream_copy};
+#ifndef INQ_STREAM_PRIORITIES
+#define INQ_STREAM_PRIORITIES 0       // measured: with priorities the join (S1) is starved under the scan and the pair kernel starts ~55 us later
+#endif
     for (int i = 0; i < 4; ++i)
-        if ((e = cudaStreamCreateWithPriority(streams[i], cudaStreamNonBlocking, i == 0 ? prio_hi : prio_lo)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(streams[i], cudaStreamNonBlocking, (INQ_STREAM_PRIORITIES && i != 0) ? prio_lo : prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < EV_COUNT; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < DEP_COUNT; ++i)
@@ -810,12 +841,12 @@ int inq_set_loci(inq_ctx *ctx, int32_t n_contigs, const int64_t *contig_locus_of
     TRY(ensure(ctx, ctx->lstart, (uint64_t)L));
     TRY(ensure(ctx, ctx->lend, (uint64_t)L));
     TRY(ensure(ctx, ctx->lpmax, (uint64_t)L));
-    TRY(ensure(ctx, ctx->delta, (uint64_t)L + 2));
+    TRY(ensure(ctx, ctx->delta, (uint64_t)L + 2 + 4));            // (+ slack: k_zero clears in 16-byte units)
     TRY(ensure(ctx, ctx->lcnt, (uint64_t)L + 3));
-    TRY(ensure(ctx, ctx->seg_off, (uint64_t)L + 2));
-    TRY(ensure(ctx, ctx->cursor, (uint64_t)L + 1));
+    TRY(ensure(ctx, ctx->seg_off, (uint64_t)L + 2 + 4));
+    TRY(ensure(ctx, ctx->cursor, (uint64_t)L + 1 + 2));
     TRY(ensure(ctx, ctx->big_list, (uint64_t)L + 1));
-    TRY(ensure(ctx, ctx->desc_scan, 2 * (((uint64_t)L + 2 + kXsTile - 1) / kXsTile + 1)));
+    TRY(ensure(ctx, ctx->desc_scan, 2 * (((uint64_t)L + 2 + kXsTile - 1) / kXsTile + 1) + 2));
     TRY(ensure(ctx, ctx->t1, (uint64_t)L));
     TRY(ensure(ctx, ctx->t2, (uint64_t)L));
     TRY(ensure(ctx, ctx->valid, (uint64_t)L));
@@ -1077,7 +1108,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     TRY(ensure(ctx, ctx->wt, n_wt + 2));
     TRY(ensure(ctx, ctx->wtot, n_wt + 2));
     TRY(ensure(ctx, ctx->wt_sbase, n_wt + 1));
-    TRY(ensure(ctx, ctx->desc_wt, 2 * ((n_wt + kXsTile - 1) / kXsTile + 2 * kMaxRanges + 1)));
+    TRY(ensure(ctx, ctx->desc_wt, 2 * ((n_wt + kXsTile - 1) / kXsTile + 2 * kMaxRanges + 1)));       // even: k_zero clears it in 16-byte units
     if (ntiles) TRY(make_tensor_map(ctx, (uint64_t)ntiles * kTileWords));
     const uint64_t raw_slack = (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm * kScanWarps * kEvChunk;
     // event storage is sized speculatively (1/16 of the words; checked and regrown after the run); it hands out
@@ -1151,7 +1182,13 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         }
         ctx->last_key = key;
         ctx->have_last_key = true;
-        CU_TRY(ctx, cudaStreamSynchronize(s));
+        {
+            // a blocking synchronize wakes the host tens of microseconds late; a pass takes 0.1 - 3 ms, so poll first
+            cudaError_t q = cudaErrorNotReady;
+            for (int spin = 0; spin < 200000 && (q = cudaStreamQuery(s)) == cudaErrorNotReady; ++spin) {}
+            if (q != cudaSuccess && q != cudaErrorNotReady) CU_TRY(ctx, q);
+            CU_TRY(ctx, cudaStreamSynchronize(s));
+        }
 
         const unsigned f = ctx->h_ctr->flags;
         bool retry = false;

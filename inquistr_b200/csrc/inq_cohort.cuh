@@ -246,6 +246,134 @@ k_outlier_zscore_rows(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
         if (s_base + k < cap) hits[s_base + k] = s_hits[k];
 }
 
+// ---------------------------------------------------------------------------------------------- z-score, warp-autonomous
+// The order-dependent sums are one lane per row, so every lane of every warp has to own a row for the SM to be busy:
+// each warp is its own pipeline over groups of 32 consecutive rows. Lane k issues ONE bulk async copy (TMA,
+// cp.async.bulk) of row k into the warp's private slab and the warp waits on its own mbarrier -- no registers and
+// no issue slots are spent on the copy, and while one warp of the SM waits for its rows the others add. The rows
+// sit `stride` words apart with stride = 4 * odd, which makes the per-lane LDS.128 of the two sequential passes
+// conflict-free (8 lanes x 16 bytes hit 8 different 4-bank groups); the flag pass reads row-major. Outliers are
+// buffered per warp and leave with one global atomic per group. The matrix is read from HBM exactly once.
+// Needs n_cols % 4 == 0 (16-byte aligned rows) -- other shapes take k_outlier_zscore_rows.
+constexpr int kZwHitBuf = 512;            // per warp and group of 32 rows
+constexpr int kZwMaxWarps = 16;
+
+__device__ __forceinline__ uint32_t zw_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__host__ __device__ inline uint32_t zw_stride(uint32_t n_cols) { return ((n_cols / 4) & 1u) ? n_cols : n_cols + 4; }
+__host__ __device__ inline size_t zw_warp_bytes(uint32_t n_cols) { return (size_t)32 * zw_stride(n_cols) * 4 + (size_t)kZwHitBuf * 8; }
+
+__global__ void __launch_bounds__(kZwMaxWarps * 32, 1)
+k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, float minsize, float cutoff,
+                      uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits, uint64_t cap,
+                      CohortCounters *__restrict__ ctr)
+{
+    extern __shared__ __align__(128) unsigned char zw_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t stride = zw_stride(n_cols);
+    float *rows = reinterpret_cast<float *>(zw_smem + (size_t)warp * zw_warp_bytes(n_cols));
+    unsigned long long *hbuf = reinterpret_cast<unsigned long long *>(rows + 32 * stride);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(zw_smem + (size_t)nwarps * zw_warp_bytes(n_cols)) + warp;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zw_smem_u32(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t n_groups = (n_rows + 31) / 32;
+    const uint32_t row_bytes = n_cols * 4u;
+    const float count = (float)n_cols;
+    const float margin = fabsf(cutoff) * 1e-5f + 1e-30f;
+    uint32_t parity = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * nwarps + warp; g < n_groups; g += (uint64_t)gridDim.x * nwarps) {
+        const uint64_t row0 = g * 32;
+        const uint32_t nr = (uint32_t)min((uint64_t)32, n_rows - row0);
+        // ---- rows in: one bulk copy per lane, all on the warp's mbarrier
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zw_smem_u32(bar)), "r"(nr * row_bytes) : "memory");
+        __syncwarp();
+        if (lane < nr)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(zw_smem_u32(rows + lane * stride)), "l"(m + (row0 + lane) * n_cols), "r"(row_bytes), "r"(zw_smem_u32(bar))
+                         : "memory");
+        {
+            uint32_t done = 0;
+            while (true) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(zw_smem_u32(bar)), "r"(parity) : "memory");
+                if (done) break;
+                __nanosleep(64);
+            }
+            parity ^= 1u;
+        }
+        // ---- one lane per row: sequential f32 sum + max, then the population variance (outlier.rs:18-31,81-90)
+        float mean = 0.0f, sd = 0.0f, rinv = 0.0f;
+        bool kept = false;
+        if (lane < nr) {
+            const float4 *row4 = reinterpret_cast<const float4 *>(rows + lane * stride);
+            float sum = 0.0f, mx = -INFINITY;
+#pragma unroll 4
+            for (uint32_t c = 0; c < n_cols / 4; ++c) {
+                const float4 v = row4[c];
+                const float a = clean(v.x), b = clean(v.y), d = clean(v.z), e = clean(v.w);     // NaN -> 0
+                sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, a), b), d), e);
+                mx = fmaxf(fmaxf(mx, fmaxf(a, b)), fmaxf(d, e));
+            }
+            mean = __fdiv_rn(sum, count);
+            float var = 0.0f;
+#pragma unroll 4
+            for (uint32_t c = 0; c < n_cols / 4; ++c) {
+                const float4 v = row4[c];
+                const float da = __fsub_rn(mean, clean(v.x)), db = __fsub_rn(mean, clean(v.y));
+                const float dc = __fsub_rn(mean, clean(v.z)), dd = __fsub_rn(mean, clean(v.w));
+                var = __fadd_rn(var, __fmul_rn(da, da));
+                var = __fadd_rn(var, __fmul_rn(db, db));
+                var = __fadd_rn(var, __fmul_rn(dc, dc));
+                var = __fadd_rn(var, __fmul_rn(dd, dd));
+            }
+            sd = __fsqrt_rn(__fdiv_rn(var, count));
+            rinv = __frcp_rn(sd);
+            kept = !(mx < minsize);
+            if (row_kept) row_kept[row0 + lane] = kept ? 1 : 0;
+        }
+        // ---- flags, element-parallel and row-major (outlier.rs:99-113)
+        const uint32_t kept_b = __ballot_sync(0xffffffffu, kept);
+        uint32_t nh = 0;                                          // warp-uniform
+        for (uint32_t r = 0; r < nr; ++r) {
+            const float mean_r = __shfl_sync(0xffffffffu, mean, r), sd_r = __shfl_sync(0xffffffffu, sd, r);
+            const float rinv_r = __shfl_sync(0xffffffffu, rinv, r);
+            if (!((kept_b >> r) & 1u)) continue;
+            const float *row = rows + r * stride;
+            for (uint32_t c0 = 0; c0 < n_cols; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                const bool hit = c < n_cols && z_at_least(__fsub_rn(clean(row[c]), mean_r), sd_r, rinv_r, cutoff, margin);
+                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                if (!hb) continue;
+                if (hit) {
+                    const uint32_t k = nh + __popc(hb & ((1u << lane) - 1u));
+                    const unsigned long long h = ((row0 + r) << 32) | c;
+                    if (k < (uint32_t)kZwHitBuf) hbuf[k] = h;
+                    else {
+                        const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                        if (slot < cap) hits[slot] = h;
+                    }
+                }
+                nh += __popc(hb);
+            }
+        }
+        __syncwarp();
+        const uint32_t nbuf = min(nh, (uint32_t)kZwHitBuf);
+        if (nbuf) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->n_hits, (unsigned long long)nbuf);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t k = lane; k < nbuf; k += 32)
+                if (base + k < cap) hits[base + k] = hbuf[k];
+        }
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the slab is refilled by the async proxy next
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- dbscan
 constexpr int kDbThreads = 128;
 
@@ -283,29 +411,44 @@ __device__ __forceinline__ void eps_range(const float *key, uint32_t n, uint32_t
     *hi = a;
 }
 
-// one CTA per row. Shared memory: key[n2] f32, idx[n2] u16, pc[n2 + 1] u32 (prefix count of core points)
+// one CTA per row. Shared memory: skey[n] u64 (sort keys), key[n] f32, pc[n + 1] u32 (prefix count of core points),
+// idx[n] u16. The sort is an all-ascending bitonic network over the next power of two with VIRTUAL +inf padding:
+// a comparator whose upper end lies at or beyond n is a no-op, so only the ~n/2 real comparators of a stage are
+// enumerated (536 columns cost 268 compare-exchanges per stage, not 512), on one packed 64-bit key
+// (order-preserving image of the f32 value << 32 | column).
+__device__ __forceinline__ uint32_t f32_orderable(float v)
+{
+    const uint32_t u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t o)
+{
+    return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
 __global__ void __launch_bounds__(kDbThreads)
 k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, uint32_t n2, float minsize,
                  uint32_t min_points, uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits,
                  uint64_t cap, CohortCounters *__restrict__ ctr)
 {
-    extern __shared__ unsigned char db_smem[];
-    float *key = reinterpret_cast<float *>(db_smem);
-    uint32_t *pc = reinterpret_cast<uint32_t *>(key + n2);
-    uint16_t *idx = reinterpret_cast<uint16_t *>(pc + n2 + 1);
+    extern __shared__ __align__(8) unsigned char db_smem[];
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(db_smem);
+    float *key = reinterpret_cast<float *>(skey + n_cols);
+    uint32_t *pc = reinterpret_cast<uint32_t *>(key + n_cols);
+    uint16_t *idx = reinterpret_cast<uint16_t *>(pc + n_cols + 1);
     __shared__ uint32_t s_warp[kDbThreads / 32];
     __shared__ float s_wmax[kDbThreads / 32];
     __shared__ unsigned long long s_best;
     const uint32_t tid = threadIdx.x;
+    const uint32_t n = n_cols;
     for (uint64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
         __syncthreads();
         if (tid == 0) s_best = 0ull;
         float mx = -INFINITY;
-        for (uint32_t i = tid; i < n2; i += blockDim.x) {
-            float v = INFINITY;                              // padding sorts last
-            if (i < n_cols) { v = clean(m[row * n_cols + i]); mx = (v > mx) ? v : mx; }
-            key[i] = v;
-            idx[i] = (uint16_t)i;
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            const float v = clean(m[row * n_cols + i]);
+            mx = (v > mx) ? v : mx;
+            skey[i] = ((unsigned long long)f32_orderable(v) << 32) | i;
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) { const float o = __shfl_xor_sync(0xffffffffu, mx, d); mx = (o > mx) ? o : mx; }
@@ -317,22 +460,39 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
         if (tid == 0 && row_kept) row_kept[row] = kept ? 1 : 0;
         if (!kept) continue;
 
-        // ---- bitonic sort by value, carrying the column index
-        for (uint32_t k = 2; k <= n2; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                __syncthreads();
-                for (uint32_t i = tid; i < n2; i += blockDim.x) {
-                    const uint32_t p = i ^ j;
-                    if (p > i) {
-                        const bool up = (i & k) == 0;
-                        const float a = key[i], b = key[p];
-                        if ((a > b) == up) {
-                            key[i] = b; key[p] = a;
-                            const uint16_t t = idx[i]; idx[i] = idx[p]; idx[p] = t;
-                        }
+        // ---- sort by (value, column)
+        for (uint32_t blk = 2; blk <= n2; blk <<= 1) {
+            // mirror step: comparator q of the stage joins i = (q / h) * blk + q % h with j = i ^ (blk - 1), h = blk / 2
+            {
+                const uint32_t h = blk >> 1;
+                for (uint32_t q = tid;; q += blockDim.x) {
+                    const uint32_t i = (q / h) * blk + (q & (h - 1));
+                    if (i >= n) break;
+                    const uint32_t j = i ^ (blk - 1);
+                    if (j < n) {
+                        const unsigned long long a = skey[i], b = skey[j];
+                        if (a > b) { skey[i] = b; skey[j] = a; }
                     }
                 }
+                __syncthreads();
             }
+            for (uint32_t d = blk >> 2; d >= 1; d >>= 1) {
+                for (uint32_t q = tid;; q += blockDim.x) {
+                    const uint32_t i = ((q / d) * 2 * d) + (q & (d - 1));
+                    if (i >= n) break;
+                    const uint32_t j = i + d;
+                    if (j < n) {
+                        const unsigned long long a = skey[i], b = skey[j];
+                        if (a > b) { skey[i] = b; skey[j] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            const unsigned long long k = skey[i];
+            key[i] = f32_from_orderable((uint32_t)(k >> 32));
+            idx[i] = (uint16_t)(k & 0xFFFFu);
         }
         __syncthreads();
 
@@ -378,27 +538,27 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
 
         // ---- core points: |x_i - x_j| < eps in f64 (dbscan's euclidean distance), j over the whole row
         __syncthreads();
-        for (uint32_t i = tid; i < n2; i += blockDim.x) {
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
             uint32_t lo = 0, hi = 0;
-            if (i < n_cols) eps_range(key, n_cols, i, eps, &lo, &hi);
-            pc[i] = (i < n_cols && hi - lo >= min_points) ? 1u : 0u;
+            eps_range(key, n_cols, i, eps, &lo, &hi);
+            pc[i] = (hi - lo >= min_points) ? 1u : 0u;
         }
         __syncthreads();
         // exclusive prefix count of core points over the sorted order: chunked block scan
         uint32_t carry = 0;
-        for (uint32_t base = 0; base < n2; base += blockDim.x) {
+        for (uint32_t base = 0; base < n; base += blockDim.x) {
             const uint32_t i = base + tid;
-            const uint32_t v = i < n2 ? pc[i] : 0u;
+            const uint32_t v = i < n ? pc[i] : 0u;
             uint32_t tot;
             const uint32_t ex = block_scan_excl(v, s_warp, &tot);
-            if (i < n2) pc[i] = carry + ex;
+            if (i < n) pc[i] = carry + ex;
             carry += tot;
         }
-        if (tid == 0) pc[n2] = carry;
+        if (tid == 0) pc[n] = carry;
         __syncthreads();
         // ---- noise = not core and no core point within eps (Edge otherwise)
         //      (flags first, then one global atomic per row reserves the slots of all its outliers)
-        uint32_t mine = 0, nmine = 0;                        // bit q: element tid + q * blockDim.x is noise (n2 <= 4096 -> q < 32)
+        uint32_t mine = 0, nmine = 0;                        // bit q: element tid + q * blockDim.x is noise (n <= 4096 -> q < 32)
         for (uint32_t i = tid, q = 0; i < n_cols; i += blockDim.x, ++q) {
             uint32_t lo, hi;
             eps_range(key, n_cols, i, eps, &lo, &hi);

@@ -80,7 +80,20 @@ int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const 
     if (method == INQ_OUTLIER_ZSCORE) {
         const uint32_t stride = n_cols | 1u;
         const size_t res_smem = (size_t)kZResRows * stride * sizeof(float);
-        if (res_smem <= 200u * 1024u) {
+        int sms = 0, smem_max = 0;
+        CC_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CC_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        const size_t per_warp = zw_warp_bytes(n_cols);
+        const int zw_warps = (int)std::min<size_t>(kZwMaxWarps, ((size_t)smem_max - 256) / per_warp);
+        if (n_cols % 4 == 0 && zw_warps >= 2) {
+            // every warp its own pipeline over groups of 32 rows (bulk async copies, one lane per row)
+            const size_t smem = (size_t)zw_warps * per_warp + (size_t)zw_warps * 8 + 128;
+            CC_TRY(cudaFuncSetAttribute(k_outlier_zscore_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint64_t groups = (n_rows + 31) / 32;
+            const unsigned grid = (unsigned)std::min<uint64_t>((groups + zw_warps - 1) / zw_warps, (uint64_t)sms);
+            k_outlier_zscore_warp<<<grid, zw_warps * 32, smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, (float)minsize, zscore_cutoff,
+                                                                     (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+        } else if (res_smem <= 200u * 1024u) {
             // 32 rows fit in shared memory: the matrix is read once
             CC_TRY(cudaFuncSetAttribute(k_outlier_zscore_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
             const unsigned grid = (unsigned)((n_rows + kZResRows - 1) / kZResRows);
@@ -94,7 +107,7 @@ int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const 
     } else {
         uint32_t n2 = 32;
         while (n2 < n_cols) n2 <<= 1;
-        const size_t smem = (size_t)n2 * (sizeof(float) + sizeof(uint32_t) + sizeof(uint16_t)) + sizeof(uint32_t);
+        const size_t smem = (size_t)n_cols * (sizeof(uint64_t) + sizeof(float) + sizeof(uint32_t) + sizeof(uint16_t)) + sizeof(uint32_t) + 16;
         uint32_t min_points = 0;                              // samples.len().ilog2(), outlier.rs:39
         while ((2ull << min_points) <= n_cols) ++min_points;
         int sms = 0;
