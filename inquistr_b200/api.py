@@ -8,7 +8,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libinqcall.so")
+_LIB_PATH = os.environ.get("INQ_LIB") or os.path.join(_HERE, "lib", "libinqcall.so")     # INQ_LIB: tools/ sweeps over library variants
 _LIB = None
 
 INQ_OK = 0
@@ -233,6 +233,16 @@ class Context:
         self._check(self._lib.inq_genotype(self._h, int(minlen), int(support), int(bool(unphased)),
                                            t1.ctypes.data, t2.ctypes.data, vm.ctypes.data, C.byref(st)))
         return GenotypeResult(t1, t2, vm, st.as_dict())
+
+    def genotype_fn(self, minlen, support, unphased, out):
+        """Pre-bound inq_genotype call for tight loops (bench.py): returns (call, stats) where call() runs one pass
+        into the `out` arrays and returns the error code, and stats is the ctypes struct it fills."""
+        t1, t2, vm = out
+        st = Stats()
+        fn, h = self._lib.inq_genotype, self._h
+        a = (h, C.c_uint32(int(minlen)), C.c_uint32(int(support)), C.c_int(int(bool(unphased))), C.c_void_p(t1.ctypes.data),
+             C.c_void_p(t2.ctypes.data), C.c_void_p(vm.ctypes.data), C.byref(st))
+        return (lambda: fn(*a)), st
 
     def debug_events(self):
         n = C.c_uint64(0)

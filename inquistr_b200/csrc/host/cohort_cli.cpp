@@ -198,15 +198,38 @@ int outlier_main(const std::vector<std::string> &v, int device)
     std::vector<std::string> keys;                       // "chrom\tbegin\tend"
     std::vector<uint64_t> hits;
     auto flush = [&]() {
-        const uint64_t rows = keys.size();
+        uint64_t rows = keys.size();
         if (!rows) return;
         uint64_t n_hits = 0;
         if (hits.size() < 1024) hits.resize(1024);
         int rc;
-        while ((rc = inq_outlier(device, meth, rows, n_cols, values.data(), (uint32_t)minsize, zscore, nullptr, &n_hits,
-                                 hits.data(), hits.size(), nullptr)) == INQ_ERR_HITS_CAP)
-            hits.resize(n_hits);
-        if (rc == INQ_ERR_NO_MODE) cpanic(std::string("No mode found for repeat (") + inq_cohort_last_error() + ")");   // outlier.rs:144
+        std::string no_mode;
+        for (;;) {
+            while ((rc = inq_outlier(device, meth, rows, n_cols, values.data(), (uint32_t)minsize, zscore, nullptr, &n_hits,
+                                     hits.data(), hits.size(), nullptr)) == INQ_ERR_HITS_CAP)
+                hits.resize(n_hits);
+            if (rc != INQ_ERR_NO_MODE || !no_mode.empty()) break;
+            // The reference streams row by row: the rows before the one without a mode have been printed when it panics
+            // (outlier.rs:144). The message names a row without a mode; the batch is cut at the FIRST one.
+            no_mode = inq_cohort_last_error();
+            const size_t at = no_mode.find("row ");
+            uint64_t bad = at == std::string::npos ? 0 : strtoull(no_mode.c_str() + at + 4, nullptr, 10);
+            // rows are independent: find the first bad row by re-running ever shorter prefixes (rare path)
+            while (bad > 0) {
+                uint64_t nh = 0;
+                const int r2 = inq_outlier(device, meth, bad, n_cols, values.data(), (uint32_t)minsize, zscore, nullptr, &nh, hits.data(), 0, nullptr);
+                if (r2 != INQ_ERR_NO_MODE) break;
+                const std::string m2 = inq_cohort_last_error();
+                const size_t a2 = m2.find("row ");
+                const uint64_t b2 = a2 == std::string::npos ? 0 : strtoull(m2.c_str() + a2 + 4, nullptr, 10);
+                if (b2 >= bad) break;
+                bad = b2;
+            }
+            rows = bad;
+            if (!rows) break;
+        }
+        if (rc == INQ_ERR_NO_MODE) cpanic(std::string("No mode found for repeat (") + no_mode + ")");          // the first row of the batch
+        if (rc != INQ_OK) { fprintf(stderr, "inquistr-b200: %s\n", inq_cohort_last_error()); exit(1); }
         if (rc != INQ_OK) { fprintf(stderr, "inquistr-b200: %s\n", inq_cohort_last_error()); exit(1); }
         std::string out;
         for (uint64_t i = 0; i < n_hits;) {
@@ -225,18 +248,21 @@ int outlier_main(const std::vector<std::string> &v, int device)
             if (wanted) fwrite(out.data(), 1, out.size(), stdout);
             i = j;
         }
+        if (!no_mode.empty()) { fflush(stdout); cpanic(std::string("No mode found for repeat (") + no_mode + ")"); }   // outlier.rs:144
         values.clear();
         keys.clear();
     };
     while (rd.next(line)) {
         split_tabs(line, cols);
-        if (cols.size() < 3) cpanic("index out of bounds: the len is " + std::to_string(cols.size()) + " but the index is 2");
-        if (cols.size() - 3 > n_cols) cpanic("index out of bounds: more values than samples in the header");
+        // the reference prints row by row, so everything before a row it panics on is already out: flush first
+        auto die = [&](const std::string &msg) { values.resize(keys.size() * (size_t)n_cols); flush(); fflush(stdout); cpanic(msg); };
+        if (cols.size() < 3) die("index out of bounds: the len is " + std::to_string(cols.size()) + " but the index is 2");
+        if (cols.size() - 3 > n_cols) die("index out of bounds: more values than samples in the header");
         if (cols.size() - 3 < n_cols)
-            cpanic("row '" + cols[0] + "\t" + cols[1] + "\t" + cols[2] + "' has fewer values than the header has samples (this build needs a rectangular matrix)");
+            die("row '" + cols[0] + "\t" + cols[1] + "\t" + cols[2] + "' has fewer values than the header has samples (this build needs a rectangular matrix)");
         for (uint32_t c = 0; c < n_cols; ++c) {
             float f;
-            if (!parse_f32(cols[3 + c], &f)) cpanic("Failed to parse number: ParseFloatError { kind: Invalid }");   // outlier.rs:79
+            if (!parse_f32(cols[3 + c], &f)) die("Failed to parse number: ParseFloatError { kind: Invalid }");   // outlier.rs:79
             values.push_back(f);
         }
         keys.push_back(cols[0] + "\t" + cols[1] + "\t" + cols[2]);

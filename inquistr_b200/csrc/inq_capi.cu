@@ -24,6 +24,17 @@
 
 using namespace inq;
 
+// shape of the pass (compile-time; the defaults are what the sweeps in profiles/README.md picked)
+#ifndef INQ_STREAM_PRIORITIES
+#define INQ_STREAM_PRIORITIES 1       // bit i: stream Si is high priority
+#endif
+#ifndef INQ_SCAN_FIRST
+#define INQ_SCAN_FIRST 0              // 1: enqueue the scan kernels before the join chain
+#endif
+#ifndef INQ_BIG_ON_S3
+#define INQ_BIG_ON_S3 0               // 1: CTA-path medians run on the copy stream instead of between two chunks
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -529,64 +540,74 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     CU_TRY(ctx, stamp(EV_START, s0));
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));
 
-    // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
-    CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_FORK], 0));
-    {
-        // (buffers come from cudaMalloc: 256-byte aligned; the sizes are rounded up to 16 bytes inside their capacity)
-        ZeroJobs z;
-        z.n = 0;
-        auto add = [&](void *p, uint64_t bytes, uint64_t cap_bytes) { if (p && bytes) z.j[z.n++] = ZeroJob{p, std::min((bytes + 15) / 16 * 16, cap_bytes / 16 * 16)}; };
-        uint64_t biggest = 0;
-        if (L) {
-            add(ctx->delta.p, ((uint64_t)L + 2) * sizeof(uint32_t), ctx->delta.cap * sizeof(uint32_t));
-            add(ctx->seg_off.p, ((uint64_t)L + 2) * sizeof(uint32_t), ctx->seg_off.cap * sizeof(uint32_t));
-            add(ctx->cursor.p, ((uint64_t)L + 1) * sizeof(unsigned long long), ctx->cursor.cap * sizeof(unsigned long long));
-            add(ctx->desc_scan.p, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), ctx->desc_scan.cap * sizeof(uint64_t));
-            biggest = ((uint64_t)L + 1) * sizeof(unsigned long long);
+    auto enqueue_join = [&]() -> int {
+        // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
+        CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_FORK], 0));
+        {
+            // (buffers come from cudaMalloc: 256-byte aligned; the sizes are rounded up to 16 bytes inside their capacity)
+            ZeroJobs z;
+            z.n = 0;
+            auto add = [&](void *p, uint64_t bytes, uint64_t cap_bytes) { if (p && bytes) z.j[z.n++] = ZeroJob{p, std::min((bytes + 15) / 16 * 16, cap_bytes / 16 * 16)}; };
+            uint64_t biggest = 0;
+            if (L) {
+                add(ctx->delta.p, ((uint64_t)L + 2) * sizeof(uint32_t), ctx->delta.cap * sizeof(uint32_t));
+                add(ctx->seg_off.p, ((uint64_t)L + 2) * sizeof(uint32_t), ctx->seg_off.cap * sizeof(uint32_t));
+                add(ctx->cursor.p, ((uint64_t)L + 1) * sizeof(unsigned long long), ctx->cursor.cap * sizeof(unsigned long long));
+                add(ctx->desc_scan.p, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), ctx->desc_scan.cap * sizeof(uint64_t));
+                biggest = ((uint64_t)L + 1) * sizeof(unsigned long long);
+            }
+            if (!ntiles) add(ctx->wt.p, 2 * sizeof(uint2), ctx->wt.cap * sizeof(uint2));      // no CIGAR words at all
+            if (n_wt) add(ctx->desc_wt.p, ctx->desc_wt.cap * sizeof(uint64_t), ctx->desc_wt.cap * sizeof(uint64_t));
+            if (z.n) {
+                const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((std::max<uint64_t>(biggest, 4096) / 16 + 255) / 256, (uint64_t)ctx->sm_count * 4));
+                k_zero<<<g, 256, 0, s1>>>(z);
+                CU_TRY(ctx, cudaGetLastError());
+            }
         }
-        if (!ntiles) add(ctx->wt.p, 2 * sizeof(uint2), ctx->wt.cap * sizeof(uint2));      // no CIGAR words at all
-        if (n_wt) add(ctx->desc_wt.p, ctx->desc_wt.cap * sizeof(uint64_t), ctx->desc_wt.cap * sizeof(uint64_t));
-        if (z.n) {
-            const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((std::max<uint64_t>(biggest, 4096) / 16 + 255) / 256, (uint64_t)ctx->sm_count * 4));
-            k_zero<<<g, 256, 0, s1>>>(z);
+        if (work) {
+            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+            const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
+            // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
+            k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
+                                                       &ctx->d_ctr->scan_counter[2], nullptr);
+            k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->lcnt.p + 1, ctx->seg_off.p, (uint64_t)L, loc_scan_tiles,
+                                                       ctx->desc_scan.p + loc_scan_tiles + 1, &ctx->d_ctr->scan_counter[3], &ctx->d_ctr->flags);
+            launches += 3;
             CU_TRY(ctx, cudaGetLastError());
+            // the call buffer holds one slot per candidate; its size is only known on the device (checked after the pass)
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s1));
         }
-    }
-    if (work) {
-        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
-        const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
-        // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
-        k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
-                                                   &ctx->d_ctr->scan_counter[2], nullptr);
-        k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->lcnt.p + 1, ctx->seg_off.p, (uint64_t)L, loc_scan_tiles,
-                                                   ctx->desc_scan.p + loc_scan_tiles + 1, &ctx->d_ctr->scan_counter[3], &ctx->d_ctr->flags);
-        launches += 3;
-        CU_TRY(ctx, cudaGetLastError());
-        // the call buffer holds one slot per candidate; its size is only known on the device (checked after the pass)
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s1));
-    }
-    CU_TRY(ctx, stamp(EV_JOIN, s1));
+        CU_TRY(ctx, stamp(EV_JOIN, s1));
 
-    // ---- S0: K2, range after range, nothing in between (the scan of a range depends on nothing but the reads)
-    for (int k = 0; k < pl.K; ++k) {
-        const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
-        CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k, s0));
-        if (t1 > t0 && L) {
-            ScanParams sp;
-            sp.tile_first = ctx->tile_first.p; sp.cig_off = ctx->cig_off.p; sp.rd_pre = ctx->rd_pre.p; sp.wt = ctx->wtot.p;
-            sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
-            sp.wt_begin = t0; sp.n_wt = t1; sp.neg1 = 0xFFFFFFFFu;
-            sp.thr = (std::min<uint32_t>(rp.minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
-            sp.debug = ctx->scan_debug;
-            const unsigned grid = (unsigned)std::min<uint64_t>((t1 - t0 + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
-            if (sp.thr >> 31) k_cigar_scan<true><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
-            else k_cigar_scan<false><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
-            ++launches;
-            CU_TRY(ctx, cudaGetLastError());
+        return INQ_OK;
+    };
+    auto enqueue_scans = [&]() -> int {
+        // ---- S0: K2, range after range, nothing in between (the scan of a range depends on nothing but the reads)
+        for (int k = 0; k < pl.K; ++k) {
+            const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
+            CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k, s0));
+            if (t1 > t0 && L) {
+                ScanParams sp;
+                sp.tile_first = ctx->tile_first.p; sp.cig_off = ctx->cig_off.p; sp.rd_pre = ctx->rd_pre.p; sp.wt = ctx->wtot.p;
+                sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
+                sp.wt_begin = t0; sp.n_wt = t1; sp.neg1 = 0xFFFFFFFFu;
+                sp.thr = (std::min<uint32_t>(rp.minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
+                sp.debug = ctx->scan_debug;
+                const unsigned grid = (unsigned)std::min<uint64_t>((t1 - t0 + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
+                if (sp.thr >> 31) k_cigar_scan<true><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
+                else k_cigar_scan<false><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
+                ++launches;
+                CU_TRY(ctx, cudaGetLastError());
+            }
+            CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0));
+            CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
         }
-        CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0));
-        CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
-    }
+
+        return INQ_OK;
+    };
+    // which of the two is enqueued first decides whose CTAs the SMs see first
+    if (INQ_SCAN_FIRST) { TRY(enqueue_scans()); TRY(enqueue_join()); }
+    else { TRY(enqueue_join()); TRY(enqueue_scans()); }
 
     // ---- S1: prefix sum over the range's warp-tile totals, then K2b ; S2: K3 per finished catalog chunk ; S3: result copies
     int c = 0;
@@ -629,18 +650,24 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 waited = true;
             }
             if (c == 0) CU_TRY(ctx, stamp(EV_MED0, s2));
-            // S2 runs the warp-per-locus kernels of all chunks back to back; the CTA path for the (rare) deep loci of a
-            // chunk and the chunk's result copy follow on S3, so that neither drains the SMs between two chunks
             k_locus_median<<<(unsigned)(((uint64_t)(l1 - l0) * 32 + 255) / 256), 256, 0, s2>>>(l0, l1, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p,
                                                                                               ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
                                                                                               ctx->big_list.p, ctx->d_ctr);
             CU_TRY(ctx, cudaGetLastError());
-            CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
-            CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
-            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, s3>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
+            // the CTA path for the (rare) deep loci of the chunk: between two chunks on S2, or on the copy stream
+            cudaStream_t sb = INQ_BIG_ON_S3 ? s3 : s2;
+            if (INQ_BIG_ON_S3) {
+                CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
+                CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
+            }
+            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, sb>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
                                                                                   ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
             launches += 2;
             CU_TRY(ctx, cudaGetLastError());
+            if (!INQ_BIG_ON_S3) {
+                CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
+                CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
+            }
             const size_t n = l1 - l0;
             CU_TRY(ctx, cudaMemcpyAsync(o1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
             CU_TRY(ctx, cudaMemcpyAsync(o2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
@@ -715,11 +742,11 @@ int inq_ctx_create(int device, inq_ctx **out)
     int prio_lo = 0, prio_hi = 0;
     if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return bail("cudaDeviceGetStreamPriorityRange", e);
     cudaStream_t *streams[4] = {&ctx->stream, &ctx->stream_join, &ctx->stream_med, &ctx->stream_copy};
-#ifndef INQ_STREAM_PRIORITIES
-#define INQ_STREAM_PRIORITIES 0       // measured: with priorities the join (S1) is starved under the scan and the pair kernel starts ~55 us later
-#endif
-    for (int i = 0; i < 4; ++i)
-        if ((e = cudaStreamCreateWithPriority(streams[i], cudaStreamNonBlocking, (INQ_STREAM_PRIORITIES && i != 0) ? prio_lo : prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < 4; ++i) {
+        // INQ_STREAM_PRIORITIES bit i: stream Si gets the high priority (default: only the scan stream S0)
+        const bool hi = (INQ_STREAM_PRIORITIES >> i) & 1;
+        if ((e = cudaStreamCreateWithPriority(streams[i], cudaStreamNonBlocking, hi ? prio_hi : prio_lo)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
     for (int i = 0; i < EV_COUNT; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < DEP_COUNT; ++i)

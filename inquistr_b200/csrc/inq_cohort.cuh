@@ -266,8 +266,11 @@ __host__ __device__ inline size_t zw_warp_bytes(uint32_t n_cols) { return (size_
 __global__ void __launch_bounds__(kZwMaxWarps * 32, 1)
 k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, float minsize, float cutoff,
                       uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits, uint64_t cap,
-                      CohortCounters *__restrict__ ctr)
+                      CohortCounters *__restrict__ ctr, uint32_t dbg)
 {
+#ifndef INQ_TIMING_EXPERIMENTS
+    dbg = 0;                                                  // timing experiments only exist in -DINQ_TIMING_EXPERIMENTS builds
+#endif
     extern __shared__ __align__(128) unsigned char zw_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t stride = zw_stride(n_cols);
@@ -308,7 +311,7 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
         // ---- one lane per row: sequential f32 sum + max, then the population variance (outlier.rs:18-31,81-90)
         float mean = 0.0f, sd = 0.0f, rinv = 0.0f;
         bool kept = false;
-        if (lane < nr) {
+        if (lane < nr && !(dbg & 2u)) {
             const float4 *row4 = reinterpret_cast<const float4 *>(rows + lane * stride);
             float sum = 0.0f, mx = -INFINITY;
 #pragma unroll 4
@@ -335,39 +338,47 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
             kept = !(mx < minsize);
             if (row_kept) row_kept[row0 + lane] = kept ? 1 : 0;
         }
-        // ---- flags, element-parallel and row-major (outlier.rs:99-113)
-        const uint32_t kept_b = __ballot_sync(0xffffffffu, kept);
-        uint32_t nh = 0;                                          // warp-uniform
-        for (uint32_t r = 0; r < nr; ++r) {
-            const float mean_r = __shfl_sync(0xffffffffu, mean, r), sd_r = __shfl_sync(0xffffffffu, sd, r);
-            const float rinv_r = __shfl_sync(0xffffffffu, rinv, r);
-            if (!((kept_b >> r) & 1u)) continue;
-            const float *row = rows + r * stride;
-            for (uint32_t c0 = 0; c0 < n_cols; c0 += 32) {
-                const uint32_t c = c0 + lane;
-                const bool hit = c < n_cols && z_at_least(__fsub_rn(clean(row[c]), mean_r), sd_r, rinv_r, cutoff, margin);
-                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
-                if (!hb) continue;
-                if (hit) {
-                    const uint32_t k = nh + __popc(hb & ((1u << lane) - 1u));
-                    const unsigned long long h = ((row0 + r) << 32) | c;
-                    if (k < (uint32_t)kZwHitBuf) hbuf[k] = h;
-                    else {
-                        const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
-                        if (slot < cap) hits[slot] = h;
+        // ---- flags (outlier.rs:99-113): still one lane per row -- a third pass with the same conflict-free LDS.128,
+        //      four independent tests per load. (A row-major, element-parallel pass leaves this warp with one dependent
+        //      load -> test -> vote chain per 32 columns and nothing to hide it behind: measured 0.96 ms of the kernel's 1.08.)
+        //      Hits go to the warp's buffer through a shared-memory counter; the host sorts them anyway.
+        constexpr uint32_t kLaneHits = kZwHitBuf / 32;          // every lane buffers its own row's hits: no atomics, no votes
+        uint32_t nl = 0;
+        if (lane < nr && kept && !(dbg & 1u)) {
+            const float4 *row4 = reinterpret_cast<const float4 *>(rows + lane * stride);
+            const unsigned long long rowbits = (row0 + lane) << 32;
+            unsigned long long *mine = hbuf + lane * kLaneHits;
+#pragma unroll 2
+            for (uint32_t c = 0; c < n_cols / 4; ++c) {
+                const float4 v = row4[c];
+                const bool h0 = z_at_least(__fsub_rn(clean(v.x), mean), sd, rinv, cutoff, margin);
+                const bool h1 = z_at_least(__fsub_rn(clean(v.y), mean), sd, rinv, cutoff, margin);
+                const bool h2 = z_at_least(__fsub_rn(clean(v.z), mean), sd, rinv, cutoff, margin);
+                const bool h3 = z_at_least(__fsub_rn(clean(v.w), mean), sd, rinv, cutoff, margin);
+                if (h0 | h1 | h2 | h3) {
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q) {
+                        const bool hq = q == 0 ? h0 : q == 1 ? h1 : q == 2 ? h2 : h3;
+                        if (!hq) continue;
+                        const unsigned long long h = rowbits | (4u * c + q);
+                        if (nl < kLaneHits) mine[nl++] = h;
+                        else {                                    // a row with more outliers than the lane's buffer holds
+                            const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                            if (slot < cap) hits[slot] = h;
+                        }
                     }
                 }
-                nh += __popc(hb);
             }
         }
-        __syncwarp();
-        const uint32_t nbuf = min(nh, (uint32_t)kZwHitBuf);
+        // one global atomic per group reserves the slots; every lane moves its own hits
+        const uint32_t incl = [&] { uint32_t v = nl; for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += o; } return v; }();
+        const uint32_t nbuf = __shfl_sync(0xffffffffu, incl, 31);
         if (nbuf) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&ctr->n_hits, (unsigned long long)nbuf);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (uint32_t k = lane; k < nbuf; k += 32)
-                if (base + k < cap) hits[base + k] = hbuf[k];
+            base = __shfl_sync(0xffffffffu, base, 0) + (incl - nl);
+            for (uint32_t k = 0; k < nl; ++k)
+                if (base + k < cap) hits[base + k] = hbuf[lane * kLaneHits + k];
         }
         __syncwarp();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the slab is refilled by the async proxy next

@@ -395,7 +395,7 @@ __device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap 
                  : "memory");
 }
 // Every warp is an independent pipeline: it owns warp tiles gwid, gwid + W, gwid + 2W, ... (W = warps
-// in the grid), a 3-stage ring of 2 KB shared-memory boxes that it fills itself with TMA, and the
+// in the grid), a kWarpStages-deep ring of 4 KB shared-memory boxes (one warp tile each) that it fills itself with TMA, and the
 // mbarriers of that ring. There is no block-level synchronisation and no producer warp.
 template <bool kThrHigh>
 __global__ void __launch_bounds__(kCtaThreads, INQ_SCAN_MIN_CTAS)
@@ -910,6 +910,8 @@ k_pair_eval(ReadView rv, uint64_t r_begin, uint64_t r_end, LocusView lv, int unp
     if (ev_lo < ev_hi) {
         const uint32_t cnt = min(ev_hi - ev_lo, (uint32_t)kPairEvPool);
         // pass 1: where each event lives (storage slot) and the consumption prefix of its tile -- parked in s_ev
+        // (enumerating the events tile by tile instead was measured: fewer instructions, but 14 dependent shared-memory
+        // round trips in a row per warp -- 0.57 ms instead of 0.52 for the kernel)
         uint32_t ta = 0;                                        // cached tiles: this lane's k only grows, so does its tile
         for (uint32_t i = lane; i < cnt; i += 32) {
             const uint32_t k = ev_lo + i;
