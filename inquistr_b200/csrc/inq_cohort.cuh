@@ -348,26 +348,57 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
             const float4 *row4 = reinterpret_cast<const float4 *>(rows + lane * stride);
             const unsigned long long rowbits = (row0 + lane) << 32;
             unsigned long long *mine = hbuf + lane * kLaneHits;
-#pragma unroll 2
-            for (uint32_t c = 0; c < n_cols / 4; ++c) {
-                const float4 v = row4[c];
-                const bool h0 = z_at_least(__fsub_rn(clean(v.x), mean), sd, rinv, cutoff, margin);
-                const bool h1 = z_at_least(__fsub_rn(clean(v.y), mean), sd, rinv, cutoff, margin);
-                const bool h2 = z_at_least(__fsub_rn(clean(v.z), mean), sd, rinv, cutoff, margin);
-                const bool h3 = z_at_least(__fsub_rn(clean(v.w), mean), sd, rinv, cutoff, margin);
-                if (h0 | h1 | h2 | h3) {
-#pragma unroll
-                    for (uint32_t q = 0; q < 4; ++q) {
-                        const bool hq = q == 0 ? h0 : q == 1 ? h1 : q == 2 ? h2 : h3;
-                        if (!hq) continue;
-                        const unsigned long long h = rowbits | (4u * c + q);
-                        if (nl < kLaneHits) mine[nl++] = h;
-                        else {                                    // a row with more outliers than the lane's buffer holds
-                            const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
-                            if (slot < cap) hits[slot] = h;
-                        }
+            auto push = [&](uint32_t col) {
+                const unsigned long long h = rowbits | col;
+                if (nl < kLaneHits) mine[nl++] = h;
+                else {                                            // a row with more outliers than the lane's buffer holds
+                    const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                    if (slot < cap) hits[slot] = h;
+                }
+            };
+            // The reference's test fl(fl(v - mean) / sd) >= cutoff (outlier.rs:109) is a step function of v: both roundings
+            // are monotone for sd > 0. Its exact threshold -- the smallest f32 that passes -- is found once per row by
+            // walking a few ulps from mean + cutoff * sd with the real predicate; the pass then costs one compare per value
+            // instead of a subtract, a divide estimate and three compares. Rows where that does not apply (sd not positive
+            // and finite, or the walk does not settle) use the predicate itself.
+            bool have_thr = false;
+            float thr = 0.0f;
+            if (sd > 0.0f && sd <= 3.0e38f && fabsf(mean) <= 3.0e38f && fabsf(cutoff) <= 3.0e38f) {
+                auto pred = [&](float v) { return __fdiv_rn(__fsub_rn(v, mean), sd) >= cutoff; };
+                auto step = [](float v, bool up) {               // next representable f32 above / below (finite v)
+                    uint32_t u = __float_as_uint(v);
+                    if ((u << 1) == 0u) return __uint_as_float(up ? 0x00000001u : 0x80000001u);
+                    const bool neg = (u >> 31) != 0u;
+                    u += (up != neg) ? 1u : 0xFFFFFFFFu;
+                    return __uint_as_float(u);
+                };
+                float t = __fmaf_rn(cutoff, sd, mean);
+                if (fabsf(t) <= 3.0e38f) {
+                    int guard = 0;
+                    if (pred(t)) {
+                        for (; guard < 16; ++guard) { const float d = step(t, false); if (!(fabsf(d) <= 3.0e38f) || !pred(d)) break; t = d; }
+                    } else {
+                        for (; guard < 16; ++guard) { t = step(t, true); if (!(fabsf(t) <= 3.0e38f) || pred(t)) break; }
+                    }
+                    have_thr = guard < 16 && fabsf(t) <= 3.0e38f && pred(t) && !pred(step(t, false));
+                    thr = t;
+                }
+            }
+            if (have_thr) {
+#pragma unroll 4
+                for (uint32_t c = 0; c < n_cols / 4; ++c) {
+                    const float4 v = row4[c];
+                    const bool h0 = clean(v.x) >= thr, h1 = clean(v.y) >= thr, h2 = clean(v.z) >= thr, h3 = clean(v.w) >= thr;
+                    if (h0 | h1 | h2 | h3) {
+                        if (h0) push(4u * c);
+                        if (h1) push(4u * c + 1u);
+                        if (h2) push(4u * c + 2u);
+                        if (h3) push(4u * c + 3u);
                     }
                 }
+            } else {
+                for (uint32_t c = 0; c < n_cols; ++c)
+                    if (z_at_least(__fsub_rn(clean(rows[lane * stride + c]), mean), sd, rinv, cutoff, margin)) push(c);
             }
         }
         // one global atomic per group reserves the slots; every lane moves its own hits
