@@ -252,16 +252,16 @@ k_outlier_zscore_rows(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
 // cp.async.bulk) of row k into the warp's private slab and the warp waits on its own mbarrier -- no registers and
 // no issue slots are spent on the copy, and while one warp of the SM waits for its rows the others add. The rows
 // sit `stride` words apart with stride = 4 * odd, which makes the per-lane LDS.128 of the two sequential passes
-// conflict-free (8 lanes x 16 bytes hit 8 different 4-bank groups); the flag pass reads row-major. Outliers are
-// buffered per warp and leave with one global atomic per group. The matrix is read from HBM exactly once.
+// conflict-free (8 lanes x 16 bytes hit 8 different 4-bank groups). The flag pass is a third lane-per-row pass that
+// leaves one bit per column; one global atomic per group reserves the output slots. The matrix is read from HBM exactly once.
 // Needs n_cols % 4 == 0 (16-byte aligned rows) -- other shapes take k_outlier_zscore_rows.
-constexpr int kZwHitBuf = 512;            // per warp and group of 32 rows
+constexpr int kZwMaskWords = 33;          // u32 hit-mask words per lane (odd stride): rows of up to 1056 columns take the fast flag pass
 constexpr int kZwMaxWarps = 16;
 
 __device__ __forceinline__ uint32_t zw_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __host__ __device__ inline uint32_t zw_stride(uint32_t n_cols) { return ((n_cols / 4) & 1u) ? n_cols : n_cols + 4; }
-__host__ __device__ inline size_t zw_warp_bytes(uint32_t n_cols) { return (size_t)32 * zw_stride(n_cols) * 4 + (size_t)kZwHitBuf * 8; }
+__host__ __device__ inline size_t zw_warp_bytes(uint32_t n_cols) { return (size_t)32 * zw_stride(n_cols) * 4 + (size_t)32 * kZwMaskWords * 4; }
 
 __global__ void __launch_bounds__(kZwMaxWarps * 32, 1)
 k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, float minsize, float cutoff,
@@ -275,7 +275,6 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t stride = zw_stride(n_cols);
     float *rows = reinterpret_cast<float *>(zw_smem + (size_t)warp * zw_warp_bytes(n_cols));
-    unsigned long long *hbuf = reinterpret_cast<unsigned long long *>(rows + 32 * stride);
     uint64_t *bar = reinterpret_cast<uint64_t *>(zw_smem + (size_t)nwarps * zw_warp_bytes(n_cols)) + warp;
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zw_smem_u32(bar)), "r"(1) : "memory");
@@ -338,24 +337,16 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
             kept = !(mx < minsize);
             if (row_kept) row_kept[row0 + lane] = kept ? 1 : 0;
         }
-        // ---- flags (outlier.rs:99-113): still one lane per row -- a third pass with the same conflict-free LDS.128,
-        //      four independent tests per load. (A row-major, element-parallel pass leaves this warp with one dependent
-        //      load -> test -> vote chain per 32 columns and nothing to hide it behind: measured 0.96 ms of the kernel's 1.08.)
-        //      Hits go to the warp's buffer through a shared-memory counter; the host sorts them anyway.
-        constexpr uint32_t kLaneHits = kZwHitBuf / 32;          // every lane buffers its own row's hits: no atomics, no votes
-        uint32_t nl = 0;
+        // ---- flags (outlier.rs:99-113): still one lane per row -- a third pass with the same conflict-free LDS.128 that
+        //      leaves one bit per column in the lane's mask words. (A row-major, element-parallel pass leaves this single
+        //      warp with one dependent load -> test -> vote chain per 32 columns and nothing to hide it behind: measured
+        //      0.96 ms of 1.08; a data-dependent branch per load costs the full LDS latency every time: 0.135 ms for the
+        //      pass without a single hit. Hence: branch-free mask build, then the set bits are enumerated.)
+        uint32_t *bits = reinterpret_cast<uint32_t *>(rows + 32 * stride) + lane * kZwMaskWords;
+        const uint32_t n4 = n_cols / 4, nwords = (n4 + 7) / 8;
+        uint32_t cnt = 0;
         if (lane < nr && kept && !(dbg & 1u)) {
             const float4 *row4 = reinterpret_cast<const float4 *>(rows + lane * stride);
-            const unsigned long long rowbits = (row0 + lane) << 32;
-            unsigned long long *mine = hbuf + lane * kLaneHits;
-            auto push = [&](uint32_t col) {
-                const unsigned long long h = rowbits | col;
-                if (nl < kLaneHits) mine[nl++] = h;
-                else {                                            // a row with more outliers than the lane's buffer holds
-                    const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
-                    if (slot < cap) hits[slot] = h;
-                }
-            };
             // The reference's test fl(fl(v - mean) / sd) >= cutoff (outlier.rs:109) is a step function of v: both roundings
             // are monotone for sd > 0. Its exact threshold -- the smallest f32 that passes -- is found once per row by
             // walking a few ulps from mean + cutoff * sd with the real predicate; the pass then costs one compare per value
@@ -373,7 +364,8 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
                     return __uint_as_float(u);
                 };
                 float t = __fmaf_rn(cutoff, sd, mean);
-                if (fabsf(t) <= 3.0e38f) {
+                if (dbg & 4u) { have_thr = true; thr = t; }              // (timing experiment: approximate threshold, wrong results)
+                else if (fabsf(t) <= 3.0e38f) {
                     int guard = 0;
                     if (pred(t)) {
                         for (; guard < 16; ++guard) { const float d = step(t, false); if (!(fabsf(d) <= 3.0e38f) || !pred(d)) break; t = d; }
@@ -385,31 +377,52 @@ k_outlier_zscore_warp(const float *__restrict__ m, uint64_t n_rows, uint32_t n_c
                 }
             }
             if (have_thr) {
-#pragma unroll 4
-                for (uint32_t c = 0; c < n_cols / 4; ++c) {
-                    const float4 v = row4[c];
-                    const bool h0 = clean(v.x) >= thr, h1 = clean(v.y) >= thr, h2 = clean(v.z) >= thr, h3 = clean(v.w) >= thr;
-                    if (h0 | h1 | h2 | h3) {
-                        if (h0) push(4u * c);
-                        if (h1) push(4u * c + 1u);
-                        if (h2) push(4u * c + 2u);
-                        if (h3) push(4u * c + 3u);
+                for (uint32_t w = 0; w < nwords; ++w) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        const uint32_t c = w * 8 + j;
+                        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                        if (c < n4) v = row4[c];
+                        const uint32_t m = (clean(v.x) >= thr ? 1u : 0u) | (clean(v.y) >= thr ? 2u : 0u) | (clean(v.z) >= thr ? 4u : 0u) |
+                                           (clean(v.w) >= thr ? 8u : 0u);
+                        acc |= m << (4 * j);
                     }
+                    bits[w] = acc;
+                    cnt += __popc(acc);
                 }
             } else {
-                for (uint32_t c = 0; c < n_cols; ++c)
-                    if (z_at_least(__fsub_rn(clean(rows[lane * stride + c]), mean), sd, rinv, cutoff, margin)) push(c);
+                const float *row = rows + lane * stride;
+                for (uint32_t w = 0; w < nwords; ++w) {
+                    uint32_t acc = 0;
+                    for (uint32_t j = 0; j < 32 && 32 * w + j < n_cols; ++j)
+                        if (z_at_least(__fsub_rn(clean(row[32 * w + j]), mean), sd, rinv, cutoff, margin)) acc |= 1u << j;
+                    bits[w] = acc;
+                    cnt += __popc(acc);
+                }
             }
         }
-        // one global atomic per group reserves the slots; every lane moves its own hits
-        const uint32_t incl = [&] { uint32_t v = nl; for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += o; } return v; }();
-        const uint32_t nbuf = __shfl_sync(0xffffffffu, incl, 31);
-        if (nbuf) {
+        // one global atomic per group reserves the slots; every lane writes its own row's hits (the host sorts them)
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += o; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total && !(dbg & 8u)) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->n_hits, (unsigned long long)nbuf);
-            base = __shfl_sync(0xffffffffu, base, 0) + (incl - nl);
-            for (uint32_t k = 0; k < nl; ++k)
-                if (base + k < cap) hits[base + k] = hbuf[lane * kLaneHits + k];
+            if (lane == 0) base = atomicAdd(&ctr->n_hits, (unsigned long long)total);
+            unsigned long long slot = __shfl_sync(0xffffffffu, base, 0) + (incl - cnt);
+            if (cnt) {
+                const unsigned long long rowbits = (row0 + lane) << 32;
+                for (uint32_t w = 0; w < nwords; ++w) {
+                    uint32_t m = bits[w];
+                    while (m) {
+                        const uint32_t bpos = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        if (slot < cap) hits[slot] = rowbits | (32u * w + bpos);
+                        ++slot;
+                    }
+                }
+            }
         }
         __syncwarp();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the slab is refilled by the async proxy next

@@ -92,7 +92,7 @@ int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const 
         if (const char *e = getenv("INQ_ZW_DEBUG")) zw_dbg = (uint32_t)atoi(e);
         if (const char *e = getenv("INQ_ZSCORE_ROWS")) force_rows = atoi(e) != 0;
 #endif
-        if (n_cols % 4 == 0 && zw_warps >= 2 && !force_rows) {
+        if (n_cols % 4 == 0 && n_cols <= 32u * kZwMaskWords && zw_warps >= 2 && !force_rows) {
             // every warp its own pipeline over groups of 32 rows (bulk async copies, one lane per row)
             const size_t smem = (size_t)zw_warps * per_warp + (size_t)zw_warps * 12 + 128;
             CC_TRY(cudaFuncSetAttribute(k_outlier_zscore_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

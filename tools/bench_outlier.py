@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--rows", type=int, default=200_000)
     ap.add_argument("--samples", type=int, default=268)       # the cohort size quoted in the reference's README
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--cutoff", type=float, default=3.0)
+    ap.add_argument("--methods", default="zscore,dbscan")
     args = ap.parse_args()
     from inquistr_b200 import cohort
     from oracle import oracle as O
@@ -34,14 +36,14 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    for method in ("zscore", "dbscan"):
+    for method in args.methods.split(","):
         best = None
         for _ in range(args.reps):
-            kept, hr, hc, ms = cohort.outlier(m, 10, 3.0, method)
+            kept, hr, hc, ms = cohort.outlier(m, 10, args.cutoff, method)
             best = ms if best is None else min(best, ms)
         n = min(args.rows, 2000)
         t0 = time.perf_counter()
-        k2, f2, st = O.outlier_matrix(m[:n], 10, 3.0, method)
+        k2, f2, st = O.outlier_matrix(m[:n], 10, args.cutoff, method)
         cpu_s = time.perf_counter() - t0
         er, ec = np.nonzero(f2)
         sel = hr < n
