@@ -495,15 +495,20 @@ int build_plan(inq_ctx *ctx, uint64_t n_wt)
         }
     }
     // median chunks: the loci that became complete with pair(k - 1), cut into pieces so that the copy of one piece
-    // runs under the medians of the next
-    const int64_t piece = std::max<int64_t>(1 << 16, (L + 7) / 8);
+    // runs under the medians of the next; the very last piece is small (its copy is the exposed one)
+    const int64_t piece = std::max<int64_t>(1 << 15, (L + 7) / 8);
+    const int64_t last_piece = std::max<int64_t>(1 << 13, L / 32);
     for (int k = 1; k <= K; ++k) {
         int64_t a = done[k - 1], b = done[k];
         if (k == K && L == 0) break;
         while (a < b) {
             int64_t e = std::min(b, a + piece);
-            if (b - e < piece / 4) e = b;                     // no tiny trailing piece
-            if (k == K && b - a > (1 << 16) && e == b && pl.n_chunks + 1 < kMaxMedianChunks && b - a > piece / 2) e = a + (b - a) / 2;   // halve the exposed tail
+            if (k == K) {
+                // the last group ends with a short piece
+                if (b - a > 2 * last_piece && e > b - last_piece) e = b - last_piece;
+            } else if (b - e < piece / 4) {
+                e = b;                                        // no tiny trailing piece
+            }
             if (pl.n_chunks == kMaxMedianChunks - 1) e = b;
             pl.chunk[pl.n_chunks++] = MedianChunk{(uint32_t)a, (uint32_t)e, k - 1};
             a = e;
@@ -680,18 +685,22 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
         CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_FORK], 0));
     }
     CU_TRY(ctx, stamp(EV_MED1, s2));
-    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S2_DONE], s2));
-    CU_TRY(ctx, stamp(EV_D2H, s3));
-    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S3_DONE], s3));
     // total number of events = the last prefix
     if (n_wt && L) CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total + 2, ctx->wt.p + n_wt, sizeof(uint2), cudaMemcpyDeviceToHost, s1));
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S1_DONE], s1));
+    // the counters go home on S2 next to the last result copy (S3) instead of after it: S2 has seen every median kernel,
+    // S1 every join / prefix / pair kernel, and those waited for the scans
+    cudaStream_t sctr = INQ_BIG_ON_S3 ? s3 : s2;              // (the stream that runs the CTA-path medians, which also raise flags)
+    CU_TRY(ctx, cudaStreamWaitEvent(sctr, ctx->dep[DEP_S1_DONE], 0));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, sctr));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S2_DONE], s2));
+    CU_TRY(ctx, stamp(EV_D2H, s3));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_S3_DONE], s3));
 
     // ---- join everything on S0
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S1_DONE], 0));
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S2_DONE], 0));
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S3_DONE], 0));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s0));
     CU_TRY(ctx, stamp(EV_END, s0));
     *n_launches = launches;
     return INQ_OK;
