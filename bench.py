@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="inq_set_option('graph', 0)")
     ap.add_argument("--bam-scale", type=float, default=0.1,
                     help="e2e_bam: `inquistr-b200 call` on a synthetic BAM with SEQ/QUAL of config 3 at this scale (0 = skip)")
+    ap.add_argument("--no-cohort", action="store_true", help="skip the extra.cohort_outlier block (SURVEY 8f rank 3 kernels)")
     ap.add_argument("--parity-seconds", type=float, default=6.0, help="budget of the per-rank oracle check at N > 1")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -141,6 +142,35 @@ def cpu_reference(w, threads: int, seconds: float):
                   f"reference is NOT included (oracle restatement of call.rs, reference is Rust and cannot be built here)",
         "op_visits_per_s": visits / dt, "seconds": dt, "rc": rc,
     }, (sel, p1, p2)
+
+
+def cohort_outlier_block(peak_gbs: float) -> dict:
+    """`inquistr-b200 outlier` kernels (include/inqcohort.h) on a 200,000 loci x 536 haplotype-column matrix (268 samples,
+    the cohort size of the reference's README): kernel time by CUDA events (H2D excluded), algorithmic bytes = 4 B per
+    value read once, parity of the first 2,000 rows against the oracle (outlier.rs restated)."""
+    from inquistr_b200 import cohort
+    from oracle import oracle as O
+    rng = np.random.default_rng(9)
+    rows, cols = 200_000, 536
+    m = (np.round(rng.gamma(2.0, 15.0, (rows, cols)) * 2) / 2).astype(np.float32)
+    m[rng.random(m.shape) < 0.05] = np.nan
+    big = rng.random(rows) < 0.2
+    m[big, rng.integers(0, cols, big.sum())] = rng.integers(150, 3000, big.sum())
+    out = {"workload": f"{rows} x {cols} f32, 5% NaN, 20% of the rows carry one expansion", "bound": "hbm", "peak": peak_gbs, "unit": "GB/s"}
+    for method, kernel in (("zscore", "k_outlier_zscore_warp"), ("dbscan", "k_outlier_dbscan")):
+        best = None
+        for _ in range(3):
+            kept, hr, hc, ms = cohort.outlier(m, 10, 3.0, method)
+            best = ms if best is None else min(best, ms)
+        n = 2000
+        k2, f2, _ = O.outlier_matrix(m[:n], 10, 3.0, method)
+        er, ec = np.nonzero(f2)
+        sel = hr < n
+        ok = bool(np.array_equal(kept[:n], k2) and np.array_equal(hr[sel], er) and np.array_equal(hc[sel], ec))
+        gbps = m.nbytes / (best * 1e-3) / 1e9
+        out[method] = {"kernel": kernel, "kernel_ms": best, "achieved": gbps, "frac": gbps / peak_gbs, "rows_per_s": rows / (best * 1e-3),
+                       "outliers": int(len(hr)), "parity_first_rows": {"rows": n, "bit_exact_vs_oracle": ok}}
+    return out
 
 
 def emit(line: dict) -> None:
@@ -399,6 +429,13 @@ def main():
                 e2e_bam = {"error": r.stderr[-400:]}
         except Exception as ex:          # the headline numbers do not depend on this leg
             e2e_bam = {"error": repr(ex)}
+    # ---- cohort follow-on kernels, so that the driver's record carries their numbers too
+    cohort_block = None
+    if rank == 0 and world == 1 and not args.no_cohort:
+        try:
+            cohort_block = cohort_outlier_block(peak)
+        except Exception as ex:
+            cohort_block = {"error": repr(ex)}
     if world > 1:
         dist.barrier()
 
@@ -426,6 +463,7 @@ def main():
                 "seconds_per_step": e2e["seconds_per_step"], "ms_h2d_rank0": e2e["ms_h2d_last"],
                 "cigar_ops_per_s": tot_words_j / e2e["seconds_per_step"]},
             "e2e_bam": e2e_bam,
+            "extra": {"cohort_outlier": cohort_block},
             "gpu_launches": int(st["n_kernel_launches"]) * args.steps,
             "clocks": clk,
             "parity": parity,

@@ -119,10 +119,15 @@ int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const 
         while ((2ull << min_points) <= n_cols) ++min_points;
         int sms = 0;
         CC_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        const unsigned grid = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sms * 8);
+        // One warp per row when the row fits 1024 columns: 55 sort stages without a block barrier, and ~20 rows in
+        // flight per SM (shared memory) hide each other's latency; wider rows keep the 128-thread CTA.
+        const unsigned threads = n_cols <= 1024 ? 32u : (unsigned)kDbThreads;
+        int per_sm = 8;
         CC_TRY(cudaFuncSetAttribute(k_outlier_dbscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_outlier_dbscan<<<grid, kDbThreads, smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, n2, (float)minsize, min_points,
-                                                          (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+        CC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_outlier_dbscan, (int)threads, smem));
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sms * std::max(per_sm, 1));
+        k_outlier_dbscan<<<grid, threads, smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, n2, (float)minsize, min_points,
+                                                       (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
     }
     CC_TRY(cudaGetLastError());
     CC_TRY(cudaEventRecord(g.e1, g.s));
