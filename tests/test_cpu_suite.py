@@ -63,9 +63,10 @@ def test_cabi_exports_every_declared_symbol():
     import inquistr_b200 as q
     from inquistr_b200 import api
     from inquistr_b200 import cohort
-    hdr = open(os.path.join(ROOT, "include", "inqcall.h")).read() + open(os.path.join(ROOT, "include", "inqcohort.h")).read()
+    from inquistr_b200 import bgzf
+    hdr = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("inqcall.h", "inqcohort.h", "inqbgzf.h"))
     declared = sorted(set(re.findall(r"\b(inq_[a-z0-9_]+)\s*\(", hdr)))
-    assert set(declared) == set(api.EXPORTS) | set(cohort.EXPORTS), (declared, api.EXPORTS, cohort.EXPORTS)
+    assert set(declared) == set(api.EXPORTS) | set(cohort.EXPORTS) | set(bgzf.EXPORTS), (declared, api.EXPORTS, cohort.EXPORTS, bgzf.EXPORTS)
     lib = q.load_library()
     for name in declared:
         assert hasattr(lib, name), name

@@ -6,7 +6,7 @@ mkdir -p variants
 for spec in "$@"; do
   name=${spec%%:*}; flags=${spec#*:}
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC $flags \
-     -o variants/$name.so inquistr_b200/csrc/inq_capi.cu inquistr_b200/csrc/inq_cohort_capi.cu &
+     -o variants/$name.so inquistr_b200/csrc/inq_capi.cu inquistr_b200/csrc/inq_cohort_capi.cu inquistr_b200/csrc/inq_inflate_capi.cu &
 done
 wait
 ls -la variants/
