@@ -46,6 +46,24 @@ int inq_bgzf_inflate(int device, const uint8_t *comp, uint64_t comp_bytes, const
                      uint8_t *out, uint64_t out_bytes, uint32_t *status, float *ms_h2d, float *ms_kernel, float *ms_d2h);
 const char *inq_bgzf_last_error(void);
 
+/*
+ * Persistent engine for a stream of batches (what `inquistr-b200 call` uses next to its zlib workers): device
+ * buffers, stream and events are created once; every run copies the compressed blocks in, inflates, copies the
+ * output back and returns when the output is in `out`. comp / out should be page-locked (inq_host_register or
+ * inq_host_alloc) so that the copies run at PCIe speed. One engine per host thread; several engines on one device
+ * overlap each other's copies and kernels.
+ */
+typedef struct inq_bgzf_engine inq_bgzf_engine;
+int inq_bgzf_engine_create(int device, uint64_t max_comp_bytes, uint64_t max_out_bytes, uint32_t max_blocks, inq_bgzf_engine **out);
+void inq_bgzf_engine_destroy(inq_bgzf_engine *eng);
+/* blocks[].in_off / out_off are offsets into comp / out; only the byte range [min out_off, max out_off + out_len) of
+ * `out` is written, and only [min in_off, max in_off + in_len) of `comp` is read. */
+int inq_bgzf_engine_run(inq_bgzf_engine *eng, const uint8_t *comp, uint64_t comp_bytes, const inq_zblock *blocks, uint32_t n_blocks,
+                        uint8_t *out, uint32_t *status, float *ms_kernel);
+/* page-lock / unlock caller-allocated host memory (cudaHostRegister) */
+int inq_host_register(void *p, size_t bytes);
+int inq_host_unregister(void *p);
+
 #ifdef __cplusplus
 }
 #endif

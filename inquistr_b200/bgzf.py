@@ -9,7 +9,8 @@ import numpy as np
 
 from .api import INQ_OK, InqError, load_library
 
-EXPORTS = ["inq_bgzf_inflate", "inq_bgzf_last_error"]
+EXPORTS = ["inq_bgzf_inflate", "inq_bgzf_last_error", "inq_bgzf_engine_create", "inq_bgzf_engine_destroy", "inq_bgzf_engine_run",
+           "inq_host_register", "inq_host_unregister"]
 _BOUND = False
 
 ZBLOCK = np.dtype([("in_off", np.uint64), ("out_off", np.uint64), ("in_len", np.uint32), ("out_len", np.uint32)])

@@ -1,6 +1,11 @@
 // bam_reader.cpp -- see bam_reader.hpp. SAM/BAM spec v1 section 4 (BGZF 4.1, BAM 4.2).
 #include "bam_reader.hpp"
 #include "inflate_fast.hpp"
+#include "../../../include/inqbgzf.h"
+#include "../../../include/inqcall.h"
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <zlib.h>
 
@@ -115,6 +120,24 @@ int BamHeader::tid(const std::string &name) const
     return -1;
 }
 
+BamReader::HostBuf BamReader::alloc_buf(size_t cap)
+{
+    HostBuf b;
+    void *p = nullptr;
+    if (posix_memalign(&p, 4096, cap) != 0) return b;
+    b.p = static_cast<uint8_t *>(p);
+    b.cap = cap;
+    return b;
+}
+
+void BamReader::free_buf(HostBuf &b)
+{
+    if (!b.p) return;
+    if (b.registered) inq_host_unregister(b.p);
+    free(b.p);
+    b = HostBuf();
+}
+
 BamReader::~BamReader()
 {
     {
@@ -125,63 +148,85 @@ BamReader::~BamReader()
     cv_work_.notify_all();
     if (producer_.joinable()) producer_.join();
     for (auto &t : workers_) t.join();
-    if (fp_) fclose(fp_);
+    if (gpu_thread_.joinable()) gpu_thread_.join();
+    for (auto &q : queue_) { free_buf(q->data); free_buf(q->comp); }
+    for (auto &b : pool_) { free_buf(b.data); free_buf(b.comp); }
+    if (cur_batch_) { free_buf(cur_batch_->data); free_buf(cur_batch_->comp); }
+    if (fd_ >= 0) close(fd_);
 }
 
-bool BamReader::open(const std::string &path, int threads)
+bool BamReader::open(const std::string &path, int threads, int gpu_device)
 {
     threads_ = std::max(1, threads);
-    fp_ = fopen(path.c_str(), "rb");
-    if (!fp_) { err_ = "cannot open " + path; return false; }
-    setvbuf(fp_, nullptr, _IOFBF, 8u << 20);
+    gpu_device_ = gpu_device;
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) { err_ = "cannot open " + path; return false; }
+    posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
     cur_batch_.reset(new Batch());
     producer_ = std::thread(&BamReader::producer, this);
     for (int t = 0; t < threads_; ++t) workers_.emplace_back(&BamReader::inflater, this);
+    if (gpu_device_ >= 0) gpu_thread_ = std::thread(&BamReader::gpu_inflater, this);
     return parse_header();
 }
 
-// read the raw bytes of one batch of BGZF blocks (I/O thread; nothing is inflated here)
+// read the raw bytes of one batch of BGZF blocks (I/O thread; nothing is inflated here): big read() calls straight
+// into the batch's buffer, then the block headers are walked in memory
 bool BamReader::read_batch(Batch &out)
 {
-    constexpr size_t kBatchBlocks = 1024;          // up to 64 MB inflated per batch
     {
         std::lock_guard<std::mutex> lk(mu_);
-        if (!pool_.empty()) { out.data = std::move(pool_.back().data); out.comp = std::move(pool_.back().comp); pool_.pop_back(); }
+        if (!pool_.empty()) { out.data = pool_.back().data; out.comp = pool_.back().comp; pool_.pop_back(); }
     }
-    std::vector<uint8_t> &comp = out.comp;
-    comp.clear();
-    size_t out_total = 0;
-    while (out.blocks.size() < kBatchBlocks) {
-        uint8_t h[12];
-        size_t n = fread(h, 1, 12, fp_);
-        if (n == 0) { out.eof = true; break; }
-        if (n != 12 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { out.err = "not a BGZF block (bad gzip header)"; return false; }
+    if (out.comp.empty()) out.comp = alloc_buf(kCompCap);
+    if (out.data.empty()) out.data = alloc_buf(kSlack + kOutCap);
+    if (out.comp.empty() || out.data.empty()) { out.err = "out of memory"; return false; }
+    uint8_t *comp = out.comp.data();
+    size_t have = carry_.size();
+    if (have) memcpy(comp, carry_.data(), have);
+    carry_.clear();
+    while (!file_eof_ && have < kReadChunk) {
+        const ssize_t k = ::read(fd_, comp + have, std::min(kReadChunk, kCompCap - have) - 0);
+        if (k < 0) { out.err = "read error"; return false; }
+        if (k == 0) { file_eof_ = true; break; }
+        have += (size_t)k;
+        if (have >= kReadChunk) break;
+    }
+    size_t p = 0, out_total = 0;
+    while (out.blocks.size() < kMaxBlocks) {
+        if (have - p < 18) break;
+        const uint8_t *h = comp + p;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { out.err = "not a BGZF block (bad gzip header)"; return false; }
         const uint16_t xlen = rd16(h + 10);
-        uint8_t extra[65536];
-        if (fread(extra, 1, xlen, fp_) != xlen) { out.err = "truncated BGZF extra field"; return false; }
+        if (have - p < 12u + xlen) break;
         int bsize = -1;
         for (size_t i = 0; i + 4 <= xlen;) {
-            const uint16_t slen = rd16(&extra[i + 2]);
-            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = rd16(&extra[i + 4]);
+            const uint16_t slen = rd16(h + 12 + i + 2);
+            if (h[12 + i] == 'B' && h[12 + i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = rd16(h + 12 + i + 4);
             i += 4 + slen;
         }
         if (bsize < 0) { out.err = "BGZF block without BC subfield"; return false; }
-        const long remaining = (long)bsize + 1 - 12 - xlen;     // deflate payload + crc32 + isize
-        if (remaining < 8) { out.err = "corrupt BGZF block size"; return false; }
-        const size_t off = comp.size();
-        comp.resize(off + (size_t)remaining);
-        if (fread(&comp[off], 1, (size_t)remaining, fp_) != (size_t)remaining) { out.err = "truncated BGZF block"; return false; }
+        const size_t total = (size_t)bsize + 1;
+        if (total < 12u + xlen + 8u) { out.err = "corrupt BGZF block size"; return false; }
+        if (have - p < total) break;                              // the block continues in the next read
         BlockRef b;
-        b.in_off = off;
-        b.in_len = (size_t)remaining - 8;
-        b.crc = rd32(&comp[off + remaining - 8]);
-        b.out_len = rd32(&comp[off + remaining - 4]);
+        b.in_off = p + 12 + xlen;
+        b.in_len = total - 12 - xlen - 8;
+        b.crc = rd32(comp + p + total - 8);
+        b.out_len = rd32(comp + p + total - 4);
+        if (b.out_len > 65536) { out.err = "BGZF block larger than 64 KB"; return false; }
+        if (out_total + b.out_len > kOutCap) break;
         b.out_off = out_total;
         out_total += b.out_len;
         out.blocks.push_back(b);
+        p += total;
+    }
+    if (p < have) carry_.assign(comp + p, comp + have);          // what the next batch starts with
+    if (file_eof_ && carry_.empty()) out.eof = true;
+    if (out.blocks.empty() && !out.eof) {
+        if (file_eof_) { out.err = "truncated BGZF block"; return false; }
+        if (carry_.size() >= kCompCap - 65536 * 2) { out.err = "BGZF block does not fit the read buffer"; return false; }
     }
     out.size = kSlack + out_total;
-    if (out.data.size() < out.size) out.data.resize(out.size + (out.size >> 3));
     return true;
 }
 
@@ -195,7 +240,7 @@ void BamReader::producer()
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&] { return stop_ || queue_.size() < kInFlight; });
-            if (stop_) return;
+            if (stop_) { free_buf(b->data); free_buf(b->comp); return; }
             queue_.push_back(std::move(b));
             if (last) producer_done_ = true;
         }
@@ -205,31 +250,107 @@ void BamReader::producer()
     }
 }
 
-// worker: take the next block of the oldest batch that still has blocks to hand out
+// worker: CRC32 of blocks the GPU inflated first (they gate the batch), then the next block of the oldest batch that
+// still has blocks to hand out
 void BamReader::inflater()
 {
     std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
         Batch *b = nullptr;
         size_t i = 0;
-        for (auto &q : queue_)
-            if (q->next_block < q->blocks.size()) { b = q.get(); i = q->next_block++; break; }
+        bool crc_only = false;
+        while (!crc_.empty() && crc_.front().next >= crc_.front().end) crc_.pop_front();
+        if (!crc_.empty()) {
+            b = crc_.front().b;
+            i = crc_.front().next++;
+            crc_only = true;
+        } else {
+            for (auto &q : queue_)
+                if (q->next_block < q->blocks.size()) { b = q.get(); i = q->next_block++; break; }
+        }
         if (!b) {
-            if (stop_ || producer_done_) {
+            if (stop_) return;
+            if (producer_done_) {
                 bool pending = false;
-                for (auto &q : queue_) pending = pending || q->next_block < q->blocks.size();
-                if (stop_ || !pending) return;
+                for (auto &q : queue_) pending = pending || q->done_blocks < q->blocks.size();
+                if (!pending) return;
             }
             cv_work_.wait(lk);
             continue;
         }
         lk.unlock();
         const BlockRef &r = b->blocks[i];
-        const bool ok = inflate_block(&b->comp[r.in_off], r.in_len, b->data.data() + kSlack + r.out_off, r.out_len, r.crc);
+        uint8_t *dst = b->data.data() + kSlack + r.out_off;
+        bool ok;
+        if (crc_only) {
+            ok = r.out_len == 0 || crc32(crc32(0L, Z_NULL, 0), dst, (uInt)r.out_len) == r.crc;
+            if (!ok) ok = inflate_block(b->comp.data() + r.in_off, r.in_len, dst, r.out_len, r.crc);   // the device got it wrong: redo here
+        } else {
+            ok = inflate_block(b->comp.data() + r.in_off, r.in_len, dst, r.out_len, r.crc);
+        }
         lk.lock();
         if (!ok) { b->bad = true; if (b->err.empty()) b->err = "BGZF inflate / CRC failure"; }
         if (++b->done_blocks == b->blocks.size()) cv_.notify_all();
     }
+}
+
+// GPU engine thread: claims runs of consecutive blocks of the oldest batch, inflates them on the device
+// (include/inqbgzf.h) and queues their CRC checks for the workers. Blocks the kernel declines are inflated here.
+void BamReader::gpu_inflater()
+{
+    constexpr size_t kRun = 1024, kMinRun = 48;
+    inq_bgzf_engine *eng = nullptr;
+    if (inq_bgzf_engine_create(gpu_device_, kCompCap, kOutCap, (uint32_t)kRun, &eng) != INQ_OK) return;   // no device: the workers do it all
+    std::vector<inq_zblock> desc(kRun);
+    std::vector<uint32_t> status(kRun);
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        Batch *b = nullptr;
+        size_t a = 0, e = 0;
+        for (auto &q : queue_)
+            if (q->blocks.size() - q->next_block >= kMinRun) {
+                b = q.get();
+                a = q->next_block;
+                e = std::min(q->blocks.size(), a + kRun);
+                q->next_block = e;
+                break;
+            }
+        if (!b) {
+            if (stop_) break;
+            if (producer_done_) {
+                bool pending = false;
+                for (auto &q : queue_) pending = pending || q->blocks.size() - q->next_block >= kMinRun;
+                if (!pending) break;
+            }
+            cv_work_.wait(lk);
+            continue;
+        }
+        lk.unlock();
+        // page-lock the batch's buffers the first time they are seen (they are recycled, so this happens a few times only)
+        if (!b->comp.registered) b->comp.registered = inq_host_register(b->comp.data(), b->comp.cap) == INQ_OK;
+        if (!b->data.registered) b->data.registered = inq_host_register(b->data.data(), b->data.cap) == INQ_OK;
+        uint64_t bytes = 0;
+        for (size_t i = a; i < e; ++i) {
+            const BlockRef &r = b->blocks[i];
+            desc[i - a] = inq_zblock{(uint64_t)r.in_off, (uint64_t)(kSlack + r.out_off), (uint32_t)r.in_len, (uint32_t)r.out_len};
+            bytes += r.out_len;
+        }
+        const int rc = inq_bgzf_engine_run(eng, b->comp.data(), b->comp.cap, desc.data(), (uint32_t)(e - a), b->data.data(), status.data(), nullptr);
+        bool bad = false;
+        for (size_t i = a; i < e; ++i)
+            if (rc != INQ_OK || status[i - a] != 0) {
+                const BlockRef &r = b->blocks[i];
+                if (!inflate_block(b->comp.data() + r.in_off, r.in_len, b->data.data() + kSlack + r.out_off, r.out_len, r.crc)) bad = true;
+            }
+        gpu_blocks_.fetch_add(e - a, std::memory_order_relaxed);
+        gpu_bytes_.fetch_add(bytes, std::memory_order_relaxed);
+        lk.lock();
+        if (bad) { b->bad = true; if (b->err.empty()) b->err = "BGZF inflate / CRC failure"; }
+        crc_.push_back(CrcRange{b, a, e});
+        cv_work_.notify_all();
+    }
+    lk.unlock();
+    inq_bgzf_engine_destroy(eng);
 }
 
 // make the next batch current, keeping the unconsumed tail of the old one in front of it
@@ -244,7 +365,12 @@ bool BamReader::next_batch()
         queue_.pop_front();
     }
     cv_.notify_all();
-    if (nb->bad || !nb->err.empty()) { err_ = nb->err.empty() ? "BGZF read failure" : nb->err; eof_ = true; return false; }
+    if (nb->bad || !nb->err.empty()) {
+        err_ = nb->err.empty() ? "BGZF read failure" : nb->err;
+        eof_ = true;
+        free_buf(nb->data); free_buf(nb->comp);
+        return false;
+    }
     const size_t tail = end_ - cur_;
     const size_t payload = nb->size - kSlack;
     total_out_ += payload;
@@ -253,19 +379,25 @@ bool BamReader::next_batch()
         if (tail) memcpy(nb->data.data() + kSlack - tail, cur_batch_->data.data() + cur_, tail);
         {
             std::lock_guard<std::mutex> lk(mu_);
-            if (!cur_batch_->data.empty() && pool_.size() < kInFlight + 1) pool_.push_back(Buffers{std::move(cur_batch_->data), std::move(cur_batch_->comp)});
+            if (!cur_batch_->data.empty()) {
+                if (pool_.size() < kInFlight + 2) pool_.push_back(Buffers{cur_batch_->data, cur_batch_->comp});
+                else { free_buf(cur_batch_->data); free_buf(cur_batch_->comp); }
+            }
         }
         cur_batch_ = std::move(nb);
         cur_ = kSlack - tail;
         end_ = cur_batch_->size;
-    } else {                                        // a record larger than the slack: concatenate
-        std::vector<uint8_t> joined(kSlack + tail + payload);
+    } else {                                        // a record larger than the slack: concatenate into a one-off buffer
+        HostBuf joined = alloc_buf(kSlack + tail + payload + 64);
+        if (joined.empty()) { err_ = "out of memory"; eof_ = true; return false; }
         memcpy(joined.data() + kSlack, cur_batch_->data.data() + cur_, tail);
         memcpy(joined.data() + kSlack + tail, nb->data.data() + kSlack, payload);
         const bool was_eof = nb->eof;
+        free_buf(cur_batch_->data); free_buf(cur_batch_->comp);
+        free_buf(nb->data); free_buf(nb->comp);
         cur_batch_.reset(new Batch());
-        cur_batch_->data = std::move(joined);
-        cur_batch_->size = cur_batch_->data.size();
+        cur_batch_->data = joined;
+        cur_batch_->size = kSlack + tail + payload;
         cur_batch_->eof = was_eof;
         cur_ = kSlack;
         end_ = cur_batch_->size;

@@ -5,6 +5,7 @@
 // SEQ/QUAL are skipped, never copied.
 #pragma once
 
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdio>
@@ -52,8 +53,10 @@ public:
     BamReader(const BamReader &) = delete;
     BamReader &operator=(const BamReader &) = delete;
 
-    // returns false and sets error() on failure
-    bool open(const std::string &path, int threads);
+    // returns false and sets error() on failure. gpu_device >= 0: a GPU engine (include/inqbgzf.h) inflates runs of
+    // blocks next to the zlib workers, which then also check the CRC32 of its output; if no engine can be created the
+    // workers simply do everything
+    bool open(const std::string &path, int threads, int gpu_device = -1);
     const BamHeader &header() const { return header_; }
     // next alignment record; false at EOF or on error (check error())
     bool next(BamRecordView &rec);
@@ -61,36 +64,52 @@ public:
     uint64_t bytes_inflated() const { return total_out_; }
 
 private:
-    // A batch of BGZF blocks: read raw by the I/O thread, inflated block by block by the worker pool, parsed by
-    // the caller. `data` starts with kSlack unused bytes so that the unconsumed tail of the previous batch can
-    // be moved in front of it without copying the batch.
+    // fixed-capacity, page-aligned host buffer (recycled between batches; page-locked once when the GPU engine is used)
+    struct HostBuf {
+        uint8_t *p = nullptr;
+        size_t cap = 0;
+        bool registered = false;
+        uint8_t *data() const { return p; }
+        bool empty() const { return p == nullptr; }
+    };
+    // A batch of BGZF blocks: read raw by the I/O thread, inflated block by block by the worker pool and / or in
+    // runs by the GPU engine, parsed by the caller. `data` starts with kSlack unused bytes so that the unconsumed
+    // tail of the previous batch can be moved in front of it without copying the batch.
     struct BlockRef {
         size_t in_off, in_len;                     // raw deflate payload inside `comp`
         size_t out_off, out_len;
         uint32_t crc;
     };
     struct Batch {
-        std::vector<uint8_t> data;                 // capacity is recycled between batches (no re-faulting of pages)
-        std::vector<uint8_t> comp;
+        HostBuf data, comp;
         std::vector<BlockRef> blocks;
         size_t size = 0;                           // kSlack + inflated payload bytes
         size_t next_block = 0, done_blocks = 0;    // guarded by mu_
         bool eof = false, bad = false;
         std::string err;
     };
-    struct Buffers { std::vector<uint8_t> data, comp; };
+    struct CrcRange { Batch *b; size_t next, end; };   // blocks the GPU inflated: CRC32 still to be checked by a worker
+    struct Buffers { HostBuf data, comp; };
     std::vector<Buffers> pool_;                    // recycled buffers (guarded by mu_)
     static constexpr size_t kSlack = 8u << 20;
     static constexpr size_t kInFlight = 4;         // batches read ahead of the parser
+    static constexpr size_t kCompCap = 40u << 20;  // compressed bytes per batch buffer
+    static constexpr size_t kOutCap = 96u << 20;   // inflated bytes per batch
+    static constexpr size_t kMaxBlocks = 2048;
+    static constexpr size_t kReadChunk = 24u << 20;
+    static HostBuf alloc_buf(size_t cap);
+    void free_buf(HostBuf &b);
     bool next_batch();                             // make the next batch current (tail preserved)
     bool ensure_bytes(size_t n);                   // at least n unconsumed bytes are contiguous at cur_
     bool parse_header();
     void producer();                               // I/O thread: reads raw batches ahead of the inflaters
-    void inflater();                               // worker: inflates blocks of the oldest unfinished batch
+    void inflater();                               // worker: CRC checks of GPU-inflated blocks first, then inflates blocks of the oldest unfinished batch
+    void gpu_inflater();                           // GPU engine thread: takes runs of blocks off the oldest batch
     bool read_batch(Batch &b);
 
-    FILE *fp_ = nullptr;
+    int fd_ = -1;
     int threads_ = 1;
+    int gpu_device_ = -1;
     BamHeader header_;
     std::string err_;
     std::unique_ptr<Batch> cur_batch_;
@@ -98,14 +117,23 @@ private:
     bool eof_ = false;
     uint64_t total_out_ = 0;
     std::vector<uint32_t> cg_;                     // aligned copy of the record's CIGAR
+    std::vector<uint8_t> carry_;                   // compressed bytes of a block that straddles two reads (I/O thread only)
+    bool file_eof_ = false;
 
-    std::thread producer_;
+    std::thread producer_, gpu_thread_;
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_;                   // consumer + producer
     std::condition_variable cv_work_;              // inflaters
     std::deque<std::unique_ptr<Batch>> queue_;     // in file order; the head is handed to the parser once complete
+    std::deque<CrcRange> crc_;                     // guarded by mu_
     bool stop_ = false, producer_done_ = false;
+    std::atomic<uint64_t> gpu_blocks_{0}, gpu_bytes_{0};
+public:
+    // blocks / bytes inflated by the GPU engine so far
+    uint64_t gpu_blocks() const { return gpu_blocks_.load(); }
+    uint64_t gpu_bytes() const { return gpu_bytes_.load(); }
+private:
 };
 
 // Parses one BAM alignment record body (the bytes after block_size) in place. `cg` receives an aligned

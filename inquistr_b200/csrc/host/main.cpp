@@ -158,7 +158,7 @@ Args parse_args(int argc, char **argv)
     if (v[0] == "bamstat" && v.size() >= 2) {
         // extension: scan a BAM with the host reader only (no GPU): record counts and inflate rate;
         // `bamstat x.bam chr:beg-end` does the same through the .bai index for one region
-        if (v.size() >= 3) {
+        if (v.size() == 3) {
             BamIndexedReader ix;
             if (!ix.open_bam(v[1]) || !ix.load_index(v[1] + ".bai")) { fprintf(stderr, "%s\n", ix.error().c_str()); exit(1); }
             const size_t c1 = v[2].find(':'), c2 = v[2].find('-', c1);
@@ -172,7 +172,9 @@ Args parse_args(int argc, char **argv)
         }
         BamReader rd;
         const auto t0 = std::chrono::steady_clock::now();
-        if (!rd.open(v[1], (int)std::max(1u, std::thread::hardware_concurrency()))) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
+        int gpu = -1;                                           // `bamstat x.bam --gpu N`: GPU engine next to the workers
+        if (v.size() >= 4 && v[2] == "--gpu") gpu = atoi(v[3].c_str());
+        if (!rd.open(v[1], (int)std::max(1u, std::thread::hardware_concurrency()), gpu)) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
         BamRecordView r;
         uint64_t n = 0, words = 0, hp = 0, sa = 0, d2 = 0;
         while (rd.next(r)) {
@@ -185,9 +187,10 @@ Args parse_args(int argc, char **argv)
         uint64_t nf = 0, nz = 0;
         inflate_counters(&nf, &nz);
         printf("{\"refs\": %zu, \"records\": %llu, \"cigar_words\": %llu, \"hp_tagged\": %llu, \"sa_tagged\": %llu, \"accidental_2d\": %llu, "
-               "\"bytes_inflated\": %llu, \"seconds\": %.3f, \"inflate_GBps\": %.3f, \"blocks_fast\": %llu, \"blocks_zlib\": %llu}\n", rd.header().ref_names.size(),
+               "\"bytes_inflated\": %llu, \"seconds\": %.3f, \"inflate_GBps\": %.3f, \"blocks_fast\": %llu, \"blocks_zlib\": %llu, \"blocks_gpu\": %llu, \"bytes_gpu\": %llu}\n", rd.header().ref_names.size(),
                (unsigned long long)n, (unsigned long long)words, (unsigned long long)hp, (unsigned long long)sa, (unsigned long long)d2,
-               (unsigned long long)rd.bytes_inflated(), s, rd.bytes_inflated() / 1e9 / s, (unsigned long long)nf, (unsigned long long)nz);
+               (unsigned long long)rd.bytes_inflated(), s, rd.bytes_inflated() / 1e9 / s, (unsigned long long)nf, (unsigned long long)nz,
+               (unsigned long long)rd.gpu_blocks(), (unsigned long long)rd.gpu_bytes());
         exit(0);
     }
     // cohort follow-ons of `call`: text in, text out; cohort_cli.cpp
@@ -532,7 +535,7 @@ int main(int argc, char **argv)
         n_routed += hit.size();
     };
 
-    uint64_t bytes_inflated = 0;
+    uint64_t bytes_inflated = 0, gpu_inflated = 0;
     if (used_index) {
         std::unordered_set<uint64_t> seen;
         for (const auto &r : regions) {
@@ -545,7 +548,11 @@ int main(int argc, char **argv)
         bytes_inflated = ibam.bytes_inflated();
     } else {
         BamReader bam;
-        if (!bam.open(args.bam, host_threads)) panic("Error opening local BAM: " + bam.error());
+        // BGZF blocks are inflated by the zlib-class workers AND, in runs, by a GPU engine on the first device
+        // (include/inqbgzf.h); INQ_GPU_INFLATE=0 leaves it all to the workers
+        const char *gi = getenv("INQ_GPU_INFLATE");
+        const int gpu_dev = (gi && atoi(gi) == 0) ? -1 : args.devices[0];
+        if (!bam.open(args.bam, host_threads, gpu_dev)) panic("Error opening local BAM: " + bam.error());
         BamRecordView rec;
         while (bam.next(rec)) {
             ++n_records;
@@ -558,6 +565,7 @@ int main(int argc, char **argv)
         }
         if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
         bytes_inflated = bam.bytes_inflated();
+        gpu_inflated = bam.gpu_bytes();
     }
     const double s_scan = since(t_scan0);
     const auto t_gen0 = std::chrono::steady_clock::now();
@@ -624,11 +632,11 @@ int main(int argc, char **argv)
     if (!args.stats_json.empty()) {
         FILE *f = fopen(args.stats_json.c_str(), "w");
         if (f) {
-            fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"records_unpairable\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64
+            fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"records_unpairable\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64 ", \"bytes_inflated_on_gpu\": %" PRIu64
                        ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
                        ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u"
                        ", \"n_shards\": %d, \"records_routed\": %" PRIu64 ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_under_scan\": %.3f, \"s_flush_genotype\": %.3f, \"s_total\": %.3f}\n",
-                    used_index ? 1 : 0, n_records, n_kept, n_unpairable, bytes_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
+                    used_index ? 1 : 0, n_records, n_kept, n_unpairable, bytes_inflated, gpu_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
                     st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, n_shards, n_routed, s_ctx, s_scan, s_push, s_gen, since(t_begin));
             fclose(f);
         }
