@@ -5,6 +5,7 @@
 #include "../../../include/inqcall.h"
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <zlib.h>
@@ -124,7 +125,8 @@ BamReader::HostBuf BamReader::alloc_buf(size_t cap)
 {
     HostBuf b;
     void *p = nullptr;
-    if (posix_memalign(&p, 4096, cap) != 0) return b;
+    if (posix_memalign(&p, 2u << 20, cap) != 0) return b;
+    madvise(p, cap, MADV_HUGEPAGE);                              // fewer first-touch faults while 16 workers write into it
     b.p = static_cast<uint8_t *>(p);
     b.cap = cap;
     return b;
@@ -307,7 +309,9 @@ void BamReader::gpu_inflater()
     for (;;) {
         Batch *b = nullptr;
         size_t a = 0, e = 0;
-        for (auto &q : queue_)
+        // newest batch first: the workers drain the oldest one, the device works ahead of them
+        for (auto it = queue_.rbegin(); it != queue_.rend(); ++it) {
+            auto &q = *it;
             if (q->blocks.size() - q->next_block >= kMinRun) {
                 b = q.get();
                 a = q->next_block;
@@ -315,6 +319,7 @@ void BamReader::gpu_inflater()
                 q->next_block = e;
                 break;
             }
+        }
         if (!b) {
             if (stop_) break;
             if (producer_done_) {
@@ -452,6 +457,79 @@ bool BamReader::next(BamRecordView &rec)
     const uint8_t *p = cur_batch_->data.data() + cur_ + 4;       // record body, parsed in place
     cur_ += (size_t)block_size + 4;
     return parse_bam_record(p, block_size, rec, cg_, err_);
+}
+
+bool BamReader::next_parsed(const RecFilter &filter, int parse_threads, std::vector<ParsedChunk> &chunks)
+{
+    chunks.clear();
+    // 1. record boundaries of what is inflated and contiguous right now (one 4-byte hop per record)
+    std::vector<std::pair<size_t, uint32_t>> recs;               // offset of the record body, block_size
+    for (;;) {
+        if (end_ - cur_ < 4) {
+            if (!recs.empty()) break;
+            if (!ensure_bytes(4)) {
+                if (err_.empty() && end_ != cur_) err_ = "truncated BAM record";
+                return false;
+            }
+        }
+        const uint32_t bs = rd32(cur_batch_->data.data() + cur_);
+        if (bs < 32) { err_ = "corrupt BAM record"; return false; }
+        if (end_ - cur_ < (size_t)bs + 4) {
+            if (!recs.empty()) break;                             // the rest of this record is in the next batch
+            if (!ensure_bytes((size_t)bs + 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
+        }
+        recs.emplace_back(cur_ + 4, bs);
+        cur_ += (size_t)bs + 4;
+    }
+    // 2. parse in parallel: chunks of consecutive records
+    constexpr size_t kChunk = 256;
+    const size_t n_chunks = (recs.size() + kChunk - 1) / kChunk;
+    chunks.resize(n_chunks);
+    const uint8_t *base = cur_batch_->data.data();
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        BamRecordView rv;
+        std::vector<uint32_t> cg;
+        std::vector<size_t> cig_off;
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= n_chunks) break;
+            ParsedChunk &pc = chunks[c];
+            const size_t a = c * kChunk, b = std::min(recs.size(), a + kChunk);
+            pc.n_records = b - a;
+            cig_off.clear();
+            for (size_t i = a; i < b; ++i) {
+                if (!parse_bam_record(base + recs[i].first, recs[i].second, rv, cg, pc.err)) break;
+                if (filter.reach && !filter.reach(filter.ctx, rv.tid, rv.pos, rv.end)) continue;
+                const bool hp_odd = filter.need_hp && (rv.hp_type == HpType::OtherInt || rv.hp_type == HpType::NotInt);
+                if (!hp_odd && (rv.mapq <= 10 || (filter.need_hp && rv.hp_type == HpType::Absent))) {
+                    // fails the filter at every locus: counted by the caller through n_records - recs.size(), never shipped.
+                    // (kept as a stub without CIGAR so that the caller's counters can tell "unpairable" from "unreachable")
+                    BamRecLite l{rv.tid, rv.pos, rv.end, 0, nullptr, rv.hp_value, rv.flag, rv.mapq, rv.hp_type, false, false};
+                    pc.recs.push_back(l);
+                    cig_off.push_back((size_t)-1);
+                    continue;
+                }
+                bool sa_panic = false, has_clip = false;
+                for (uint32_t k = 0; k < rv.n_cigar && !has_clip; ++k) has_clip = (cg[k] & 0xF) == 4;
+                const bool two_d = has_clip ? is_accidental_2d(rv, &sa_panic) : false;
+                BamRecLite l{rv.tid, rv.pos, rv.end, rv.n_cigar, nullptr, rv.hp_value, rv.flag, rv.mapq, rv.hp_type, two_d, sa_panic};
+                cig_off.push_back(pc.cigar.size());
+                pc.cigar.insert(pc.cigar.end(), cg.begin(), cg.begin() + rv.n_cigar);
+                pc.recs.push_back(l);
+            }
+            for (size_t k = 0; k < pc.recs.size(); ++k)
+                if (cig_off[k] != (size_t)-1) pc.recs[k].cigar = pc.cigar.data() + cig_off[k];
+        }
+    };
+    const int nt = (int)std::min<size_t>((size_t)std::max(1, parse_threads), n_chunks);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    for (auto &pc : chunks)
+        if (!pc.err.empty()) { err_ = pc.err; return false; }
+    return true;
 }
 
 bool parse_bam_record(const uint8_t *p, uint32_t block_size, BamRecordView &rec, std::vector<uint32_t> &cg_, std::string &err_)

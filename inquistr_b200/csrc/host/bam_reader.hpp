@@ -44,6 +44,33 @@ struct BamRecordView {
     bool is_reverse() const { return (flag & 0x10) != 0; }
 };
 
+// What the `call` driver needs of one record, produced by the parallel parse (BamReader::next_parsed)
+struct BamRecLite {
+    int32_t tid, pos, end;
+    uint32_t n_cigar;
+    const uint32_t *cigar;        // into the chunk's own storage; null when the record was not kept
+    int64_t hp_value;
+    uint16_t flag;
+    uint8_t mapq;
+    HpType hp_type;
+    bool two_d, sa_panic;
+};
+struct ParsedChunk {
+    std::vector<BamRecLite> recs; // the records the filter kept, in file order
+    std::vector<uint32_t> cigar;
+    uint64_t n_records = 0;       // all records of the chunk
+    std::string err;
+};
+// decides in the parse workers which records are worth keeping: reach(ctx, tid, pos, end) says whether any locus
+// window can fetch the record (call.rs:285-288); records with mapq <= 10 and, when need_hp, without an HP tag fail the
+// filter everywhere (call.rs:297-300,350-352) -- but a reachable record with an HP tag of an unexpected type is kept
+// so that the caller can raise the reference's panic (call.rs:487) in file order
+struct RecFilter {
+    bool (*reach)(const void *ctx, int32_t tid, int32_t pos, int32_t end) = nullptr;
+    const void *ctx = nullptr;
+    bool need_hp = false;
+};
+
 // Streaming reader: BGZF blocks are read in batches and inflated by a small thread pool, records are
 // parsed in file order.
 class BamReader {
@@ -60,6 +87,9 @@ public:
     const BamHeader &header() const { return header_; }
     // next alignment record; false at EOF or on error (check error())
     bool next(BamRecordView &rec);
+    // the records of the next inflated batch, parsed on `parse_threads` threads in chunks of consecutive records; the
+    // chunks come back in file order and stay valid until the next call. false at EOF or on error.
+    bool next_parsed(const RecFilter &filter, int parse_threads, std::vector<ParsedChunk> &chunks);
     const std::string &error() const { return err_; }
     uint64_t bytes_inflated() const { return total_out_; }
 

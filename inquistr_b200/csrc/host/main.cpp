@@ -553,15 +553,45 @@ int main(int argc, char **argv)
         const char *gi = getenv("INQ_GPU_INFLATE");
         const int gpu_dev = (gi && atoi(gi) == 0) ? -1 : args.devices[0];
         if (!bam.open(args.bam, host_threads, gpu_dev)) panic("Error opening local BAM: " + bam.error());
-        BamRecordView rec;
-        while (bam.next(rec)) {
-            ++n_records;
-            consider(rec);
-            if ((n_records & 0xFFFF) == 0) {                 // a shard that died (no device, out of memory) ends the scan early
-                bool dead = false;
-                for (auto &sh : shards) dead = dead || sh->failed();
-                if (dead) break;
+        // records are parsed on the host threads in chunks (field extraction, CIGAR copy, reference length, the
+        // fetch predicate and the SA classification run in parallel); this thread only keeps the file order: the
+        // reference's aux-type panic, the routing into the shards' pinned batches and the counters
+        struct ReachCtx { const std::vector<std::unique_ptr<ShardWorker>> *shards; };
+        const ReachCtx rctx{&shards};
+        RecFilter filt;
+        filt.ctx = &rctx;
+        filt.reach = [](const void *c, int32_t tid, int32_t pos, int32_t end) {
+            for (const auto &sh : *static_cast<const ReachCtx *>(c)->shards)
+                if (sh->reaches(tid, pos, end)) return true;
+            return false;
+        };
+        filt.need_hp = !args.unphased;
+        std::vector<ParsedChunk> chunks;
+        bool dead = false;
+        while (!dead && bam.next_parsed(filt, host_threads, chunks)) {
+            for (const ParsedChunk &pc : chunks) {
+                n_records += pc.n_records;
+                for (const BamRecLite &r : pc.recs) {
+                    uint8_t hp = 0xFF;
+                    if (!args.unphased) {                              // get_phase, call.rs:349,482-491 (see consider())
+                        switch (r.hp_type) {
+                        case HpType::Absent: break;
+                        case HpType::U8: hp = (uint8_t)r.hp_value; break;
+                        case HpType::I32: hp = (uint8_t)r.hp_value; break;
+                        default: panic("Unexpected type of Aux for HP (call.rs:487)");
+                        }
+                        if (hp == 0xFF && r.hp_type != HpType::Absent) hp = 0xFE;
+                    }
+                    if (!r.cigar && r.n_cigar == 0 && (r.mapq <= 10 || (!args.unphased && hp == 0xFF))) { ++n_unpairable; continue; }
+                    const uint8_t fl = (uint8_t)((r.two_d ? INQ_FLAG_ACCIDENTAL_2D : 0) | (r.sa_panic ? INQ_FLAG_SA_PANIC : 0));
+                    size_t n_hit = 0;
+                    for (int g = 0; g < n_shards; ++g)
+                        if (shards[g]->reaches(r.tid, r.pos, r.end)) { shards[g]->add(r.tid, r.pos, r.end, r.mapq, hp, fl, r.cigar, r.n_cigar); ++n_hit; }
+                    ++n_kept;
+                    n_routed += n_hit;
+                }
             }
+            for (auto &sh : shards) dead = dead || sh->failed();     // a shard that died (no device, out of memory) ends the scan early
         }
         if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
         bytes_inflated = bam.bytes_inflated();
