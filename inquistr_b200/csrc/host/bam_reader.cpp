@@ -6,6 +6,7 @@
 
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <zlib.h>
@@ -150,10 +151,11 @@ BamReader::~BamReader()
     cv_work_.notify_all();
     if (producer_.joinable()) producer_.join();
     for (auto &t : workers_) t.join();
-    if (gpu_thread_.joinable()) gpu_thread_.join();
-    for (auto &q : queue_) { free_buf(q->data); free_buf(q->comp); }
-    for (auto &b : pool_) { free_buf(b.data); free_buf(b.comp); }
-    if (cur_batch_) { free_buf(cur_batch_->data); free_buf(cur_batch_->comp); }
+    for (auto &t : gpu_threads_) t.join();
+    for (auto &q : queue_) free_buf(q->data);
+    for (auto &b : pool_) free_buf(b.data);
+    if (cur_batch_) free_buf(cur_batch_->data);
+    if (map_) munmap(const_cast<uint8_t *>(map_), map_len_);
     if (fd_ >= 0) close(fd_);
 }
 
@@ -163,43 +165,43 @@ bool BamReader::open(const std::string &path, int threads, int gpu_device)
     gpu_device_ = gpu_device;
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) { err_ = "cannot open " + path; return false; }
-    posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
+    struct stat st;
+    if (fstat(fd_, &st) != 0) { err_ = "cannot stat " + path; return false; }
+    map_len_ = (size_t)st.st_size;
+    if (map_len_) {
+        void *m = mmap(nullptr, map_len_, PROT_READ, MAP_SHARED, fd_, 0);
+        if (m == MAP_FAILED) { err_ = "cannot map " + path; return false; }
+        map_ = static_cast<const uint8_t *>(m);
+        madvise(m, map_len_, MADV_SEQUENTIAL);
+    }
     cur_batch_.reset(new Batch());
     producer_ = std::thread(&BamReader::producer, this);
     for (int t = 0; t < threads_; ++t) workers_.emplace_back(&BamReader::inflater, this);
-    if (gpu_device_ >= 0) gpu_thread_ = std::thread(&BamReader::gpu_inflater, this);
+    if (gpu_device_ >= 0)
+        for (int g = 0; g < kGpuEngines; ++g) gpu_threads_.emplace_back(&BamReader::gpu_inflater, this);
     return parse_header();
 }
 
-// read the raw bytes of one batch of BGZF blocks (I/O thread; nothing is inflated here): big read() calls straight
-// into the batch's buffer, then the block headers are walked in memory
+// one batch of BGZF blocks: the file is memory-mapped, so the I/O thread only walks the block headers (two cache lines
+// per block); the inflaters read the compressed payloads straight from the page cache, nothing is copied on the host
 bool BamReader::read_batch(Batch &out)
 {
     {
         std::lock_guard<std::mutex> lk(mu_);
-        if (!pool_.empty()) { out.data = pool_.back().data; out.comp = pool_.back().comp; pool_.pop_back(); }
+        if (!pool_.empty()) { out.data = pool_.back().data; pool_.pop_back(); }
     }
-    if (out.comp.empty()) out.comp = alloc_buf(kCompCap);
     if (out.data.empty()) out.data = alloc_buf(kSlack + kOutCap);
-    if (out.comp.empty() || out.data.empty()) { out.err = "out of memory"; return false; }
-    uint8_t *comp = out.comp.data();
-    size_t have = carry_.size();
-    if (have) memcpy(comp, carry_.data(), have);
-    carry_.clear();
-    while (!file_eof_ && have < kReadChunk) {
-        const ssize_t k = ::read(fd_, comp + have, std::min(kReadChunk, kCompCap - have) - 0);
-        if (k < 0) { out.err = "read error"; return false; }
-        if (k == 0) { file_eof_ = true; break; }
-        have += (size_t)k;
-        if (have >= kReadChunk) break;
-    }
-    size_t p = 0, out_total = 0;
-    while (out.blocks.size() < kMaxBlocks) {
-        if (have - p < 18) break;
+    if (out.data.empty()) { out.err = "out of memory"; return false; }
+    out.comp.p = const_cast<uint8_t *>(map_);                   // (not owned: BlockRef::in_off is an offset into the mapping)
+    out.comp.cap = map_len_;
+    size_t p = map_pos_, out_total = 0;
+    const uint8_t *comp = map_;
+    while (out.blocks.size() < kMaxBlocks && p < map_len_) {
+        if (map_len_ - p < 18) { out.err = "truncated BGZF block"; return false; }
         const uint8_t *h = comp + p;
         if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { out.err = "not a BGZF block (bad gzip header)"; return false; }
         const uint16_t xlen = rd16(h + 10);
-        if (have - p < 12u + xlen) break;
+        if (map_len_ - p < 12u + xlen) { out.err = "truncated BGZF extra field"; return false; }
         int bsize = -1;
         for (size_t i = 0; i + 4 <= xlen;) {
             const uint16_t slen = rd16(h + 12 + i + 2);
@@ -209,7 +211,7 @@ bool BamReader::read_batch(Batch &out)
         if (bsize < 0) { out.err = "BGZF block without BC subfield"; return false; }
         const size_t total = (size_t)bsize + 1;
         if (total < 12u + xlen + 8u) { out.err = "corrupt BGZF block size"; return false; }
-        if (have - p < total) break;                              // the block continues in the next read
+        if (map_len_ - p < total) { out.err = "truncated BGZF block"; return false; }
         BlockRef b;
         b.in_off = p + 12 + xlen;
         b.in_len = total - 12 - xlen - 8;
@@ -222,12 +224,8 @@ bool BamReader::read_batch(Batch &out)
         out.blocks.push_back(b);
         p += total;
     }
-    if (p < have) carry_.assign(comp + p, comp + have);          // what the next batch starts with
-    if (file_eof_ && carry_.empty()) out.eof = true;
-    if (out.blocks.empty() && !out.eof) {
-        if (file_eof_) { out.err = "truncated BGZF block"; return false; }
-        if (carry_.size() >= kCompCap - 65536 * 2) { out.err = "BGZF block does not fit the read buffer"; return false; }
-    }
+    map_pos_ = p;
+    if (p >= map_len_) out.eof = true;
     out.size = kSlack + out_total;
     return true;
 }
@@ -242,7 +240,7 @@ void BamReader::producer()
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&] { return stop_ || queue_.size() < kInFlight; });
-            if (stop_) { free_buf(b->data); free_buf(b->comp); return; }
+            if (stop_) { free_buf(b->data); return; }
             queue_.push_back(std::move(b));
             if (last) producer_done_ = true;
         }
@@ -302,7 +300,11 @@ void BamReader::gpu_inflater()
 {
     constexpr size_t kRun = 1024, kMinRun = 48;
     inq_bgzf_engine *eng = nullptr;
-    if (inq_bgzf_engine_create(gpu_device_, kCompCap, kOutCap, (uint32_t)kRun, &eng) != INQ_OK) return;   // no device: the workers do it all
+    constexpr size_t kStage = kRun * (65536 + 64);
+    if (inq_bgzf_engine_create(gpu_device_, kStage, kOutCap, (uint32_t)kRun, &eng) != INQ_OK) return;   // no device: the workers do it all
+    void *stage_v = nullptr;
+    if (inq_host_alloc(kStage + 64, &stage_v) != INQ_OK) { inq_bgzf_engine_destroy(eng); return; }
+    uint8_t *stage = static_cast<uint8_t *>(stage_v);
     std::vector<inq_zblock> desc(kRun);
     std::vector<uint32_t> status(kRun);
     std::unique_lock<std::mutex> lk(mu_);
@@ -331,16 +333,24 @@ void BamReader::gpu_inflater()
             continue;
         }
         lk.unlock();
-        // page-lock the batch's buffers the first time they are seen (they are recycled, so this happens a few times only)
-        if (!b->comp.registered) b->comp.registered = inq_host_register(b->comp.data(), b->comp.cap) == INQ_OK;
+        // page-lock the batch's output buffer the first time it is seen (buffers are recycled: a few times only); the
+        // compressed bytes of the run go from the page cache into this thread's page-locked staging buffer
         if (!b->data.registered) b->data.registered = inq_host_register(b->data.data(), b->data.cap) == INQ_OK;
         uint64_t bytes = 0;
+        const size_t in_lo = b->blocks[a].in_off & ~(size_t)7, in_hi = b->blocks[e - 1].in_off + b->blocks[e - 1].in_len;
+        if (in_hi - in_lo > kStage) {                             // cannot happen with <= 64 KB blocks and kRun of them; be safe
+            lk.lock();
+            b->next_block = a;                                    // hand the run back to the workers
+            cv_work_.notify_all();
+            break;
+        }
+        memcpy(stage, b->comp.data() + in_lo, in_hi - in_lo);
         for (size_t i = a; i < e; ++i) {
             const BlockRef &r = b->blocks[i];
-            desc[i - a] = inq_zblock{(uint64_t)r.in_off, (uint64_t)(kSlack + r.out_off), (uint32_t)r.in_len, (uint32_t)r.out_len};
+            desc[i - a] = inq_zblock{(uint64_t)(r.in_off - in_lo), (uint64_t)(kSlack + r.out_off), (uint32_t)r.in_len, (uint32_t)r.out_len};
             bytes += r.out_len;
         }
-        const int rc = inq_bgzf_engine_run(eng, b->comp.data(), b->comp.cap, desc.data(), (uint32_t)(e - a), b->data.data(), status.data(), nullptr);
+        const int rc = inq_bgzf_engine_run(eng, stage, in_hi - in_lo, desc.data(), (uint32_t)(e - a), b->data.data(), status.data(), nullptr);
         bool bad = false;
         for (size_t i = a; i < e; ++i)
             if (rc != INQ_OK || status[i - a] != 0) {
@@ -355,6 +365,7 @@ void BamReader::gpu_inflater()
         cv_work_.notify_all();
     }
     lk.unlock();
+    inq_host_free(stage);
     inq_bgzf_engine_destroy(eng);
 }
 
@@ -373,7 +384,7 @@ bool BamReader::next_batch()
     if (nb->bad || !nb->err.empty()) {
         err_ = nb->err.empty() ? "BGZF read failure" : nb->err;
         eof_ = true;
-        free_buf(nb->data); free_buf(nb->comp);
+        free_buf(nb->data);
         return false;
     }
     const size_t tail = end_ - cur_;
@@ -385,8 +396,8 @@ bool BamReader::next_batch()
         {
             std::lock_guard<std::mutex> lk(mu_);
             if (!cur_batch_->data.empty()) {
-                if (pool_.size() < kInFlight + 2) pool_.push_back(Buffers{cur_batch_->data, cur_batch_->comp});
-                else { free_buf(cur_batch_->data); free_buf(cur_batch_->comp); }
+                if (pool_.size() < kInFlight + 3) pool_.push_back(Buffers{cur_batch_->data, HostBuf()});
+                else free_buf(cur_batch_->data);
             }
         }
         cur_batch_ = std::move(nb);
@@ -398,8 +409,8 @@ bool BamReader::next_batch()
         memcpy(joined.data() + kSlack, cur_batch_->data.data() + cur_, tail);
         memcpy(joined.data() + kSlack + tail, nb->data.data() + kSlack, payload);
         const bool was_eof = nb->eof;
-        free_buf(cur_batch_->data); free_buf(cur_batch_->comp);
-        free_buf(nb->data); free_buf(nb->comp);
+        free_buf(cur_batch_->data);
+        free_buf(nb->data);
         cur_batch_.reset(new Batch());
         cur_batch_->data = joined;
         cur_batch_->size = kSlack + tail + payload;
@@ -462,12 +473,18 @@ bool BamReader::next(BamRecordView &rec)
 bool BamReader::next_parsed(const RecFilter &filter, int parse_threads, std::vector<ParsedChunk> &chunks)
 {
     chunks.clear();
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_waited = 0;
     // 1. record boundaries of what is inflated and contiguous right now (one 4-byte hop per record)
     std::vector<std::pair<size_t, uint32_t>> recs;               // offset of the record body, block_size
     for (;;) {
         if (end_ - cur_ < 4) {
             if (!recs.empty()) break;
-            if (!ensure_bytes(4)) {
+            const double tw = now();
+            const bool okb = ensure_bytes(4);
+            t_waited += now() - tw;
+            if (!okb) {
                 if (err_.empty() && end_ != cur_) err_ = "truncated BAM record";
                 return false;
             }
@@ -476,11 +493,17 @@ bool BamReader::next_parsed(const RecFilter &filter, int parse_threads, std::vec
         if (bs < 32) { err_ = "corrupt BAM record"; return false; }
         if (end_ - cur_ < (size_t)bs + 4) {
             if (!recs.empty()) break;                             // the rest of this record is in the next batch
-            if (!ensure_bytes((size_t)bs + 4)) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
+            const double tw = now();
+            const bool okb = ensure_bytes((size_t)bs + 4);
+            t_waited += now() - tw;
+            if (!okb) { if (err_.empty()) err_ = "truncated BAM record"; return false; }
         }
         recs.emplace_back(cur_ + 4, bs);
         cur_ += (size_t)bs + 4;
     }
+    const double t_indexed = now();
+    s_wait_batch += t_waited;
+    s_index += t_indexed - t_begin - t_waited;
     // 2. parse in parallel: chunks of consecutive records
     constexpr size_t kChunk = 256;
     const size_t n_chunks = (recs.size() + kChunk - 1) / kChunk;
@@ -527,6 +550,7 @@ bool BamReader::next_parsed(const RecFilter &filter, int parse_threads, std::vec
     for (int t = 1; t < nt; ++t) th.emplace_back(work);
     work();
     for (auto &t : th) t.join();
+    s_parse += now() - t_indexed;
     for (auto &pc : chunks)
         if (!pc.err.empty()) { err_ = pc.err; return false; }
     return true;

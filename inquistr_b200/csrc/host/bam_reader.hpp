@@ -122,11 +122,11 @@ private:
     struct Buffers { HostBuf data, comp; };
     std::vector<Buffers> pool_;                    // recycled buffers (guarded by mu_)
     static constexpr size_t kSlack = 8u << 20;
-    static constexpr size_t kInFlight = 4;         // batches read ahead of the parser
-    static constexpr size_t kCompCap = 40u << 20;  // compressed bytes per batch buffer
+    static constexpr size_t kInFlight = 6;         // batches read ahead of the parser
+    static constexpr int kGpuEngines = 3;          // a run of ~1000 blocks fills a quarter of a B200 (one warp per block, ~10 ms per block):
+                                                   // several engines on their own streams keep more blocks in flight
     static constexpr size_t kOutCap = 96u << 20;   // inflated bytes per batch
     static constexpr size_t kMaxBlocks = 2048;
-    static constexpr size_t kReadChunk = 24u << 20;
     static HostBuf alloc_buf(size_t cap);
     void free_buf(HostBuf &b);
     bool next_batch();                             // make the next batch current (tail preserved)
@@ -147,10 +147,11 @@ private:
     bool eof_ = false;
     uint64_t total_out_ = 0;
     std::vector<uint32_t> cg_;                     // aligned copy of the record's CIGAR
-    std::vector<uint8_t> carry_;                   // compressed bytes of a block that straddles two reads (I/O thread only)
-    bool file_eof_ = false;
+    const uint8_t *map_ = nullptr;                 // the whole file, memory-mapped read-only
+    size_t map_len_ = 0, map_pos_ = 0;             // map_pos_: next block header (I/O thread only)
 
-    std::thread producer_, gpu_thread_;
+    std::thread producer_;
+    std::vector<std::thread> gpu_threads_;
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_;                   // consumer + producer
@@ -163,6 +164,8 @@ public:
     // blocks / bytes inflated by the GPU engine so far
     uint64_t gpu_blocks() const { return gpu_blocks_.load(); }
     uint64_t gpu_bytes() const { return gpu_bytes_.load(); }
+    // seconds the consumer spent waiting for an inflated batch / walking record boundaries / in the parallel parse
+    double s_wait_batch = 0, s_index = 0, s_parse = 0;
 private:
 };
 

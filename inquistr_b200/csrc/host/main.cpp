@@ -490,7 +490,7 @@ int main(int argc, char **argv)
     std::vector<std::unique_ptr<ShardWorker>> shards;
     for (int g = 0; g < n_shards; ++g)
         shards.emplace_back(new ShardWorker(args.devices[g], cuts[g], cuts[g + 1], n_contigs, contig_off, lstart.data(), lend.data(),
-                                            args.minlen, (uint32_t)args.support, args.unphased));
+                                            args.minlen, (uint32_t)args.support, args.unphased, n_shards <= 2 ? 4 : 2));
     const auto t_scan0 = std::chrono::steady_clock::now();
 
     // one pass over the BAM; every record goes to the shards for which htslib's fetch would return it for some
@@ -536,6 +536,7 @@ int main(int argc, char **argv)
     };
 
     uint64_t bytes_inflated = 0, gpu_inflated = 0;
+    double s_wait_batch = 0, s_index = 0, s_parse = 0;
     if (used_index) {
         std::unordered_set<uint64_t> seen;
         for (const auto &r : regions) {
@@ -568,7 +569,8 @@ int main(int argc, char **argv)
         filt.need_hp = !args.unphased;
         std::vector<ParsedChunk> chunks;
         bool dead = false;
-        while (!dead && bam.next_parsed(filt, host_threads, chunks)) {
+        const int parse_threads = std::max(2, host_threads / 2);     // the inflate workers own the other half of the time
+        while (!dead && bam.next_parsed(filt, parse_threads, chunks)) {
             for (const ParsedChunk &pc : chunks) {
                 n_records += pc.n_records;
                 for (const BamRecLite &r : pc.recs) {
@@ -596,6 +598,7 @@ int main(int argc, char **argv)
         if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
         bytes_inflated = bam.bytes_inflated();
         gpu_inflated = bam.gpu_bytes();
+        s_wait_batch = bam.s_wait_batch; s_index = bam.s_index; s_parse = bam.s_parse;
     }
     const double s_scan = since(t_scan0);
     const auto t_gen0 = std::chrono::steady_clock::now();
@@ -665,9 +668,9 @@ int main(int argc, char **argv)
             fprintf(f, "{\"used_index\": %d, \"records\": %" PRIu64 ", \"records_pushed\": %" PRIu64 ", \"records_unpairable\": %" PRIu64 ", \"bytes_inflated\": %" PRIu64 ", \"bytes_inflated_on_gpu\": %" PRIu64
                        ", \"n_loci\": %" PRIu64 ", \"n_reads\": %" PRIu64 ", \"n_cigar_words\": %" PRIu64 ", \"n_pairs\": %" PRIu64
                        ", \"n_events\": %" PRIu64 ", \"ms_total\": %.4f, \"ms_cigar\": %.4f, \"ms_h2d\": %.4f, \"launches\": %u"
-                       ", \"n_shards\": %d, \"records_routed\": %" PRIu64 ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_under_scan\": %.3f, \"s_flush_genotype\": %.3f, \"s_total\": %.3f}\n",
+                       ", \"n_shards\": %d, \"records_routed\": %" PRIu64 ", \"s_ctx_create_set_loci\": %.3f, \"s_bam_scan\": %.3f, \"s_push_under_scan\": %.3f, \"s_flush_genotype\": %.3f, \"s_total\": %.3f, \"s_scan_wait_inflate\": %.3f, \"s_scan_index\": %.3f, \"s_scan_parse\": %.3f}\n",
                     used_index ? 1 : 0, n_records, n_kept, n_unpairable, bytes_inflated, gpu_inflated, st.n_loci, st.n_reads, st.n_cigar_words, st.n_pairs, st.n_events,
-                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, n_shards, n_routed, s_ctx, s_scan, s_push, s_gen, since(t_begin));
+                    st.ms_total, st.ms_cigar, st.ms_h2d, st.n_kernel_launches, n_shards, n_routed, s_ctx, s_scan, s_push, s_gen, since(t_begin), s_wait_batch, s_index, s_parse);
             fclose(f);
         }
     }

@@ -1,13 +1,16 @@
 // shard_driver.cpp -- see shard_driver.hpp
 #include "shard_driver.hpp"
+#include "../../../include/inqbgzf.h"
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 namespace inqhost {
 
 namespace {
+size_t meta_bytes() { const size_t R = ReadBatch::kReads; return R * 12 + (R + 1) * 8 + R * 3 + 64; }
 double now_s()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -33,7 +36,7 @@ std::vector<size_t> balanced_cuts(size_t L, int n, const double *weight)
 }
 
 ShardWorker::ShardWorker(int device, size_t lo, size_t hi, int n_contigs, const std::vector<int64_t> &contig_off,
-                         const int32_t *lstart, const int32_t *lend, uint32_t minlen, uint32_t support, bool unphased)
+                         const int32_t *lstart, const int32_t *lend, uint32_t minlen, uint32_t support, bool unphased, int n_batches)
     : device_(device), lo_(lo), hi_(hi), n_contigs_(n_contigs), lstart_(lstart + lo), lend_(lend + lo), minlen_(minlen),
       support_(support), unphased_(unphased)
 {
@@ -46,6 +49,29 @@ ShardWorker::ShardWorker(int device, size_t lo, size_t hi, int n_contigs, const 
         for (int64_t i = off_[c]; i < off_[c + 1]; ++i) { m = std::max(m, lend_[i]); pmax_[i] = m; }
     }
     memset(&res_.stats, 0, sizeof(res_.stats));
+    // staging batches: the reader fills one while others are on their way to the device (or wait for the context)
+    batches_.resize((size_t)std::max(2, n_batches));
+    for (ReadBatch &b : batches_) {
+        const size_t R = ReadBatch::kReads;
+        void *cig = nullptr, *meta = nullptr;
+        if (posix_memalign(&cig, 4096, ReadBatch::kWords * 4) != 0 || posix_memalign(&meta, 4096, meta_bytes()) != 0) {
+            failed_ = true;
+            res_.rc = INQ_ERR_NOMEM;
+            res_.error = "staging allocation failed";
+            break;
+        }
+        b.cigar = static_cast<uint32_t *>(cig);
+        b.meta_block = meta;
+        uint8_t *m = static_cast<uint8_t *>(meta);
+        b.off = reinterpret_cast<uint64_t *>(m); m += (R + 1) * 8;
+        b.contig = reinterpret_cast<int32_t *>(m); m += R * 4;
+        b.start = reinterpret_cast<int32_t *>(m); m += R * 4;
+        b.end = reinterpret_cast<int32_t *>(m); m += R * 4;
+        b.mapq = m; m += R;
+        b.hp = m; m += R;
+        b.flags = m;
+        free_.push_back(&b);
+    }
     th_ = std::thread([this] { run(); });
 }
 
@@ -56,6 +82,7 @@ ShardWorker::~ShardWorker()
         cv_.notify_all();
         th_.join();
     }
+    for (ReadBatch &b : batches_) { free(b.cigar); free(b.meta_block); }
 }
 
 bool ShardWorker::reaches(int32_t tid, int32_t pos, int32_t end) const
@@ -143,33 +170,12 @@ void ShardWorker::run()
     // shard view of the catalog: offsets relative to the slice, loci coordinates as they are
     rc = inq_set_loci(ctx, n_contigs_, off_.data(), lstart_, lend_);
     if (rc != INQ_OK) { fail(rc, inq_last_error(ctx)); inq_ctx_destroy(ctx); return; }
-    // two staging batches in pinned memory: the reader fills one while the other is on its way to the device
-    batches_.resize(2);
+    // the staging batches were handed to the reader as ordinary memory before the context existed (CUDA start-up takes
+    // 1-2 s next to the inflate threads: the reader must not wait for it); page-lock them now for the pushes
     for (ReadBatch &b : batches_) {
-        const size_t R = ReadBatch::kReads;
-        void *cig = nullptr, *meta = nullptr;
-        if (inq_host_alloc(ReadBatch::kWords * 4, &cig) != INQ_OK || inq_host_alloc(R * 12 + (R + 1) * 8 + R * 3 + 64, &meta) != INQ_OK) {
-            fail(INQ_ERR_NOMEM, "pinned staging allocation failed");
-            inq_ctx_destroy(ctx);
-            return;
-        }
-        b.cigar = static_cast<uint32_t *>(cig);
-        b.meta_block = meta;
-        uint8_t *m = static_cast<uint8_t *>(meta);
-        b.off = reinterpret_cast<uint64_t *>(m); m += (R + 1) * 8;
-        b.contig = reinterpret_cast<int32_t *>(m); m += R * 4;
-        b.start = reinterpret_cast<int32_t *>(m); m += R * 4;
-        b.end = reinterpret_cast<int32_t *>(m); m += R * 4;
-        b.mapq = m; m += R;
-        b.hp = m; m += R;
-        b.flags = m;
+        inq_host_register(b.cigar, ReadBatch::kWords * 4);
+        inq_host_register(b.meta_block, meta_bytes());
     }
-    {
-        std::lock_guard<std::mutex> g(mu_);
-        for (ReadBatch &b : batches_) free_.push_back(&b);
-        ready_ = true;
-    }
-    cv_.notify_all();
     res_.s_ctx = now_s() - t0;
 
     for (;;) {
@@ -202,7 +208,7 @@ void ShardWorker::run()
         res_.s_genotype = now_s() - tg;
         if (rc != INQ_OK) fail(rc, inq_last_error(ctx));
     }
-    for (ReadBatch &b : batches_) { inq_host_free(b.cigar); inq_host_free(b.meta_block); }
+    for (ReadBatch &b : batches_) { inq_host_unregister(b.cigar); inq_host_unregister(b.meta_block); }
     inq_ctx_destroy(ctx);
 }
 

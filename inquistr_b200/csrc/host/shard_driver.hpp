@@ -4,8 +4,9 @@
 //     caller knows about the expected work of a locus: 1, or the BAM bytes the .bai index says cover it);
 //   * every record the reader yields is routed to each shard for which htslib's fetch would return it for some
 //     locus of the shard (pos < end+10 && endpos > start-10, call.rs:285-288): reads at a cut go to both sides;
-//   * a shard's worker thread owns one inq_ctx: it pushes full staging batches (pinned memory, filled directly
-//     by the reader thread) while the reader keeps decoding, and genotypes its range once the input ends;
+//   * a shard's worker thread owns one inq_ctx: it pushes full staging batches (filled directly by the reader thread,
+//     which gets them before the CUDA context exists; page-locked once it does) while the reader keeps decoding, and
+//     genotypes its range once the input ends;
 //   * results are concatenated in shard order, which is catalog order. No collective, no device-to-device traffic.
 // A device may be listed several times (one context each), which exercises the sharding on a single GPU.
 #pragma once
@@ -49,7 +50,7 @@ class ShardWorker {
 public:
     // catalog slice [lo, hi) of the global sorted arrays; contig_off are the GLOBAL per-contig offsets
     ShardWorker(int device, size_t lo, size_t hi, int n_contigs, const std::vector<int64_t> &contig_off,
-                const int32_t *lstart, const int32_t *lend, uint32_t minlen, uint32_t support, bool unphased);
+                const int32_t *lstart, const int32_t *lend, uint32_t minlen, uint32_t support, bool unphased, int n_batches = 2);
     ~ShardWorker();
     ShardWorker(const ShardWorker &) = delete;
     ShardWorker &operator=(const ShardWorker &) = delete;
