@@ -551,8 +551,11 @@ int main(int argc, char **argv)
         BamReader bam;
         // BGZF blocks are inflated by the zlib-class workers AND, in runs, by a GPU engine on the first device
         // (include/inqbgzf.h); INQ_GPU_INFLATE=0 leaves it all to the workers
+        // (default: for files of 2 GB and more -- below that CUDA start-up takes longer than the workers need for the file)
         const char *gi = getenv("INQ_GPU_INFLATE");
-        const int gpu_dev = (gi && atoi(gi) == 0) ? -1 : args.devices[0];
+        struct stat bst;
+        const bool big = stat(args.bam.c_str(), &bst) == 0 && (uint64_t)bst.st_size >= (2ull << 30);
+        const int gpu_dev = (gi ? atoi(gi) != 0 : big) ? args.devices[0] : -1;
         if (!bam.open(args.bam, host_threads, gpu_dev)) panic("Error opening local BAM: " + bam.error());
         // records are parsed on the host threads in chunks (field extraction, CIGAR copy, reference length, the
         // fetch predicate and the SA classification run in parallel); this thread only keeps the file order: the
