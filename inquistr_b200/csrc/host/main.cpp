@@ -17,8 +17,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <array>
@@ -570,10 +574,14 @@ int main(int argc, char **argv)
             return false;
         };
         filt.need_hp = !args.unphased;
-        std::vector<ParsedChunk> chunks;
-        bool dead = false;
-        const int parse_threads = std::max(2, host_threads / 2);     // the inflate workers own the other half of the time
-        while (!dead && bam.next_parsed(filt, parse_threads, chunks)) {
+        // two-stage consumer: this thread waits for inflated batches, walks the record boundaries and runs the parallel
+        // parse; a routing thread takes the parsed chunks in file order (aux-type panic, shard routing, counters)
+        std::mutex qmu;
+        std::condition_variable qcv;
+        std::deque<std::vector<ParsedChunk>> parsed;
+        bool parse_done = false;
+        std::atomic<bool> dead{false};
+        auto route = [&](const std::vector<ParsedChunk> &chunks) {
             for (const ParsedChunk &pc : chunks) {
                 n_records += pc.n_records;
                 for (const BamRecLite &r : pc.recs) {
@@ -596,8 +604,36 @@ int main(int argc, char **argv)
                     n_routed += n_hit;
                 }
             }
-            for (auto &sh : shards) dead = dead || sh->failed();     // a shard that died (no device, out of memory) ends the scan early
+            for (auto &sh : shards)
+                if (sh->failed()) dead = true;                         // a shard that died (no device, out of memory) ends the scan early
+        };
+        std::thread router([&] {
+            for (;;) {
+                std::vector<ParsedChunk> chunks;
+                {
+                    std::unique_lock<std::mutex> lk(qmu);
+                    qcv.wait(lk, [&] { return !parsed.empty() || parse_done; });
+                    if (parsed.empty()) return;
+                    chunks = std::move(parsed.front());
+                    parsed.pop_front();
+                }
+                qcv.notify_all();
+                route(chunks);
+            }
+        });
+        const int parse_threads = std::max(2, host_threads / 2);     // the inflate workers own the other half of the time
+        for (;;) {
+            std::vector<ParsedChunk> chunks;
+            if (dead || !bam.next_parsed(filt, parse_threads, chunks)) break;
+            std::unique_lock<std::mutex> lk(qmu);
+            qcv.wait(lk, [&] { return parsed.size() < 2; });
+            parsed.push_back(std::move(chunks));
+            lk.unlock();
+            qcv.notify_all();
         }
+        { std::lock_guard<std::mutex> lk(qmu); parse_done = true; }
+        qcv.notify_all();
+        router.join();
         if (!bam.error().empty()) panic("Error reading BAM file: " + bam.error());
         bytes_inflated = bam.bytes_inflated();
         gpu_inflated = bam.gpu_bytes();
