@@ -655,7 +655,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 waited = true;
             }
             if (c == 0) CU_TRY(ctx, stamp(EV_MED0, s2));
-            k_locus_median<<<(unsigned)(((uint64_t)(l1 - l0) * 32 + 255) / 256), 256, 0, s2>>>(l0, l1, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p,
+            k_locus_median<<<(unsigned)((((uint64_t)(l1 - l0) + kMedianLociPerWarp - 1) / kMedianLociPerWarp * 32 + 255) / 256), 256, 0, s2>>>(l0, l1, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p,
                                                                                               ctx->vals.p, ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p,
                                                                                               ctx->big_list.p, ctx->d_ctr);
             CU_TRY(ctx, cudaGetLastError());

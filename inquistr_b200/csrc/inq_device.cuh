@@ -1323,38 +1323,77 @@ __device__ __forceinline__ void warp_locus(const uint64_t *__restrict__ vals, ui
 
 constexpr int kMedianWarpMax = 128;         // loci with more calls go to the CTA kernel
 
-#ifndef INQ_MEDIAN_MIN_CTAS
-#define INQ_MEDIAN_MIN_CTAS 8
+#ifndef INQ_MEDIAN_LOCI_PER_WARP
+#define INQ_MEDIAN_LOCI_PER_WARP 1     // measured: 1 -> 0.357 ms, 2 -> 0.369-0.389, 3 -> 0.473 (the kernel is issue-bound, not latency-bound)
 #endif
-__global__ void __launch_bounds__(256, INQ_MEDIAN_MIN_CTAS)
-k_locus_median(uint32_t l0, uint32_t l1, int chunk, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
-               const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ vals, uint64_t vals_cap,
-               int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
-               uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
+#ifndef INQ_MEDIAN_MIN_CTAS
+#define INQ_MEDIAN_MIN_CTAS (INQ_MEDIAN_LOCI_PER_WARP == 1 ? 8 : 6)
+#endif
+constexpr int kMedianLociPerWarp = INQ_MEDIAN_LOCI_PER_WARP;
+
+// header of one locus' segment
+struct LocusSeg {
+    uint32_t seg, cap, nf, nb;
+    bool ok;
+};
+__device__ __forceinline__ LocusSeg locus_seg(uint32_t seg, uint32_t cap, unsigned long long cur, uint64_t vals_cap)
 {
-    // loci [l0, l1) of the catalog (chunk < kMaxMedianChunks); the chunk's CTA-path loci are listed in big_list[l0 ...]
-    const uint32_t l = l0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (l >= l1) return;
-    const uint32_t seg = seg_off[l], cap = seg_off[l + 1] - seg;
-    if ((uint64_t)seg + cap > vals_cap) {               // speculatively sized call buffer too small: the run is repeated
+    LocusSeg h;
+    h.seg = seg;
+    h.cap = cap;
+    h.ok = (uint64_t)seg + cap <= vals_cap;
+    h.nf = min((uint32_t)cur, cap);
+    h.nb = min((uint32_t)(cur >> 32), cap - h.nf);
+    return h;
+}
+// the common phased case (both haplotypes <= 16 calls): lane i < 16 holds H1's call i, lane 16 + i H2's call i
+__device__ __forceinline__ uint64_t fast16_load(const uint64_t *__restrict__ vals, const LocusSeg &h)
+{
+    const uint32_t i = lane_id();
+    if (i < h.nf) return vals[h.seg + i];
+    if (i >= 16u && i - 16u < h.nb) return vals[h.seg + h.cap - h.nb + (i - 16u)];
+    return kKeyInf;
+}
+
+// one locus: everything after the header. `pre`: the keys of the fast path, already loaded (kKeyInf lanes are empty).
+__device__ __forceinline__ void median_one(uint32_t l, uint32_t l0, int chunk, int unphased, uint32_t support, const LocusSeg &h, bool fast, uint64_t pre,
+                                           const uint64_t *__restrict__ vals, int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2,
+                                           uint8_t *__restrict__ valid, uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
+{
+    if (!h.ok) {                                        // speculatively sized call buffer too small: the run is repeated
         if (lane_id() == 0) atomicOr(&ctr->flags, kFlagValsOverflow);
         return;
     }
-    const unsigned long long cur = cursor[l];
-    const uint32_t nf = min((uint32_t)cur, cap), nb = min((uint32_t)(cur >> 32), cap - nf);
+    const uint32_t nf = h.nf, nb = h.nb, seg = h.seg, cap = h.cap;
     const uint32_t ntot = nf + nb;
     const uint32_t n1 = unphased ? (ntot >> 1) : nf;               // call.rs:314 split_at(len/2)
     int64_t t1 = 0, t2 = 0;
     uint32_t vm = 0;
     bool panicked = false;
-    if (!unphased && nf <= 16 && nb <= 16) warp_locus<1, 16>(vals, seg, cap, nf, nb, n1, true, support, &t1, &t2, &vm, &panicked);
-    else if (ntot <= 32) warp_locus<1>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
-    else if (!unphased && nf <= 32 && nb <= 32) warp_locus<2, 32>(vals, seg, cap, nf, nb, n1, true, support, &t1, &t2, &vm, &panicked);
-    else if (ntot <= 64) warp_locus<2>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
-    else if (ntot <= kMedianWarpMax) warp_locus<4>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
-    else {
-        if (lane_id() == 0) big_list[l0 + atomicAdd(&ctr->big_count[chunk], 1u)] = l;
-        return;
+    bool done = false;
+    if (fast) {
+        // keys are here already: 32-bit layout when every call fits 30 bits (practically always)
+        const bool have = pre != kKeyInf;
+        const int64_t c = key_call(pre);
+        const bool small = !have || (c >= -(int64_t)KeyTraits<uint32_t>::bias && c < (int64_t)KeyTraits<uint32_t>::bias);
+        if (__all_sync(0xffffffffu, small)) {
+            uint32_t k32[1];
+            k32[0] = have ? ((uint32_t)((c + KeyTraits<uint32_t>::bias) << 1) | (uint32_t)(pre & 1ull)) : KeyTraits<uint32_t>::inf;
+            warp_sort<1, uint32_t, 16>(k32);
+            median_halves32(k32[0], nf, nb, support, &t1, &t2, &vm, &panicked);
+            done = true;
+        }
+    }
+    if (!done) {
+        if (!unphased && nf <= 16 && nb <= 16) warp_locus<1, 16>(vals, seg, cap, nf, nb, n1, true, support, &t1, &t2, &vm, &panicked);
+        else if (ntot <= 32) warp_locus<1>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+        else if (!unphased && nf <= 32 && nb <= 32) warp_locus<2, 32>(vals, seg, cap, nf, nb, n1, true, support, &t1, &t2, &vm, &panicked);
+        else if (ntot <= 64) warp_locus<2>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+        else if (ntot <= kMedianWarpMax) warp_locus<4>(vals, seg, cap, nf, nb, n1, !unphased, support, &t1, &t2, &vm, &panicked);
+        else {
+            if (lane_id() == 0) big_list[l0 + atomicAdd(&ctr->big_count[chunk], 1u)] = l;
+            return;
+        }
     }
     if (lane_id() == 0) {
         twice_h1[l] = t1;
@@ -1362,6 +1401,46 @@ k_locus_median(uint32_t l0, uint32_t l1, int chunk, int unphased, uint32_t suppo
         valid[l] = (uint8_t)vm;
         if (panicked) atomicOr(&ctr->flags, kFlagMedianEmpty);
     }
+}
+
+// A warp owns kMedianLociPerWarp consecutive loci (default 1). Each locus costs two dependent round trips (segment header,
+// then its calls); with several loci per warp all headers and then all key loads are in flight together before any locus is
+// reduced -- measured, it does not pay: 68 % of the issue slots are busy already and the extra registers cost occupancy.
+__global__ void __launch_bounds__(256, INQ_MEDIAN_MIN_CTAS)
+k_locus_median(uint32_t l0, uint32_t l1, int chunk, int unphased, uint32_t support, const uint32_t *__restrict__ seg_off,
+               const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ vals, uint64_t vals_cap,
+               int64_t *__restrict__ twice_h1, int64_t *__restrict__ twice_h2, uint8_t *__restrict__ valid,
+               uint32_t *__restrict__ big_list, DevCounters *__restrict__ ctr)
+{
+    // loci [l0, l1) of the catalog (chunk < kMaxMedianChunks); the chunk's CTA-path loci are listed in big_list[l0 ...]
+    const uint32_t lw = l0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (uint32_t)kMedianLociPerWarp;
+    if (lw >= l1) return;
+    LocusSeg h[kMedianLociPerWarp];
+    bool live[kMedianLociPerWarp], fast[kMedianLociPerWarp];
+    uint64_t pre[kMedianLociPerWarp];
+    // round trip 1: the headers of all the warp's loci
+    {
+        uint32_t so[kMedianLociPerWarp + 1];
+        unsigned long long cur[kMedianLociPerWarp];
+#pragma unroll
+        for (int i = 0; i <= kMedianLociPerWarp; ++i) so[i] = (lw + i <= l1) ? seg_off[lw + i] : 0u;
+#pragma unroll
+        for (int i = 0; i < kMedianLociPerWarp; ++i) {
+            live[i] = lw + i < l1;
+            cur[i] = live[i] ? cursor[lw + i] : 0ull;
+        }
+#pragma unroll
+        for (int i = 0; i < kMedianLociPerWarp; ++i) h[i] = locus_seg(so[i], live[i] ? so[i + 1] - so[i] : 0u, cur[i], vals_cap);
+    }
+    // round trip 2: the calls of the loci on the common path
+#pragma unroll
+    for (int i = 0; i < kMedianLociPerWarp; ++i) {
+        fast[i] = live[i] && h[i].ok && !unphased && h[i].nf <= 16u && h[i].nb <= 16u;
+        pre[i] = fast[i] ? fast16_load(vals, h[i]) : kKeyInf;
+    }
+#pragma unroll
+    for (int i = 0; i < kMedianLociPerWarp; ++i)
+        if (live[i]) median_one(lw + i, l0, chunk, unphased, support, h[i], fast[i], pre[i], vals, twice_h1, twice_h2, valid, big_list, ctr);
 }
 
 // CTA-wide path for loci with more than kMedianWarpMax calls: bitonic sort in shared memory when
