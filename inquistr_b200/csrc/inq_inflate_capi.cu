@@ -224,6 +224,7 @@ int inq_host_register(void *p, size_t bytes)
 {
     if (!p || !bytes) return INQ_ERR_ARG;
     const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return INQ_OK; }      // (two engines met on one buffer)
     if (e != cudaSuccess) { cudaGetLastError(); return zfail(INQ_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
     return INQ_OK;
 }
