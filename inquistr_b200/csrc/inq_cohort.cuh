@@ -515,13 +515,14 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
         if (tid == 0 && row_kept) row_kept[row] = kept ? 1 : 0;
         if (!kept) continue;
 
-        // ---- sort by (value, column)
-        for (uint32_t blk = 2; blk <= n2; blk <<= 1) {
-            // mirror step: comparator q of the stage joins i = (q / h) * blk + q % h with j = i ^ (blk - 1), h = blk / 2
+        // ---- sort by (value, column). Comparator q of a stage is found with shifts only (blk and d are powers of two).
+        for (uint32_t lb = 1; (1u << lb) <= n2; ++lb) {
+            const uint32_t blk = 1u << lb;
+            // mirror step: comparator q joins i = (q >> (lb-1)) * blk + (q & (h-1)) with j = i ^ (blk - 1), h = blk / 2
             {
                 const uint32_t h = blk >> 1;
                 for (uint32_t q = tid;; q += blockDim.x) {
-                    const uint32_t i = (q / h) * blk + (q & (h - 1));
+                    const uint32_t i = ((q >> (lb - 1)) << lb) + (q & (h - 1));
                     if (i >= n) break;
                     const uint32_t j = i ^ (blk - 1);
                     if (j < n) {
@@ -531,9 +532,10 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
                 }
                 __syncthreads();
             }
-            for (uint32_t d = blk >> 2; d >= 1; d >>= 1) {
+            for (int ld = (int)lb - 2; ld >= 0; --ld) {
+                const uint32_t d = 1u << ld;
                 for (uint32_t q = tid;; q += blockDim.x) {
-                    const uint32_t i = ((q / d) * 2 * d) + (q & (d - 1));
+                    const uint32_t i = ((q >> ld) << (ld + 1)) + (q & (d - 1));
                     if (i >= n) break;
                     const uint32_t j = i + d;
                     if (j < n) {
