@@ -453,24 +453,20 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t *s_warp
     return base + x - v;
 }
 
-// neighbours of sorted element i: the contiguous run [lo, hi) with |key[i] - key[j]| < eps, compared in f64
-// like dbscan's euclidean distance (range_query's `distance < eps`)
-__device__ __forceinline__ void eps_range(const float *key, uint32_t n, uint32_t i, double eps, uint32_t *lo, uint32_t *hi)
-{
-    const double x = (double)key[i];
-    uint32_t a = 0, b = i;                               // first j <= i with x - key[j] < eps
-    while (a < b) { const uint32_t mid = (a + b) >> 1; if (!(x - (double)key[mid] < eps)) a = mid + 1; else b = mid; }
-    *lo = a;
-    a = i; b = n;                                        // first j >= i with key[j] - x >= eps
-    while (a < b) { const uint32_t mid = (a + b) >> 1; if ((double)key[mid] - x < eps) a = mid + 1; else b = mid; }
-    *hi = a;
-}
-
-// one CTA per row. Shared memory: skey[n] u64 (sort keys), key[n] f32, pc[n + 1] u32 (prefix count of core points),
-// idx[n] u16. The sort is an all-ascending bitonic network over the next power of two with VIRTUAL +inf padding:
-// a comparator whose upper end lies at or beyond n is a no-op, so only the ~n/2 real comparators of a stage are
-// enumerated (536 columns cost 268 compare-exchanges per stage, not 512), on one packed 64-bit key
-// (order-preserving image of the f32 value << 32 | column).
+// one CTA per row, two sort engines:
+//  * CH == 0 (rows wider than 1024 columns, or narrower than 64): 128 threads (one warp for tiny rows), an
+//    all-ascending bitonic network in shared memory over the next power of two with VIRTUAL +inf padding: a
+//    comparator whose upper end lies at or beyond n is a no-op, so only the ~n/2 real comparators of a stage are
+//    enumerated.
+//  * CH  > 0 (n2 = 32 * CH <= 1024): one warp, the whole row in registers, lane-major (element e = lane * CH + k):
+//    the 40 of 55 stages whose comparators span fewer than CH elements are min/max pairs on a lane's own
+//    registers, the rest exchange with `shfl.xor` — no shared memory, no barrier, no index arithmetic.
+// Only the VALUES are sorted (order-preserving u32 image of the f32): in one dimension a point's class depends on
+// its value alone, so the columns of the few noise values are recovered at the end by scanning the row for them,
+// which is far cheaper than dragging a column index through every comparator.
+// Shared memory after the sort: key[] f32 sorted values, pc[n + 1] u32 prefix count of core points, rng[n] u32 each
+// element's neighbour range (then the list of noise values). In register mode key[] is written lane-major, so it
+// carries one pad slot per 32 elements to keep those stores off a single bank.
 __device__ __forceinline__ uint32_t f32_orderable(float v)
 {
     const uint32_t u = __float_as_uint(v);
@@ -481,29 +477,129 @@ __device__ __forceinline__ float f32_from_orderable(uint32_t o)
     return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
 }
 
-__global__ void __launch_bounds__(kDbThreads)
+template <bool PAD> struct SortedKeys {
+    const float *key;
+    __device__ __forceinline__ float operator[](uint32_t i) const { return key[PAD ? i + (i >> 5) : i]; }
+};
+
+// neighbours of sorted element i: the contiguous run [lo, hi) with |key[i] - key[j]| < eps, decided in f64
+// like dbscan's euclidean distance (range_query's `distance < eps`). The binary searches run on f32 thresholds
+// rounded towards the side that keeps them exact for an exact x -+ eps (key > T <=> key > rd(T); key >= U <=>
+// key >= ru(U)); the f64 predicate itself then settles the boundary, so a difference that rounds in f64 still
+// lands where the reference's comparison puts it.
+template <bool PAD>
+__device__ __forceinline__ void eps_range(const SortedKeys<PAD> key, uint32_t n, uint32_t i, double eps, uint32_t *lo, uint32_t *hi)
+{
+    const double x = (double)key[i];
+    const float tg = __double2float_rd(x - eps);
+    uint32_t a = 0, b = i;                               // first j <= i with x - key[j] < eps
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (!(key[mid] > tg)) a = mid + 1; else b = mid; }
+    while (a > 0 && (x - (double)key[a - 1] < eps)) --a;
+    while (a < i && !(x - (double)key[a] < eps)) ++a;
+    *lo = a;
+    const float uf = __double2float_ru(x + eps);
+    a = i; b = n;                                        // first j >= i with key[j] - x >= eps
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (key[mid] < uf) a = mid + 1; else b = mid; }
+    while (a > i && !((double)key[a - 1] - x < eps)) --a;
+    while (a < n && ((double)key[a] - x < eps)) ++a;
+    *hi = a;
+}
+
+__device__ __forceinline__ void cmpswap(uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t a = lo, b = hi;
+    lo = min(a, b);
+    hi = max(a, b);
+}
+// this lane keeps the smaller or (upper) the larger of its own and its partner's key: one predicated VIMNMX
+__device__ __forceinline__ uint32_t keep_of(uint32_t mine, uint32_t other, bool upper)
+{
+    return upper ? max(mine, other) : min(mine, other);
+}
+
+template <int CH>
+__device__ __forceinline__ void warp_sort(uint32_t (&r)[CH], uint32_t lane)
+{
+#pragma unroll
+    for (int blk = 2; blk <= CH * 32; blk <<= 1) {
+        // mirror step: element i meets i ^ (blk - 1)
+        if (blk <= CH) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+                if ((k ^ (blk - 1)) > k) cmpswap(r[k], r[k ^ (blk - 1)]);
+        } else {
+            const int lm = blk / CH - 1;                     // partner lane = lane ^ lm, partner slot = CH - 1 - k
+            const bool upper = (lane & (uint32_t)(blk / CH / 2)) != 0;
+#pragma unroll
+            for (int k = 0; k < CH / 2; ++k) {
+                const uint32_t pa = __shfl_xor_sync(0xffffffffu, r[CH - 1 - k], lm);
+                const uint32_t pb = __shfl_xor_sync(0xffffffffu, r[k], lm);
+                r[k] = keep_of(r[k], pa, upper);
+                r[CH - 1 - k] = keep_of(r[CH - 1 - k], pb, upper);
+            }
+        }
+        // half-cleaners: element i (bit d clear) meets i + d
+#pragma unroll
+        for (int d = blk / 4; d >= 1; d >>= 1) {
+            if (d >= CH) {
+                const bool upper = (lane & (uint32_t)(d / CH)) != 0;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) r[k] = keep_of(r[k], __shfl_xor_sync(0xffffffffu, r[k], d / CH), upper);
+            } else {
+#pragma unroll
+                for (int k = 0; k < CH; ++k)
+                    if ((k & d) == 0) cmpswap(r[k], r[k + d]);
+            }
+        }
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(CH ? 32 : kDbThreads)
 k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, uint32_t n2, float minsize,
                  uint32_t min_points, uint8_t *__restrict__ row_kept, unsigned long long *__restrict__ hits,
                  uint64_t cap, CohortCounters *__restrict__ ctr)
 {
+    constexpr bool PAD = CH > 0;
+    constexpr int CHR = CH ? CH : 1;
     extern __shared__ __align__(8) unsigned char db_smem[];
-    unsigned long long *skey = reinterpret_cast<unsigned long long *>(db_smem);
-    float *key = reinterpret_cast<float *>(skey + n_cols);
-    uint32_t *pc = reinterpret_cast<uint32_t *>(key + n_cols);
-    uint16_t *idx = reinterpret_cast<uint16_t *>(pc + n_cols + 1);
+    const uint32_t n = n_cols;
+    const uint32_t nk = PAD ? n + (n >> 5) + 1 : n;        // slots of key[]
+    uint32_t *rng = reinterpret_cast<uint32_t *>(db_smem);
+    uint32_t *pc = rng + n;
+    float *key = reinterpret_cast<float *>(pc + n + 1);
+    uint32_t *ukey = reinterpret_cast<uint32_t *>(key);    // CH == 0: the keys are sorted in place as u32 images
+    float *noise_val = reinterpret_cast<float *>(rng);     // once the ranges are consumed
+    const SortedKeys<PAD> skeys{key};
     __shared__ uint32_t s_warp[kDbThreads / 32];
     __shared__ float s_wmax[kDbThreads / 32];
     __shared__ unsigned long long s_best;
+    __shared__ uint32_t s_nnoise;
     const uint32_t tid = threadIdx.x;
-    const uint32_t n = n_cols;
+    (void)nk;
     for (uint64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const float *mrow = m + row * n_cols;
         __syncthreads();
-        if (tid == 0) s_best = 0ull;
+        if (tid == 0) { s_best = 0ull; s_nnoise = 0u; }
         float mx = -INFINITY;
-        for (uint32_t i = tid; i < n; i += blockDim.x) {
-            const float v = clean(m[row * n_cols + i]);
-            mx = (v > mx) ? v : mx;
-            skey[i] = ((unsigned long long)f32_orderable(v) << 32) | i;
+        uint32_t r[CHR];
+        if constexpr (PAD) {
+#pragma unroll
+            for (int k = 0; k < CHR; ++k) {
+                const uint32_t e = tid * CHR + k;
+                r[k] = 0xFFFFFFFFu;                          // above every real image (that pattern is a NaN, cleaned to 0)
+                if (e < n) {
+                    const float v = clean(__ldg(mrow + e));
+                    mx = (v > mx) ? v : mx;
+                    r[k] = f32_orderable(v);
+                }
+            }
+        } else {
+            for (uint32_t i = tid; i < n; i += blockDim.x) {
+                const float v = clean(mrow[i]);
+                mx = (v > mx) ? v : mx;
+                ukey[i] = f32_orderable(v);
+            }
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) { const float o = __shfl_xor_sync(0xffffffffu, mx, d); mx = (o > mx) ? o : mx; }
@@ -515,62 +611,65 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
         if (tid == 0 && row_kept) row_kept[row] = kept ? 1 : 0;
         if (!kept) continue;
 
-        // ---- sort by (value, column). Comparator q of a stage is found with shifts only (blk and d are powers of two).
-        for (uint32_t lb = 1; (1u << lb) <= n2; ++lb) {
-            const uint32_t blk = 1u << lb;
-            // mirror step: comparator q joins i = (q >> (lb-1)) * blk + (q & (h-1)) with j = i ^ (blk - 1), h = blk / 2
-            {
-                const uint32_t h = blk >> 1;
-                for (uint32_t q = tid;; q += blockDim.x) {
-                    const uint32_t i = ((q >> (lb - 1)) << lb) + (q & (h - 1));
-                    if (i >= n) break;
-                    const uint32_t j = i ^ (blk - 1);
-                    if (j < n) {
-                        const unsigned long long a = skey[i], b = skey[j];
-                        if (a > b) { skey[i] = b; skey[j] = a; }
-                    }
-                }
-                __syncthreads();
+        // ---- sort the values
+        if constexpr (PAD) {
+            warp_sort<CHR>(r, tid);
+#pragma unroll
+            for (int k = 0; k < CHR; ++k) {
+                const uint32_t e = tid * CHR + k;
+                if (e < n) key[e + (e >> 5)] = f32_from_orderable(r[k]);
             }
-            for (int ld = (int)lb - 2; ld >= 0; --ld) {
-                const uint32_t d = 1u << ld;
-                for (uint32_t q = tid;; q += blockDim.x) {
-                    const uint32_t i = ((q >> ld) << (ld + 1)) + (q & (d - 1));
-                    if (i >= n) break;
-                    const uint32_t j = i + d;
-                    if (j < n) {
-                        const unsigned long long a = skey[i], b = skey[j];
-                        if (a > b) { skey[i] = b; skey[j] = a; }
+        } else {
+            // comparator q of a stage is found with shifts only (blk and d are powers of two)
+            for (uint32_t lb = 1; (1u << lb) <= n2; ++lb) {
+                const uint32_t blk = 1u << lb;
+                // mirror step: comparator q joins i = (q >> (lb-1)) * blk + (q & (h-1)) with j = i ^ (blk - 1), h = blk / 2
+                {
+                    const uint32_t h = blk >> 1;
+                    for (uint32_t q = tid;; q += blockDim.x) {
+                        const uint32_t i = ((q >> (lb - 1)) << lb) + (q & (h - 1));
+                        if (i >= n) break;
+                        const uint32_t j = i ^ (blk - 1);
+                        if (j < n) {
+                            const uint32_t a = ukey[i], b = ukey[j];
+                            if (a > b) { ukey[i] = b; ukey[j] = a; }
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
+                for (int ld = (int)lb - 2; ld >= 0; --ld) {
+                    const uint32_t d = 1u << ld;
+                    for (uint32_t q = tid;; q += blockDim.x) {
+                        const uint32_t i = ((q >> ld) << (ld + 1)) + (q & (d - 1));
+                        if (i >= n) break;
+                        const uint32_t j = i + d;
+                        if (j < n) {
+                            const uint32_t a = ukey[i], b = ukey[j];
+                            if (a > b) { ukey[i] = b; ukey[j] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
             }
-        }
-        for (uint32_t i = tid; i < n; i += blockDim.x) {
-            const unsigned long long k = skey[i];
-            key[i] = f32_from_orderable((uint32_t)(k >> 32));
-            idx[i] = (uint16_t)(k & 0xFFFFu);
+            for (uint32_t i = tid; i < n; i += blockDim.x) key[i] = f32_from_orderable(ukey[i]);
         }
         __syncthreads();
 
         // ---- mode of `value as usize` over the positive values (outlier.rs:133-145): the sorted order
-        //      is also the order of the truncated values, so a value's count is a pair of binary searches.
+        //      is also the order of the truncated values, so a run's length is one binary search from its first element.
         //      Ties: the smallest value (the reference's HashMap order is random).
         unsigned long long best = 0ull;                      // (count << 32) | ~rank  -> max = most frequent, then smallest
         for (uint32_t i = tid; i < n_cols; i += blockDim.x) {
-            const float v = key[i];
+            const float v = skeys[i];
             if (!(v > 0.0f)) continue;
             const float t = truncf(v);
-            uint32_t lo = 0, hi = n_cols;                    // first j with trunc(key[j]) >= t  (key[j] >= t)
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (key[mid] < t) lo = mid + 1; else hi = mid; }
-            uint32_t lo2 = lo, hi2 = n_cols;                 // first j with key[j] >= t + 1
-            const float t1 = t + 1.0f;
-            while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (key[mid] < t1) lo2 = mid + 1; else hi2 = mid; }
-            // positives only: for t == 0 the run starts at the first positive value
-            uint32_t first = lo;
-            if (t == 0.0f) { uint32_t a = 0, b = n_cols; while (a < b) { const uint32_t mid = (a + b) >> 1; if (!(key[mid] > 0.0f)) a = mid + 1; else b = mid; } first = a; }
-            const uint32_t cnt = lo2 - first;
-            const unsigned long long cand = ((unsigned long long)cnt << 32) | (0xFFFFFFFFu - first);
+            if (i > 0) {                                     // only the first element of a run of equal truncations counts it
+                const float p = skeys[i - 1];
+                if (p > 0.0f && truncf(p) == t) continue;
+            }
+            uint32_t lo2 = i + 1, hi2 = n_cols;              // first j whose truncation exceeds t (exact at any magnitude)
+            while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (truncf(skeys[mid]) <= t) lo2 = mid + 1; else hi2 = mid; }
+            const unsigned long long cand = ((unsigned long long)(lo2 - i) << 32) | (0xFFFFFFFFu - i);
             best = cand > best ? cand : best;
         }
 #pragma unroll
@@ -589,15 +688,15 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
             continue;
         }
         const uint32_t mode_first = 0xFFFFFFFFu - (uint32_t)(s_best & 0xFFFFFFFFull);
-        const float mode_f = truncf(key[mode_first]);
+        const float mode_f = truncf(skeys[mode_first]);
         // eps = max(2 * mode, 10) as f64 (outlier.rs:118); mode < 2^24 is exact in f32 and doubling is exact in f64
         const double eps = fmax(2.0 * (double)mode_f, 10.0);
 
         // ---- core points: |x_i - x_j| < eps in f64 (dbscan's euclidean distance), j over the whole row
-        __syncthreads();
         for (uint32_t i = tid; i < n; i += blockDim.x) {
             uint32_t lo = 0, hi = 0;
-            eps_range(key, n_cols, i, eps, &lo, &hi);
+            eps_range(skeys, n_cols, i, eps, &lo, &hi);
+            rng[i] = lo | (hi << 16);                        // n_cols <= 4096: both fit 16 bits
             pc[i] = (hi - lo >= min_points) ? 1u : 0u;
         }
         __syncthreads();
@@ -613,26 +712,27 @@ k_outlier_dbscan(const float *__restrict__ m, uint64_t n_rows, uint32_t n_cols, 
         }
         if (tid == 0) pc[n] = carry;
         __syncthreads();
-        // ---- noise = not core and no core point within eps (Edge otherwise)
-        //      (flags first, then one global atomic per row reserves the slots of all its outliers)
-        uint32_t mine = 0, nmine = 0;                        // bit q: element tid + q * blockDim.x is noise (n <= 4096 -> q < 32)
+        // ---- noise = not core and no core point within eps (Edge otherwise). Equal values share a class, so a
+        //      noise VALUE is listed once (by the first element of its run)
+        uint32_t mine = 0;                                   // bit q: element tid + q * blockDim.x opens a run of noise values
         for (uint32_t i = tid, q = 0; i < n_cols; i += blockDim.x, ++q) {
-            uint32_t lo, hi;
-            eps_range(key, n_cols, i, eps, &lo, &hi);
+            const uint32_t lo = rng[i] & 0xFFFFu, hi = rng[i] >> 16;
             const bool core = hi - lo >= min_points;
             const bool near_core = pc[hi] - pc[lo] > 0u;
-            if (!core && !near_core) { mine |= 1u << q; ++nmine; }
+            if (!core && !near_core && (i == 0 || !(skeys[i - 1] == skeys[i]))) mine |= 1u << q;
         }
-        uint32_t tot;
-        const uint32_t off = block_scan_excl(nmine, s_warp, &tot);
-        if (tid == 0 && tot) s_best = atomicAdd(&ctr->n_hits, (unsigned long long)tot);    // s_best is free again: slot base
+        __syncthreads();                                     // every range is consumed: rng becomes the noise list
+        for (uint32_t q = 0; mine; ++q, mine >>= 1)
+            if (mine & 1u) noise_val[atomicAdd(&s_nnoise, 1u)] = skeys[tid + q * blockDim.x];
         __syncthreads();
-        if (tot) {
-            unsigned long long slot = s_best + off;
-            for (uint32_t q = 0; mine; ++q, mine >>= 1)
-                if (mine & 1u) {
-                    if (slot < cap) hits[slot] = (row << 32) | idx[tid + q * blockDim.x];
-                    ++slot;
+        // ---- the columns holding a noise value are the row's outliers (host sorts the (row, column) list)
+        const uint32_t nn = s_nnoise;
+        for (uint32_t w = 0; w < nn; ++w) {
+            const float v = noise_val[w];
+            for (uint32_t c = tid; c < n_cols; c += blockDim.x)
+                if (clean(__ldg(mrow + c)) == v) {
+                    const unsigned long long slot = atomicAdd(&ctr->n_hits, 1ull);
+                    if (slot < cap) hits[slot] = (row << 32) | c;
                 }
         }
     }

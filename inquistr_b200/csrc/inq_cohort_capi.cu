@@ -114,20 +114,35 @@ int inq_outlier(int device, int method, uint64_t n_rows, uint32_t n_cols, const 
     } else {
         uint32_t n2 = 32;
         while (n2 < n_cols) n2 <<= 1;
-        const size_t smem = (size_t)n_cols * (sizeof(uint64_t) + sizeof(float) + sizeof(uint32_t) + sizeof(uint16_t)) + sizeof(uint32_t) + 16;
         uint32_t min_points = 0;                              // samples.len().ilog2(), outlier.rs:39
         while ((2ull << min_points) <= n_cols) ++min_points;
         int sms = 0;
         CC_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        // One warp per row when the row fits 1024 columns: 55 sort stages without a block barrier, and ~20 rows in
-        // flight per SM (shared memory) hide each other's latency; wider rows keep the 128-thread CTA.
+        // 64..1024 padded columns: one warp per row, sorted in registers (n2 / 32 keys per lane). Otherwise the
+        // shared-memory network: one warp for tiny rows, the 128-thread CTA for rows wider than 1024 columns.
+        const int ch = (n2 >= 64 && n2 <= 1024) ? (int)(n2 / 32) : 0;
+        const size_t nk = ch ? (size_t)n_cols + (n_cols >> 5) + 1 : n_cols;
+        const size_t smem = ((size_t)n_cols * 2 + 1 + nk) * sizeof(uint32_t) + 16;   // rng[n], pc[n + 1], key[nk]
         const unsigned threads = n_cols <= 1024 ? 32u : (unsigned)kDbThreads;
-        int per_sm = 8;
-        CC_TRY(cudaFuncSetAttribute(k_outlier_dbscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_outlier_dbscan, (int)threads, smem));
-        const unsigned grid = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sms * std::max(per_sm, 1));
-        k_outlier_dbscan<<<grid, threads, smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, n2, (float)minsize, min_points,
-                                                       (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+        auto launch = [&](auto kernel) -> int {
+            int per_sm = 8;
+            CC_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem));
+            const unsigned grid = (unsigned)std::min<uint64_t>(n_rows, (uint64_t)sms * std::max(per_sm, 1));
+            kernel<<<grid, threads, smem, g.s>>>((const float *)g.d_m, n_rows, n_cols, n2, (float)minsize, min_points,
+                                                 (uint8_t *)g.d_kept, (unsigned long long *)g.d_hits, cap, (CohortCounters *)g.d_ctr);
+            return INQ_OK;
+        };
+        int lrc;
+        switch (ch) {
+        case 2: lrc = launch(k_outlier_dbscan<2>); break;
+        case 4: lrc = launch(k_outlier_dbscan<4>); break;
+        case 8: lrc = launch(k_outlier_dbscan<8>); break;
+        case 16: lrc = launch(k_outlier_dbscan<16>); break;
+        case 32: lrc = launch(k_outlier_dbscan<32>); break;
+        default: lrc = launch(k_outlier_dbscan<0>); break;
+        }
+        if (lrc != INQ_OK) return lrc;
     }
     CC_TRY(cudaGetLastError());
     CC_TRY(cudaEventRecord(g.e1, g.s));

@@ -87,6 +87,36 @@ def test_gpu_outlier_matches_oracle(rows, cols, method):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cols", [3, 31, 33, 63, 64, 65, 100, 128, 129, 255, 257, 511, 513, 1023, 1024, 1025, 1500, 4096])
+def test_gpu_dbscan_every_sort_engine(cols):
+    """The dbscan kernel picks a register sort by padded width (2..32 keys per lane) or the shared-memory network
+    (tiny and > 1024-column rows); every boundary against the oracle, with the inputs that stress the value-only
+    sort: heavy ties, +-0, infinities, negative values and an outlier value that occurs in several columns."""
+    from inquistr_b200 import cohort
+    rng = np.random.default_rng(cols)
+    rows = 48
+    m = random_matrix(7000 + cols, rows, cols)
+    m[1, :] = 30.0                                                            # one value only
+    m[2, : cols // 2] = 0.0
+    m[2, cols // 2:] = -0.0
+    m[2, -1] = 40.0
+    if cols >= 31:
+        m[3, :] = 12.0
+        m[3, [1, 5, cols - 1]] = 900.0                                        # the same noise value in three columns
+        m[4, 0] = np.inf
+        m[4, 1] = -np.inf
+        m[5, : cols // 3] = -rng.integers(1, 50, cols // 3)
+        m[6, :] = rng.integers(10, 14, cols)                                  # four distinct values
+    kept, flags, status = O.outlier_matrix(m, 10, 3.0, "dbscan")
+    assert (status == 0).all()
+    k, hr, hc, _ = cohort.outlier(m, 10, 3.0, "dbscan")
+    er, ec = np.nonzero(flags)
+    assert np.array_equal(k, kept) and np.array_equal(hr, er) and np.array_equal(hc, ec)
+    if cols >= 31:
+        assert set(hc[hr == 3]) == {1, 5, cols - 1}
+
+
+@pytest.mark.gpu
 def test_gpu_outlier_reference_vectors_and_errors():
     from inquistr_b200 import cohort
     from inquistr_b200.api import InqError
@@ -231,6 +261,28 @@ def test_cli_outlier_tsv_matches_oracle(cli, cohort_files, tmp_path):
     sub.write_text("sample1\nsample20\n")
     r = run(cli, "outlier", "-S", str(sub), "--method", "dbscan", str(cpath))
     assert r.returncode == 0 and r.stdout.decode() == expected_outlier_tsv(combined, 10, 3.0, "dbscan", {"sample1", "sample20"})
+
+
+@pytest.mark.gpu
+def test_cli_outlier_prints_rows_before_a_panic(cli, tmp_path):
+    """The reference writes each row as it is decided (outlier.rs:70-120), so what precedes the row it panics on is
+    already on stdout; the batched CLI must flush those rows before it exits 101."""
+    samples = [f"s{i}" for i in range(12)]
+    head = "chrom\tbegin\tend\t" + "\t".join(f"{s}_H1\t{s}_H2" for s in samples)
+    normal = ["20.0"] * 24
+    good = list(normal)
+    good[5] = "900.0"                                                     # s2_H2: a clear expansion
+    good_row = "chr1\t100\t200\t" + "\t".join(good)
+    bad = tmp_path / "bad_later.tsv"
+    bad.write_text(head + "\n" + good_row + "\nchr1\t300\t400\t" + "\t".join(normal[:-1] + ["x"]) + "\n")
+    r = run(cli, "outlier", str(bad))
+    assert r.returncode == 101 and b"Failed to parse number" in r.stderr
+    assert r.stdout.decode() == "chrom\tbegin\tend\toutliers\nchr1\t100\t200\ts2\n"
+    nomode = tmp_path / "nomode.tsv"
+    nomode.write_text(head + "\n" + good_row + "\nchr1\t300\t400\t" + "\t".join(["0.0"] * 24) + "\n" + good_row + "\n")
+    r = run(cli, "outlier", "--method", "dbscan", "--minsize", "0", str(nomode))
+    assert r.returncode == 101 and b"No mode found for repeat" in r.stderr  # outlier.rs:144
+    assert r.stdout.decode() == "chrom\tbegin\tend\toutliers\nchr1\t100\t200\ts2\n"
 
 
 def test_outlier_fails_loudly_without_gpu(cli, cohort_files, tmp_path):
