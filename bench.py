@@ -40,6 +40,7 @@ def parse_args():
                     help="ship every generated read (also the ones with mapq <= 10 / without HP that can never pair)")
     ap.add_argument("--ranges", type=int, default=None, help="inq_set_option('ranges') (default: automatic)")
     ap.add_argument("--no-graph", action="store_true", help="inq_set_option('graph', 0)")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="inq_set_option(NAME, VALUE), repeatable (experiments)")
     ap.add_argument("--bam-scale", type=float, default=0.1,
                     help="e2e_bam: `inquistr-b200 call` on a synthetic BAM with SEQ/QUAL of config 3 at this scale (0 = skip)")
     ap.add_argument("--no-cohort", action="store_true", help="skip the extra.cohort_outlier block (SURVEY 8f rank 3 kernels)")
@@ -199,6 +200,7 @@ def main():
         "workload": None, "config_index": args.config, "scale": args.scale, "minlen": 5, "support": 3,
         "sharding": f"locus catalog range-sharded over {world} rank(s), no collective",
         "l2": "inputs (packed CIGAR stream) are far larger than the 126 MB L2; no flush needed",
+        "timed_region": "per rank: barrier + synchronize, K calls, synchronize; the job's time is the max over ranks; the closing barrier follows the clock",
         "data_seed": args.config,
         "pack_filter": (not args.no_pack_filter),
         "pack_filter_note": "the host packer drops reads that fail the per-read part of call.rs:297-300/350-352 for every "
@@ -254,6 +256,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_ranks(x: float) -> list:
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def sum_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -276,6 +286,9 @@ def main():
         ctx.set_option("ranges", args.ranges)
     if args.no_graph:
         ctx.set_option("graph", 0)
+    for kv in args.set:
+        name, _, val = kv.partition("=")
+        ctx.set_option(name, int(val))
     ctx.set_loci(w.contig_locus_off, w.locus_start, w.locus_end)
     ctx.reserve_reads(rd.n, len(rd.cigar))
 
@@ -313,14 +326,19 @@ def main():
         acc[0] += cst.ms_total
         for i, k in enumerate(stage_keys):
             acc[i + 1] += getattr(cst, k)
+    torch.cuda.synchronize()
+    t_rank = time.perf_counter() - t0
     barrier()
-    # every inq_genotype call ends with a synchronize of the library's stream, so the bracket
-    # barrier -> K calls -> barrier is device time + launch gaps + the D2H of the results
-    wall_resident = max_over_ranks(time.perf_counter() - t0)
+    # every inq_genotype call ends with a synchronize of the library's streams, so each rank's bracket
+    # barrier -> K calls -> synchronize is device time + launch gaps + the D2H of the results; the job's time is
+    # the slowest rank's (the closing barrier's own NCCL latency is not part of any rank's K steps)
+    wall_resident = max_over_ranks(t_rank)
+    wall_per_rank = gather_ranks(t_rank / args.steps * 1e3)
     dev_ms = acc[0]
     cigar_ms = acc[1 + stage_keys.index("ms_cigar")]
     stage_ms = {k: acc[i + 1] / args.steps for i, k in enumerate(stage_keys)}
     dev_ms_max = max_over_ranks(dev_ms)
+    dev_per_rank = gather_ranks(dev_ms / args.steps)
     st = cst.as_dict()
     res = q.GenotypeResult(out[0], out[1], out[2], st)
 
@@ -334,8 +352,10 @@ def main():
             ctx.clear_reads()
             push_all()
             res2 = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
+        torch.cuda.synchronize()
+        e2e_rank = time.perf_counter() - t1
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t1)
+        e2e_s = max_over_ranks(e2e_rank)
         h2d = rd.nbytes() + w.locus_start.nbytes + w.locus_end.nbytes + w.contig_locus_off.nbytes
         d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes
         e2e = {"seconds_per_step": e2e_s / args.steps, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
@@ -343,6 +363,7 @@ def main():
     clk = clocks.stop() if clocks else None
 
     tot_loci = sum_over_ranks(st["n_loci"])
+    cj_per_rank = [int(v) for v in gather_ranks(float(st["n_cigar_words_joined"]))]
     tot_words = sum_over_ranks(st["n_cigar_words"])
     tot_words_j = sum_over_ranks(st["n_cigar_words_joined"])
     tot_visits = sum_over_ranks(st["op_visits"])
@@ -451,6 +472,8 @@ def main():
                        "cigar_words_joined": int(tot_words_j), "pairs": int(tot_pairs),
                        "events_rank0": int(st["n_events"]), "tiles_rank0": int(st["n_tiles"])},
             "device_ms_per_step": dev_sec_per_step * 1e3,
+            "per_rank": {"ms_per_step": [round(v, 4) for v in wall_per_rank], "device_ms_per_step": [round(v, 4) for v in dev_per_rank],
+                         "cigar_words_joined": cj_per_rank},
             "stage_ms_rank0": stage_ms,
             "pipeline": {"ranges": int(st["n_ranges"]), "median_chunks": int(st["n_median_chunks"]),
                          "cuda_graph": bool(st["used_graph"]), "reads_sorted": bool(st["reads_sorted"]),

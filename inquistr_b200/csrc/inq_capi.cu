@@ -178,6 +178,9 @@ struct inq_ctx {
     int opt_max_ranges = 1;               // measured (profiles/README.md, r2 sweeps): co-scheduling pair/median CTAs under the scan is zero-sum on B200
     int opt_graph = 1;
     int opt_timing = 1;
+    int opt_median_pieces = 8;        // median chunks per pass (the last one is a quarter piece)
+    int64_t opt_min_piece = 1 << 15;  // ... but no piece smaller than this many loci
+    int opt_push_kernel = 1;          // results leave through k_push_results (0: three copy-engine operations per chunk)
 
     // locus catalog
     int32_t n_contigs = 0;
@@ -410,6 +413,35 @@ __global__ void k_check_sorted(const int32_t *__restrict__ contig, const int32_t
 // on the critical path of a small workload)
 struct ZeroJob { void *p; uint64_t bytes; };
 struct ZeroJobs { ZeroJob j[6]; int n; };
+// The results of one median chunk go home through a kernel that stores into the caller's pinned (mapped) arrays:
+// one launch in place of three copy-engine operations, whose ~10 us apiece of fixed latency is what a chunk's
+// transfer costs at the per-rank sizes of a multi-GPU run. Fully coalesced 8-byte stores; the byte mask is moved
+// 4 bytes per lane between its aligned edges.
+__global__ void __launch_bounds__(256)
+k_push_results(uint32_t l0, uint32_t l1, const int64_t *__restrict__ t1, const int64_t *__restrict__ t2, const uint8_t *__restrict__ valid,
+               int64_t *__restrict__ o1, int64_t *__restrict__ o2, uint8_t *__restrict__ ov)
+{
+    const uint32_t n = l1 - l0, stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = tid; i < n; i += stride) {
+        __stcs(o1 + l0 + i, t1[l0 + i]);
+        __stcs(o2 + l0 + i, t2[l0 + i]);
+    }
+    // mask: head bytes up to the first 4-byte boundary of the device array, whole words, tail bytes (the host array
+    // shares the index, not necessarily the alignment: word stores only when both are aligned)
+    const bool words = ((reinterpret_cast<uintptr_t>(valid) ^ reinterpret_cast<uintptr_t>(ov)) & 3u) == 0;
+    if (!words) {
+        for (uint32_t i = tid; i < n; i += stride) ov[l0 + i] = valid[l0 + i];
+        return;
+    }
+    const uint32_t head = min(n, (uint32_t)((4u - ((reinterpret_cast<uintptr_t>(valid) + l0) & 3u)) & 3u));
+    const uint32_t nw = (n - head) >> 2, tail0 = head + (nw << 2);
+    if (tid < head) ov[l0 + tid] = valid[l0 + tid];
+    const uint32_t *vw = reinterpret_cast<const uint32_t *>(valid + l0 + head);
+    uint32_t *ow = reinterpret_cast<uint32_t *>(ov + l0 + head);
+    for (uint32_t i = tid; i < nw; i += stride) __stcs(ow + i, vw[i]);
+    if (tid < n - tail0) ov[l0 + tail0 + tid] = valid[l0 + tail0 + tid];
+}
+
 __global__ void k_zero(ZeroJobs jobs)
 {
     for (int k = 0; k < jobs.n; ++k) {
@@ -444,6 +476,8 @@ struct RunParams {
     int64_t *o1, *o2;
     uint8_t *ov;
     bool timing;
+    int64_t *d1 = nullptr, *d2 = nullptr;   // device views of o1/o2/ov (mapped pinned memory); null: use the copy engines
+    uint8_t *dv = nullptr;
 };
 
 // Cut the pass into ranges (see the file header). Needs one small device read-back, so it is cached until
@@ -496,8 +530,8 @@ int build_plan(inq_ctx *ctx, uint64_t n_wt)
     }
     // median chunks: the loci that became complete with pair(k - 1), cut into pieces so that the copy of one piece
     // runs under the medians of the next; the very last piece is small (its copy is the exposed one)
-    const int64_t piece = std::max<int64_t>(1 << 15, (L + 7) / 8);
-    const int64_t last_piece = std::max<int64_t>(1 << 13, L / 32);
+    const int64_t piece = std::max<int64_t>(ctx->opt_min_piece, (L + ctx->opt_median_pieces - 1) / ctx->opt_median_pieces);
+    const int64_t last_piece = std::max<int64_t>(ctx->opt_min_piece / 4, L / (4 * ctx->opt_median_pieces));
     for (int k = 1; k <= K; ++k) {
         int64_t a = done[k - 1], b = done[k];
         if (k == K && L == 0) break;
@@ -674,9 +708,16 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
             }
             const size_t n = l1 - l0;
-            CU_TRY(ctx, cudaMemcpyAsync(o1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
-            CU_TRY(ctx, cudaMemcpyAsync(o2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
-            CU_TRY(ctx, cudaMemcpyAsync(ov + l0, ctx->valid.p + l0, n, cudaMemcpyDeviceToHost, s3));
+            if (rp.d1) {
+                const unsigned g = (unsigned)std::min<size_t>(64, (n + 2047) / 2048);
+                k_push_results<<<std::max(g, 1u), 256, 0, s3>>>(l0, l1, ctx->t1.p, ctx->t2.p, ctx->valid.p, rp.d1, rp.d2, rp.dv);
+                ++launches;
+                CU_TRY(ctx, cudaGetLastError());
+            } else {
+                CU_TRY(ctx, cudaMemcpyAsync(o1 + l0, ctx->t1.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
+                CU_TRY(ctx, cudaMemcpyAsync(o2 + l0, ctx->t2.p + l0, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s3));
+                CU_TRY(ctx, cudaMemcpyAsync(ov + l0, ctx->valid.p + l0, n, cudaMemcpyDeviceToHost, s3));
+            }
         }
     }
     if (pl.n_chunks == 0) {                                   // nothing to do on S2/S3: keep them in the DAG for the join below
@@ -837,6 +878,14 @@ int inq_set_option(inq_ctx *ctx, const char *name, int64_t value)
         ctx->opt_min_range_tiles = value;
     } else if (n == "graph") ctx->opt_graph = value != 0;
     else if (n == "timing") ctx->opt_timing = value != 0;
+    else if (n == "push_kernel") ctx->opt_push_kernel = value != 0;
+    else if (n == "median_pieces") {
+        if (value < 1 || value > kMaxMedianChunks / 2) return fail(ctx, INQ_ERR_ARG, "median_pieces must be in [1, %d]", kMaxMedianChunks / 2);
+        ctx->opt_median_pieces = (int)value;
+    } else if (n == "min_piece") {
+        if (value < 256) return fail(ctx, INQ_ERR_ARG, "min_piece must be at least 256 loci");
+        ctx->opt_min_piece = value;
+    }
     else return fail(ctx, INQ_ERR_ARG, "unknown option '%s'", name);
     ctx->plan.valid = false;
     drop_graph(ctx);
@@ -1167,6 +1216,18 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         rp.o1 = static_cast<int64_t *>(ctx->h_stage);
         rp.o2 = rp.o1 + L;
         rp.ov = reinterpret_cast<uint8_t *>(rp.o2 + L);
+    }
+
+    if (ctx->opt_push_kernel && L) {
+        void *a = nullptr, *b = nullptr, *c = nullptr;
+        if (cudaHostGetDevicePointer(&a, rp.o1, 0) == cudaSuccess && cudaHostGetDevicePointer(&b, rp.o2, 0) == cudaSuccess &&
+            cudaHostGetDevicePointer(&c, rp.ov, 0) == cudaSuccess) {
+            rp.d1 = static_cast<int64_t *>(a);
+            rp.d2 = static_cast<int64_t *>(b);
+            rp.dv = static_cast<uint8_t *>(c);
+        } else {
+            cudaGetLastError();                               // pinned but not mapped: the copy engines take it
+        }
     }
 
     // the call buffer holds one slot per candidate; on the first call of a context its size is read back from a
