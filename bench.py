@@ -317,15 +317,14 @@ def main():
     dev_ms, cigar_ms, stage_ms = 0.0, 0.0, {}
     call, cst = ctx.genotype_fn(w.minlen, w.support, w.unphased, out)     # pre-bound C call: no Python work inside the timed loop
     stage_keys = ("ms_index", "ms_join", "ms_cigar", "ms_fixup", "ms_scan", "ms_pairs", "ms_median", "ms_d2h")
-    acc = [0.0] * (len(stage_keys) + 1)
+    acc = [0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         rc = call()
         if rc != 0:
             raise SystemExit(f"inq_genotype failed with {rc}")
         acc[0] += cst.ms_total
-        for i, k in enumerate(stage_keys):
-            acc[i + 1] += getattr(cst, k)
+        acc[1] += cst.ms_cigar
     torch.cuda.synchronize()
     t_rank = time.perf_counter() - t0
     barrier()
@@ -335,8 +334,7 @@ def main():
     wall_resident = max_over_ranks(t_rank)
     wall_per_rank = gather_ranks(t_rank / args.steps * 1e3)
     dev_ms = acc[0]
-    cigar_ms = acc[1 + stage_keys.index("ms_cigar")]
-    stage_ms = {k: acc[i + 1] / args.steps for i, k in enumerate(stage_keys)}
+    cigar_ms = acc[1]
     dev_ms_max = max_over_ranks(dev_ms)
     dev_per_rank = gather_ranks(dev_ms / args.steps)
     st = cst.as_dict()
@@ -361,6 +359,20 @@ def main():
         e2e = {"seconds_per_step": e2e_s / args.steps, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_h2d_last": res2.stats["ms_h2d"]}
     clk = clocks.stop() if clocks else None
+
+    # ---- diagnostic, outside every timed region: the per-stage event records (timing level 2) cost ~5 us apiece on
+    #      the chain of the replayed graph, so the timed steps run with the three records of level 1 only
+    ctx.set_option("timing", 2)
+    for _ in range(3):
+        res = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
+    n_diag = 5
+    acc2 = {k: 0.0 for k in stage_keys}
+    for _ in range(n_diag):
+        res = ctx.genotype(w.minlen, w.support, w.unphased, out=out)
+        for k in stage_keys:
+            acc2[k] += res.stats[k]
+    stage_ms = {k: v / n_diag for k, v in acc2.items()}
+    ctx.set_option("timing", 1)
 
     tot_loci = sum_over_ranks(st["n_loci"])
     cj_per_rank = [int(v) for v in gather_ranks(float(st["n_cigar_words_joined"]))]
@@ -477,7 +489,7 @@ def main():
             "stage_ms_rank0": stage_ms,
             "pipeline": {"ranges": int(st["n_ranges"]), "median_chunks": int(st["n_median_chunks"]),
                          "cuda_graph": bool(st["used_graph"]), "reads_sorted": bool(st["reads_sorted"]),
-                         "note": "stage_ms are per-stage sums under overlap (they add up to more than the step)"},
+                         "note": "stage_ms: separate passes with one event record per stage (timing level 2, ~50 us slower than the timed steps); per-stage sums under overlap, they add up to more than the step"},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": None if e2e is None else {

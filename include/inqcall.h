@@ -60,7 +60,8 @@ extern "C" {
 typedef struct inq_ctx inq_ctx;
 
 /* Counters and device timings of the last inq_genotype call. Times are CUDA-event
- * milliseconds measured on the library's own stream. */
+ * milliseconds measured on the library's own streams; the per-stage ones other than ms_total, ms_cigar
+ * and ms_scan are 0 unless inq_set_option("timing", 2). */
 typedef struct inq_stats {
     uint64_t n_loci;
     uint64_t n_reads;
@@ -103,7 +104,13 @@ const char *inq_version(void);
  *                     pair / median kernels of a range run next to the scan of the following one)
  *   "min_range_tiles" automatic choice: at least this many 4 KB warp tiles per range (default 65536)
  *   "graph"           1 (default): replay the steady state from a CUDA graph; 0: always launch directly
- *   "timing"          1 (default): record the CUDA events behind inq_stats.ms_*; 0: none
+ *   "timing"          1 (default): three CUDA event records per pass -> inq_stats.ms_total, ms_cigar, ms_scan;
+ *                     2: one per stage as well -> every inq_stats.ms_* (each record is a node of the replayed graph
+ *                     and costs ~5 us on the chain: ~50 us per pass); 0: none
+ *   "push_kernel"     1 (default): a chunk's results are stored into the caller's pinned arrays by a kernel;
+ *                     0: three copy-engine operations per chunk
+ *   "median_pieces"   median chunks per pass (default 12; the transfer of one runs under the medians of the next)
+ *   "min_piece"       ... but no chunk smaller than this many loci (default 65536)
  */
 int inq_set_option(inq_ctx *ctx, const char *name, int64_t value);
 

@@ -178,8 +178,8 @@ struct inq_ctx {
     int opt_max_ranges = 1;               // measured (profiles/README.md, r2 sweeps): co-scheduling pair/median CTAs under the scan is zero-sum on B200
     int opt_graph = 1;
     int opt_timing = 1;
-    int opt_median_pieces = 8;        // median chunks per pass (the last one is a quarter piece)
-    int64_t opt_min_piece = 1 << 15;  // ... but no piece smaller than this many loci
+    int opt_median_pieces = 12;       // median chunks per pass (the last one is a quarter piece)
+    int64_t opt_min_piece = 1 << 16;  // ... but no piece smaller than this many loci
     int opt_push_kernel = 1;          // results leave through k_push_results (0: three copy-engine operations per chunk)
 
     // locus catalog
@@ -475,7 +475,7 @@ struct RunParams {
     int unphased;
     int64_t *o1, *o2;
     uint8_t *ov;
-    bool timing;
+    int timing;                             // 0: none; 1: pass + CIGAR scan (3 event records); 2: every stage (~10, ~5 us apiece in a replayed graph)
     int64_t *d1 = nullptr, *d2 = nullptr;   // device views of o1/o2/ov (mapped pinned memory); null: use the copy engines
     uint8_t *dv = nullptr;
 };
@@ -566,8 +566,8 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     const uint32_t loc_scan_tiles = (uint32_t)(((uint64_t)L + 1 + kXsTile - 1) / kXsTile);
     const bool work = R && L;
     uint32_t launches = 0;
-    auto stamp = [&](int e, cudaStream_t s) -> cudaError_t {
-        if (!rp.timing) return cudaSuccess;
+    auto stamp = [&](int e, cudaStream_t s, int level = 2) -> cudaError_t {
+        if (rp.timing < level) return cudaSuccess;
         return cudaEventRecordWithFlags(ctx->ev[e], s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     };
     ReadView rv{ctx->contig.p, ctx->rs.p, ctx->re.p, ctx->mapq.p, ctx->hp.p, ctx->flags.p, ctx->cig_off.p, R};
@@ -576,7 +576,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     // S0 only needs the counters zeroed before the scan starts; everything the join / pair / median kernels need
     // zeroed is cleared on S1, off the scan's critical path
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s0));
-    CU_TRY(ctx, stamp(EV_START, s0));
+    CU_TRY(ctx, stamp(EV_START, s0, 1));
     CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));
 
     auto enqueue_join = [&]() -> int {
@@ -638,8 +638,9 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 ++launches;
                 CU_TRY(ctx, cudaGetLastError());
             }
-            CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0));
+            // the dependants hang off the kernel, not off the event-record node that follows it
             CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
+            CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0, k == pl.K - 1 ? 1 : 2));
         }
 
         return INQ_OK;
@@ -742,7 +743,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S1_DONE], 0));
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S2_DONE], 0));
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S3_DONE], 0));
-    CU_TRY(ctx, stamp(EV_END, s0));
+    CU_TRY(ctx, stamp(EV_END, s0, 1));
     *n_launches = launches;
     return INQ_OK;
 }
@@ -877,7 +878,10 @@ int inq_set_option(inq_ctx *ctx, const char *name, int64_t value)
         if (value < 1) return fail(ctx, INQ_ERR_ARG, "min_range_tiles must be positive");
         ctx->opt_min_range_tiles = value;
     } else if (n == "graph") ctx->opt_graph = value != 0;
-    else if (n == "timing") ctx->opt_timing = value != 0;
+    else if (n == "timing") {
+        if (value < 0 || value > 2) return fail(ctx, INQ_ERR_ARG, "timing must be 0 (off), 1 (pass and CIGAR scan) or 2 (every stage)");
+        ctx->opt_timing = (int)value;
+    }
     else if (n == "push_kernel") ctx->opt_push_kernel = value != 0;
     else if (n == "median_pieces") {
         if (value < 1 || value > kMaxMedianChunks / 2) return fail(ctx, INQ_ERR_ARG, "median_pieces must be in [1, %d]", kMaxMedianChunks / 2);
@@ -1203,7 +1207,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
 
     // results go straight to the caller's arrays when those are pinned, otherwise through a pinned staging buffer
     const bool direct_out = L == 0 || (is_pinned(twice_h1) && is_pinned(twice_h2) && is_pinned(valid_mask));
-    RunParams rp{minlen, support, unphased, twice_h1, twice_h2, valid_mask, ctx->opt_timing != 0};
+    RunParams rp{minlen, support, unphased, twice_h1, twice_h2, valid_mask, ctx->opt_timing};
     if (!direct_out) {
         const size_t need = (size_t)L * 17 + 64;
         if (need > ctx->h_stage_bytes) {
@@ -1254,7 +1258,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     uint32_t launches = 0;
     bool used_graph = false, done = false;
     for (int attempt = 0; attempt < 4 && !done; ++attempt) {
-        const GraphKey key{ctx->data_gen, ctx->buf_gen, minlen, support, unphased, rp.timing ? 1 : 0, rp.o1, rp.o2, rp.ov};
+        const GraphKey key{ctx->data_gen, ctx->buf_gen, minlen, support, unphased, rp.timing, rp.o1, rp.o2, rp.ov};
         used_graph = false;
         if (ctx->graph && !(ctx->graph_key == key)) drop_graph(ctx);
         if (ctx->opt_graph && !ctx->graph && ctx->have_last_key && ctx->last_key == key) {
@@ -1344,16 +1348,22 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             auto el = [&](int a, int b) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; } return ms; };
             stats->ms_total = el(EV_START, EV_END);
             stats->ms_index = 0.f;
-            stats->ms_join = el(EV_START, EV_JOIN);          // memsets + join + segment offsets, under the CIGAR scan
-            for (int k = 0; k < ctx->plan.K; ++k) {
-                stats->ms_cigar += el(EV_SCAN0 + 2 * k, EV_SCAN0 + 2 * k + 1);
-                stats->ms_pairs += el(EV_PAIR0 + 2 * k, EV_PAIR0 + 2 * k + 1);
+            if (rp.timing >= 2) {
+                stats->ms_join = el(EV_START, EV_JOIN);          // memsets + join + segment offsets, under the CIGAR scan
+                for (int k = 0; k < ctx->plan.K; ++k) {
+                    stats->ms_cigar += el(EV_SCAN0 + 2 * k, EV_SCAN0 + 2 * k + 1);
+                    stats->ms_pairs += el(EV_PAIR0 + 2 * k, EV_PAIR0 + 2 * k + 1);
+                }
+                // prefix scan over the last range's warp-tile totals (incl. waiting for the join stream)
+                stats->ms_fixup = el(EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1, EV_PAIR0 + 2 * (ctx->plan.K - 1));
+                stats->ms_median = el(EV_MED0, EV_MED1);
+                stats->ms_d2h = el(EV_MED1, EV_D2H);
+            } else {
+                // S0 runs the K scans back to back right after the pass starts: start of the pass -> end of the last scan
+                // (a few us of fork on top of the kernels: the conservative side for a bandwidth figure)
+                stats->ms_cigar = el(EV_START, EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1);
             }
-            // prefix scan over the last range's warp-tile totals (incl. waiting for the join stream)
-            stats->ms_fixup = el(EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1, EV_PAIR0 + 2 * (ctx->plan.K - 1));
             stats->ms_scan = el(EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1, EV_END);      // what is left exposed after the last range is scanned
-            stats->ms_median = el(EV_MED0, EV_MED1);
-            stats->ms_d2h = el(EV_MED1, EV_D2H);
         }
         stats->ms_h2d = ctx->ms_h2d;
     }
