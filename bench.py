@@ -193,6 +193,20 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     threads = os.cpu_count() or 1
+    affinity = None
+    if world > 1 and args.impl == "ours" and hasattr(os, "sched_setaffinity"):
+        # one process per GPU, each on its own slice of the host cores: the routing / packing threads of a rank and
+        # its launch thread do not migrate onto another rank's cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 1:
+                mine = cores[local_rank * per:(local_rank + 1) * per]
+                os.sched_setaffinity(0, mine)
+                affinity = f"{per} cores per rank"
+                threads = len(cores)
+        except OSError:
+            affinity = None
 
     from synth.synth import make_workload
 
@@ -502,7 +516,7 @@ def main():
             "gpu_launches": int(st["n_kernel_launches"]) * args.steps,
             "clocks": clk,
             "parity": parity,
-            "host": {"cores": threads, "gen_seconds": t_gen, "wall_resident_s": wall_resident,
+            "host": {"cores": threads, "affinity": affinity, "gen_seconds": t_gen, "wall_resident_s": wall_resident,
                      "reads_host_rank0": int(rd.n), "reads_pushed_rank0": int(n_pushed),
                      "push": "inq_push_reads_routed" if world > 1 else "inq_push_reads"},
         }

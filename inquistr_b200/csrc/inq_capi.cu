@@ -576,8 +576,8 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     // S0 only needs the counters zeroed before the scan starts; everything the join / pair / median kernels need
     // zeroed is cleared on S1, off the scan's critical path
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s0));
-    CU_TRY(ctx, stamp(EV_START, s0, 1));
-    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));      // S1..S3 fork off the memset, not off the event-record node
+    CU_TRY(ctx, stamp(EV_START, s0, 1));                         // ... which only the scan on S0 follows
 
     auto enqueue_join = [&]() -> int {
         // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
