@@ -116,7 +116,7 @@ enum {
 };
 // dependency-only events (no timing)
 enum {
-    DEP_FORK = 0, DEP_JOIN_DONE, DEP_S1_DONE, DEP_S2_DONE, DEP_S3_DONE,
+    DEP_FORK = 0, DEP_JOIN_DONE, DEP_S1_DONE, DEP_S2_DONE, DEP_S3_DONE, DEP_ZEROED, DEP_SCAN_ONLY,
     DEP_SCANNED,                                // + k: range k scanned
     DEP_PAIRED = DEP_SCANNED + kMaxRanges,      // + k: pair(k) done
     DEP_CHUNK = DEP_PAIRED + kMaxRanges,        // + c: median chunk c done
@@ -138,6 +138,11 @@ struct Plan {
     int n_chunks = 0;
     MedianChunk chunk[kMaxMedianChunks];
     bool reads_sorted = false;
+    // the CTA-path median kernel of a chunk is only launched where the last completed pass over the same reads had
+    // deep loci (it is empty almost everywhere and costs a launch on the S2 chain per chunk); verified after every
+    // pass from the per-chunk counters, like the speculative buffer sizes
+    bool big_known = false;
+    bool need_big[kMaxMedianChunks] = {};
 };
 
 struct GraphKey {
@@ -180,6 +185,8 @@ struct inq_ctx {
     int opt_timing = 1;
     int opt_median_pieces = 12;       // median chunks per pass (the last one is a quarter piece)
     int64_t opt_min_piece = 1 << 16;  // ... but no piece smaller than this many loci
+    int opt_join_coop = 1;            // k_join_ranges: warp-cooperative lower bounds (0: two scalar binary searches per read)
+    int opt_push_ctas = 8;            // CTAs of k_push_results (PCIe-bound stores: a few SMs' worth is plenty)
     int opt_push_kernel = 1;          // results leave through k_push_results (0: three copy-engine operations per chunk)
 
     // locus catalog
@@ -415,31 +422,36 @@ struct ZeroJob { void *p; uint64_t bytes; };
 struct ZeroJobs { ZeroJob j[6]; int n; };
 // The results of one median chunk go home through a kernel that stores into the caller's pinned (mapped) arrays:
 // one launch in place of three copy-engine operations, whose ~10 us apiece of fixed latency is what a chunk's
-// transfer costs at the per-rank sizes of a multi-GPU run. Fully coalesced 8-byte stores; the byte mask is moved
-// 4 bytes per lane between its aligned edges.
+// transfer costs at the per-rank sizes of a multi-GPU run. 16-byte streaming stores between the aligned edges
+// of each array (source and destination share the index; when they do not share the alignment: bytes).
+__device__ __forceinline__ void push_bytes(unsigned char *__restrict__ dst, const unsigned char *__restrict__ src, size_t n, uint32_t tid, uint32_t stride)
+{
+    if (((reinterpret_cast<uintptr_t>(dst) ^ reinterpret_cast<uintptr_t>(src)) & 15u) != 0) {
+        if ((((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | n) & 7u) == 0)) {
+            for (size_t i = tid; i < n / 8; i += stride) __stcs(reinterpret_cast<unsigned long long *>(dst) + i, reinterpret_cast<const unsigned long long *>(src)[i]);
+        } else {
+            for (size_t i = tid; i < n; i += stride) dst[i] = src[i];
+        }
+        return;
+    }
+    const size_t head = min(n, (size_t)((16u - (reinterpret_cast<uintptr_t>(src) & 15u)) & 15u));
+    const size_t nv = (n - head) / 16, tail0 = head + nv * 16;
+    if (tid < head) dst[tid] = src[tid];
+    const uint4 *sv = reinterpret_cast<const uint4 *>(src + head);
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    for (size_t i = tid; i < nv; i += stride) __stcs(dv + i, sv[i]);
+    if (tid < n - tail0) dst[tail0 + tid] = src[tail0 + tid];
+}
+
 __global__ void __launch_bounds__(256)
 k_push_results(uint32_t l0, uint32_t l1, const int64_t *__restrict__ t1, const int64_t *__restrict__ t2, const uint8_t *__restrict__ valid,
                int64_t *__restrict__ o1, int64_t *__restrict__ o2, uint8_t *__restrict__ ov)
 {
-    const uint32_t n = l1 - l0, stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t i = tid; i < n; i += stride) {
-        __stcs(o1 + l0 + i, t1[l0 + i]);
-        __stcs(o2 + l0 + i, t2[l0 + i]);
-    }
-    // mask: head bytes up to the first 4-byte boundary of the device array, whole words, tail bytes (the host array
-    // shares the index, not necessarily the alignment: word stores only when both are aligned)
-    const bool words = ((reinterpret_cast<uintptr_t>(valid) ^ reinterpret_cast<uintptr_t>(ov)) & 3u) == 0;
-    if (!words) {
-        for (uint32_t i = tid; i < n; i += stride) ov[l0 + i] = valid[l0 + i];
-        return;
-    }
-    const uint32_t head = min(n, (uint32_t)((4u - ((reinterpret_cast<uintptr_t>(valid) + l0) & 3u)) & 3u));
-    const uint32_t nw = (n - head) >> 2, tail0 = head + (nw << 2);
-    if (tid < head) ov[l0 + tid] = valid[l0 + tid];
-    const uint32_t *vw = reinterpret_cast<const uint32_t *>(valid + l0 + head);
-    uint32_t *ow = reinterpret_cast<uint32_t *>(ov + l0 + head);
-    for (uint32_t i = tid; i < nw; i += stride) __stcs(ow + i, vw[i]);
-    if (tid < n - tail0) ov[l0 + tail0 + tid] = valid[l0 + tail0 + tid];
+    const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = l1 - l0;
+    push_bytes(reinterpret_cast<unsigned char *>(o1 + l0), reinterpret_cast<const unsigned char *>(t1 + l0), n * 8, tid, stride);
+    push_bytes(reinterpret_cast<unsigned char *>(o2 + l0), reinterpret_cast<const unsigned char *>(t2 + l0), n * 8, tid, stride);
+    push_bytes(ov + l0, valid + l0, n, tid, stride);
 }
 
 __global__ void k_zero(ZeroJobs jobs)
@@ -576,8 +588,9 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     // S0 only needs the counters zeroed before the scan starts; everything the join / pair / median kernels need
     // zeroed is cleared on S1, off the scan's critical path
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s0));
-    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));      // S1..S3 fork off the memset, not off the event-record node
-    CU_TRY(ctx, stamp(EV_START, s0, 1));                         // ... which only the scan on S0 follows
+    CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_FORK], s0));
+    // (EV_START / EV_END are plain event records on S0 around the pass -- or around the graph launch --, made by
+    // inq_genotype: no nodes of the graph)
 
     auto enqueue_join = [&]() -> int {
         // ---- S1: K1 candidate ranges + difference array, then the per-locus segment offsets
@@ -602,9 +615,12 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 k_zero<<<g, 256, 0, s1>>>(z);
                 CU_TRY(ctx, cudaGetLastError());
             }
+            CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_ZEROED], s1));
+            CU_TRY(ctx, stamp(EV_INDEX, s1));
         }
         if (work) {
-            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->opt_join_coop, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+            CU_TRY(ctx, stamp(EV_JOIN0, s1));
             const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
             // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
             k_exclusive_scan<<<g, kXsThreads, 0, s1>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
@@ -614,12 +630,32 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
             launches += 3;
             CU_TRY(ctx, cudaGetLastError());
             // the call buffer holds one slot per candidate; its size is only known on the device (checked after the pass)
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s1));
+            // (read home on S2, idle until the first medians: a copy-engine operation in front of k_pair_eval costs the chain ~10 us)
+            CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_JOIN_DONE], s1));
+            CU_TRY(ctx, cudaStreamWaitEvent(s2, ctx->dep[DEP_JOIN_DONE], 0));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_total, ctx->seg_off.p + L, sizeof(uint32_t), cudaMemcpyDeviceToHost, s2));
         }
         CU_TRY(ctx, stamp(EV_JOIN, s1));
 
         return INQ_OK;
     };
+    uint64_t desc_base = 0;
+    auto enqueue_xscan2 = [&](int k, cudaStream_t st) -> int {
+        const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
+        if (t1 > t0 && L) {
+            const uint64_t n = t1 - t0;
+            const uint32_t xt = (uint32_t)((n + kXsTile - 1) / kXsTile);
+            const unsigned g = std::min<unsigned>(xt, (unsigned)ctx->sm_count * 4);
+            uint64_t *dx = ctx->desc_wt.p + desc_base, *dy = dx + xt + 1;
+            desc_base += 2 * ((uint64_t)xt + 1);
+            k_exclusive_scan2<<<g, kXsThreads, 0, st>>>(ctx->wtot.p + t0, ctx->wt.p + t0, n, xt, dx, dy, &ctx->d_ctr->wt_scan_counter[k],
+                                                        ctx->d_ctr->wt_carry[k], ctx->d_ctr->wt_carry[k + 1], &ctx->d_ctr->flags);
+            ++launches;
+            CU_TRY(ctx, cudaGetLastError());
+        }
+        return INQ_OK;
+    };
+    const bool xs_on_s0 = pl.K == 1 && !INQ_SCAN_FIRST;
     auto enqueue_scans = [&]() -> int {
         // ---- S0: K2, range after range, nothing in between (the scan of a range depends on nothing but the reads)
         for (int k = 0; k < pl.K; ++k) {
@@ -638,9 +674,22 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 ++launches;
                 CU_TRY(ctx, cudaGetLastError());
             }
-            // the dependants hang off the kernel, not off the event-record node that follows it
-            CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
-            CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0, k == pl.K - 1 ? 1 : 2));
+            if (xs_on_s0) {
+                // one range: the prefix sum over the warp-tile totals follows the scan on its own stream, so the join chain
+                // on S1 (slow under the scan) has until the end of it; the scan's end is time-stamped on the idle S3
+                CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCAN_ONLY], s0));
+                if (rp.timing >= 1) {
+                    CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_SCAN_ONLY], 0));
+                    CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s3, 1));
+                }
+                CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_ZEROED], 0));       // desc_wt is cleared by k_zero
+                TRY(enqueue_xscan2(k, s0));
+                CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
+            } else {
+                // the dependants hang off the kernel, not off the event-record node that follows it
+                CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_SCANNED + k], s0));
+                CU_TRY(ctx, stamp(EV_SCAN0 + 2 * k + 1, s0, k == pl.K - 1 ? 1 : 2));
+            }
         }
 
         return INQ_OK;
@@ -653,22 +702,11 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     int c = 0;
     int64_t *o1 = rp.o1, *o2 = rp.o2;
     uint8_t *ov = rp.ov;
-    uint64_t desc_base = 0;
     for (int k = 0; k < pl.K; ++k) {
         const uint64_t r0 = pl.read_end[k], r1 = pl.read_end[k + 1];
         const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
         CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_SCANNED + k], 0));
-        if (t1 > t0 && L) {
-            const uint64_t n = t1 - t0;
-            const uint32_t xt = (uint32_t)((n + kXsTile - 1) / kXsTile);
-            const unsigned g = std::min<unsigned>(xt, (unsigned)ctx->sm_count * 4);
-            uint64_t *dx = ctx->desc_wt.p + desc_base, *dy = dx + xt + 1;
-            desc_base += 2 * ((uint64_t)xt + 1);
-            k_exclusive_scan2<<<g, kXsThreads, 0, s1>>>(ctx->wtot.p + t0, ctx->wt.p + t0, n, xt, dx, dy, &ctx->d_ctr->wt_scan_counter[k],
-                                                        ctx->d_ctr->wt_carry[k], ctx->d_ctr->wt_carry[k + 1], &ctx->d_ctr->flags);
-            ++launches;
-            CU_TRY(ctx, cudaGetLastError());
-        }
+        if (!xs_on_s0) TRY(enqueue_xscan2(k, s1));
         CU_TRY(ctx, stamp(EV_PAIR0 + 2 * k, s1));
         if (work && r1 > r0) {
             const unsigned threads = kPairWarps * 32;
@@ -700,9 +738,12 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
                 CU_TRY(ctx, cudaStreamWaitEvent(s3, ctx->dep[DEP_CHUNK + c], 0));
             }
-            k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, sb>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
-                                                                                  ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
-            launches += 2;
+            if (!pl.big_known || pl.need_big[c]) {
+                k_locus_median_big<<<(unsigned)ctx->sm_count * 2, kBigThreads, 0, sb>>>(l0, c, rp.unphased, rp.support, ctx->seg_off.p, ctx->cursor.p, ctx->vals.p,
+                                                                                      ctx->vals.cap, ctx->t1.p, ctx->t2.p, ctx->valid.p, ctx->big_list.p, ctx->d_ctr);
+                ++launches;
+            }
+            ++launches;
             CU_TRY(ctx, cudaGetLastError());
             if (!INQ_BIG_ON_S3) {
                 CU_TRY(ctx, cudaEventRecord(ctx->dep[DEP_CHUNK + c], s2));
@@ -710,7 +751,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
             }
             const size_t n = l1 - l0;
             if (rp.d1) {
-                const unsigned g = (unsigned)std::min<size_t>(64, (n + 2047) / 2048);
+                const unsigned g = (unsigned)std::min<size_t>((size_t)ctx->opt_push_ctas, (n + 2047) / 2048);
                 k_push_results<<<std::max(g, 1u), 256, 0, s3>>>(l0, l1, ctx->t1.p, ctx->t2.p, ctx->valid.p, rp.d1, rp.d2, rp.dv);
                 ++launches;
                 CU_TRY(ctx, cudaGetLastError());
@@ -743,7 +784,6 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S1_DONE], 0));
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S2_DONE], 0));
     CU_TRY(ctx, cudaStreamWaitEvent(s0, ctx->dep[DEP_S3_DONE], 0));
-    CU_TRY(ctx, stamp(EV_END, s0, 1));
     *n_launches = launches;
     return INQ_OK;
 }
@@ -795,7 +835,9 @@ int inq_ctx_create(int device, inq_ctx **out)
     cudaStream_t *streams[4] = {&ctx->stream, &ctx->stream_join, &ctx->stream_med, &ctx->stream_copy};
     for (int i = 0; i < 4; ++i) {
         // INQ_STREAM_PRIORITIES bit i: stream Si gets the high priority (default: only the scan stream S0)
-        const bool hi = (INQ_STREAM_PRIORITIES >> i) & 1;
+        int prio_mask = INQ_STREAM_PRIORITIES;
+        if (const char *pm = getenv("INQ_STREAM_PRIORITY_MASK")) prio_mask = atoi(pm);       // experiments
+        const bool hi = (prio_mask >> i) & 1;
         if ((e = cudaStreamCreateWithPriority(streams[i], cudaStreamNonBlocking, hi ? prio_hi : prio_lo)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
     for (int i = 0; i < EV_COUNT; ++i)
@@ -883,6 +925,11 @@ int inq_set_option(inq_ctx *ctx, const char *name, int64_t value)
         ctx->opt_timing = (int)value;
     }
     else if (n == "push_kernel") ctx->opt_push_kernel = value != 0;
+    else if (n == "join_coop") ctx->opt_join_coop = value != 0;
+    else if (n == "push_ctas") {
+        if (value < 1 || value > 1024) return fail(ctx, INQ_ERR_ARG, "push_ctas must be in [1, 1024]");
+        ctx->opt_push_ctas = (int)value;
+    }
     else if (n == "median_pieces") {
         if (value < 1 || value > kMaxMedianChunks / 2) return fail(ctx, INQ_ERR_ARG, "median_pieces must be in [1, %d]", kMaxMedianChunks / 2);
         ctx->opt_median_pieces = (int)value;
@@ -1243,7 +1290,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
         CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
         CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s));
-        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->opt_join_coop, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
         const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
         k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
                                                   &ctx->d_ctr->scan_counter[2], nullptr);
@@ -1274,6 +1321,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             if (e != cudaSuccess) { ctx->graph = nullptr; return fail(ctx, INQ_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
             ctx->graph_key = key;
         }
+        if (rp.timing >= 1) CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_START], s));
         if (ctx->graph) {
             CU_TRY(ctx, cudaGraphLaunch(ctx->graph, s));
             launches = ctx->graph_launches;
@@ -1281,6 +1329,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         } else {
             TRY(enqueue_pass(ctx, rp, false, &launches));
         }
+        if (rp.timing >= 1) CU_TRY(ctx, cudaEventRecord(ctx->ev[EV_END], s));
         ctx->last_key = key;
         ctx->have_last_key = true;
         {
@@ -1306,6 +1355,14 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
             retry = true;
         }
         if (retry) { ctx->have_last_key = false; continue; }       // buffers moved: the next attempt launches directly
+        if (ctx->plan.big_known) {
+            // a chunk whose CTA-path kernel was left out turned out to have deep loci (other parameters than the pass the
+            // guess came from): run again with it
+            bool again = false;
+            for (int c = 0; c < ctx->plan.n_chunks; ++c)
+                if (ctx->h_ctr->big_count[c] && !ctx->plan.need_big[c]) { ctx->plan.need_big[c] = true; again = true; }
+            if (again) { drop_graph(ctx); ctx->have_last_key = false; continue; }
+        }
         if (f & kFlagCountOverflow) return fail(ctx, INQ_ERR_TOO_LARGE, "pair or event count exceeds 2^32");
         if (f & kFlagValsOverflow) return fail(ctx, INQ_ERR_STATE, "internal: call buffer overflow");
         if (f & kFlagBadSa)
@@ -1316,6 +1373,10 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
                         (unsigned long long)ctx->h_ctr->bad_hp_read, ctx->h_ctr->bad_hp_value);
         if (f & kFlagMedianEmpty)
             return fail(ctx, INQ_ERR_MEDIAN_EMPTY, "support == 0 with a bucket without usable calls (the reference panics, call.rs:516)");
+        if (!ctx->plan.big_known) {
+            for (int c = 0; c < ctx->plan.n_chunks; ++c) ctx->plan.need_big[c] = ctx->h_ctr->big_count[c] != 0;
+            ctx->plan.big_known = true;
+        }
         done = true;
     }
     if (!done) return fail(ctx, INQ_ERR_STATE, "internal: speculative buffers still too small after 4 attempts");
@@ -1347,9 +1408,12 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         if (rp.timing) {
             auto el = [&](int a, int b) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; } return ms; };
             stats->ms_total = el(EV_START, EV_END);
-            stats->ms_index = 0.f;
             if (rp.timing >= 2) {
                 stats->ms_join = el(EV_START, EV_JOIN);          // memsets + join + segment offsets, under the CIGAR scan
+                stats->ms_index = el(EV_START, EV_INDEX);        // ... of which the zeroing kernel
+                if (getenv("INQ_DEBUG_TIMING"))
+                    fprintf(stderr, "[inq timing] zero done %.3f  join done %.3f  offsets done %.3f  scan done %.3f ms after the start\n",
+                            el(EV_START, EV_INDEX), work ? el(EV_START, EV_JOIN0) : 0.f, el(EV_START, EV_JOIN), el(EV_START, EV_SCAN0 + 2 * (ctx->plan.K - 1) + 1));
                 for (int k = 0; k < ctx->plan.K; ++k) {
                     stats->ms_cigar += el(EV_SCAN0 + 2 * k, EV_SCAN0 + 2 * k + 1);
                     stats->ms_pairs += el(EV_PAIR0 + 2 * k, EV_PAIR0 + 2 * k + 1);

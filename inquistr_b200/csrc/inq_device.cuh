@@ -259,30 +259,139 @@ __device__ __forceinline__ void candidate_range(bool unphased, const LocusView &
     if (hi < lo) hi = lo;
 }
 
+// ---- the same two lower bounds, found by the warp together (k_join_ranges runs under the HBM-saturating CIGAR scan,
+// where a dependent L2 round trip costs ~1 us: 2 x 17 of them per read are what the kernel's time is made of).
+// Reads arrive coordinate-sorted, so the 32 answers of a warp lie within a few catalog entries of each other:
+//   1. one 33-ary search by all lanes for the smallest key of the warp (4-5 round trips instead of 17),
+//   2. the 32 entries from there on are loaded once, one per lane, and every lane finds its own bound among them
+//      with shuffles (no memory),
+//   3. the second bound lies within a 32-entry window of the first one; same trick.
+// A lane whose answer falls outside a window (unsorted reads, very long reads) finishes with the plain binary search
+// over the rest, and a warp that straddles contigs takes the scalar path: the results are the unique lower bounds
+// either way.
+__device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ a, int lo, int hi, int64_t key)
+{
+    const int lane = (int)lane_id();
+    while (hi - lo > 32) {
+        const int n = hi - lo;
+        const int p = lo + (int)(((int64_t)(lane + 1) * n) / 33);            // lo < p < hi, increasing with the lane
+        const uint32_t m = __ballot_sync(0xffffffffu, (int64_t)__ldg(a + p) >= key);
+        const int f = m ? __ffs(m) - 1 : 32;                                 // first probe that is >= key
+        const int new_hi = f < 32 ? lo + (int)(((int64_t)(f + 1) * n) / 33) : hi;
+        const int new_lo = f > 0 ? lo + (int)(((int64_t)f * n) / 33) + 1 : lo;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    const int p = lo + lane;
+    const uint32_t m = __ballot_sync(0xffffffffu, p < hi && (int64_t)__ldg(a + p) >= key);
+    return m ? lo + __ffs(m) - 1 : hi;
+}
+
+// number of entries of the window a[win, win + wn) (wn <= 32, entry j held by lane j in `v`) that are < key
+__device__ __forceinline__ int window_count_less(int32_t v, int wn, int64_t key)
+{
+    int cnt = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int32_t probe = __shfl_sync(0xffffffffu, v, (cnt + step - 1) & 31);
+        if (cnt + step - 1 < wn && (int64_t)probe < key) cnt += step;
+    }
+    const int32_t last = __shfl_sync(0xffffffffu, v, 31);
+    if (cnt == 31 && wn == 32 && (int64_t)last < key) cnt = 32;
+    return cnt;
+}
+
+// all 32 lanes call this; `act` lanes carry a read on contig c (warp-uniform among the active lanes)
+__device__ __forceinline__ void candidate_range_warp(bool unphased, const LocusView &lv, int c, bool act, int32_t rs, int32_t re,
+                                                     int &lo, int &hi)
+{
+    const int lane = (int)lane_id();
+    const int l0 = (int)lv.contig_off[c], l1 = (int)lv.contig_off[c + 1];
+    // first bound: over start[l0, l1)
+    const int64_t key1 = unphased ? (int64_t)rs + 10 : (int64_t)re + 10;
+    const int64_t big = 0x7fffffffffffffffll;
+    int64_t kmin = act ? key1 : big;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { const int64_t o = __shfl_xor_sync(0xffffffffu, kmin, d); kmin = o < kmin ? o : kmin; }
+    const int p1 = warp_lower_bound(lv.start, l0, l1, kmin);
+    const int wn1 = min(32, l1 - p1);
+    const int32_t v1 = lane < wn1 ? __ldg(lv.start + p1 + lane) : 0;
+    const int c1 = window_count_less(v1, wn1, key1);
+    int b1 = p1 + c1;
+    if (act && c1 == 32 && p1 + 32 < l1) b1 = lower_bound_i32(lv.start, p1 + 32, l1, key1);
+    if (unphased) {
+        lo = b1;                                                             // start - 10 >= rs
+        // hi = lower_bound(start[lo, l1), re - 9): at or after the warp's smallest lo
+        const int64_t key2 = (int64_t)re - 10 + 1;
+        const int w2 = __reduce_min_sync(0xffffffffu, act ? lo : 0x7fffffff);
+        const bool any = w2 != 0x7fffffff;
+        const int wn2 = any ? min(32, l1 - w2) : 0;
+        const int32_t v2 = lane < wn2 ? __ldg(lv.start + w2 + lane) : 0;
+        const int c2 = window_count_less(v2, wn2, key2);
+        int b2 = w2 + c2;
+        if (act && c2 == 32 && w2 + 32 < l1) b2 = lower_bound_i32(lv.start, w2 + 32, l1, key2);
+        hi = b2 > lo ? b2 : lo;
+    } else {
+        hi = b1;                                                             // start - 10 < re
+        // lo = lower_bound(pmax[l0, hi), rs - 9): at most the warp's largest hi, usually within 32 entries below it
+        const int64_t key2 = (int64_t)rs - 10 + 1;
+        const int hmax = __reduce_max_sync(0xffffffffu, act ? hi : -1);
+        const int w2 = hmax - 32 > l0 ? hmax - 32 : l0;
+        const int wn2 = hmax > w2 ? min(32, hmax - w2) : 0;
+        const int32_t v2 = lane < wn2 ? __ldg(lv.pmax + w2 + lane) : 0;
+        const int c2 = window_count_less(v2, wn2, key2);
+        int b2 = w2 + c2;
+        if (act && c2 == 0 && w2 > l0) b2 = lower_bound_i32(lv.pmax, l0, w2, key2);
+        lo = b2 < hi ? b2 : hi;
+    }
+    if (hi < lo) hi = lo;
+}
+
 // K1: per read, the contiguous range [lo, lo+n) of catalog loci whose window it can pair with
-// (two binary searches over the sorted, L2-resident catalog). Instead of visiting the candidates,
+// (two lower bounds over the sorted, L2-resident catalog). Instead of visiting the candidates,
 // the kernel adds +1/-1 to a difference array; its prefix sum is the number of candidate reads of
 // every locus, which sizes that locus' segment of the call buffer (an upper bound on its pairs).
 __global__ void __launch_bounds__(256)
-k_join_ranges(ReadView rv, LocusView lv, int unphased, uint32_t *__restrict__ cand_lo, uint32_t *__restrict__ cand_n,
+k_join_ranges(ReadView rv, LocusView lv, int unphased, int coop, uint32_t *__restrict__ cand_lo, uint32_t *__restrict__ cand_n,
               uint32_t *__restrict__ delta /* L+1, zeroed */, DevCounters *__restrict__ ctr)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     int lo = 0, n = 0;
+    int c = -1;
+    int32_t rs = 0, re = 0;
+    bool act = false;
     if (r < rv.R) {
-        const int c = rv.contig[r];
+        c = rv.contig[r];
         const uint32_t mq = rv.mapq[r], h = rv.hp[r];
-        if (c >= 0 && c < lv.n_contigs && mq > 10u && (unphased || h != 0xFFu)) {
-            int hi;
-            candidate_range(unphased != 0, lv, c, rv.rs[r], rv.re[r], lo, hi);
-            n = hi - lo;
-            if (n > 0) {
-                atomicAdd(delta + lo, 1u);
-                atomicAdd(delta + hi, 0xFFFFFFFFu);              // -1 (mod 2^32)
-            }
-        }
+        rs = rv.rs[r];
+        re = rv.re[r];
+        act = c >= 0 && c < lv.n_contigs && mq > 10u && (unphased || h != 0xFFu);
+    }
+    // one contig for the whole warp? (all warps but the few that straddle a contig boundary)
+    const int cmin = __reduce_min_sync(0xffffffffu, act ? c : 0x7fffffff), cmax = __reduce_max_sync(0xffffffffu, act ? c : -1);
+    int hi = 0;
+    if (coop && cmin == cmax) {
+        candidate_range_warp(unphased != 0, lv, cmin, act, rs, re, lo, hi);
+    } else if (act) {
+        candidate_range(unphased != 0, lv, c, rs, re, lo, hi);
+    }
+    if (r < rv.R) {
+        if (act) n = hi - lo;
+        else lo = 0;
         cand_lo[r] = (uint32_t)lo;
         cand_n[r] = (uint32_t)n;
+    }
+    // +1 at lo, -1 at hi: neighbouring reads share their bounds, so the lanes that hit the same entry send one atomic
+    // (11.6 M same-address-heavy atomics per pass were what kept this kernel busy for the whole CIGAR scan)
+    {
+        const bool has = n > 0;
+        const uint32_t mlo = __match_any_sync(0xffffffffu, has ? (uint32_t)lo : 0xFFFFFFFFu);
+        const uint32_t mhi = __match_any_sync(0xffffffffu, has ? (uint32_t)hi : 0xFFFFFFFFu);
+        if (has) {
+            const uint32_t lane = lane_id();
+            if ((uint32_t)__ffs(mlo) - 1u == lane) atomicAdd(delta + lo, (uint32_t)__popc(mlo));
+            if ((uint32_t)__ffs(mhi) - 1u == lane) atomicAdd(delta + hi, 0u - (uint32_t)__popc(mhi));   // -count (mod 2^32)
+        }
     }
     const uint32_t cand_w = __reduce_add_sync(0xffffffffu, (uint32_t)n);
     if (lane_id() == 0 && cand_w)

@@ -87,6 +87,31 @@ def test_deep_loci_take_the_cta_path(ctx):
     run_case(ctx, case, 0, 2000, True)
 
 
+def test_cta_path_guess_is_verified(ctx):
+    """The CTA-path median kernel is only launched for catalog chunks that had deep loci in the last completed pass over
+    the same reads; when other parameters make a locus deep (unphased counts the untagged and HP-0 reads too) the
+    pass is repeated with the kernel. Same reads, alternating parameters, direct / captured / replayed."""
+    case = make_case(77, n_contigs=1, n_loci=6, n_reads=330, dense_locus=True, max_read=3000,
+                     hp_probs=(0.45, 0.05, 0.25, 0.25))
+    rd = case["reads"]
+    ctx.set_loci(case["contig_off"], case["locus_start"], case["locus_end"])
+    ctx.clear_reads()
+    ctx.push(rd)
+    expect = {}
+    for unphased in (False, True):
+        rc, p1, p2, _ = O.genotype_loci(rd, case["n_contigs"], case["locus_contig"], case["locus_start"], case["locus_end"],
+                                        5, 3, unphased, threads=2)
+        assert rc == 0
+        expect[unphased] = (p1, p2)
+    # the case must straddle the 128-call limit of the warp path: per-locus pair counts of both modes
+    per = {u: max(int(((rd.ref_start < e + 10) & (rd.ref_end > s - 10) & (rd.mapq > 10) & (u | (rd.hp <= 2))).sum())
+                  for s, e in zip(case["locus_start"], case["locus_end"])) for u in (False, True)}
+    assert per[True] > 128, per
+    for unphased in (False, False, False, True, True, True, False, True, False):
+        res = ctx.genotype(5, 3, unphased)
+        assert same(res.phase1, expect[unphased][0]) and same(res.phase2, expect[unphased][1]), unphased
+
+
 def test_long_reads_span_many_tiles(ctx):
     # reads with > 4096 CIGAR words cross tile boundaries of the scan kernel
     case = make_case(41, n_contigs=1, contig_len=3_000_000, n_loci=400, n_reads=300, max_read=900_000,
