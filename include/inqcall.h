@@ -109,6 +109,9 @@ const char *inq_version(void);
  *                     and costs ~5 us on the chain: ~50 us per pass); 0: none
  *   "push_kernel"     1 (default): a chunk's results are stored into the caller's pinned arrays by a kernel;
  *                     0: three copy-engine operations per chunk
+ *   "push_ctas"       CTAs of that kernel (default 8: its stores are PCIe-bound)
+ *   "join_coop"       1 (default): k_join_ranges finds a warp's lower bounds together; 0: two binary searches per read
+ *   "evict_first"     1 (default): k_cigar_scan loads the stream with the L2 evict-first policy
  *   "median_pieces"   median chunks per pass (default 12; the transfer of one runs under the medians of the next)
  *   "min_piece"       ... but no chunk smaller than this many loci (default 65536)
  */

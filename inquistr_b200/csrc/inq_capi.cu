@@ -185,6 +185,9 @@ struct inq_ctx {
     int opt_timing = 1;
     int opt_median_pieces = 12;       // median chunks per pass (the last one is a quarter piece)
     int64_t opt_min_piece = 1 << 16;  // ... but no piece smaller than this many loci
+    unsigned long long *join_trace = nullptr;   // experiments (INQ_JOIN_TRACE=file): per-CTA start / end / SM of k_join_ranges
+    uint64_t join_trace_ctas = 0;
+    int opt_evict_first = 1;          // k_cigar_scan loads the stream with the L2 evict-first policy
     int opt_join_coop = 1;            // k_join_ranges: warp-cooperative lower bounds (0: two scalar binary searches per read)
     int opt_push_ctas = 8;            // CTAs of k_push_results (PCIe-bound stores: a few SMs' worth is plenty)
     int opt_push_kernel = 1;          // results leave through k_push_results (0: three copy-engine operations per chunk)
@@ -619,7 +622,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
             CU_TRY(ctx, stamp(EV_INDEX, s1));
         }
         if (work) {
-            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->opt_join_coop, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+            k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s1>>>(rv, lv, rp.unphased, ctx->opt_join_coop, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr, ctx->join_trace);
             CU_TRY(ctx, stamp(EV_JOIN0, s1));
             const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
             // lcnt[i+1] = number of candidate reads of locus i ; seg_off = exclusive scan of those counts
@@ -667,6 +670,7 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
                 sp.wt_sbase = ctx->wt_sbase.p; sp.evraw = ctx->evraw.p; sp.ctr = ctx->d_ctr; sp.raw_cap = ctx->evraw.cap;
                 sp.wt_begin = t0; sp.n_wt = t1; sp.neg1 = 0xFFFFFFFFu;
                 sp.thr = (std::min<uint32_t>(rp.minlen, (1u << 28) - 1u) << 4) | 15u;      // BAM op lengths have 28 bits
+                sp.evict_first = (uint32_t)ctx->opt_evict_first;
                 sp.debug = ctx->scan_debug;
                 const unsigned grid = (unsigned)std::min<uint64_t>((t1 - t0 + kScanWarps - 1) / kScanWarps, (uint64_t)ctx->sm_count * ctx->scan_ctas_per_sm);
                 if (sp.thr >> 31) k_cigar_scan<true><<<grid, kCtaThreads, kScanSmemBytes, s0>>>(ctx->tmap, sp);
@@ -704,7 +708,6 @@ int enqueue_pass(inq_ctx *ctx, const RunParams &rp, bool capturing, uint32_t *n_
     uint8_t *ov = rp.ov;
     for (int k = 0; k < pl.K; ++k) {
         const uint64_t r0 = pl.read_end[k], r1 = pl.read_end[k + 1];
-        const uint64_t t0 = pl.tile_end[k], t1 = pl.tile_end[k + 1];
         CU_TRY(ctx, cudaStreamWaitEvent(s1, ctx->dep[DEP_SCANNED + k], 0));
         if (!xs_on_s0) TRY(enqueue_xscan2(k, s1));
         CU_TRY(ctx, stamp(EV_PAIR0 + 2 * k, s1));
@@ -926,6 +929,7 @@ int inq_set_option(inq_ctx *ctx, const char *name, int64_t value)
     }
     else if (n == "push_kernel") ctx->opt_push_kernel = value != 0;
     else if (n == "join_coop") ctx->opt_join_coop = value != 0;
+    else if (n == "evict_first") ctx->opt_evict_first = value != 0;
     else if (n == "push_ctas") {
         if (value < 1 || value > 1024) return fail(ctx, INQ_ERR_ARG, "push_ctas must be in [1, 1024]");
         ctx->opt_push_ctas = (int)value;
@@ -1251,6 +1255,17 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     // kEvChunk-slot chunks and a warp strands the remainder of its chunk whenever a tile does not fit any more
     if (ctx->evraw.cap == 0) TRY(ensure(ctx, ctx->evraw, C / 16 + 4096 + raw_slack));
     TRY(build_plan(ctx, n_wt));
+    if (getenv("INQ_JOIN_TRACE") && R) {
+        const uint64_t ctas = (R + 255) / 256;
+        if (ctas != ctx->join_trace_ctas) {
+            if (ctx->join_trace) cudaFree(ctx->join_trace);
+            ctx->join_trace = nullptr;
+            CU_TRY(ctx, cudaMalloc(&ctx->join_trace, (ctas * 3 + 8) * sizeof(unsigned long long)));
+            ctx->join_trace_ctas = ctas;
+            drop_graph(ctx);
+            ctx->have_last_key = false;
+        }
+    }
 
     // results go straight to the caller's arrays when those are pinned, otherwise through a pinned staging buffer
     const bool direct_out = L == 0 || (is_pinned(twice_h1) && is_pinned(twice_h2) && is_pinned(valid_mask));
@@ -1290,7 +1305,7 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DevCounters), s));
         CU_TRY(ctx, cudaMemsetAsync(ctx->delta.p, 0, ((uint64_t)L + 2) * sizeof(uint32_t), s));
         CU_TRY(ctx, cudaMemsetAsync(ctx->desc_scan.p, 0, 2 * ((uint64_t)loc_scan_tiles + 1) * sizeof(uint64_t), s));
-        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->opt_join_coop, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr);
+        k_join_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(rv, lv, unphased, ctx->opt_join_coop, ctx->cand_lo.p, ctx->cand_n.p, ctx->delta.p, ctx->d_ctr, ctx->join_trace);
         const unsigned g = std::min<unsigned>(loc_scan_tiles, (unsigned)ctx->sm_count * 4);
         k_exclusive_scan<<<g, kXsThreads, 0, s>>>(ctx->delta.p, ctx->lcnt.p, (uint64_t)L + 1, loc_scan_tiles, ctx->desc_scan.p,
                                                   &ctx->d_ctr->scan_counter[2], nullptr);
@@ -1381,6 +1396,14 @@ int inq_genotype(inq_ctx *ctx, uint32_t minlen, uint32_t support, int unphased, 
     }
     if (!done) return fail(ctx, INQ_ERR_STATE, "internal: speculative buffers still too small after 4 attempts");
     ctx->last_n_events = (ntiles && L) ? ctx->h_total[3] : 0;      // .y of wt[n_wt]
+    if (ctx->join_trace) {
+        // experiments: dump the trace of the last pass (binary u64 triples: start ns, end ns, SM), plus the pass start
+        if (const char *path = getenv("INQ_JOIN_TRACE")) {
+            std::vector<unsigned long long> h(ctx->join_trace_ctas * 3);
+            CU_TRY(ctx, cudaMemcpy(h.data(), ctx->join_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+        }
+    }
     if (!direct_out && L) {
         memcpy(twice_h1, rp.o1, (size_t)L * sizeof(int64_t));
         memcpy(twice_h2, rp.o2, (size_t)L * sizeof(int64_t));

@@ -353,8 +353,16 @@ __device__ __forceinline__ void candidate_range_warp(bool unphased, const LocusV
 // every locus, which sizes that locus' segment of the call buffer (an upper bound on its pairs).
 __global__ void __launch_bounds__(256)
 k_join_ranges(ReadView rv, LocusView lv, int unphased, int coop, uint32_t *__restrict__ cand_lo, uint32_t *__restrict__ cand_n,
-              uint32_t *__restrict__ delta /* L+1, zeroed */, DevCounters *__restrict__ ctr)
+              uint32_t *__restrict__ delta /* L+1, zeroed */, DevCounters *__restrict__ ctr, unsigned long long *__restrict__ trace)
 {
+    // (trace, experiments only: globaltimer at the start and the end of every CTA, and the SM it ran on)
+    if (trace && threadIdx.x == 0) {
+        unsigned long long t; unsigned int sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        trace[3ull * blockIdx.x] = t;
+        trace[3ull * blockIdx.x + 2] = sm;
+    }
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     int lo = 0, n = 0;
     int c = -1;
@@ -396,6 +404,14 @@ k_join_ranges(ReadView rv, LocusView lv, int unphased, int coop, uint32_t *__res
     const uint32_t cand_w = __reduce_add_sync(0xffffffffu, (uint32_t)n);
     if (lane_id() == 0 && cand_w)
         atomicAdd(&ctr->stat[(blockIdx.x * 8u + (threadIdx.x >> 5)) % kStatSlots][ST_CANDIDATES], (unsigned long long)cand_w);
+    if (trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[3ull * blockIdx.x + 1] = t;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -449,6 +465,7 @@ struct ScanParams {
     uint64_t n_wt;
     uint32_t thr;                 // (min(minlen, 2^28 - 1) << 4) | 15: an op is longer than minlen iff its word > thr
     uint32_t neg1;                // 0xFFFFFFFF as a run-time value (keeps thr - w a multiply-add on the FMA pipe)
+    uint32_t evict_first;         // 1: the CIGAR words are loaded with the L2 evict-first policy
     uint32_t debug;               // timing experiments only, compiled in with -DINQ_TIMING_EXPERIMENTS: results are wrong when != 0
 };
 #ifdef INQ_TIMING_EXPERIMENTS
@@ -497,11 +514,26 @@ constexpr size_t kScanSmemBytes = sizeof(ScanSmem) + 1024;   // slack to align t
 // (16-byte chunk index bits [2:4] ^= 128-byte row index bits [5:7])
 __device__ __forceinline__ uint32_t swz(uint32_t idx) { return idx ^ (((idx >> 5) & 7u) << 2); }
 
-__device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap *tmap, uint32_t row, uint64_t *bar)
+// `policy`: L2 cache policy of the load, 0 = none. The stream is read exactly once, so its lines are marked evict-first:
+// otherwise 10 GB of them flush the catalog and the per-read arrays out of the 126 MB L2, and every probe of the join
+// chain that runs next to the scan (and of the pair kernel after it) goes to the saturated HBM instead.
+__device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap *tmap, uint32_t row, uint64_t *bar, uint64_t policy)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar))
-                 : "memory");
+    if (policy) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                     ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar)), "l"(policy)
+                     : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar))
+                     : "memory");
+    }
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 // Every warp is an independent pipeline: it owns warp tiles gwid, gwid + W, gwid + 2W, ... (W = warps
 // in the grid), a kWarpStages-deep ring of 4 KB shared-memory boxes (one warp tile each) that it fills itself with TMA, and the
@@ -518,6 +550,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
     constexpr uint32_t kRowsPerBox = kWarpTileWords / 32;       // 128-byte rows
     const uint64_t gwid = p.wt_begin + (uint64_t)blockIdx.x * kScanWarps + warp, stride = (uint64_t)gridDim.x * kScanWarps;
     uint64_t *full = sm.full[warp];
+    const uint64_t l2_policy = p.evict_first ? l2_evict_first_policy() : 0ull;
 
     if (lane == 0) {
         for (int s = 0; s < kWarpStages; ++s) mbar_init(&full[s], 1);
@@ -526,7 +559,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             const uint64_t gw = gwid + (uint64_t)s * stride;
             if (gw < p.n_wt) {
                 mbar_expect_tx(&full[s], kBoxBytes);
-                tma_load_tile(sm.stage[warp][s], &tmap, (uint32_t)gw * kRowsPerBox, &full[s]);
+                tma_load_tile(sm.stage[warp][s], &tmap, (uint32_t)gw * kRowsPerBox, &full[s], l2_policy);
             }
         }
     }
@@ -681,7 +714,7 @@ k_cigar_scan(const __grid_constant__ CUtensorMap tmap, ScanParams p)
             if (nxt < p.n_wt) {
                 fence_proxy_async();
                 mbar_expect_tx(&full[s], kBoxBytes);
-                tma_load_tile(sm.stage[warp][s], &tmap, (uint32_t)nxt * kRowsPerBox, &full[s]);
+                tma_load_tile(sm.stage[warp][s], &tmap, (uint32_t)nxt * kRowsPerBox, &full[s], l2_policy);
             }
         }
     }
