@@ -82,6 +82,12 @@ bool bgzf_selfcheck(const std::string &path, std::string *report)
     while (p + 28 <= file.size() - 16) {
         const uint16_t xlen = rd16(&file[p + 10]);
         const size_t bsize = (size_t)rd16(&file[p + 16]) + 1;
+        // a BGZF member: gzip magic, deflate, FEXTRA, the 6-byte 'BC' subfield first (what every BGZF writer emits)
+        if (file[p] != 0x1f || file[p + 1] != 0x8b || file[p + 2] != 8 || !(file[p + 3] & 4) || file[p + 12] != 'B' || file[p + 13] != 'C' ||
+            bsize < (size_t)12 + xlen + 8 || p + bsize > file.size() - 16) {
+            *report = "not a BGZF member at offset " + std::to_string(p);
+            return false;
+        }
         const uint8_t *pay = &file[p + 12 + xlen];
         const size_t in_len = bsize - 12 - xlen - 8;
         const uint32_t crc = rd32(&file[p + bsize - 8]), isize = rd32(&file[p + bsize - 4]);

@@ -12,6 +12,13 @@
 
 namespace inqhost {
 
+#ifdef INQ_INFLATE_STATS
+inline uint64_t g_st[8];                // experiments: lookups / bytes by kind
+#define INQ_ST(i, n) (g_st[i] += (n))
+#else
+#define INQ_ST(i, n) ((void)0)
+#endif
+
 class FastInflater {
 public:
     // decodes exactly out_len bytes from in[0, in_len); in must be readable up to in + in_len + 8
@@ -21,11 +28,14 @@ public:
 private:
     static constexpr int kLitBits = 11, kDistBits = 8;
     static constexpr uint32_t kTypeLiteral = 0, kTypeBase = 1, kTypeEob = 2, kTypeSub = 3;
+    static constexpr uint32_t kLitFlag = 1u << 15;     // set in literal entries: one bit test in the hot loop
     // entry: bits 0-3 code bits to consume at this level, 4-7 extra bits (type base) or sub-table index bits
     // (type sub), 8-9 type, 16-31 literal / base value / sub-table offset. 0 = invalid.
     static uint32_t make(uint32_t type, uint32_t bits, uint32_t extra, uint32_t value)
     {
-        return bits | (extra << 4) | (type << 8) | (value << 16);
+        // (bits 10-14: everything a base entry takes from the stream, code + extra bits, so that the hot loop advances the
+        // buffer with one shift and reads the extra bits from a copy, off the dependent chain)
+        return bits | (extra << 4) | (type << 8) | ((type == kTypeBase ? bits + extra : 0u) << 10) | (type == kTypeLiteral ? kLitFlag : 0u) | (value << 16);
     }
     bool build(const uint8_t *lens, int n, int primary_bits, uint32_t *table, int table_cap, bool is_dist);
     bool read_dynamic_header();
@@ -33,7 +43,11 @@ private:
 
     uint32_t lit_[(1 << kLitBits) + 2048];
     uint32_t dist_[(1 << kDistBits) + 1024];
-    uint32_t lit2_[1 << kLitBits];                     // two literals at once: bits 0-3 total code bits (<= 11), 4-7 unused, 16-31 the two bytes; 0 = no pair
+    static constexpr int kMultiBits = 10;
+    // up to three literals per lookup: bits 0-3 total code bits (<= kMultiBits), 4-5 how many, 8-31 the bytes in output
+    // order; 0 = the next symbol is not a literal whose code fits the index. The dependent chain lookup -> shift -> lookup
+    // is what bounds a literal-heavy stream (BAM SEQ / QUAL), so each lookup should retire as many bytes as it can.
+    uint32_t litn_[1 << kMultiBits];
     void build_pairs();
     bool fixed_loaded_ = false;
 
@@ -66,11 +80,13 @@ static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 
 static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 static const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-inline uint32_t bitrev(uint32_t v, int n)
+inline uint32_t bitrev(uint32_t v, int n)              // the low n (<= 16) bits of v, reversed
 {
-    uint32_t r = 0;
-    for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
-    return r;
+    v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
+    v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+    v = ((v & 0x0F0Fu) << 4) | ((v >> 4) & 0x0F0Fu);
+    v = ((v & 0x00FFu) << 8) | ((v >> 8) & 0x00FFu);
+    return v >> (16 - n);
 }
 }  // namespace inflate_detail
 
@@ -151,24 +167,27 @@ inline bool FastInflater::build(const uint8_t *lens, int n, int P, uint32_t *tab
     return true;
 }
 
-// lit2_[i]: when the next 11 bits hold two complete literal codes, both bytes and the bits they take
+// litn_[i]: the literals (up to three) whose codes are complete within the next 12 bits
 inline void FastInflater::build_pairs()
 {
-    for (uint32_t i = 0; i < (1u << kLitBits); ++i) {
+    constexpr uint32_t kPrimMask = (1u << kLitBits) - 1u;
+    for (uint32_t i = 0; i < (1u << kMultiBits); ++i) {
         uint32_t v = 0;
-        const uint32_t e1 = lit_[i];
-        if (e1 && ((e1 >> 8) & 3u) == kTypeLiteral) {
-            const uint32_t l1 = e1 & 15u;
-            if (l1 < (uint32_t)kLitBits) {
-                // the entry at (i >> l1) was filled for every value of the bits above its own code, so it is the right
-                // one exactly when its code fits in the 11 - l1 bits that are known
-                const uint32_t e2 = lit_[i >> l1];
-                const uint32_t l2 = e2 & 15u;
-                if (e2 && ((e2 >> 8) & 3u) == kTypeLiteral && l1 + l2 <= (uint32_t)kLitBits)
-                    v = (l1 + l2) | ((e1 >> 16) << 16) | ((e2 >> 16) << 24);
+        const uint32_t e1 = lit_[i & kPrimMask];
+        if ((e1 & kLitFlag) && (e1 & 15u) <= (uint32_t)kMultiBits) {
+            // an entry found through bits that are not all known (zeros above the 12) is the right one exactly when
+            // its own code fits in the bits that are known: the table repeats it for every value of the bits above
+            uint32_t used = e1 & 15u, n = 1, bytes = e1 >> 16;
+            while (n < 3) {
+                const uint32_t e = lit_[(i >> used) & kPrimMask];
+                if (!(e & kLitFlag) || used + (e & 15u) > (uint32_t)kMultiBits) break;
+                bytes |= (e >> 16) << (8 * n);
+                used += e & 15u;
+                ++n;
             }
+            v = used | (n << 4) | (bytes << 8);
         }
-        lit2_[i] = v;
+        litn_[i] = v;
     }
 }
 
@@ -233,6 +252,7 @@ inline bool FastInflater::read_dynamic_header()
     if (!build(lens + hlit, hdist, kDistBits, dist_, (int)(sizeof(dist_) / sizeof(dist_[0])), true)) return false;
     fixed_loaded_ = false;
     build_pairs();
+    INQ_ST(5, 1);
     return true;
 }
 
@@ -266,77 +286,119 @@ inline bool FastInflater::inflate(const uint8_t *in, size_t in_len, uint8_t *out
         } else if (btype == 1 || btype == 2) {
             if (btype == 1) {
                 if (!fixed_loaded_) { load_fixed(); fixed_loaded_ = true; }
-            } else if (!read_dynamic_header()) {
-                return false;
+            } else {
+#ifdef INQ_INFLATE_STATS
+                const uint64_t t0_ = __builtin_ia32_rdtsc();
+#endif
+                if (!read_dynamic_header()) return false;
+#ifdef INQ_INFLATE_STATS
+                g_st[2] += __builtin_ia32_rdtsc() - t0_;
+#endif
             }
             // fast loop: far enough from the end of the output (a symbol writes at most 258 + 7 bytes, three
-            // literals 3) that nothing needs a bounds check; the checked loop below finishes the block
+            // literals 3) that nothing needs a bounds check, and far enough from the end of the input that every
+            // refill is an unconditional 8-byte load (the 8 trailer bytes behind the payload are readable); the
+            // checked loop below finishes the block. The reader's state lives in locals here: the byte stores through
+            // `out` may alias the members as far as the compiler can tell, which would cost a reload per symbol.
             bool eob = false;
-            if (out_len > 320) {
+            if (out_len > 320 && bitcnt_ >= 0) {
                 uint8_t *const fast_end = out_end - 320;
-                while (out < fast_end) {
-                    refill();
-                    // literal pairs first: up to 5 lookups (55 bits) per refill, two bytes each
-                    {
-                        uint32_t p2 = lit2_[peek(kLitBits)];
-                        if (p2) {
-                            int budget = bitcnt_ < 56 ? 0 : 5;
-                            do {
-                                consume((int)(p2 & 15u));
-                                const uint16_t two = (uint16_t)(p2 >> 16);
-                                memcpy(out, &two, 2);
-                                out += 2;
-                                if (--budget <= 0) break;
-                                p2 = lit2_[peek(kLitBits)];
-                            } while (p2);
+                const uint8_t *in = in_;
+                const uint8_t *const in_last = in_end_;              // a load may start here at the latest
+                uint64_t bb = bitbuf_;
+                int bc = bitcnt_;
+                const uint32_t *const lit = lit_, *const litn = litn_, *const dtab = dist_;
+                constexpr uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u, kMultiMask = (1u << kMultiBits) - 1u;
+#define INQ_REFILL()                                   \
+    do {                                               \
+        uint64_t w_;                                   \
+        memcpy(&w_, in, 8);                            \
+        bb |= w_ << bc;                                \
+        in += (63 - bc) >> 3;                          \
+        bc |= 56;                                      \
+    } while (0)
+                bool bad = false;
+                // `e` is always the litlen entry for the bits at the front of the buffer, loaded one step ahead: after a
+                // match it is fetched before the copy, so the table latency hides behind it
+                INQ_REFILL();
+                uint32_t e = lit[(uint32_t)bb & kLitMask];
+                while (out < fast_end && in <= in_last) {
+                    if (e & kLitFlag) {
+                        // literals: up to 4 lookups (48 bits) per refill, up to three bytes each (a 4-byte store, the
+                        // pointer advances by the count; the fast loop's margin covers the spill)
+                        uint32_t m = litn[(uint32_t)bb & kMultiMask];
+                        if (kMultiBits < kLitBits && !m) {
+                            // a literal whose code is longer than the multi-literal table's index
+                            bb >>= (e & 15u);
+                            bc -= (int)(e & 15u);
+                            *out++ = (uint8_t)(e >> 16);
+                            INQ_REFILL();
+                            e = lit[(uint32_t)bb & kLitMask];
                             continue;
                         }
-                    }
-                    uint32_t e = lit_[peek(kLitBits)];
-                    if (__builtin_expect(((e >> 8) & 3u) == kTypeLiteral && e, 1)) {
-                    lit1:
-                        // single literals (codes too long to pair up): up to three per refill (3 x 15 <= 56 bits)
-                        consume((int)(e & 15u));
-                        *out++ = (uint8_t)(e >> 16);
-                        if (bitcnt_ >= 30) {
-                            e = lit_[peek(kLitBits)];
-                            if (((e >> 8) & 3u) == kTypeLiteral && e) {
-                                consume((int)(e & 15u));
-                                *out++ = (uint8_t)(e >> 16);
-                                e = lit_[peek(kLitBits)];
-                                if (((e >> 8) & 3u) == kTypeLiteral && e) {
-                                    consume((int)(e & 15u));
-                                    *out++ = (uint8_t)(e >> 16);
-                                }
-                            }
-                        }
+                        int budget = 4;
+                        do {
+                            const uint32_t nb = m & 15u;
+                            bb >>= nb;
+                            bc -= (int)nb;
+                            const uint32_t bytes = m >> 8;
+                            memcpy(out, &bytes, 4);
+                            out += (m >> 4) & 3u;
+                            INQ_ST(0, 1); INQ_ST(1, (m >> 4) & 3u);
+                            if (--budget <= 0) break;
+                            m = litn[(uint32_t)bb & kMultiMask];
+                        } while (m);
+                        INQ_REFILL();
+                        e = lit[(uint32_t)bb & kLitMask];
                         continue;
                     }
                     if (((e >> 8) & 3u) == kTypeSub) {
-                        consume(kLitBits);
-                        e = lit_[(e >> 16) + peek((int)((e >> 4) & 15u))];
-                        if (((e >> 8) & 3u) == kTypeLiteral && e) goto lit1;
+                        bb >>= kLitBits;
+                        bc -= kLitBits;
+                        e = lit[(e >> 16) + ((uint32_t)bb & ((1u << ((e >> 4) & 15u)) - 1u))];
+                        if (e & kLitFlag) {
+                            // (a long literal code: at most 15 bits gone)
+                            bb >>= (e & 15u);
+                            bc -= (int)(e & 15u);
+                            *out++ = (uint8_t)(e >> 16);
+                            INQ_REFILL();
+                            e = lit[(uint32_t)bb & kLitMask];
+                            continue;
+                        }
                     }
-                    if (!e) return false;
-                    consume((int)(e & 15u));
-                    if (((e >> 8) & 3u) == kTypeEob) { eob = true; break; }
-                    const uint32_t xl = (e >> 4) & 15u;
-                    const uint32_t len = (e >> 16) + peek((int)xl);
-                    consume((int)xl);
-                    uint32_t d = dist_[peek(kDistBits)];
+                    if (!e) { bad = true; break; }
+                    if (((e >> 8) & 3u) == kTypeEob) {
+                        bb >>= (e & 15u);
+                        bc -= (int)(e & 15u);
+                        eob = true;
+                        break;
+                    }
+                    // length: one shift on the chain (code + extra bits), the extra bits come from the copy
+                    const uint64_t sl = bb;
+                    const uint32_t tl = (e >> 10) & 31u;
+                    bb >>= tl;
+                    bc -= (int)tl;
+                    const uint32_t len = (e >> 16) + ((uint32_t)(sl >> (e & 15u)) & ((1u << ((e >> 4) & 15u)) - 1u));
+                    uint32_t d = dtab[(uint32_t)bb & kDistMask];
                     if (((d >> 8) & 3u) == kTypeSub) {
-                        consume(kDistBits);
-                        d = dist_[(d >> 16) + peek((int)((d >> 4) & 15u))];
+                        bb >>= kDistBits;
+                        bc -= kDistBits;
+                        d = dtab[(d >> 16) + ((uint32_t)bb & ((1u << ((d >> 4) & 15u)) - 1u))];
                     }
-                    if (!d || ((d >> 8) & 3u) != kTypeBase) return false;
-                    consume((int)(d & 15u));
-                    const uint32_t xd = (d >> 4) & 15u;
-                    const uint32_t dist = (d >> 16) + peek((int)xd);
-                    consume((int)xd);
-                    if (dist > (size_t)(out - out_begin)) return false;
+                    if (!d || ((d >> 8) & 3u) != kTypeBase) { bad = true; break; }
+                    const uint64_t sd = bb;
+                    const uint32_t td = (d >> 10) & 31u;
+                    bb >>= td;
+                    bc -= (int)td;
+                    const uint32_t dist = (d >> 16) + ((uint32_t)(sd >> (d & 15u)) & ((1u << ((d >> 4) & 15u)) - 1u));
+                    if (dist > (size_t)(out - out_begin)) { bad = true; break; }
+                    // next symbol's entry first (at most 48 of the 56 bits are gone: the refill cannot be skipped)
+                    INQ_REFILL();
+                    e = lit[(uint32_t)bb & kLitMask];
                     const uint8_t *src = out - dist;
                     uint8_t *dst = out;
                     out += len;
+                    INQ_ST(3, 1); INQ_ST(4, len); INQ_ST(6, dist < 8); INQ_ST(7, len > 8);
                     if (dist >= 8) {
                         do {
                             uint64_t w;
@@ -348,13 +410,15 @@ inline bool FastInflater::inflate(const uint8_t *in, size_t in_len, uint8_t *out
                     } else if (dist == 1) {
                         memset(dst, *src, len);
                     } else {
-                        // short period: replicate the pattern until the copy distance is at least a word
-                        uint32_t done = 0;
-                        while (done < len && done < 8) { dst[done] = src[done]; ++done; }
-                        // from here on source and destination are >= dist * k apart; grow by copying what is already written
-                        while (done < len) { dst[done] = dst[done - dist]; ++done; }
+                        // short period: plain forward byte copy (source and destination overlap)
+                        for (uint32_t k = 0; k < len; ++k) dst[k] = src[k];
                     }
                 }
+#undef INQ_REFILL
+                in_ = in;
+                bitbuf_ = bb;
+                bitcnt_ = bc;
+                if (bad) return false;
             }
             while (!eob) {
                 refill();                                            // >= 56 bits: enough for one length/distance pair (48)

@@ -209,6 +209,27 @@ def test_host_bam_reader_matches_workload(cli, tmp_path):
         assert st["accidental_2d"] == int((w.reads.flags & 1).sum()) == st["sa_tagged"]
 
 
+def test_own_deflate_decoder_equals_zlib_on_every_block(cli, tmp_path):
+    """`bgzf-check`: the host ingest's own DEFLATE decoder against zlib, block by block, bytes compared -- stored blocks
+    (level 0), the match-heavy streams of level 1, the literal-heavy ones of level 6 (with SEQ/QUAL: long dynamic
+    codes, two-level tables), and the reference's own BGZF fixture where it exists. A declined block would fall back
+    to zlib in the product; here it fails the test."""
+    import json
+    from synth import synth as S
+    w = S.make_workload(3, scale=0.0006, threads=2)
+    for level, with_seq in ((0, False), (1, True), (6, True), (9, False)):
+        bam = str(tmp_path / f"l{level}.bam")
+        assert S.write_bam(w, bam, with_seq=with_seq, level=level) > 0
+        r = run(cli, "bgzf-check", bam)
+        assert r.returncode == 0, r.stderr
+        st = json.loads(r.stdout)
+        assert st["blocks"] > 1 and st["mismatch"] == 0 and st["fast_declined"] == 0, (level, st)
+    ref_gz = "/root/reference/test-data/file1.inq.gz"
+    if os.path.exists(ref_gz):                      # plain gzip is not BGZF: the walker says so
+        r = run(cli, "bgzf-check", ref_gz)
+        assert r.returncode == 1 and b"not a BGZF member" in r.stdout
+
+
 @pytest.mark.gpu
 def test_cli_on_synthetic_bam_with_seq(cli, tmp_path):
     """tools/bench_bam.py path: config 3 (shrunk) written as a BAM with SEQ/QUAL, shuffled BED, -t 8"""
