@@ -26,6 +26,16 @@ public:
     bool inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
 
 private:
+    enum { kReady = 0, kDone = 1, kFail = 2 };
+    static constexpr size_t kFastMargin = 320;
+    void start(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+    int prepare();
+    int fast_single();
+    bool finish_block(bool eob);
+    // the fast loop may run: room for its unchecked stores, input left for its unconditional loads, a sane bit count
+    bool fast_ok() const { return (size_t)(out_end_ - out_) > kFastMargin && in_ <= in_end_ && bitcnt_ >= 0; }
+    uint8_t *out_ = nullptr, *out_begin_ = nullptr, *out_end_ = nullptr;
+    bool bfinal_ = false, finished_ = false;
     static constexpr int kLitBits = 11, kDistBits = 8;
     static constexpr uint32_t kTypeLiteral = 0, kTypeBase = 1, kTypeEob = 2, kTypeSub = 3;
     static constexpr uint32_t kLitFlag = 1u << 15;     // set in literal entries: one bit test in the hot loop
@@ -256,211 +266,266 @@ inline bool FastInflater::read_dynamic_header()
     return true;
 }
 
-inline bool FastInflater::inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
+inline void FastInflater::start(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
 {
     in_ = in_begin_ = in;
     in_end_ = in + in_len;
     bitbuf_ = 0;
     bitcnt_ = 0;
-    uint8_t *const out_begin = out, *const out_end = out + out_len;
+    out_ = out_begin_ = out;
+    out_end_ = out + out_len;
+    bfinal_ = false;
+    finished_ = false;
+}
+
+// block headers (and whole stored blocks) up to the first symbol of a Huffman block
+inline int FastInflater::prepare()
+{
     for (;;) {
+        if (finished_) return kDone;
         refill();
-        const uint32_t bfinal = peek(1), btype = (uint32_t)(bitbuf_ >> 1) & 3u;
+        bfinal_ = peek(1) != 0;
+        const uint32_t btype = (uint32_t)(bitbuf_ >> 1) & 3u;
         consume(3);
         if (btype == 0) {
             // stored: skip to the byte boundary, LEN / NLEN, raw bytes
-            if (bitcnt_ < 0) return false;
+            if (bitcnt_ < 0) return kFail;
             consume(bitcnt_ & 7);
             // unread bytes sit in the bit buffer: step the input pointer back to the first unconsumed byte
             const uint8_t *p = in_ - (bitcnt_ >> 3);
-            if (p + 4 > in_end_) return false;
+            if (p + 4 > in_end_) return kFail;
             const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8), nlen = (uint32_t)p[2] | ((uint32_t)p[3] << 8);
-            if ((len ^ 0xFFFFu) != nlen) return false;
+            if ((len ^ 0xFFFFu) != nlen) return kFail;
             p += 4;
-            if (p + len > in_end_ || out + len > out_end) return false;
-            memcpy(out, p, len);
-            out += len;
+            if (p + len > in_end_ || out_ + len > out_end_) return kFail;
+            memcpy(out_, p, len);
+            out_ += len;
             in_ = p + len;
             bitbuf_ = 0;
             bitcnt_ = 0;
-        } else if (btype == 1 || btype == 2) {
-            if (btype == 1) {
-                if (!fixed_loaded_) { load_fixed(); fixed_loaded_ = true; }
-            } else {
+            if (!consumed_ok()) return kFail;
+            if (bfinal_) finished_ = true;
+            continue;
+        }
+        if (btype == 1) {
+            if (!fixed_loaded_) { load_fixed(); fixed_loaded_ = true; }
+            return kReady;
+        }
+        if (btype == 2) {
 #ifdef INQ_INFLATE_STATS
-                const uint64_t t0_ = __builtin_ia32_rdtsc();
+            const uint64_t t0_ = __builtin_ia32_rdtsc();
 #endif
-                if (!read_dynamic_header()) return false;
+            const bool ok = read_dynamic_header();
 #ifdef INQ_INFLATE_STATS
-                g_st[2] += __builtin_ia32_rdtsc() - t0_;
+            g_st[2] += __builtin_ia32_rdtsc() - t0_;
 #endif
-            }
-            // fast loop: far enough from the end of the output (a symbol writes at most 258 + 7 bytes, three
-            // literals 3) that nothing needs a bounds check, and far enough from the end of the input that every
-            // refill is an unconditional 8-byte load (the 8 trailer bytes behind the payload are readable); the
-            // checked loop below finishes the block. The reader's state lives in locals here: the byte stores through
-            // `out` may alias the members as far as the compiler can tell, which would cost a reload per symbol.
-            bool eob = false;
-            if (out_len > 320 && bitcnt_ >= 0) {
-                uint8_t *const fast_end = out_end - 320;
-                const uint8_t *in = in_;
-                const uint8_t *const in_last = in_end_;              // a load may start here at the latest
-                uint64_t bb = bitbuf_;
-                int bc = bitcnt_;
-                const uint32_t *const lit = lit_, *const litn = litn_, *const dtab = dist_;
-                constexpr uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u, kMultiMask = (1u << kMultiBits) - 1u;
-#define INQ_REFILL()                                   \
+            return ok ? kReady : kFail;
+        }
+        return kFail;
+    }
+}
+
+// One symbol step of the fast loop on the stream whose locals carry the prefix P. (Stepping two independent blocks
+// alternately in one loop -- two dependent chains for the out-of-order core -- was measured: the same MB/s, so the chain
+// lookup -> shift -> lookup is not what bounds it; the data-dependent literal / match branch is.) Far enough from
+// the end of the output (a symbol writes at most 258 + 7 bytes, three literals 4) that nothing needs a bounds check,
+// and far enough from the end of the input that every refill is an unconditional 8-byte load (the 8 trailer bytes
+// behind the payload are readable); the checked loop of finish_block() ends the block. The reader's state lives in
+// locals: the byte stores through `out` may alias the members as far as the compiler can tell. P##e is always the
+// litlen entry for the bits at the front of the buffer, loaded one step ahead: after a match it is fetched before the
+// copy, so the table latency hides behind it. Sets P##ex: 1 end of block, 2 invalid stream.
+#define INQ_REFILL(P)                                  \
     do {                                               \
         uint64_t w_;                                   \
-        memcpy(&w_, in, 8);                            \
-        bb |= w_ << bc;                                \
-        in += (63 - bc) >> 3;                          \
-        bc |= 56;                                      \
+        memcpy(&w_, P##in, 8);                         \
+        P##bb |= w_ << P##bc;                          \
+        P##in += (63 - P##bc) >> 3;                    \
+        P##bc |= 56;                                   \
     } while (0)
-                bool bad = false;
-                // `e` is always the litlen entry for the bits at the front of the buffer, loaded one step ahead: after a
-                // match it is fetched before the copy, so the table latency hides behind it
-                INQ_REFILL();
-                uint32_t e = lit[(uint32_t)bb & kLitMask];
-                while (out < fast_end && in <= in_last) {
-                    if (e & kLitFlag) {
-                        // literals: up to 4 lookups (48 bits) per refill, up to three bytes each (a 4-byte store, the
-                        // pointer advances by the count; the fast loop's margin covers the spill)
-                        uint32_t m = litn[(uint32_t)bb & kMultiMask];
-                        if (kMultiBits < kLitBits && !m) {
-                            // a literal whose code is longer than the multi-literal table's index
-                            bb >>= (e & 15u);
-                            bc -= (int)(e & 15u);
-                            *out++ = (uint8_t)(e >> 16);
-                            INQ_REFILL();
-                            e = lit[(uint32_t)bb & kLitMask];
-                            continue;
-                        }
-                        int budget = 4;
-                        do {
-                            const uint32_t nb = m & 15u;
-                            bb >>= nb;
-                            bc -= (int)nb;
-                            const uint32_t bytes = m >> 8;
-                            memcpy(out, &bytes, 4);
-                            out += (m >> 4) & 3u;
-                            INQ_ST(0, 1); INQ_ST(1, (m >> 4) & 3u);
-                            if (--budget <= 0) break;
-                            m = litn[(uint32_t)bb & kMultiMask];
-                        } while (m);
-                        INQ_REFILL();
-                        e = lit[(uint32_t)bb & kLitMask];
-                        continue;
-                    }
-                    if (((e >> 8) & 3u) == kTypeSub) {
-                        bb >>= kLitBits;
-                        bc -= kLitBits;
-                        e = lit[(e >> 16) + ((uint32_t)bb & ((1u << ((e >> 4) & 15u)) - 1u))];
-                        if (e & kLitFlag) {
-                            // (a long literal code: at most 15 bits gone)
-                            bb >>= (e & 15u);
-                            bc -= (int)(e & 15u);
-                            *out++ = (uint8_t)(e >> 16);
-                            INQ_REFILL();
-                            e = lit[(uint32_t)bb & kLitMask];
-                            continue;
-                        }
-                    }
-                    if (!e) { bad = true; break; }
-                    if (((e >> 8) & 3u) == kTypeEob) {
-                        bb >>= (e & 15u);
-                        bc -= (int)(e & 15u);
-                        eob = true;
-                        break;
-                    }
-                    // length: one shift on the chain (code + extra bits), the extra bits come from the copy
-                    const uint64_t sl = bb;
-                    const uint32_t tl = (e >> 10) & 31u;
-                    bb >>= tl;
-                    bc -= (int)tl;
-                    const uint32_t len = (e >> 16) + ((uint32_t)(sl >> (e & 15u)) & ((1u << ((e >> 4) & 15u)) - 1u));
-                    uint32_t d = dtab[(uint32_t)bb & kDistMask];
-                    if (((d >> 8) & 3u) == kTypeSub) {
-                        bb >>= kDistBits;
-                        bc -= kDistBits;
-                        d = dtab[(d >> 16) + ((uint32_t)bb & ((1u << ((d >> 4) & 15u)) - 1u))];
-                    }
-                    if (!d || ((d >> 8) & 3u) != kTypeBase) { bad = true; break; }
-                    const uint64_t sd = bb;
-                    const uint32_t td = (d >> 10) & 31u;
-                    bb >>= td;
-                    bc -= (int)td;
-                    const uint32_t dist = (d >> 16) + ((uint32_t)(sd >> (d & 15u)) & ((1u << ((d >> 4) & 15u)) - 1u));
-                    if (dist > (size_t)(out - out_begin)) { bad = true; break; }
-                    // next symbol's entry first (at most 48 of the 56 bits are gone: the refill cannot be skipped)
-                    INQ_REFILL();
-                    e = lit[(uint32_t)bb & kLitMask];
-                    const uint8_t *src = out - dist;
-                    uint8_t *dst = out;
-                    out += len;
-                    INQ_ST(3, 1); INQ_ST(4, len); INQ_ST(6, dist < 8); INQ_ST(7, len > 8);
-                    if (dist >= 8) {
-                        do {
-                            uint64_t w;
-                            memcpy(&w, src, 8);
-                            memcpy(dst, &w, 8);
-                            src += 8;
-                            dst += 8;
-                        } while (dst < out);
-                    } else if (dist == 1) {
-                        memset(dst, *src, len);
-                    } else {
-                        // short period: plain forward byte copy (source and destination overlap)
-                        for (uint32_t k = 0; k < len; ++k) dst[k] = src[k];
-                    }
-                }
-#undef INQ_REFILL
-                in_ = in;
-                bitbuf_ = bb;
-                bitcnt_ = bc;
-                if (bad) return false;
-            }
-            while (!eob) {
-                refill();                                            // >= 56 bits: enough for one length/distance pair (48)
-                uint32_t e = lit_[peek(kLitBits)];
-                if (((e >> 8) & 3u) == kTypeSub) {
-                    consume(kLitBits);
-                    e = lit_[(e >> 16) + peek((int)((e >> 4) & 15u))];
-                }
-                if (!e) return false;
-                consume((int)(e & 15u));
-                const uint32_t type = (e >> 8) & 3u;
-                if (type == kTypeLiteral) {
-                    if (out >= out_end) return false;
-                    *out++ = (uint8_t)(e >> 16);
-                    continue;
-                }
-                if (type == kTypeEob) break;
-                const uint32_t xl = (e >> 4) & 15u;
-                const uint32_t len = (e >> 16) + peek((int)xl);
-                consume((int)xl);
-                uint32_t d = dist_[peek(kDistBits)];
-                if (((d >> 8) & 3u) == kTypeSub) {
-                    consume(kDistBits);
-                    d = dist_[(d >> 16) + peek((int)((d >> 4) & 15u))];
-                }
-                if (!d || ((d >> 8) & 3u) != kTypeBase) return false;
-                consume((int)(d & 15u));
-                const uint32_t xd = (d >> 4) & 15u;
-                const uint32_t dist = (d >> 16) + peek((int)xd);
-                consume((int)xd);
-                if (dist > (size_t)(out - out_begin) || len > (size_t)(out_end - out)) return false;
-                const uint8_t *src = out - dist;
-                for (uint32_t k = 0; k < len; ++k) out[k] = src[k];
-                out += len;
-            }
-        } else {
-            return false;
-        }
-        if (!consumed_ok()) return false;
-        if (bfinal) break;
+#define INQ_FAST_STEP(P)                                                                                              \
+    do {                                                                                                              \
+        uint32_t e = P##e;                                                                                            \
+        if (e & kLitFlag) {                                                                                           \
+            /* literals: up to 4 lookups (48 bits) per refill, up to three bytes each (a 4-byte store, the pointer */ \
+            /* advances by the count; the fast loop's margin covers the spill) */                                     \
+            uint32_t m = P##litn[(uint32_t)P##bb & kMultiMask];                                                       \
+            if (kMultiBits < kLitBits && !m) {                                                                        \
+                /* a literal whose code is longer than the multi-literal table's index */                             \
+                P##bb >>= (e & 15u);                                                                                  \
+                P##bc -= (int)(e & 15u);                                                                              \
+                *P##out++ = (uint8_t)(e >> 16);                                                                       \
+            } else {                                                                                                  \
+                int budget = 4;                                                                                       \
+                do {                                                                                                  \
+                    const uint32_t nb = m & 15u;                                                                      \
+                    P##bb >>= nb;                                                                                     \
+                    P##bc -= (int)nb;                                                                                 \
+                    const uint32_t bytes = m >> 8;                                                                    \
+                    memcpy(P##out, &bytes, 4);                                                                        \
+                    P##out += (m >> 4) & 3u;                                                                          \
+                    INQ_ST(0, 1); INQ_ST(1, (m >> 4) & 3u);                                                           \
+                    if (--budget <= 0) break;                                                                         \
+                    m = P##litn[(uint32_t)P##bb & kMultiMask];                                                        \
+                } while (m);                                                                                          \
+            }                                                                                                         \
+            INQ_REFILL(P);                                                                                            \
+            P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                                \
+            break;                                                                                                    \
+        }                                                                                                             \
+        if (((e >> 8) & 3u) == kTypeSub) {                                                                            \
+            P##bb >>= kLitBits;                                                                                       \
+            P##bc -= kLitBits;                                                                                        \
+            e = P##lit[(e >> 16) + ((uint32_t)P##bb & ((1u << ((e >> 4) & 15u)) - 1u))];                              \
+            if (e & kLitFlag) {                                                                                       \
+                /* (a long literal code: at most 15 bits gone) */                                                     \
+                P##bb >>= (e & 15u);                                                                                  \
+                P##bc -= (int)(e & 15u);                                                                              \
+                *P##out++ = (uint8_t)(e >> 16);                                                                       \
+                INQ_REFILL(P);                                                                                        \
+                P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                            \
+                break;                                                                                                \
+            }                                                                                                         \
+        }                                                                                                             \
+        if (!e) { P##ex = 2; break; }                                                                                 \
+        if (((e >> 8) & 3u) == kTypeEob) {                                                                            \
+            P##bb >>= (e & 15u);                                                                                      \
+            P##bc -= (int)(e & 15u);                                                                                  \
+            P##ex = 1;                                                                                                \
+            break;                                                                                                    \
+        }                                                                                                             \
+        /* length: one shift on the chain (code + extra bits), the extra bits come from the copy */                   \
+        const uint64_t sl = P##bb;                                                                                    \
+        const uint32_t tl = (e >> 10) & 31u;                                                                          \
+        P##bb >>= tl;                                                                                                 \
+        P##bc -= (int)tl;                                                                                             \
+        const uint32_t len = (e >> 16) + ((uint32_t)(sl >> (e & 15u)) & ((1u << ((e >> 4) & 15u)) - 1u));             \
+        uint32_t d = P##dtab[(uint32_t)P##bb & kDistMask];                                                            \
+        if (((d >> 8) & 3u) == kTypeSub) {                                                                            \
+            P##bb >>= kDistBits;                                                                                      \
+            P##bc -= kDistBits;                                                                                       \
+            d = P##dtab[(d >> 16) + ((uint32_t)P##bb & ((1u << ((d >> 4) & 15u)) - 1u))];                             \
+        }                                                                                                             \
+        if (!d || ((d >> 8) & 3u) != kTypeBase) { P##ex = 2; break; }                                                 \
+        const uint64_t sd = P##bb;                                                                                    \
+        const uint32_t td = (d >> 10) & 31u;                                                                          \
+        P##bb >>= td;                                                                                                 \
+        P##bc -= (int)td;                                                                                             \
+        const uint32_t dist = (d >> 16) + ((uint32_t)(sd >> (d & 15u)) & ((1u << ((d >> 4) & 15u)) - 1u));            \
+        if (dist > (size_t)(P##out - P##out_begin)) { P##ex = 2; break; }                                             \
+        /* next symbol's entry first (at most 48 of the 56 bits are gone: the refill cannot be skipped) */            \
+        INQ_REFILL(P);                                                                                                \
+        P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                                    \
+        const uint8_t *src = P##out - dist;                                                                           \
+        uint8_t *dst = P##out;                                                                                        \
+        P##out += len;                                                                                                \
+        INQ_ST(3, 1); INQ_ST(4, len); INQ_ST(6, dist < 8); INQ_ST(7, len > 8);                                        \
+        if (dist >= 8) {                                                                                              \
+            do {                                                                                                      \
+                uint64_t w;                                                                                           \
+                memcpy(&w, src, 8);                                                                                   \
+                memcpy(dst, &w, 8);                                                                                   \
+                src += 8;                                                                                             \
+                dst += 8;                                                                                             \
+            } while (dst < P##out);                                                                                   \
+        } else if (dist == 1) {                                                                                       \
+            memset(dst, *src, len);                                                                                   \
+        } else {                                                                                                      \
+            /* short period: plain forward byte copy (source and destination overlap) */                              \
+            for (uint32_t k = 0; k < len; ++k) dst[k] = src[k];                                                       \
+        }                                                                                                             \
+    } while (0)
+#define INQ_FAST_LOAD(P, obj)                                                                                          \
+    const uint8_t *P##in = (obj).in_;                                                                                 \
+    const uint8_t *const P##in_last = (obj).in_end_; /* a load may start here at the latest */                        \
+    uint64_t P##bb = (obj).bitbuf_;                                                                                   \
+    int P##bc = (obj).bitcnt_;                                                                                        \
+    uint8_t *P##out = (obj).out_;                                                                                     \
+    uint8_t *const P##out_begin = (obj).out_begin_;                                                                   \
+    uint8_t *const P##fast_end = (obj).out_end_ - kFastMargin;                                                        \
+    const uint32_t *const P##lit = (obj).lit_, *const P##litn = (obj).litn_, *const P##dtab = (obj).dist_;            \
+    int P##ex = 0;                                                                                                    \
+    INQ_REFILL(P);                                                                                                    \
+    uint32_t P##e = P##lit[(uint32_t)P##bb & kLitMask]
+#define INQ_FAST_STORE(P, obj)                                                                                         \
+    (obj).in_ = P##in;                                                                                                \
+    (obj).bitbuf_ = P##bb;                                                                                            \
+    (obj).bitcnt_ = P##bc;                                                                                            \
+    (obj).out_ = P##out
+
+// fast loop of one stream; returns 0 (left the fast region), 1 (end of block) or 2 (invalid)
+inline int FastInflater::fast_single()
+{
+    if (!fast_ok()) return 0;
+    constexpr uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u, kMultiMask = (1u << kMultiBits) - 1u;
+    INQ_FAST_LOAD(a_, *this);
+    while (a_out < a_fast_end && a_in <= a_in_last) {
+        INQ_FAST_STEP(a_);
+        if (a_ex) break;
     }
-    return out == out_end;
+    INQ_FAST_STORE(a_, *this);
+    return a_ex;
+}
+
+#undef INQ_FAST_LOAD
+#undef INQ_FAST_STORE
+#undef INQ_FAST_STEP
+#undef INQ_REFILL
+
+// the rest of the current block with every bound checked; `eob`: the fast loop has already consumed the end-of-block code
+inline bool FastInflater::finish_block(bool eob)
+{
+    uint8_t *out = out_;
+    while (!eob) {
+        refill();                                            // >= 56 bits: enough for one length/distance pair (48)
+        uint32_t e = lit_[peek(kLitBits)];
+        if (((e >> 8) & 3u) == kTypeSub) {
+            consume(kLitBits);
+            e = lit_[(e >> 16) + peek((int)((e >> 4) & 15u))];
+        }
+        if (!e) return false;
+        consume((int)(e & 15u));
+        const uint32_t type = (e >> 8) & 3u;
+        if (type == kTypeLiteral) {
+            if (out >= out_end_) return false;
+            *out++ = (uint8_t)(e >> 16);
+            continue;
+        }
+        if (type == kTypeEob) break;
+        const uint32_t xl = (e >> 4) & 15u;
+        const uint32_t len = (e >> 16) + peek((int)xl);
+        consume((int)xl);
+        uint32_t d = dist_[peek(kDistBits)];
+        if (((d >> 8) & 3u) == kTypeSub) {
+            consume(kDistBits);
+            d = dist_[(d >> 16) + peek((int)((d >> 4) & 15u))];
+        }
+        if (!d || ((d >> 8) & 3u) != kTypeBase) return false;
+        consume((int)(d & 15u));
+        const uint32_t xd = (d >> 4) & 15u;
+        const uint32_t dist = (d >> 16) + peek((int)xd);
+        consume((int)xd);
+        if (dist > (size_t)(out - out_begin_) || len > (size_t)(out_end_ - out)) return false;
+        const uint8_t *src = out - dist;
+        for (uint32_t k = 0; k < len; ++k) out[k] = src[k];
+        out += len;
+    }
+    out_ = out;
+    if (!consumed_ok()) return false;
+    if (bfinal_) finished_ = true;
+    return true;
+}
+
+inline bool FastInflater::inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
+{
+    start(in, in_len, out, out_len);
+    for (;;) {
+        const int r = prepare();
+        if (r == kFail) return false;
+        if (r == kDone) break;
+        const int ex = fast_single();
+        if (ex == 2 || !finish_block(ex == 1)) return false;
+    }
+    return out_ == out_end_;
 }
 
 }  // namespace inqhost
