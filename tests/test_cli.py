@@ -230,6 +230,26 @@ def test_own_deflate_decoder_equals_zlib_on_every_block(cli, tmp_path):
         assert r.returncode == 1 and b"not a BGZF member" in r.stdout
 
 
+def test_own_deflate_decoder_survives_corrupted_blocks(tmp_path):
+    """tests/fuzz_inflate.cpp under ASan + UBSan: bit flips, random spans, damaged headers, truncated input, output
+    buffers that are too small or too large -- the decoder declines or decodes, and never reads outside
+    [in, in + in_len + 8) or writes outside [out, out + out_len). (In the product a declined block goes to zlib and
+    every block is CRC-checked.)"""
+    from synth import synth as S
+    exe = str(tmp_path / "fuzz_inflate")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                         "-I", os.path.join(ROOT, "inquistr_b200", "csrc", "host"), "-o", exe,
+                         os.path.join(ROOT, "tests", "fuzz_inflate.cpp")], capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + cc.stderr[-300:])
+    w = S.make_workload(3, scale=0.0005, threads=2)
+    for level, with_seq in ((1, True), (6, False)):
+        bam = str(tmp_path / f"f{level}.bam")
+        assert S.write_bam(w, bam, with_seq=with_seq, level=level) > 0
+        r = subprocess.run([exe, bam, "4000"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "fuzz: 4000 cases" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
 @pytest.mark.gpu
 def test_cli_on_synthetic_bam_with_seq(cli, tmp_path):
     """tools/bench_bam.py path: config 3 (shrunk) written as a BAM with SEQ/QUAL, shuffled BED, -t 8"""
