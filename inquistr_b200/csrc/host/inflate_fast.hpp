@@ -38,15 +38,25 @@ private:
     bool bfinal_ = false, finished_ = false;
     static constexpr int kLitBits = 11, kDistBits = 8;
     static constexpr uint32_t kTypeLiteral = 0, kTypeBase = 1, kTypeEob = 2, kTypeSub = 3;
-    static constexpr uint32_t kLitFlag = 1u << 15;     // set in literal entries: one bit test in the hot loop
-    // entry: bits 0-3 code bits to consume at this level, 4-7 extra bits (type base) or sub-table index bits
-    // (type sub), 8-9 type, 16-31 literal / base value / sub-table offset. 0 = invalid.
+    // Table entry (0 = invalid), laid out for the fewest instructions in the symbol loop:
+    //   bits 0-7   everything the entry takes from the stream at this level: a literal's or the end-of-block code, a
+    //              length / distance code PLUS its extra bits (one shift advances the buffer), the primary index bits in
+    //              front of a sub-table
+    //   bits 8-11  base entries: the code bits alone (the extra bits start there in a copy of the buffer; bits 12-13 are
+    //              clear in a base entry, so (e >> 8) is a valid 6-bit shift count as it stands); sub entries: index bits
+    //   bit 12 sub-table pointer, bit 13 end of block, bit 14 length / distance base, bit 15 literal
+    //   bits 16-31 literal byte | base value | sub-table offset
+    static constexpr uint32_t kSubFlag = 1u << 12, kEobFlag = 1u << 13, kBaseFlag = 1u << 14, kLitFlag = 1u << 15;
     static uint32_t make(uint32_t type, uint32_t bits, uint32_t extra, uint32_t value)
     {
-        // (bits 10-14: everything a base entry takes from the stream, code + extra bits, so that the hot loop advances the
-        // buffer with one shift and reads the extra bits from a copy, off the dependent chain)
-        return bits | (extra << 4) | (type << 8) | ((type == kTypeBase ? bits + extra : 0u) << 10) | (type == kTypeLiteral ? kLitFlag : 0u) | (value << 16);
+        switch (type) {
+        case kTypeLiteral: return bits | kLitFlag | (value << 16);
+        case kTypeEob: return bits | kEobFlag;
+        case kTypeBase: return (bits + extra) | (bits << 8) | kBaseFlag | (value << 16);
+        default: return bits | (extra << 8) | kSubFlag | (value << 16);      // sub-table: `extra` = its index bits
+        }
     }
+    static uint32_t entry_bits(uint32_t e) { return e & 0xFFu; }
     bool build(const uint8_t *lens, int n, int primary_bits, uint32_t *table, int table_cap, bool is_dist);
     bool read_dynamic_header();
     void load_fixed();
@@ -89,6 +99,11 @@ static const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 1
 static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
 static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+// kExtraMask[n] = n low bits set (n <= 15); kTotalMask[n] likewise for 64-bit values (n <= 28: code + extra bits)
+static const uint32_t kExtraMask[16] = {0x0, 0x1, 0x3, 0x7, 0xF, 0x1F, 0x3F, 0x7F, 0xFF, 0x1FF, 0x3FF, 0x7FF, 0xFFF, 0x1FFF, 0x3FFF, 0x7FFF};
+static const uint64_t kTotalMask[32] = {0x0, 0x1, 0x3, 0x7, 0xF, 0x1F, 0x3F, 0x7F, 0xFF, 0x1FF, 0x3FF, 0x7FF, 0xFFF, 0x1FFF, 0x3FFF, 0x7FFF, 0xFFFF,
+                                        0x1FFFF, 0x3FFFF, 0x7FFFF, 0xFFFFF, 0x1FFFFF, 0x3FFFFF, 0x7FFFFF, 0xFFFFFF, 0x1FFFFFF, 0x3FFFFFF, 0x7FFFFFF,
+                                        0xFFFFFFF, 0x1FFFFFFF, 0x3FFFFFFF, 0x7FFFFFFF};
 static const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 inline uint32_t bitrev(uint32_t v, int n)              // the low n (<= 16) bits of v, reversed
 {
@@ -169,7 +184,7 @@ inline bool FastInflater::build(const uint8_t *lens, int n, int P, uint32_t *tab
         } else {
             const uint32_t prefix = rev & (uint32_t)(psize - 1);
             const uint32_t pe = table[prefix];
-            const uint32_t sb = (pe >> 4) & 15u, off = pe >> 16;
+            const uint32_t sb = (pe >> 8) & 15u, off = pe >> 16;
             const uint32_t e = make(type, (uint32_t)(l - P), extra, value);
             for (uint32_t i = rev >> P; i < (1u << sb); i += 1u << (l - P)) table[off + i] = e;
         }
@@ -184,15 +199,15 @@ inline void FastInflater::build_pairs()
     for (uint32_t i = 0; i < (1u << kMultiBits); ++i) {
         uint32_t v = 0;
         const uint32_t e1 = lit_[i & kPrimMask];
-        if ((e1 & kLitFlag) && (e1 & 15u) <= (uint32_t)kMultiBits) {
+        if ((e1 & kLitFlag) && (e1 & 0xFFu) <= (uint32_t)kMultiBits) {
             // an entry found through bits that are not all known (zeros above the 12) is the right one exactly when
             // its own code fits in the bits that are known: the table repeats it for every value of the bits above
-            uint32_t used = e1 & 15u, n = 1, bytes = e1 >> 16;
+            uint32_t used = e1 & 0xFFu, n = 1, bytes = e1 >> 16;
             while (n < 3) {
                 const uint32_t e = lit_[(i >> used) & kPrimMask];
-                if (!(e & kLitFlag) || used + (e & 15u) > (uint32_t)kMultiBits) break;
+                if (!(e & kLitFlag) || used + (e & 0xFFu) > (uint32_t)kMultiBits) break;
                 bytes |= (e >> 16) << (8 * n);
-                used += e & 15u;
+                used += e & 0xFFu;
                 ++n;
             }
             v = used | (n << 4) | (bytes << 8);
@@ -238,8 +253,8 @@ inline bool FastInflater::read_dynamic_header()
     while (i < total) {
         if (bitcnt_ < 7 + 7) refill();
         const uint32_t e = cltab[peek(7)];
-        if (!e || ((e >> 8) & 3u) != kTypeLiteral) return false;
-        consume((int)(e & 15u));
+        if (!(e & kLitFlag)) return false;
+        consume((int)(e & 0xFFu));
         const uint32_t sym = e >> 16;
         if (sym < 16) { lens[i++] = (uint8_t)sym; continue; }
         int rep;
@@ -351,8 +366,8 @@ inline int FastInflater::prepare()
             uint32_t m = P##litn[(uint32_t)P##bb & kMultiMask];                                                       \
             if (kMultiBits < kLitBits && !m) {                                                                        \
                 /* a literal whose code is longer than the multi-literal table's index */                             \
-                P##bb >>= (e & 15u);                                                                                  \
-                P##bc -= (int)(e & 15u);                                                                              \
+                P##bb >>= (e & 0xFFu);                                                                                \
+                P##bc -= (int)(e & 0xFFu);                                                                            \
                 *P##out++ = (uint8_t)(e >> 16);                                                                       \
             } else {                                                                                                  \
                 int budget = 4;                                                                                       \
@@ -372,45 +387,48 @@ inline int FastInflater::prepare()
             P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                                \
             break;                                                                                                    \
         }                                                                                                             \
-        if (((e >> 8) & 3u) == kTypeSub) {                                                                            \
-            P##bb >>= kLitBits;                                                                                       \
-            P##bc -= kLitBits;                                                                                        \
-            e = P##lit[(e >> 16) + ((uint32_t)P##bb & ((1u << ((e >> 4) & 15u)) - 1u))];                              \
-            if (e & kLitFlag) {                                                                                       \
-                /* (a long literal code: at most 15 bits gone) */                                                     \
-                P##bb >>= (e & 15u);                                                                                  \
-                P##bc -= (int)(e & 15u);                                                                              \
-                *P##out++ = (uint8_t)(e >> 16);                                                                       \
-                INQ_REFILL(P);                                                                                        \
-                P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                            \
+        if (__builtin_expect(!(e & kBaseFlag), 0)) {                                                                  \
+            /* rare: a code longer than the primary index, the end of the block, or an invalid entry */               \
+            if (e & kSubFlag) {                                                                                       \
+                P##bb >>= kLitBits;                                                                                   \
+                P##bc -= kLitBits;                                                                                    \
+                e = P##lit[(e >> 16) + ((uint32_t)P##bb & kExtraMask[(e >> 8) & 15u])];                               \
+                if (e & kLitFlag) {                                                                                   \
+                    /* (a long literal code: at most 15 bits gone) */                                                 \
+                    P##bb >>= (e & 0xFFu);                                                                            \
+                    P##bc -= (int)(e & 0xFFu);                                                                        \
+                    *P##out++ = (uint8_t)(e >> 16);                                                                   \
+                    INQ_REFILL(P);                                                                                    \
+                    P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                        \
+                    break;                                                                                            \
+                }                                                                                                     \
+            }                                                                                                         \
+            if (e & kEobFlag) {                                                                                       \
+                P##bb >>= (e & 0xFFu);                                                                                \
+                P##bc -= (int)(e & 0xFFu);                                                                            \
+                P##ex = 1;                                                                                            \
                 break;                                                                                                \
             }                                                                                                         \
+            if (!(e & kBaseFlag)) { P##ex = 2; break; }                                                               \
         }                                                                                                             \
-        if (!e) { P##ex = 2; break; }                                                                                 \
-        if (((e >> 8) & 3u) == kTypeEob) {                                                                            \
-            P##bb >>= (e & 15u);                                                                                      \
-            P##bc -= (int)(e & 15u);                                                                                  \
-            P##ex = 1;                                                                                                \
-            break;                                                                                                    \
-        }                                                                                                             \
-        /* length: one shift on the chain (code + extra bits), the extra bits come from the copy */                   \
+        /* length: one shift on the chain (code + extra bits); the extra bits are read from the copy: everything  */ \
+        /* below the entry's total, shifted down by its code bits ((e >> 8) is a clean 6-bit count in a base entry) */ \
         const uint64_t sl = P##bb;                                                                                    \
-        const uint32_t tl = (e >> 10) & 31u;                                                                          \
-        P##bb >>= tl;                                                                                                 \
-        P##bc -= (int)tl;                                                                                             \
-        const uint32_t len = (e >> 16) + ((uint32_t)(sl >> (e & 15u)) & ((1u << ((e >> 4) & 15u)) - 1u));             \
+        P##bb >>= (e & 0xFFu);                                                                                        \
+        P##bc -= (int)(e & 0xFFu);                                                                                    \
+        const uint32_t len = (e >> 16) + (uint32_t)((sl & kTotalMask[e & 0xFFu]) >> ((e >> 8) & 63u));                \
         uint32_t d = P##dtab[(uint32_t)P##bb & kDistMask];                                                            \
-        if (((d >> 8) & 3u) == kTypeSub) {                                                                            \
+        if (__builtin_expect(!(d & kBaseFlag), 0)) {                                                                  \
+            if (!(d & kSubFlag)) { P##ex = 2; break; }                                                                \
             P##bb >>= kDistBits;                                                                                      \
             P##bc -= kDistBits;                                                                                       \
-            d = P##dtab[(d >> 16) + ((uint32_t)P##bb & ((1u << ((d >> 4) & 15u)) - 1u))];                             \
+            d = P##dtab[(d >> 16) + ((uint32_t)P##bb & kExtraMask[(d >> 8) & 15u])];                                  \
+            if (!(d & kBaseFlag)) { P##ex = 2; break; }                                                               \
         }                                                                                                             \
-        if (!d || ((d >> 8) & 3u) != kTypeBase) { P##ex = 2; break; }                                                 \
         const uint64_t sd = P##bb;                                                                                    \
-        const uint32_t td = (d >> 10) & 31u;                                                                          \
-        P##bb >>= td;                                                                                                 \
-        P##bc -= (int)td;                                                                                             \
-        const uint32_t dist = (d >> 16) + ((uint32_t)(sd >> (d & 15u)) & ((1u << ((d >> 4) & 15u)) - 1u));            \
+        P##bb >>= (d & 0xFFu);                                                                                        \
+        P##bc -= (int)(d & 0xFFu);                                                                                    \
+        const uint32_t dist = (d >> 16) + (uint32_t)((sd & kTotalMask[d & 0xFFu]) >> ((d >> 8) & 63u));               \
         if (dist > (size_t)(P##out - P##out_begin)) { P##ex = 2; break; }                                             \
         /* next symbol's entry first (at most 48 of the 56 bits are gone: the refill cannot be skipped) */            \
         INQ_REFILL(P);                                                                                                \
@@ -456,6 +474,8 @@ inline int FastInflater::prepare()
 inline int FastInflater::fast_single()
 {
     if (!fast_ok()) return 0;
+    using inflate_detail::kExtraMask;
+    using inflate_detail::kTotalMask;
     constexpr uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u, kMultiMask = (1u << kMultiBits) - 1u;
     INQ_FAST_LOAD(a_, *this);
     while (a_out < a_fast_end && a_in <= a_in_last) {
@@ -478,30 +498,30 @@ inline bool FastInflater::finish_block(bool eob)
     while (!eob) {
         refill();                                            // >= 56 bits: enough for one length/distance pair (48)
         uint32_t e = lit_[peek(kLitBits)];
-        if (((e >> 8) & 3u) == kTypeSub) {
+        if (e & kSubFlag) {
             consume(kLitBits);
-            e = lit_[(e >> 16) + peek((int)((e >> 4) & 15u))];
+            e = lit_[(e >> 16) + peek((int)((e >> 8) & 15u))];
         }
-        if (!e) return false;
-        consume((int)(e & 15u));
-        const uint32_t type = (e >> 8) & 3u;
-        if (type == kTypeLiteral) {
+        if (!e || (e & kSubFlag)) return false;
+        if (e & kLitFlag) {
+            consume((int)entry_bits(e));
             if (out >= out_end_) return false;
             *out++ = (uint8_t)(e >> 16);
             continue;
         }
-        if (type == kTypeEob) break;
-        const uint32_t xl = (e >> 4) & 15u;
+        if (e & kEobFlag) { consume((int)entry_bits(e)); break; }
+        const uint32_t cl = (e >> 8) & 15u, xl = entry_bits(e) - cl;
+        consume((int)cl);
         const uint32_t len = (e >> 16) + peek((int)xl);
         consume((int)xl);
         uint32_t d = dist_[peek(kDistBits)];
-        if (((d >> 8) & 3u) == kTypeSub) {
+        if (d & kSubFlag) {
             consume(kDistBits);
-            d = dist_[(d >> 16) + peek((int)((d >> 4) & 15u))];
+            d = dist_[(d >> 16) + peek((int)((d >> 8) & 15u))];
         }
-        if (!d || ((d >> 8) & 3u) != kTypeBase) return false;
-        consume((int)(d & 15u));
-        const uint32_t xd = (d >> 4) & 15u;
+        if (!(d & kBaseFlag)) return false;
+        const uint32_t cd = (d >> 8) & 15u, xd = entry_bits(d) - cd;
+        consume((int)cd);
         const uint32_t dist = (d >> 16) + peek((int)xd);
         consume((int)xd);
         if (dist > (size_t)(out - out_begin_) || len > (size_t)(out_end_ - out)) return false;
