@@ -63,12 +63,6 @@ private:
 
     uint32_t lit_[(1 << kLitBits) + 2048];
     uint32_t dist_[(1 << kDistBits) + 1024];
-    static constexpr int kMultiBits = 10;
-    // up to three literals per lookup: bits 0-3 total code bits (<= kMultiBits), 4-5 how many, 8-31 the bytes in output
-    // order; 0 = the next symbol is not a literal whose code fits the index. The dependent chain lookup -> shift -> lookup
-    // is what bounds a literal-heavy stream (BAM SEQ / QUAL), so each lookup should retire as many bytes as it can.
-    uint32_t litn_[1 << kMultiBits];
-    void build_pairs();
     bool fixed_loaded_ = false;
 
     // bit reader
@@ -192,30 +186,6 @@ inline bool FastInflater::build(const uint8_t *lens, int n, int P, uint32_t *tab
     return true;
 }
 
-// litn_[i]: the literals (up to three) whose codes are complete within the next 12 bits
-inline void FastInflater::build_pairs()
-{
-    constexpr uint32_t kPrimMask = (1u << kLitBits) - 1u;
-    for (uint32_t i = 0; i < (1u << kMultiBits); ++i) {
-        uint32_t v = 0;
-        const uint32_t e1 = lit_[i & kPrimMask];
-        if ((e1 & kLitFlag) && (e1 & 0xFFu) <= (uint32_t)kMultiBits) {
-            // an entry found through bits that are not all known (zeros above the 12) is the right one exactly when
-            // its own code fits in the bits that are known: the table repeats it for every value of the bits above
-            uint32_t used = e1 & 0xFFu, n = 1, bytes = e1 >> 16;
-            while (n < 3) {
-                const uint32_t e = lit_[(i >> used) & kPrimMask];
-                if (!(e & kLitFlag) || used + (e & 0xFFu) > (uint32_t)kMultiBits) break;
-                bytes |= (e >> 16) << (8 * n);
-                used += e & 0xFFu;
-                ++n;
-            }
-            v = used | (n << 4) | (bytes << 8);
-        }
-        litn_[i] = v;
-    }
-}
-
 inline void FastInflater::load_fixed()
 {
     // RFC 1951 3.2.6; symbols 286/287 and distance codes 30/31 exist only to complete the codes
@@ -228,7 +198,6 @@ inline void FastInflater::load_fixed()
     uint8_t dl[32];
     for (int i = 0; i < 32; ++i) dl[i] = 5;
     build(dl, 32, kDistBits, dist_, (int)(sizeof(dist_) / sizeof(dist_[0])), true);
-    build_pairs();
 }
 
 inline bool FastInflater::read_dynamic_header()
@@ -276,7 +245,6 @@ inline bool FastInflater::read_dynamic_header()
     if (!build(lens, hlit, kLitBits, lit_, (int)(sizeof(lit_) / sizeof(lit_[0])), false)) return false;
     if (!build(lens + hlit, hdist, kDistBits, dist_, (int)(sizeof(dist_) / sizeof(dist_[0])), true)) return false;
     fixed_loaded_ = false;
-    build_pairs();
     INQ_ST(5, 1);
     return true;
 }
@@ -361,27 +329,33 @@ inline int FastInflater::prepare()
     do {                                                                                                              \
         uint32_t e = P##e;                                                                                            \
         if (e & kLitFlag) {                                                                                           \
-            /* literals: up to 4 lookups (48 bits) per refill, up to three bytes each (a 4-byte store, the pointer */ \
-            /* advances by the count; the fast loop's margin covers the spill) */                                     \
-            uint32_t m = P##litn[(uint32_t)P##bb & kMultiMask];                                                       \
-            if (kMultiBits < kLitBits && !m) {                                                                        \
-                /* a literal whose code is longer than the multi-literal table's index */                             \
+            /* a run of literals: up to four primary-table codes (4 x 11 bits) on one refill. (A table that retires */  \
+            /* two or three literals per lookup was measured: slower on both the level-1 and the level-6 streams --  */  \
+            /* 1.0 to 1.3 literals per lookup there -- and it costs 10 k cycles per block to build.) */                 \
+            P##bb >>= (e & 0xFFu);                                                                                    \
+            P##bc -= (int)(e & 0xFFu);                                                                                \
+            *P##out++ = (uint8_t)(e >> 16);                                                                           \
+            INQ_ST(0, 1); INQ_ST(1, 1);                                                                               \
+            e = P##lit[(uint32_t)P##bb & kLitMask];                                                                   \
+            if (e & kLitFlag) {                                                                                       \
                 P##bb >>= (e & 0xFFu);                                                                                \
                 P##bc -= (int)(e & 0xFFu);                                                                            \
                 *P##out++ = (uint8_t)(e >> 16);                                                                       \
-            } else {                                                                                                  \
-                int budget = 4;                                                                                       \
-                do {                                                                                                  \
-                    const uint32_t nb = m & 15u;                                                                      \
-                    P##bb >>= nb;                                                                                     \
-                    P##bc -= (int)nb;                                                                                 \
-                    const uint32_t bytes = m >> 8;                                                                    \
-                    memcpy(P##out, &bytes, 4);                                                                        \
-                    P##out += (m >> 4) & 3u;                                                                          \
-                    INQ_ST(0, 1); INQ_ST(1, (m >> 4) & 3u);                                                           \
-                    if (--budget <= 0) break;                                                                         \
-                    m = P##litn[(uint32_t)P##bb & kMultiMask];                                                        \
-                } while (m);                                                                                          \
+                INQ_ST(1, 1);                                                                                         \
+                e = P##lit[(uint32_t)P##bb & kLitMask];                                                               \
+                if (e & kLitFlag) {                                                                                   \
+                    P##bb >>= (e & 0xFFu);                                                                            \
+                    P##bc -= (int)(e & 0xFFu);                                                                        \
+                    *P##out++ = (uint8_t)(e >> 16);                                                                   \
+                    INQ_ST(1, 1);                                                                                     \
+                    e = P##lit[(uint32_t)P##bb & kLitMask];                                                           \
+                    if (e & kLitFlag) {                                                                               \
+                        P##bb >>= (e & 0xFFu);                                                                        \
+                        P##bc -= (int)(e & 0xFFu);                                                                    \
+                        *P##out++ = (uint8_t)(e >> 16);                                                               \
+                        INQ_ST(1, 1);                                                                                 \
+                    }                                                                                                 \
+                }                                                                                                     \
             }                                                                                                         \
             INQ_REFILL(P);                                                                                            \
             P##e = P##lit[(uint32_t)P##bb & kLitMask];                                                                \
@@ -460,7 +434,7 @@ inline int FastInflater::prepare()
     uint8_t *P##out = (obj).out_;                                                                                     \
     uint8_t *const P##out_begin = (obj).out_begin_;                                                                   \
     uint8_t *const P##fast_end = (obj).out_end_ - kFastMargin;                                                        \
-    const uint32_t *const P##lit = (obj).lit_, *const P##litn = (obj).litn_, *const P##dtab = (obj).dist_;            \
+    const uint32_t *const P##lit = (obj).lit_, *const P##dtab = (obj).dist_;            \
     int P##ex = 0;                                                                                                    \
     INQ_REFILL(P);                                                                                                    \
     uint32_t P##e = P##lit[(uint32_t)P##bb & kLitMask]
@@ -476,7 +450,7 @@ inline int FastInflater::fast_single()
     if (!fast_ok()) return 0;
     using inflate_detail::kExtraMask;
     using inflate_detail::kTotalMask;
-    constexpr uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u, kMultiMask = (1u << kMultiBits) - 1u;
+    constexpr uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u;
     INQ_FAST_LOAD(a_, *this);
     while (a_out < a_fast_end && a_in <= a_in_last) {
         INQ_FAST_STEP(a_);
