@@ -161,8 +161,9 @@ Args parse_args(int argc, char **argv)
     }
     if (v[0] == "bamstat" && v.size() >= 2) {
         // extension: scan a BAM with the host reader only (no GPU): record counts and inflate rate;
-        // `bamstat x.bam chr:beg-end` does the same through the .bai index for one region
-        if (v.size() == 3) {
+        // `bamstat x.bam chr:beg-end` does the same through the .bai index for one region; `bamstat x.bam --parsed` runs
+        // the parallel parse of the call driver instead of the sequential record walk
+        if (v.size() == 3 && v[2] != "--parsed") {
             BamIndexedReader ix;
             if (!ix.open_bam(v[1]) || !ix.load_index(v[1] + ".bai")) { fprintf(stderr, "%s\n", ix.error().c_str()); exit(1); }
             const size_t c1 = v[2].find(':'), c2 = v[2].find('-', c1);
@@ -178,13 +179,30 @@ Args parse_args(int argc, char **argv)
         const auto t0 = std::chrono::steady_clock::now();
         int gpu = -1;                                           // `bamstat x.bam --gpu N`: GPU engine next to the workers
         if (v.size() >= 4 && v[2] == "--gpu") gpu = atoi(v[3].c_str());
-        if (!rd.open(v[1], (int)std::max(1u, std::thread::hardware_concurrency()), gpu)) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
+        const int host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+        if (!rd.open(v[1], host_threads, gpu)) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
         BamRecordView r;
         uint64_t n = 0, words = 0, hp = 0, sa = 0, d2 = 0;
-        while (rd.next(r)) {
-            ++n; words += r.n_cigar; hp += r.hp_type != HpType::Absent; sa += r.has_sa;
-            bool pn = false;
-            d2 += is_accidental_2d(r, &pn);
+        if (v.size() >= 3 && v[2] == "--parsed") {
+            // the host side of `call` without a device: batches parsed on the host threads exactly as the call driver
+            // does it (every record kept: no catalog, phased-mode filter off), counted instead of pushed
+            RecFilter filt;
+            filt.reach = [](const void *, int32_t, int32_t, int32_t) { return true; };
+            std::vector<ParsedChunk> chunks;
+            const int parse_threads = std::max(2, host_threads / 2);
+            while (rd.next_parsed(filt, parse_threads, chunks))
+                for (const ParsedChunk &c : chunks) {
+                    if (!c.err.empty()) { fprintf(stderr, "%s\n", c.err.c_str()); exit(1); }
+                    n += c.n_records;
+                    for (const BamRecLite &q : c.recs) { words += q.cigar ? q.n_cigar : 0; hp += q.hp_type != HpType::Absent; d2 += q.two_d; }
+                }
+            sa = d2;                                            // (the lite record only says whether the SA test came out true)
+        } else {
+            while (rd.next(r)) {
+                ++n; words += r.n_cigar; hp += r.hp_type != HpType::Absent; sa += r.has_sa;
+                bool pn = false;
+                d2 += is_accidental_2d(r, &pn);
+            }
         }
         if (!rd.error().empty()) { fprintf(stderr, "%s\n", rd.error().c_str()); exit(1); }
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

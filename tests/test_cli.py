@@ -207,6 +207,13 @@ def test_host_bam_reader_matches_workload(cli, tmp_path):
         assert st["cigar_words"] == len(w.reads.cigar)
         assert st["hp_tagged"] == int((w.reads.hp != 0xFF).sum())
         assert st["accidental_2d"] == int((w.reads.flags & 1).sum()) == st["sa_tagged"]
+        # the call driver's parallel parse (no device needed): every record seen, the CIGARs of the records that can
+        # pair somewhere (mapq > 10) kept
+        r = run(cli, "bamstat", bam, "--parsed")
+        assert r.returncode == 0, r.stderr
+        sp = json.loads(r.stdout)
+        n_cig = (w.reads.cigar_off[1:] - w.reads.cigar_off[:-1]).astype(np.int64)
+        assert sp["records"] == w.reads.n and sp["cigar_words"] == int(n_cig[w.reads.mapq > 10].sum())
 
 
 def test_own_deflate_decoder_equals_zlib_on_every_block(cli, tmp_path):
