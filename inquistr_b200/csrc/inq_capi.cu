@@ -3,13 +3,15 @@
 // No CPU implementation of the hot path lives here: without a CUDA device every entry fails.
 //
 // One genotyping pass is a small DAG over four streams:
-//   S0  memsets, then per range k of the CIGAR stream: k_cigar_scan(k) -> k_exclusive_scan2(k)
-//   S1  k_join_ranges + two scans (under scan(0)), then k_pair_eval(k) as soon as range k is scanned
-//   S2  k_locus_median(+big) over the catalog chunk that became complete with pair(k)
-//   S3  device->host copies of finished chunks
-// so that the latency-bound pair/median kernels and the result copy run under the HBM-bound scan of
-// the next range. The steady state (same reads, same parameters, pinned outputs) is replayed from a
-// CUDA graph; the first call of a shape and every regrow retry launch the same DAG directly.
+//   S0  counter memset, k_cigar_scan(k) per range k of the CIGAR stream; with one range (the default) also the prefix
+//       sum over its warp-tile totals (k_exclusive_scan2)
+//   S1  k_zero, k_join_ranges + two offset scans (next to scan(0)), then -- with several ranges k_exclusive_scan2(k)
+//       and -- k_pair_eval(k) as soon as range k is scanned
+//   S2  k_locus_median (+ the CTA-path kernel where the last pass had deep loci) over the catalog chunk that became
+//       complete with pair(k); the counters go home from here
+//   S3  k_push_results: finished chunks stored into the caller's pinned arrays (copy engines when they are not mapped)
+// The steady state (same reads, same parameters, same pinned outputs) is replayed from a CUDA graph; the first call
+// of a shape and every retry (speculative buffer regrown, CTA-path guess wrong) launch the same DAG directly.
 #include "../../include/inqcall.h"
 #include "inq_device.cuh"
 
