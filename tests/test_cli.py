@@ -237,6 +237,15 @@ def test_own_deflate_decoder_equals_zlib_on_every_block(cli, tmp_path):
         assert r.returncode == 1 and b"not a BGZF member" in r.stdout
 
 
+def test_clmul_crc32_equals_zlib(tmp_path):
+    """csrc/host/crc32_fast.hpp: every BGZF block's CRC-32 goes through it (PCLMULQDQ where the CPU has it)"""
+    exe = str(tmp_path / "crc32_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "inquistr_b200", "csrc", "host"), "-o", exe,
+                    os.path.join(ROOT, "tests", "crc32_check.cpp"), "-lz"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "bad 0", r.stdout
+
+
 def test_own_deflate_decoder_survives_corrupted_blocks(tmp_path):
     """tests/fuzz_inflate.cpp under ASan + UBSan: bit flips, random spans, damaged headers, truncated input, output
     buffers that are too small or too large -- the decoder declines or decodes, and never reads outside
